@@ -1,0 +1,252 @@
+// kpconv.cu — K5: KPConv forward (rigid kernel points, linear influence, sum aggregation).
+//
+// Replaces KPConv.forward (/root/reference/Predator_APR/models/blocks.py:229-374, non-deformable branch):
+//   w[n,k,h]   = max(0, 1 - |s[idx[n,h]] - q[n] - kp[k]| / extent)                  (:269-289, :328-329)
+//   wf[n,k,:]  = sum_h w[n,k,h] * x[idx[n,h],:]     (shadow idx == Ns -> zero row)   (:348-354)
+//   out[n,:]   = (sum_k wf[n,k,:] @ W[k]) / max(1, #{h : sum_c x[idx[n,h],c] > 0})   (:361-372)
+// Stage A+B (kp_weighted_kernel): one warp per query; influence weights are produced in shared memory, then the
+// neighbour feature rows are streamed once per 128-channel slab and accumulated only for the kernel points whose
+// influence is non-zero (a neighbour is inside the extent of ~1.4 of the 15 kernel points on average; the test is
+// warp-uniform, so skipping costs no divergence). wf is written as the [Nq, K*Cin] A operand of stage C.
+// Stage C: [Nq, K*Cin] x [K*Cin, Cout] contraction with the 1/neighbor_num row scale in the epilogue —
+// fp32 CUDA-core tiles here (mode 1); the tcgen05 TF32 path lives in gemm_tcgen05.cu (mode 2).
+#include "common.cuh"
+
+namespace aprb {
+
+int gemm_tf32_rowscale(const float* d_A, const float* d_Bt, int M, int N, int K, const float* d_rowscale, float* d_C,
+                       cudaStream_t st);  // gemm_tcgen05.cu
+bool gemm_tf32_supported(int M, int N, int K);
+
+constexpr int KP_MAX_K = 16;
+
+// flag[s] = 1 iff sum_c x[s,c] > 0 (one warp per support row; fixed reduction order)
+__global__ void rowsum_pos_kernel(const float* __restrict__ x, int Ns, int C, unsigned char* __restrict__ flag) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= Ns) return;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += x[(size_t)row * C + c];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) flag[row] = s > 0.f ? 1 : 0;
+}
+
+// Dynamic smem per warp: K*Hp floats of weights + Hp ints of indices (Hp = H rounded up to 32).
+template <typename IdxT, bool ROUND_TF32>
+__global__ void __launch_bounds__(128)
+kp_weighted_kernel(const float* __restrict__ q, const float* __restrict__ s, const IdxT* __restrict__ idx, int ld,
+                   const float* __restrict__ x, const float* __restrict__ kp, const unsigned char* __restrict__ posflag,
+                   float extent, int Nq, int Ns, int H, int K, int Cin, float* __restrict__ wf,
+                   float* __restrict__ inv_nn) {
+    extern __shared__ float s_dyn[];
+    __shared__ float s_kp[KP_MAX_K * 3];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int Hp = (H + 31) & ~31;
+    if (threadIdx.x < K * 3) s_kp[threadIdx.x] = kp[threadIdx.x];
+    __syncthreads();
+    const int n = blockIdx.x * wpb + wib;
+    if (n >= Nq) return;
+    float* s_w = s_dyn + (size_t)wib * (K + 1) * Hp;           // [K][Hp]
+    int* s_idx = reinterpret_cast<int*>(s_w + (size_t)K * Hp);  // [Hp]
+    const float qx = q[3 * (size_t)n], qy = q[3 * (size_t)n + 1], qz = q[3 * (size_t)n + 2];
+
+    int nn = 0;
+    for (int h = lane; h < Hp; h += 32) {
+        int si = Ns;
+        if (h < H) {
+            long long v = (long long)idx[(size_t)n * ld + h];
+            si = (v >= 0 && v < Ns) ? (int)v : Ns;
+        }
+        s_idx[h] = si;
+        if (si < Ns) {
+            nn += posflag[si];
+            const float rx = s[3 * (size_t)si] - qx, ry = s[3 * (size_t)si + 1] - qy, rz = s[3 * (size_t)si + 2] - qz;
+            for (int k = 0; k < K; ++k) {
+                const float ddx = rx - s_kp[3 * k], ddy = ry - s_kp[3 * k + 1], ddz = rz - s_kp[3 * k + 2];
+                const float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+                s_w[k * Hp + h] = fmaxf(1.0f - __fdiv_rn(__fsqrt_rn(d2), extent), 0.0f);
+            }
+        } else {
+            for (int k = 0; k < K; ++k) s_w[k * Hp + h] = 0.0f;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, d);
+    if (lane == 0) inv_nn[n] = 1.0f / (float)max(nn, 1);
+    __syncwarp();
+
+    // feature slabs of 128 channels: lane owns channels c0 + lane + 32*j, j < 4
+    float* wrow = wf + (size_t)n * K * Cin;
+    for (int c0 = 0; c0 < Cin; c0 += 128) {
+        float acc[KP_MAX_K][4];
+#pragma unroll
+        for (int k = 0; k < KP_MAX_K; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[k][j] = 0.f;
+        for (int h = 0; h < H; ++h) {
+            const int si = s_idx[h];
+            if (si >= Ns) continue;  // warp-uniform
+            float xv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = c0 + lane + 32 * j;
+                xv[j] = c < Cin ? x[(size_t)si * Cin + c] : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < KP_MAX_K; ++k) {
+                if (k < K) {
+                    const float w = s_w[k * Hp + h];  // broadcast
+                    if (w != 0.f) {                   // warp-uniform skip
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[k][j] = fmaf(w, xv[j], acc[k][j]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < KP_MAX_K; ++k) {
+            if (k < K) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int c = c0 + lane + 32 * j;
+                    if (c < Cin) {
+                        float v = acc[k][j];
+                        if (ROUND_TF32) {
+                            unsigned u;
+                            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+                            v = __uint_as_float(u);
+                        }
+                        wrow[(size_t)k * Cin + c] = v;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Plain fp32 tiled GEMM with row scale: C[M,N] = (A[M,K] @ B[K,N]) * rowscale[M]; A, B row-major. 64x64x16 tiles,
+// 256 threads, 4x4 outputs per thread. The parity baseline of stage C (CUDA cores, exact fp32 products).
+__global__ void __launch_bounds__(256)
+sgemm_rowscale_kernel(const float* __restrict__ A, const float* __restrict__ B, int M, int N, int K,
+                      const float* __restrict__ rowscale, float* __restrict__ C) {
+    __shared__ float sA[16][64 + 4];
+    __shared__ float sB[16][64 + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        for (int t = threadIdx.x; t < 64 * 16; t += 256) {
+            int r = t >> 4, c = t & 15;  // A tile: 64 rows x 16 k
+            int gm = m0 + r, gk = k0 + c;
+            sA[c][r] = (gm < M && gk < K) ? A[(size_t)gm * K + gk] : 0.f;
+            int kr = t >> 6, nc = t & 63;  // B tile: 16 k x 64 cols
+            int gk2 = k0 + kr, gn = n0 + nc;
+            sB[kr][nc] = (gk2 < K && gn < N) ? B[(size_t)gk2 * N + gn] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = sA[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = sB[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+        float sc = rowscale ? rowscale[gm] : 1.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int gn = n0 + tx * 4 + j;
+            if (gn < N) C[(size_t)gm * N + gn] = acc[i][j] * sc;
+        }
+    }
+}
+
+// W [K,Cin,Cout] -> Wt [Cout, K*Cin] (K-major B operand), rounded to TF32 (round-to-nearest, ties away)
+__global__ void prep_weights_kernel(const float* __restrict__ W, int KC, int Cout, float* __restrict__ Wt) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)KC * Cout) return;
+    int o = (int)(t / KC), kc = (int)(t % KC);
+    float v = W[(size_t)kc * Cout + o];
+    unsigned u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    Wt[t] = __uint_as_float(u);
+}
+
+}  // namespace aprb
+
+using namespace aprb;
+
+extern "C" int aprb_kpconv_prepare_weights(const float* d_W, int K, int Cin, int Cout, float* d_wprep, void* stream) {
+    APRB_REQUIRE(d_W && d_wprep && K >= 1 && Cin >= 1 && Cout >= 1, "bad argument");
+    long long total = (long long)K * Cin * Cout;
+    APRB_TIMED("prep_weights_kernel", (cudaStream_t)stream, 1, (prep_weights_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(d_W, K * Cin, Cout, d_wprep)));
+    APRB_LAUNCH_OK();
+    return APRB_OK;
+}
+
+extern "C" size_t aprb_kpconv_ws_bytes(int Nq, int Ns, int H, int K, int Cin, int Cout) {
+    (void)H; (void)Cout;
+    if (Nq < 0 || Ns < 0 || K < 0 || Cin < 0) return 0;
+    // wf is padded to a multiple of 128 rows so the tensor path can read whole M tiles
+    size_t rows = ((size_t)(Nq > 0 ? Nq : 1) + 127) & ~size_t(127);
+    return align256(rows * K * Cin * sizeof(float)) + align256(rows * sizeof(float)) + align256((size_t)Ns + 1) + 256;
+}
+
+extern "C" int aprb_kpconv_forward(const float* d_q, const float* d_s, const void* d_idx, int idx_is_i64, int ld_idx,
+                                   const float* d_x, const float* d_kp, const float* d_W, const float* d_wprep,
+                                   float extent, int Nq, int Ns, int H, int K, int Cin, int Cout, float* d_out, int mode,
+                                   void* d_ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    APRB_REQUIRE(Nq >= 0 && Ns >= 0 && H >= 1 && H <= 1024, "need Nq,Ns >= 0 and 1 <= H <= 1024");
+    APRB_REQUIRE(K >= 1 && K <= KP_MAX_K && Cin >= 1 && Cout >= 1 && ld_idx >= H, "need 1 <= K <= 16, Cin,Cout >= 1, ld >= H");
+    APRB_REQUIRE(extent > 0.f, "extent must be positive");
+    if (Nq == 0) return APRB_OK;
+    APRB_REQUIRE(d_q && d_idx && d_kp && d_out && d_ws && (Ns == 0 || (d_s && d_x)), "null pointer");
+    APRB_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
+    if (ws_bytes < aprb_kpconv_ws_bytes(Nq, Ns, H, K, Cin, Cout)) { set_error("aprb_kpconv_forward: workspace too small"); return APRB_ERR_WORKSPACE; }
+    const int KC = K * Cin;
+    bool tensor_ok = d_wprep && gemm_tf32_supported(Nq, Cout, KC);
+    if (mode == 2 && !tensor_ok) { set_error("aprb_kpconv_forward: tcgen05 path unsupported for K*Cin=%d Cout=%d", KC, Cout); return APRB_ERR_UNSUPPORTED; }
+    bool use_tensor = (mode == 2) || (mode == 0 && tensor_ok);
+    if (!use_tensor) APRB_REQUIRE(d_W, "fp32 path needs the raw [K,Cin,Cout] weights");
+
+    Carver c(d_ws, ws_bytes);
+    size_t rows = ((size_t)Nq + 127) & ~size_t(127);
+    float* wf = c.take<float>(rows * KC);
+    float* inv_nn = c.take<float>(rows);
+    unsigned char* flag = c.take<unsigned char>((size_t)Ns + 1);
+
+    if (Ns > 0) APRB_TIMED("rowsum_pos_kernel", st, 1, (rowsum_pos_kernel<<<cdiv(Ns, 8), 256, 0, st>>>(d_x, Ns, Cin, flag)));
+    const int wpb = 4, Hp = (H + 31) & ~31;
+    size_t smem = (size_t)wpb * (K + 1) * Hp * sizeof(float);
+#define KPW_LAUNCH(IDX, RND)                                                                                         \
+    do {                                                                                                             \
+        if (smem > 48 * 1024)                                                                                        \
+            APRB_CUDA_OK(cudaFuncSetAttribute(kp_weighted_kernel<IDX, RND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        APRB_TIMED("kp_weighted_kernel", st, 1, (kp_weighted_kernel<IDX, RND><<<cdiv(Nq, wpb), wpb * 32, smem, st>>>(             \
+            d_q, d_s, (const IDX*)d_idx, ld_idx, d_x, d_kp, flag, extent, Nq, Ns, H, K, Cin, wf, inv_nn)));         \
+    } while (0)
+    if (use_tensor) {
+        if (rows > (size_t)Nq)  // zero the pad rows the tensor path reads
+            APRB_CUDA_OK(cudaMemsetAsync(wf + (size_t)Nq * KC, 0, (rows - Nq) * KC * sizeof(float), st));
+        if (idx_is_i64) KPW_LAUNCH(long long, true); else KPW_LAUNCH(int, true);
+        APRB_LAUNCH_OK();
+        return gemm_tf32_rowscale(wf, d_wprep, Nq, Cout, KC, inv_nn, d_out, st);
+    }
+    if (idx_is_i64) KPW_LAUNCH(long long, false); else KPW_LAUNCH(int, false);
+#undef KPW_LAUNCH
+    APRB_LAUNCH_OK();
+    APRB_TIMED("sgemm_rowscale_kernel", st, 1, (sgemm_rowscale_kernel<<<dim3(cdiv(Cout, 64), cdiv(Nq, 64)), 256, 0, st>>>(wf, d_W, Nq, Cout, KC, inv_nn, d_out)));
+    APRB_LAUNCH_OK();
+    return APRB_OK;
+}

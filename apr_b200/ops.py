@@ -1,0 +1,193 @@
+"""Device-resident operators: CUDA tensors in, CUDA tensors out, all work done by libaprb200.so.
+
+These are the stream-ordered building blocks behind the reference-facing modules
+(`apr_b200.cpp_wrappers.*`, `apr_b200.blocks`). torch only allocates memory and provides the current stream.
+"""
+import torch
+
+from . import _native as N
+
+_ws_cache = {}
+TRACE = None   # when a list: every op appends its shape record (bench.py derives algorithmic bytes/flops from it)
+
+
+def _workspace(nbytes, device):
+    """Grow-only scratch buffer per (device, stream). Calls on one stream are ordered, so reuse is safe."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def _dev_f32(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise N.NativeError(f"{name}: expected a CUDA tensor (no CPU fallback)")
+    return t.contiguous().float() if (t.dtype != torch.float32 or not t.is_contiguous()) else t
+
+
+def _dev_i32(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise N.NativeError(f"{name}: expected a CUDA tensor (no CPU fallback)")
+    return t.contiguous().int() if (t.dtype != torch.int32 or not t.is_contiguous()) else t
+
+
+def _idx(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise N.NativeError(f"{name}: expected a CUDA tensor (no CPU fallback)")
+    if t.dtype not in (torch.int32, torch.int64):
+        t = t.long()
+    if t.stride(-1) != 1:
+        t = t.contiguous()
+    return t, (1 if t.dtype == torch.int64 else 0), (t.stride(0) if t.dim() == 2 and t.shape[0] > 1 else t.shape[-1])
+
+
+# --------------------------------------------------------------------------------------------------------------
+def grid_subsample(points, lens, dl, max_p=0, features=None, sync=True):
+    """K1. points [N,3] f32 cuda, lens [B] i32 cuda. Returns (sub_points [M,3], sub_lens [B] i32[, sub_feats]).
+    With sync=False returns the full-capacity buffers plus the device scalar M (no host round trip)."""
+    N.require_cuda()
+    points, lens = _dev_f32(points, "points"), _dev_i32(lens, "lens")
+    n, b = points.shape[0], lens.shape[0]
+    dev = points.device
+    out = torch.empty((max(n, 1), 3), dtype=torch.float32, device=dev)
+    out_lens = torch.empty(b, dtype=torch.int32, device=dev)
+    m_dev = torch.zeros(2, dtype=torch.int32, device=dev)      # [M, status]
+    fdim, feats, out_f = 0, None, None
+    if features is not None:
+        feats = _dev_f32(features, "features")
+        fdim = feats.shape[1]
+        out_f = torch.empty((max(n, 1), fdim), dtype=torch.float32, device=dev)
+    nbytes = N.lib().aprb_grid_subsample_ws_bytes(n, b, fdim)
+    ws = _workspace(nbytes, dev)
+    rc = N.lib().aprb_grid_subsample_batch(N.ptr(points), N.ptr(lens), b, n, float(dl), int(max_p), N.ptr(feats), fdim,
+                                           N.ptr(out), N.ptr(out_lens), N.ptr(m_dev[0:1]), N.ptr(out_f),
+                                           N.ptr(m_dev[1:2]), N.ptr(ws), ws.numel(), N.stream_ptr())
+    N.check(rc, "aprb_grid_subsample_batch")
+    if not sync:
+        return (out, out_lens, m_dev) if features is None else (out, out_lens, m_dev, out_f)
+    m, status = m_dev.tolist()
+    if TRACE is not None:
+        TRACE.append(("sub", n, m))
+    if status != 0:
+        raise N.NativeError("grid_subsample: voxel grid does not fit the 64-bit sort key (cloud extent / sampleDl too large)")
+    if features is None:
+        return out[:m], out_lens
+    return out[:m], out_lens, out_f[:m]
+
+
+def radius_neighbors(queries, supports, q_lens, s_lens, radius, width, want_counts=False):
+    """K2+K3. Returns idx [Nq,width] i32 (pad = Ns), and optionally (counts [Nq] i32, max_count [1] i32) on device."""
+    N.require_cuda()
+    q, s = _dev_f32(queries, "queries"), _dev_f32(supports, "supports")
+    ql, sl = _dev_i32(q_lens, "q_lens"), _dev_i32(s_lens, "s_lens")
+    nq, ns, b = q.shape[0], s.shape[0], ql.shape[0]
+    dev = q.device
+    width = int(width)
+    out = torch.empty((nq, width), dtype=torch.int32, device=dev)
+    counts = torch.empty(max(nq, 1), dtype=torch.int32, device=dev) if want_counts else None
+    maxc = torch.zeros(1, dtype=torch.int32, device=dev) if want_counts else None
+    nbytes = N.lib().aprb_radius_neighbors_ws_bytes(nq, ns, b)
+    ws = _workspace(nbytes, dev)
+    rc = N.lib().aprb_radius_neighbors_batch(N.ptr(q), N.ptr(s), N.ptr(ql), N.ptr(sl), b, nq, ns, float(radius), width,
+                                             N.ptr(out), width, N.ptr(counts), N.ptr(maxc), N.ptr(ws), ws.numel(),
+                                             N.stream_ptr())
+    N.check(rc, "aprb_radius_neighbors_batch")
+    if TRACE is not None:
+        TRACE.append(("nb", nq, ns, width))
+    if want_counts:
+        return out, counts[:nq], maxc
+    return out
+
+
+def kpconv_prepare_weights(weights):
+    """[K,Cin,Cout] f32 -> prepared TF32 K-major operand [Cout, K*Cin]."""
+    N.require_cuda()
+    w = _dev_f32(weights.detach(), "weights")
+    k, cin, cout = w.shape
+    out = torch.empty((cout, k * cin), dtype=torch.float32, device=w.device)
+    N.check(N.lib().aprb_kpconv_prepare_weights(N.ptr(w), k, cin, cout, N.ptr(out), N.stream_ptr()),
+            "aprb_kpconv_prepare_weights")
+    return out
+
+
+def kpconv(q_pts, s_pts, neighb_inds, x, kernel_points, weights, extent, wprep=None, mode=0):
+    """K5. Returns [Nq,Cout] f32."""
+    N.require_cuda()
+    q, s, xx = _dev_f32(q_pts, "q_pts"), _dev_f32(s_pts, "s_pts"), _dev_f32(x, "x")
+    kp, w = _dev_f32(kernel_points.detach(), "kernel_points"), _dev_f32(weights.detach(), "weights")
+    idx, is64, ld = _idx(neighb_inds, "neighb_inds")
+    nq, ns, h = q.shape[0], s.shape[0], idx.shape[1]
+    k, cin, cout = w.shape
+    if xx.shape[0] != ns or xx.shape[1] != cin:
+        raise N.NativeError(f"kpconv: x has shape {tuple(xx.shape)}, expected ({ns}, {cin})")
+    out = torch.empty((nq, cout), dtype=torch.float32, device=q.device)
+    nbytes = N.lib().aprb_kpconv_ws_bytes(nq, ns, h, k, cin, cout)
+    ws = _workspace(nbytes, q.device)
+    rc = N.lib().aprb_kpconv_forward(N.ptr(q), N.ptr(s), N.ptr(idx), is64, ld, N.ptr(xx), N.ptr(kp), N.ptr(w),
+                                     N.ptr(wprep), float(extent), nq, ns, h, k, cin, cout, N.ptr(out), int(mode),
+                                     N.ptr(ws), ws.numel(), N.stream_ptr())
+    N.check(rc, "aprb_kpconv_forward")
+    if TRACE is not None:
+        TRACE.append(("kpconv", nq, ns, h, k, cin, cout))
+    return out
+
+
+def max_pool(x, inds, width_dev=None):
+    """K4. x [Ns,C], inds [Nq,H] -> [Nq,C]; the shadow index Ns contributes an all-zero row."""
+    N.require_cuda()
+    xx = _dev_f32(x, "x")
+    idx, is64, ld = _idx(inds, "inds")
+    nq, h = idx.shape
+    ns, c = xx.shape
+    out = torch.empty((nq, c), dtype=torch.float32, device=xx.device)
+    rc = N.lib().aprb_max_pool(N.ptr(xx), N.ptr(idx), is64, ld, nq, ns, h, c, N.ptr(width_dev), N.ptr(out), N.stream_ptr())
+    N.check(rc, "aprb_max_pool")
+    return out
+
+
+def closest_pool(x, inds):
+    """K4. out[n] = (x ++ 0)[inds[n,0]]."""
+    N.require_cuda()
+    xx = _dev_f32(x, "x")
+    if inds.dim() == 1:
+        inds = inds.unsqueeze(1)
+    idx, is64, ld = _idx(inds, "inds")
+    nq = idx.shape[0]
+    ns, c = xx.shape
+    out = torch.empty((nq, c), dtype=torch.float32, device=xx.device)
+    rc = N.lib().aprb_closest_pool(N.ptr(xx), N.ptr(idx), is64, ld, nq, ns, c, N.ptr(out), N.stream_ptr())
+    N.check(rc, "aprb_closest_pool")
+    return out
+
+
+def instnorm_lrelu(x, slope=0.1, residual=None, norm_residual=False, eps=1e-5, out=None):
+    """K6. y = act(standardise_cols(x) [+ residual | + standardise_cols(residual)]); slope=1.0 disables the activation."""
+    N.require_cuda()
+    xx = _dev_f32(x, "x")
+    n, c = xx.shape
+    res = _dev_f32(residual, "residual") if residual is not None else None
+    y = out if out is not None else torch.empty_like(xx)
+    ws = _workspace(N.lib().aprb_instnorm_ws_bytes(n, c), xx.device)
+    rc = N.lib().aprb_instnorm_lrelu(N.ptr(xx), n, c, float(eps), float(slope), N.ptr(res), 1 if norm_residual else 0,
+                                     N.ptr(y), N.ptr(ws), ws.numel(), N.stream_ptr())
+    N.check(rc, "aprb_instnorm_lrelu")
+    return y
+
+
+def linear_tf32_supported(n, cin, cout):
+    return cin % 32 == 0 and cout % 16 == 0 and n > 0
+
+
+def linear_tf32(x, weight):
+    """y = x @ weight.T on tcgen05 (TF32 operands, fp32 accumulate). weight is nn.Linear's [Cout,Cin]."""
+    N.require_cuda()
+    xx, w = _dev_f32(x, "x"), _dev_f32(weight.detach(), "weight")
+    n, cin = xx.shape
+    cout = w.shape[0]
+    y = torch.empty((n, cout), dtype=torch.float32, device=xx.device)
+    N.check(N.lib().aprb_linear_tf32(N.ptr(xx), N.ptr(w), n, cin, cout, N.ptr(y), N.stream_ptr()), "aprb_linear_tf32")
+    if TRACE is not None:
+        TRACE.append(("linear", n, cin, cout))
+    return y

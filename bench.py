@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — KITTI-shaped clouds/sec through subsample + radius search + KPConv KFE encoder (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (B200, libaprb200.so)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path on this box's host cores
+
+A step = one synthetic KITTI-shaped PAIR (2 clouds, first_subsampling_dl = 0.3; BASELINE.json configs[1]) through
+the whole hot path: 3 grid subsamplings + 10 radius searches (the pyramid of datasets/dataloader.py:93-176) and the
+11 KFE encoder blocks (models/architectures.py:149-153), random-init weights, features = ones.
+`value`  : device-resident (level-0 points already in HBM), CUDA-event time per step, L2 flushed between steps.
+`e2e`    : same metric from HOST buffers: pinned H2D of the points, the pipeline, D2H of the encoder output.
+N > 1    : one process per GPU (torchrun), independent pairs per rank, no collective on the data path (weak scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from apr_b200 import synth  # noqa: E402
+from apr_b200.config import kitti_config  # noqa: E402
+
+METRIC = "KITTI-shaped clouds/sec (subsample+radius+KPConv KFE)"
+UNIT = "clouds/s"
+LIMITS_FALLBACK = [57, 56, 57, 55]       # SURVEY.md §6 (80th percentile), used only if calibration is skipped
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops_sustained"], src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+def raw_pairs(n_pairs, seed0):
+    return [synth.pair_raw(seed0 + i, "kitti") for i in range(n_pairs)]
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def reference_step(ref, oracle_mod, cfg, sd, limits, p0, l0):
+    """The reference's CPU path for one pair: cpp_wrappers object code (oracle/_ref) for the pyramid, then the fp32
+    torch-CPU restatement of the KFE encoder blocks (the reference's models/ cannot travel to this box)."""
+    from oracle import blocks_ref
+    from oracle.ref import collate_ref
+    pyr = collate_ref(p0, l0, cfg, limits, ref.subsample_batch, ref.batch_query)
+    batch = dict(points=[torch.from_numpy(p) for p in pyr["points"]],
+                 neighbors=[torch.from_numpy(n).long() for n in pyr["neighbors"]],   # dataloader.py:164-166
+                 pools=[torch.from_numpy(n).long() for n in pyr["pools"]],
+                 features=torch.ones(len(p0), 1))
+    with torch.no_grad():
+        return blocks_ref.encoder_ref(batch, sd, cfg)
+
+
+def reference_setup(cfg, n_pairs, seed0):
+    from oracle.ref import Oracle, RefL1
+    ref = RefL1() if RefL1.available() else Oracle()
+    kind = "reference" if RefL1.available() else "port"
+    pairs = []
+    for a, b in raw_pairs(n_pairs, seed0):
+        raw = np.concatenate([a, b]); lens = np.array([len(a), len(b)], np.int32)
+        pairs.append(ref.subsample_batch(raw, lens, sampleDl=cfg.first_subsampling_dl))   # first-level voxelisation
+    from apr_b200.architectures import KPFCNNEncoder
+    torch.manual_seed(0); np.random.seed(0)
+    enc = KPFCNNEncoder(cfg)
+    sd = {k: v.detach().clone() for k, v in enc.state_dict().items()}
+    return ref, kind, pairs, sd
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0                                            # rank 0 alone runs the CPU arm
+    cfg = kitti_config()
+    ref, kind, pairs, sd = reference_setup(cfg, 2, 0)
+    cores = torch.get_num_threads()
+    limits = LIMITS_FALLBACK
+    warm = min(args.warmup, 1)
+    for i in range(warm):
+        reference_step(ref, None, cfg, sd, limits, *pairs[i % len(pairs)])
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(args.steps):
+        reference_step(ref, None, cfg, sd, limits, *pairs[i % len(pairs)])
+        done += 1
+        if time.perf_counter() - t0 > 420 and done >= 1:    # keep the whole run within a few minutes
+            break
+    dt = time.perf_counter() - t0
+    value = 2.0 * done / dt
+    sample = (f"{done} step(s) x 1 KITTI-shaped pair; pyramid = "
+              f"{'reference object code oracle/_ref (nanoflann, 1 thread)' if kind == 'reference' else 'oracle C port'}"
+              f"; encoder = fp32 torch-CPU restatement oracle/blocks_ref.py on {cores} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+            "warmup": warm, "ms_per_step": 1e3 * dt / done, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "kitti_pair_kfe_encoder", "pairs_per_step": 1, "points_stacked": int(len(pairs[0][0])),
+                       "limits": limits},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port" if kind == "port" else "reference",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def algorithmic_work(trace):
+    """Per-kernel algorithmic bytes / flops for ONE step from the op trace."""
+    w = {"kpconv_flops": 0.0, "kp_weighted_bytes": 0.0, "nb_query_bytes": 0.0, "subsample_bytes": 0.0}
+    n = {"kpconv": 0, "nb": 0}
+    for rec in trace:
+        if rec[0] == "kpconv":
+            _, nq, ns, h, k, cin, cout = rec
+            w["kpconv_flops"] += 2.0 * nq * k * cin * cout
+            w["kp_weighted_bytes"] += 4.0 * (ns * cin + nq * k * cin) + 4.0 * nq * h + 12.0 * (nq + ns)
+            n["kpconv"] += 1
+        elif rec[0] == "nb":
+            _, nq, ns, width = rec
+            w["nb_query_bytes"] += 12.0 * nq + 16.0 * ns + 4.0 * nq * width
+            n["nb"] += 1
+        elif rec[0] == "sub":
+            _, nin, m = rec
+            w["subsample_bytes"] += 12.0 * nin + 12.0 * m
+    return w, n
+
+
+def run_ours(args):
+    from apr_b200 import _native, blocks, dataloader, ops
+    from apr_b200.architectures import KPFCNNEncoder
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    _native.require_cuda()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = kitti_config()
+    torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32_linear)
+    if args.linear_mode:
+        blocks.LINEAR_MODE = args.linear_mode
+
+    # ---- inputs: n_pairs distinct pairs per rank, first-level 0.3 m voxelisation done up front (not part of the path)
+    pairs_dev, pairs_host = [], []
+    for a, b in raw_pairs(args.pairs, 1000 * rank):
+        raw = torch.from_numpy(np.concatenate([a, b])).to(dev)
+        lens = torch.tensor([len(a), len(b)], dtype=torch.int32, device=dev)
+        p0, l0 = ops.grid_subsample(raw, lens, cfg.first_subsampling_dl)
+        pairs_dev.append((p0.contiguous(), l0))
+        pairs_host.append((p0.cpu().pin_memory(), l0.cpu().pin_memory()))
+    torch.manual_seed(0); np.random.seed(0)
+    enc = KPFCNNEncoder(cfg).to(dev).eval()
+    limits = dataloader.calibrate_neighbors_device(pairs_dev, cfg) if not args.no_calibrate else LIMITS_FALLBACK
+    limits = [int(x) for x in limits]
+
+    def step_dev(i):
+        p0, l0 = pairs_dev[i % len(pairs_dev)]
+        pyr = dataloader.build_pyramid_device(p0, l0, cfg, limits)
+        return enc(pyr)
+
+    out_host = {}
+
+    def step_e2e(i):
+        hp, hl = pairs_host[i % len(pairs_host)]
+        p0 = hp.to(dev, non_blocking=True); l0 = hl.to(dev, non_blocking=True)
+        y = enc(dataloader.build_pyramid_device(p0, l0, cfg, limits))
+        buf = out_host.get(y.shape)
+        if buf is None:
+            buf = out_host[y.shape] = torch.empty(y.shape, dtype=y.dtype).pin_memory()
+        buf.copy_(y, non_blocking=True)
+        return hp.numel() * 4 + hl.numel() * 4, y.numel() * 4
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        l0 = _native.launch_count()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            flush.zero_()                                    # L2 flush (256 MiB), outside the timed event pair
+            ev[i][0].record()
+            r = fn(warmup + i)
+            ev[i][1].record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        return ms, wall, _native.launch_count() - l0, r
+
+    clk = ClockSampler(local)
+    clk.start()
+    ms_dev, wall_dev, launches, _ = timed(step_dev, args.steps, args.warmup)
+    clocks = clk.stop()
+    ms_e2e, wall_e2e, _, io = timed(step_e2e, args.steps, max(args.warmup, 3))
+
+    # ---- per-kernel pass (same steps, CUDA events around every launch on the launching stream) for the roofline
+    ops.TRACE = []
+    _native.prof_enable(True)
+    for i in range(args.steps):
+        flush.zero_()
+        step_dev(args.warmup + i)
+    prof = _native.prof_report()
+    _native.prof_enable(False)
+    trace, ops.TRACE = ops.TRACE, None
+    work, ncalls = algorithmic_work(trace)
+
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = t.tolist()
+    clouds = 2.0 * args.steps * world
+    value = clouds / (ms_dev * 1e-3)
+    e2e = clouds / (ms_e2e * 1e-3)
+
+    pk = peaks()
+    mine = {k: v for k, v in prof.items()}
+    top = max(mine.items(), key=lambda kv: kv[1][1]) if mine else (None, (0, 0.0))
+    total_kernel_ms = sum(v[1] for v in mine.values())
+    tensor_names = ("gemm_tf32_kernel", "sgemm_rowscale_kernel")
+    roof = None
+    if top[0] is not None:
+        name, (cnt, tot_ms) = top
+        steps = args.steps
+        if name in tensor_names:
+            peak = pk["bf16"] / 2.0                          # TF32 dense = half the bf16 rate
+            ach = work["kpconv_flops"] / steps / (tot_ms / steps * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+            # the GEMM kernel also serves the unary Linear layers when LINEAR_MODE == 'tf32': count those flops too
+            lin = sum(2.0 * r[1] * r[2] * r[3] for r in trace if r[0] == "linear")
+            ach = (work["kpconv_flops"] + lin) / steps / (tot_ms / steps * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+            roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                    "frac": ach / peak, "traffic": None,
+                    "note": f"TF32 peak taken as half of {pk['src']} bf16 sustained; share of kernel time "
+                            f"{tot_ms / max(total_kernel_ms, 1e-9):.2f}"}
+        else:
+            key = {"kp_weighted_kernel": "kp_weighted_bytes", "nb_query_kernel": "nb_query_bytes"}.get(name)
+            by = work.get(key, 0.0) if key else 0.0
+            ach = by / steps / (tot_ms / steps * 1e-3) / 1e9 if tot_ms > 0 else 0.0
+            roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": ach / pk["hbm"], "traffic": None,
+                    "note": f"peak = {pk['src']}; share of kernel time {tot_ms / max(total_kernel_ms, 1e-9):.2f}"}
+    kernels = {k: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps} for k, v in
+               sorted(mine.items(), key=lambda kv: -kv[1][1])[:12]}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32" if blocks.KPCONV_MODE != 1 else "f32", "data": "synthetic",
+            "config": {"workload": "kitti_pair_kfe_encoder", "pairs_per_step": 1,
+                       "points_stacked": int(pairs_dev[0][0].shape[0]), "limits": limits, "parallelism": f"pairs x{world}",
+                       "l2": "flushed between steps (256 MiB memset outside the event pair)",
+                       "linear": blocks.LINEAR_MODE, "kpconv_mode": blocks.KPCONV_MODE},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(io[0]), "d2h_bytes_per_step": int(io[1]),
+                    "ms_per_step": ms_e2e / args.steps},
+            "roofline": roof, "kernels": kernels,
+            "wall_ms_per_step": 1e3 * wall_dev / args.steps}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cfg_r = kitti_config()
+        ref, kind, pairs, sd = reference_setup(cfg_r, 1, 0)
+        t0 = time.perf_counter()
+        reference_step(ref, None, cfg_r, sd, limits, *pairs[0])
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": 2.0 / dt, "unit": UNIT, "cores": torch.get_num_threads(),
+                                "kind": "reference" if kind == "reference" else "port",
+                                "sample": "1 KITTI-shaped pair: pyramid by oracle/_ref (reference object code, 1 thread) + "
+                                          "KFE encoder by oracle/blocks_ref.py (fp32 torch CPU, all threads)"}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=3, help="distinct synthetic pairs cycled through (per rank)")
+    ap.add_argument("--no-calibrate", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tf32-linear", type=int, default=0, help="allow TF32 in the cuBLAS unary GEMMs (LINEAR_MODE=fp32)")
+    ap.add_argument("--linear-mode", default="", choices=["", "fp32", "tf32"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,127 @@
+/* aprb200.h — C-ABI of libaprb200.so: the B200-native (sm_100a) KPConv neighbourhood pipeline.
+ *
+ * Drop-in boundary for the hot path of Predator_APR's KFE encoder. Every entry point replaces one reference
+ * interface (paths relative to /root/reference/Predator_APR):
+ *
+ *   aprb_grid_subsample_batch      <- batch_grid_subsampling()      cpp_wrappers/cpp_subsampling/grid_subsampling/grid_subsampling.h:95-104
+ *                                     (bound by cpp_subsampling/wrapper.cpp:62-333 as grid_subsampling.subsample_batch,
+ *                                      and :338-566 as grid_subsampling.subsample with B = 1)
+ *   aprb_radius_neighbors_batch    <- batch_nanoflann_neighbors()   cpp_wrappers/cpp_neighbors/neighbors/neighbors.h:24-29
+ *                                     (bound by cpp_neighbors/wrapper.cpp:58-238 as radius_neighbors.batch_query;
+ *                                      the [:, :max_neighbors] cut of datasets/dataloader.py:66-70 is folded in)
+ *   aprb_kpconv_forward            <- KPConv.forward                models/blocks.py:229-374 (rigid, linear influence, sum)
+ *   aprb_max_pool / aprb_closest_pool <- max_pool / closest_pool    models/blocks.py:86-102 / :71-83
+ *   aprb_instnorm_lrelu            <- BatchNormBlock.forward (= InstanceNorm1d over all rows) + LeakyReLU(0.1)
+ *                                                                   models/blocks.py:459-468, :496-510, :592, :669, :681
+ *   aprb_linear_tf32               <- UnaryBlock.mlp (nn.Linear, no bias)  models/blocks.py:493, :500
+ *
+ * Conventions: every pointer named d_* is a DEVICE pointer; `stream` is a cudaStream_t passed as void*; calls are
+ * stream-ordered and asynchronous unless stated. Every function returns 0 on success or a negative aprb_status;
+ * aprb_last_error() returns a thread-local message for the last failure. No C++ exception crosses this boundary.
+ * Points are packed [N,3] fp32 rows (12-byte stride, the layout of PointXYZ, cpp_utils/cloud/cloud.h:40-104).
+ */
+#ifndef APRB200_H
+#define APRB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    APRB_OK = 0,
+    APRB_ERR_INVALID = -1,     /* bad argument (null pointer, negative size, unsupported shape)      */
+    APRB_ERR_WORKSPACE = -2,   /* workspace too small for the request                                */
+    APRB_ERR_CUDA = -3,        /* a CUDA runtime call or kernel launch failed                        */
+    APRB_ERR_UNSUPPORTED = -4, /* valid in the reference but not implemented on this path            */
+    APRB_ERR_EMPTY = -5        /* result is empty: the reference raises RuntimeError("Error") here   */
+} aprb_status;
+
+int aprb_version(void);
+const char* aprb_last_error(void);
+/* Kernel launches issued by this library since load (CUB calls count their internal kernels). */
+long long aprb_launch_count(void);
+/* Per-kernel timing with CUDA events on the launching stream: enable, run, then aprb_prof_report() synchronises the
+ * device and writes "kernel_name launches total_ms" lines into buf and clears the records. */
+int aprb_prof_enable(int on);
+int aprb_prof_report(char* buf, size_t cap);
+/* Device properties the host side sizes grids with (SM count etc.). Returns status. */
+int aprb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------- K1: voxel-grid barycentre subsampling ------ */
+/* Workspace bytes needed for a stacked batch of N points in B clouds (fdim feature columns, 0 if none). */
+size_t aprb_grid_subsample_ws_bytes(int N, int B, int fdim);
+
+/* d_pts [N,3] fp32 stacked clouds, d_lens [B] int32 (sum == N). Output rows are emitted per cloud in ascending
+ * voxel-key order (canonical order; the reference's order is unordered_map iteration order, unspecified).
+ * d_out_pts capacity N rows; d_out_lens [B]; d_out_M [1] int32 (device) receives the total row count.
+ * Optional: d_feats [N,fdim] -> d_out_feats [<=N,fdim] (per-voxel mean), pass NULL/0 to skip.
+ * max_p <= 0 means unlimited (grid_subsampling.cpp:133-134). Asynchronous: read d_out_M / d_out_lens after
+ * synchronising `stream`. d_status [1] int32 (device, optional) is set non-zero if the voxel grid does not fit
+ * the 64-bit sort key. */
+int aprb_grid_subsample_batch(const float* d_pts, const int32_t* d_lens, int B, int N, float dl, int max_p,
+                              const float* d_feats, int fdim,
+                              float* d_out_pts, int32_t* d_out_lens, int32_t* d_out_M, float* d_out_feats,
+                              int32_t* d_status, void* d_ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- K2+K3: batched radius neighbour search ----- */
+size_t aprb_radius_neighbors_ws_bytes(int Nq, int Ns, int B);
+
+/* For every query, the supports of the same batch element with d2 < radius^2 (fp32, d2 = (dx*dx+dy*dy)+dz*dz,
+ * no FMA), ascending by (d2, support index), truncated to `width` columns, padded with Ns.
+ * d_out_idx is [Nq, ld] int32 row-major (ld >= width); columns [0,width) of every row are written.
+ * d_counts [Nq] int32 (optional) receives the untruncated neighbour count of every query;
+ * d_max_count [1] int32 (optional, device) receives max over queries (the reference's output width,
+ * neighbors.cpp:296-304). width must be in [1, 16384]. Asynchronous. */
+int aprb_radius_neighbors_batch(const float* d_q, const float* d_s, const int32_t* d_qlens, const int32_t* d_slens,
+                                int B, int Nq, int Ns, float radius, int width,
+                                int32_t* d_out_idx, int ld, int32_t* d_counts, int32_t* d_max_count,
+                                void* d_ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- K5: KPConv forward ------------------------- */
+/* Prepared weights: the [K,Cin,Cout] fp32 parameter re-laid as the K-major, TF32-rounded B operand
+ * [Cout, K*Cin] used by the tcgen05 contraction. d_wprep has K*Cin*Cout floats. Run once per weight update. */
+int aprb_kpconv_prepare_weights(const float* d_W, int K, int Cin, int Cout, float* d_wprep, void* stream);
+
+size_t aprb_kpconv_ws_bytes(int Nq, int Ns, int H, int K, int Cin, int Cout);
+
+/* out[n,:] = (sum_k (sum_h max(0, 1 - |s[idx[n,h]] - q[n] - kp[k]| / extent) * x[idx[n,h],:]) @ W[k]) / max(1, nn[n])
+ * with nn[n] = #{h : sum_c x[idx[n,h],c] > 0}; idx == Ns is the shadow neighbour (far point, zero feature row).
+ * d_idx is [Nq, ld_idx] int32 (idx_is_i64 == 0) or int64 (idx_is_i64 != 0); only columns [0,H) are read.
+ * d_W is the raw [K,Cin,Cout] parameter (used by the fp32 path), d_wprep the prepared operand (tensor path;
+ * may be NULL to force the fp32 CUDA-core path). mode: 0 = auto (tensor path when supported), 1 = fp32 CUDA cores,
+ * 2 = tcgen05 TF32 (error if unsupported shape). */
+int aprb_kpconv_forward(const float* d_q, const float* d_s, const void* d_idx, int idx_is_i64, int ld_idx,
+                        const float* d_x, const float* d_kp, const float* d_W, const float* d_wprep,
+                        float extent, int Nq, int Ns, int H, int K, int Cin, int Cout,
+                        float* d_out, int mode, void* d_ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- K4: pooling / upsampling gathers ----------- */
+/* out[n,c] = max_h (x ++ 0)[idx[n,h], c] over h < min(H, *d_width if non-NULL). */
+int aprb_max_pool(const float* d_x, const void* d_idx, int idx_is_i64, int ld_idx, int Nq, int Ns, int H, int C,
+                  const int32_t* d_width, float* d_out, void* stream);
+/* out[n,:] = (x ++ 0)[idx[n,0], :] */
+int aprb_closest_pool(const float* d_x, const void* d_idx, int idx_is_i64, int ld_idx, int Nq, int Ns, int C,
+                      float* d_out, void* stream);
+
+/* ---------------------------------------------------------------- K6: InstanceNorm (+residual) (+LeakyReLU) -- */
+size_t aprb_instnorm_ws_bytes(int N, int C);
+/* y = act( (x - mean_col) * rsqrt(var_col + eps) + (d_residual ? residual : 0) ), statistics per column over all
+ * N rows (biased variance), act = LeakyReLU(slope) when slope != 1, identity when slope == 1.
+ * norm_residual != 0 additionally standardises the residual with its own column statistics before adding
+ * (ResnetBottleneckBlock: unary2 + unary_shortcut, models/blocks.py:672-681). In-place (d_y == d_x) allowed. */
+int aprb_instnorm_lrelu(const float* d_x, int N, int C, float eps, float slope,
+                        const float* d_residual, int norm_residual, float* d_y,
+                        void* d_ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- Linear (UnaryBlock.mlp) on tcgen05 TF32 ---- */
+/* y[N,Cout] = x[N,Cin] @ W[Cout,Cin]^T (nn.Linear layout, no bias), TF32 operands (round-to-nearest), fp32
+ * accumulate in TMEM. Cin % 32 == 0 and Cout % 16 == 0 required, else APRB_ERR_UNSUPPORTED. */
+int aprb_linear_tf32(const float* d_x, const float* d_W, int N, int Cin, int Cout, float* d_y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APRB200_H */

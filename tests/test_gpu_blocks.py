@@ -1,0 +1,185 @@
+"""GPU parity: KPConv (K5), pooling gathers (K4), InstanceNorm(+LeakyReLU) (K6), the block modules and the KFE encoder
+vs the reference golden vectors and the fp32 CPU oracle (oracle/blocks_ref.py).
+Tolerances: fp32 CUDA-core path 2e-5 relative (Frobenius); tcgen05 TF32 path 1e-3 relative (TF32 operands rounded to
+nearest, fp32 accumulation in TMEM) — the bar north_star states for KPConv features."""
+import numpy as np
+import pytest
+import torch
+
+from apr_b200 import blocks, ops
+from apr_b200.architectures import KPFCNNEncoder
+from apr_b200.config import kitti_config
+from oracle import blocks_ref
+from oracle.ref import collate_ref
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP32 = 2e-5
+TOL_TF32 = 1e-3
+
+
+def rel(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _t(a, cuda):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+
+
+@pytest.mark.parametrize("tag,strided", [("c1", False), ("c8", False), ("c32s", True), ("c64", False)])
+@pytest.mark.parametrize("idx_dtype", [torch.int32, torch.int64])
+def test_kpconv_golden_fp32(cuda, gold_kpconv, tag, strided, idx_dtype):
+    g = gold_kpconv
+    q, s, inds = (g["p1"], g["p0"], g["pool"]) if strided else (g["p0"], g["p0"], g["conv"])
+    y = ops.kpconv(_t(q, cuda), _t(s, cuda), _t(inds, cuda).to(idx_dtype), _t(g[f"{tag}_x"], cuda),
+                   _t(g[f"{tag}_kp"], cuda), _t(g[f"{tag}_W"], cuda), 0.6, mode=1)
+    assert rel(y, torch.from_numpy(g[f"{tag}_y"])) < TOL_FP32
+
+
+def test_kpconv_quirks_vs_oracle(cuda):
+    """Shadow rows, neighbor_num on the SIGN of the feature sum, all-pad rows, non-contiguous index views."""
+    gen = torch.Generator().manual_seed(5)
+    ns, nq, h, cin, cout = 300, 200, 19, 24, 40
+    s = torch.rand(ns, 3, generator=gen) * 2
+    q = torch.rand(nq, 3, generator=gen) * 2
+    inds = torch.randint(0, ns + 1, (nq, h + 5), generator=gen)
+    inds[:7] = ns                                                         # queries with no neighbour at all
+    x = torch.randn(ns, cin, generator=gen)
+    x[::3] = -x[::3].abs()                                                # rows with negative sums (not counted)
+    x[5] = 0
+    kp = torch.randn(15, 3, generator=gen) * 0.4
+    w = torch.randn(15, cin, cout, generator=gen) * 0.1
+    view = inds[:, :h]                                                    # column-sliced view, like neighbors[:, :limit]
+    want = blocks_ref.kpconv_ref(q, s, view, x, kp, w, 0.7)
+    got = ops.kpconv(q.to(cuda), s.to(cuda), inds.to(cuda)[:, :h], x.to(cuda), kp.to(cuda), w.to(cuda), 0.7, mode=1)
+    assert rel(got, want) < TOL_FP32
+    assert torch.all(got[:7] == 0)
+
+
+def test_kpconv_tensor_path_vs_oracle(cuda, gold_kpconv):
+    """tcgen05 TF32 contraction (mode 2) on shapes the tensor path accepts."""
+    g = gold_kpconv
+    gen = torch.Generator().manual_seed(9)
+    p0, conv = torch.from_numpy(g["p0"]), torch.from_numpy(g["conv"]).long()
+    for cin, cout in ((32, 32), (64, 64), (128, 128), (64, 256)):
+        x = torch.randn(len(p0), cin, generator=gen)
+        kp = torch.from_numpy(g["c8_kp"])
+        w = torch.randn(15, cin, cout, generator=gen) / np.sqrt(15 * cin)
+        want = blocks_ref.kpconv_ref(p0, p0, conv, x, kp, w, 0.6)
+        wd = w.to(cuda)
+        prep = ops.kpconv_prepare_weights(wd)
+        got = ops.kpconv(p0.to(cuda), p0.to(cuda), conv.to(cuda).int(), x.to(cuda), kp.to(cuda), wd, 0.6, wprep=prep, mode=2)
+        e = rel(got, want)
+        assert e < TOL_TF32, f"Cin={cin} Cout={cout}: rel err {e:.2e}"
+
+
+def test_linear_tf32_vs_fp32(cuda):
+    gen = torch.Generator().manual_seed(2)
+    for n, cin, cout in ((1000, 64, 128), (4255, 256, 64), (129, 32, 16), (1567, 512, 2048)):
+        x = torch.randn(n, cin, generator=gen)
+        w = torch.randn(cout, cin, generator=gen) / np.sqrt(cin)
+        want = x.double() @ w.double().t()
+        got = ops.linear_tf32(x.to(cuda), w.to(cuda))
+        e = rel(got, want)
+        assert e < TOL_TF32, f"{n}x{cin}x{cout}: {e:.2e}"
+
+
+def test_pools_golden_bit_exact(cuda, gold_kpconv):
+    g = gold_kpconv
+    for dt in (torch.int32, torch.int64):
+        y = ops.max_pool(_t(g["pool_x"], cuda), _t(g["pool"], cuda).to(dt))
+        assert torch.equal(y.cpu(), torch.from_numpy(g["max_pool_y"]))
+        y = ops.closest_pool(_t(g["closest_x"], cuda), _t(g["up"], cuda).to(dt))
+        assert torch.equal(y.cpu(), torch.from_numpy(g["closest_pool_y"]))
+    # all-negative neighbourhood with a shadow entry pools to 0 (the zero row takes part in the max, blocks.py:95-101)
+    x = -torch.rand(10, 6) - 1
+    inds = torch.tensor([[0, 1, 10], [2, 3, 4]])
+    y = ops.max_pool(x.to(cuda), inds.to(cuda)).cpu()
+    assert torch.all(y[0] == 0) and torch.equal(y[1], x[2:5].max(0)[0])
+    # odd channel count -> scalar kernel
+    x = torch.randn(50, 7); inds = torch.randint(0, 51, (20, 9))
+    assert torch.equal(ops.max_pool(x.to(cuda), inds.to(cuda)).cpu(), blocks_ref.max_pool_ref(x, inds))
+
+
+def test_instnorm_lrelu_vs_torch(cuda):
+    gen = torch.Generator().manual_seed(3)
+    for n, c in ((1567, 512), (27782, 64), (300, 7), (1, 5)):
+        x = torch.randn(n, c, generator=gen) * 3 + 50                      # large mean: stresses the variance formula
+        want = torch.nn.functional.leaky_relu(blocks_ref.instnorm_ref(x.double()), 0.1).float() if n > 1 else None
+        got = ops.instnorm_lrelu(x.to(cuda), slope=0.1).cpu()
+        if n > 1:
+            assert (got - want).abs().max() < 2e-4
+        r = torch.randn(n, c, generator=gen)
+        got = ops.instnorm_lrelu(x.to(cuda), slope=1.0, residual=r.to(cuda)).cpu()
+        if n > 1:
+            assert (got - (blocks_ref.instnorm_ref(x.double()) + r).float()).abs().max() < 2e-4
+            got = ops.instnorm_lrelu(x.to(cuda), slope=0.1, residual=r.to(cuda), norm_residual=True).cpu()
+            want = torch.nn.functional.leaky_relu(blocks_ref.instnorm_ref(x.double()) + blocks_ref.instnorm_ref(r.double()), 0.1)
+            assert (got - want.float()).abs().max() < 2e-4
+    # same semantics as the reference module (nn.InstanceNorm1d on [1,C,N])
+    x = torch.randn(500, 16, generator=gen)
+    ref = torch.nn.InstanceNorm1d(16)(x.unsqueeze(2).transpose(0, 2)).transpose(0, 2).squeeze()
+    assert (ops.instnorm_lrelu(x.to(cuda), slope=1.0).cpu() - ref).abs().max() < 1e-5
+
+
+def _pyramid(oracle, cfg, p0, l0, limits, cuda):
+    pyr = collate_ref(p0, l0, cfg, limits, oracle.subsample_batch, oracle.batch_query)
+    cpu = dict(points=[torch.from_numpy(p) for p in pyr["points"]],
+               neighbors=[torch.from_numpy(n).long() for n in pyr["neighbors"]],
+               pools=[torch.from_numpy(n).long() for n in pyr["pools"]],
+               upsamples=[torch.from_numpy(n).long() for n in pyr["upsamples"]],
+               features=torch.ones(len(p0), 1))
+    gpu = {k: ([t.to(cuda) for t in v] if isinstance(v, list) else v.to(cuda)) for k, v in cpu.items()}
+    return cpu, gpu
+
+
+@pytest.mark.parametrize("mode,tol", [(1, 5e-5), (0, 2e-3)])
+def test_encoder_golden_small(cuda, oracle, gold_encoder, mode, tol):
+    """Whole KFE encoder (first_feats_dim=16) vs the REAL reference's output; weights loaded through load_state_dict
+    with the reference's own keys."""
+    g = gold_encoder
+    cfg = kitti_config(first_feats_dim=16)
+    cpu, gpu = _pyramid(oracle, cfg, g["p0"], g["l0"], list(g["limits"]), cuda)
+    enc = KPFCNNEncoder(cfg)
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd/")}
+    missing, unexpected = enc.load_state_dict(sd, strict=True), None
+    enc = enc.to(cuda).eval()
+    blocks.KPCONV_MODE = mode
+    try:
+        y = enc(gpu)
+    finally:
+        blocks.KPCONV_MODE = 0
+    assert y.shape == g["y_final"].shape
+    assert rel(y, torch.from_numpy(g["y_final"])) < tol
+
+
+def test_blocks_vs_oracle_kitti_width(cuda, oracle):
+    """Each block type at KITTI channel widths, fed IDENTICAL inputs on both sides (per-block parity, tensor path on)."""
+    from apr_b200 import synth
+    cfg = kitti_config()
+    a, b = synth.small_cloud(41, 2600), synth.small_cloud(42, 2400)
+    raw = np.concatenate([a, b]); lens = np.array([len(a), len(b)], np.int32)
+    p0, l0 = oracle.subsample_batch(raw, lens, sampleDl=0.3)
+    cpu, gpu = _pyramid(oracle, cfg, p0, l0, [35, 35, 35, 35], cuda)
+    torch.manual_seed(0); np.random.seed(0)
+    gen = torch.Generator().manual_seed(1)
+    cases = [("simple", 1, 128, 0), ("resnetb", 64, 128, 0), ("resnetb_strided", 128, 128, 0), ("resnetb", 128, 256, 1),
+             ("resnetb_strided", 256, 256, 1), ("resnetb", 512, 1024, 2), ("resnetb", 2048, 2048, 3)]
+    worst = 0.0
+    for name, cin, cout, layer in cases:
+        r = cfg.first_subsampling_dl * cfg.conv_radius * 2 ** layer
+        blk = blocks.block_decider(name, r, cin, cout, layer, cfg)
+        sd = {"encoder_blocks.0." + k: v.detach().clone() for k, v in blk.state_dict().items()}
+        x = torch.ones(len(cpu["points"][layer]), 1) if cin == 1 else torch.randn(len(cpu["points"][layer]), cin, generator=gen)
+        extent = r * cfg.KP_extent / cfg.conv_radius
+        if "simple" in name:
+            want = blocks_ref.simple_ref(x, cpu, sd, "encoder_blocks.0.", name, layer, extent)
+        else:
+            want = blocks_ref.resnetb_ref(x, cpu, sd, "encoder_blocks.0.", name, layer, extent)
+        with torch.no_grad():
+            got = blk.to(cuda)(x.to(cuda), gpu)
+        e = rel(got, want)
+        worst = max(worst, e)
+        assert e < TOL_TF32, f"{name} {cin}->{cout}: rel err {e:.2e}"
+    print(f"worst per-block rel err {worst:.2e}")

@@ -1,0 +1,107 @@
+"""CPU: pins the oracle (oracle/oracle_l1.c, oracle/blocks_ref.py) against the golden vectors produced by the real
+reference (oracle/make_golden.py) and, when oracle/_ref is present, against the reference's object code directly."""
+import numpy as np
+import pytest
+import torch
+
+from apr_b200 import synth
+from apr_b200.config import kitti_config
+from oracle import blocks_ref
+from oracle.ref import collate_ref, calibrate_ref, equal_modulo_ties, lexsort_rows_per_cloud, d2_rows
+
+
+def test_subsample_matches_reference_golden(oracle, gold_l1):
+    raw, lens = gold_l1["raw"], gold_l1["lens"]
+    for dl in (0.3, 0.6):
+        p, l = oracle.subsample_batch(raw, lens, sampleDl=dl)
+        assert np.array_equal(l, gold_l1[f"sub_{dl}_lens"])
+        assert np.array_equal(p, gold_l1[f"sub_{dl}_points_canonical"])
+        # as a set, bit-identical to the reference's (unordered_map-ordered) output
+        assert np.array_equal(lexsort_rows_per_cloud(p, l), gold_l1[f"sub_{dl}_points_ref_lexsorted"])
+
+
+@pytest.mark.parametrize("name,r", [("conv0", 1.275), ("pool0", 1.275), ("up0", 2.55)])
+def test_neighbors_match_reference_golden(oracle, gold_l1, name, r):
+    p0, l0, p1, l1 = gold_l1["p0"], gold_l1["l0"], gold_l1["p1"], gold_l1["l1"]
+    q, s, ql, sl = {"conv0": (p0, p0, l0, l0), "pool0": (p1, p0, l1, l0), "up0": (p0, p1, l0, l1)}[name]
+    nn = oracle.batch_query(q, s, ql, sl, radius=r)
+    assert np.array_equal(nn, gold_l1[f"nn_{name}_ordered"])              # bit-exact vs batch_ordered_neighbors
+    ok, rows, nontie = equal_modulo_ties(nn, gold_l1[f"nn_{name}_nanoflann"], q, s)
+    assert ok and nontie == 0                                             # nanoflann differs only inside d2 ties
+
+
+def test_neighbor_invariants(oracle, gold_l1):
+    p0, l0 = gold_l1["p0"], gold_l1["l0"]
+    nn, counts = oracle.batch_query(p0, p0, l0, l0, radius=1.275, return_counts=True)
+    ns = len(p0)
+    d2 = d2_rows(p0, p0, nn)
+    assert np.all(np.diff(np.where(np.isinf(d2), np.float32(3e38), d2), axis=1) >= 0)   # ascending, pads last
+    assert np.array_equal(nn[:, 0], np.arange(ns))                        # self is the nearest neighbour
+    assert np.array_equal((nn < ns).sum(1), counts)
+    r2 = np.float32(1.275) * np.float32(1.275)
+    assert np.all(d2[nn < ns] < r2)
+    off = np.concatenate([[0], np.cumsum(l0)])
+    for b in range(len(l0)):                                              # indices stay inside their own cloud
+        blk = nn[off[b]:off[b + 1]]
+        v = blk[blk < ns]
+        assert v.min() >= off[b] and v.max() < off[b + 1]
+    # truncation == leading columns (dataloader.py:66-70)
+    assert np.array_equal(oracle.batch_query(p0, p0, l0, l0, radius=1.275, max_neighbors=10), nn[:, :10])
+
+
+def test_oracle_vs_reference_object_code(oracle, ref_l1):
+    a, b = synth.small_cloud(11, 900), synth.small_cloud(12, 700)
+    raw = np.concatenate([a, b]); lens = np.array([len(a), len(b)], np.int32)
+    pr, lr = ref_l1.subsample_batch(raw, lens, sampleDl=0.45)
+    po, lo = oracle.subsample_batch(raw, lens, sampleDl=0.45)
+    assert np.array_equal(lr, lo)
+    assert np.array_equal(lexsort_rows_per_cloud(pr, lr), lexsort_rows_per_cloud(po, lo))
+    nn_o = oracle.batch_query(po, po, lo, lo, radius=1.9)
+    assert np.array_equal(nn_o, ref_l1.batch_query(po, po, lo, lo, radius=1.9, variant="ordered"))
+    ok, _, nontie = equal_modulo_ties(nn_o, ref_l1.batch_query(po, po, lo, lo, radius=1.9), po, po)
+    assert ok and nontie == 0
+
+
+def test_kpconv_restatement_matches_reference_golden(gold_kpconv):
+    g = gold_kpconv
+    p0, p1 = torch.from_numpy(g["p0"]), torch.from_numpy(g["p1"])
+    conv, pool = torch.from_numpy(g["conv"]).long(), torch.from_numpy(g["pool"]).long()
+    for tag, strided in (("c1", False), ("c8", False), ("c32s", True), ("c64", False)):
+        q, s, inds = (p1, p0, pool) if strided else (p0, p0, conv)
+        y = blocks_ref.kpconv_ref(q, s, inds, torch.from_numpy(g[f"{tag}_x"]), torch.from_numpy(g[f"{tag}_kp"]),
+                                  torch.from_numpy(g[f"{tag}_W"]), 0.6)
+        ref = torch.from_numpy(g[f"{tag}_y"])
+        assert (y - ref).norm() / ref.norm() < 1e-6
+    assert torch.equal(blocks_ref.max_pool_ref(torch.from_numpy(g["pool_x"]), pool), torch.from_numpy(g["max_pool_y"]))
+    assert torch.equal(blocks_ref.closest_pool_ref(torch.from_numpy(g["closest_x"]), torch.from_numpy(g["up"]).long()),
+                       torch.from_numpy(g["closest_pool_y"]))
+
+
+def test_encoder_restatement_matches_reference_golden(oracle, gold_encoder):
+    g = gold_encoder
+    cfg = kitti_config(first_feats_dim=16)
+    pyr = collate_ref(g["p0"], g["l0"], cfg, list(g["limits"]), oracle.subsample_batch, oracle.batch_query)
+    batch = dict(points=[torch.from_numpy(p) for p in pyr["points"]],
+                 neighbors=[torch.from_numpy(n).long() for n in pyr["neighbors"]],
+                 pools=[torch.from_numpy(n).long() for n in pyr["pools"]],
+                 features=torch.ones(len(g["p0"]), 1))
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd/")}
+    outs = blocks_ref.encoder_ref(batch, sd, cfg, return_all=True)
+    ref = torch.from_numpy(g["y_final"])
+    assert (outs[-1] - ref).norm() / ref.norm() < 1e-5
+    assert np.allclose([o.norm().item() for o in outs], g["block_norms"], rtol=1e-5)
+
+
+def test_pyramid_schedule_and_calibration(oracle):
+    cfg = kitti_config()
+    a, b = synth.small_cloud(21, 1500), synth.small_cloud(22, 1500)
+    raw = np.concatenate([a, b]); lens = np.array([len(a), len(b)], np.int32)
+    p0, l0 = oracle.subsample_batch(raw, lens, sampleDl=0.3)
+    pyr = collate_ref(p0, l0, cfg, [20, 20, 20, 20], oracle.subsample_batch, oracle.batch_query)
+    assert len(pyr["points"]) == 4 and pyr["pools"][3].shape[0] == 0 and pyr["upsamples"][3].shape[0] == 0
+    for l in range(3):
+        assert pyr["pools"][l].shape[0] == len(pyr["points"][l + 1])
+        assert pyr["upsamples"][l].shape[0] == len(pyr["points"][l])
+        assert pyr["neighbors"][l].shape[1] <= 20
+    lims = calibrate_ref([(p0, l0)], cfg, oracle.subsample_batch, oracle.batch_query)
+    assert lims.shape == (4,) and np.all(lims > 0)
