@@ -32,7 +32,9 @@ def lidar(seed, beams, el_lo, el_hi, n_az, h, rmax, n_cyl=80, wall_lo=20., wall_
             r = np.minimum(r, np.where((disc > 0) & (t > 0) & (t * dz < top - h) & (t * dz > -h), t, np.inf))
     m = np.isfinite(r) & (r < rmax) & (r > 2.0)
     r = r + np.random.default_rng(seed * 7919 + int(pose_x * 1000) + 1).normal(0, 0.02, r.shape)
-    return np.stack([r * dx, r * dy, r * dz], -1)[m].astype(np.float32)
+    with np.errstate(invalid='ignore'):
+        pts = np.stack([r * dx, r * dy, r * dz], -1)
+    return pts[m].astype(np.float32)
 
 
 def kitti(seed, pose_x=0.0):
