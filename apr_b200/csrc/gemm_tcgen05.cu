@@ -1,20 +1,271 @@
-// gemm_tcgen05.cu — TF32 GEMM on 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA operand staging).
-// Placeholder until the tcgen05 path lands: reports "unsupported" so callers take the fp32 CUDA-core path.
+// gemm_tcgen05.cu — TF32 GEMM on Blackwell 5th-gen tensor cores: C[M,N] = (A[M,K] @ Bt[N,K]^T) * rowscale[M].
+//
+// This is stage C of KPConv (A = kernel-point-weighted features [Nq, K*Cin], Bt = prepared weights [Cout, K*Cin],
+// rowscale = 1/neighbor_num; replaces the batched matmul + sum of /root/reference/Predator_APR/models/blocks.py:
+// 361-372) and the UnaryBlock nn.Linear (A = features, Bt = mlp.weight [Cout,Cin]; blocks.py:493,500).
+//
+// Structure (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0      : TMA producer — cp.async.bulk.tensor 2D loads of the A (128 x 32 fp32) and B (BN x 32 fp32) k-blocks
+//                 into a STAGES-deep ring of 128B-swizzled shared-memory tiles, completion on "full" mbarriers;
+//   warp 1      : allocates TMEM (BN fp32 columns) and, through one elected lane, issues tcgen05.mma
+//                 (cta_group::1, kind::tf32, M=128, N=BN, K=8; 4 per k-block) with the accumulator in TMEM;
+//                 tcgen05.commit releases each smem stage ("empty" mbarriers) and finally signals "tmem_full";
+//   warps 2..5  : epilogue — tcgen05.ld (32 lanes x 32 columns per warp and step) -> row scale -> global stores.
+// Operands are fp32 in memory; the tensor core reads them as TF32 (producers round to nearest beforehand where the
+// 1e-3 parity budget needs it), accumulation is fp32 in TMEM. Out-of-range rows/cols are zero-filled by TMA and masked
+// in the epilogue, so M and N need no padding (N % 16 == 0, K % 32 == 0 required).
 #include "common.cuh"
+#include <cuda.h>
 
 namespace aprb {
 
-bool gemm_tf32_supported(int M, int N, int K) { (void)M; (void)N; (void)K; return false; }
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 32;  // fp32 elements per k-block = 128 bytes = one SWIZZLE_128B row
 
-int gemm_tf32_rowscale(const float*, const float*, int, int, int, const float*, float*, cudaStream_t) {
-    set_error("gemm_tf32_rowscale: tcgen05 path not built");
-    return APRB_ERR_UNSUPPORTED;
+// ---- PTX wrappers ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a broken pipeline traps (error at the next sync) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// start address >> 4 in [0,14), LBO [16,30) (unused for swizzled K-major; 1), SBO = 1024 B (8 rows x 128 B) [32,46),
+// version 1 [46,48), layout SWIZZLE_128B (2) [61,64). The tile base must be 1024-byte aligned.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int A_BYTES = GEMM_BM * 128;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+                 const float* __restrict__ rowscale, float* __restrict__ C) {
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;                    // SWIZZLE_128B tiles need 1024 B alignment
+    const uint32_t sA = base, sB = base + Cfg::STAGES * Cfg::A_BYTES;
+    const uint32_t bars = sB + Cfg::STAGES * Cfg::B_BYTES;           // full[STAGES], empty[STAGES], tmem_full
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * Cfg::STAGES, bar_tmem = bars + 16 * Cfg::STAGES;
+    __shared__ uint32_t s_tmem_base;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * GEMM_BM, n0 = blockIdx.x * BN;
+    const int num_kb = K / GEMM_BK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_tmem, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1) {   // TMEM allocation: BN fp32 accumulator columns (power of two >= 32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "n"(BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {                                             // ===== TMA producer =====
+            int s = 0; uint32_t ph = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::A_BYTES + Cfg::B_BYTES);
+                tma_load_2d(sA + s * Cfg::A_BYTES, &tmA, bar_full + 8 * s, kb * GEMM_BK, m0);
+                tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, bar_full + 8 * s, kb * GEMM_BK, n0);
+                if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                             // ===== MMA issuer =====
+            // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2,
+            // B=TF32 [10,13)=2, A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
+            int s = 0; uint32_t ph = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(bar_full + 8 * s, ph);
+                tc_fence_after();
+                const uint64_t da = make_smem_desc(sA + s * Cfg::A_BYTES), db = make_smem_desc(sB + s * Cfg::B_BYTES);
+#pragma unroll
+                for (int k4 = 0; k4 < GEMM_BK / 8; ++k4)             // +32 bytes (>>4 = 2) per K=8 step inside the atom
+                    tc_mma_tf32(tmem_base, da + 2 * k4, db + 2 * k4, idesc, (kb | k4) != 0);
+                tc_commit(bar_empty + 8 * s);                        // frees the stage when these MMAs retire
+                if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+            }
+            tc_commit(bar_tmem);                                     // accumulator complete
+        }
+    } else {                                                         // ===== epilogue (warps 2..5) =====
+        mbar_wait(bar_tmem, 0);
+        tc_fence_after();
+        const int quarter = warp & 3;                                // TMEM lane quarter this warp may access
+        const int row = m0 + quarter * 32 + lane;
+        const float sc = (rowscale && row < M) ? rowscale[row] : 1.0f;
+        float* crow = C + (size_t)row * N + n0;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t v[32];
+            tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, v);
+            if (row < M) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (n0 + c + j < N) {                            // N % 16 == 0: a float4 is all-in or all-out
+                        float4 o = make_float4(__uint_as_float(v[j]) * sc, __uint_as_float(v[j + 1]) * sc,
+                                               __uint_as_float(v[j + 2]) * sc, __uint_as_float(v[j + 3]) * sc);
+                        *reinterpret_cast<float4*>(crow + c + j) = o;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+// 2-D fp32 row-major [rows, cols] tensor, box = [box_rows, 32 cols], 128B swizzle, zero OOB fill
+static int make_tmap(CUtensorMap* tm, const float* ptr, int rows, int cols, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return APRB_ERR_CUDA; }
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)cols * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d box_rows=%d", (int)r, rows, cols, box_rows); return APRB_ERR_CUDA; }
+    return APRB_OK;
+}
+
+bool gemm_tf32_supported(int M, int N, int K) {
+    return M >= 1 && N >= 16 && N % 16 == 0 && K >= GEMM_BK && K % GEMM_BK == 0;
+}
+
+template <int BN>
+static int launch_gemm(const float* A, const float* Bt, int M, int N, int K, const float* rowscale, float* C,
+                       cudaStream_t st) {
+    CUtensorMap tmA, tmB;
+    int rc = make_tmap(&tmA, A, M, K, GEMM_BM);
+    if (rc) return rc;
+    rc = make_tmap(&tmB, Bt, N, K, BN);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        APRB_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM));
+        attr_set = true;
+    }
+    dim3 grid(cdiv(N, BN), cdiv(M, GEMM_BM));
+    APRB_TIMED("gemm_tf32_kernel", st, 1, (gemm_tf32_kernel<BN><<<grid, 192, GemmCfg<BN>::SMEM, st>>>(tmA, tmB, M, N, K, rowscale, C)));
+    APRB_LAUNCH_OK();
+    return APRB_OK;
+}
+
+int gemm_tf32_rowscale(const float* d_A, const float* d_Bt, int M, int N, int K, const float* d_rowscale, float* d_C,
+                       cudaStream_t st) {
+    if (!gemm_tf32_supported(M, N, K)) { set_error("gemm_tf32: unsupported shape M=%d N=%d K=%d", M, N, K); return APRB_ERR_UNSUPPORTED; }
+    if (((uintptr_t)d_A | (uintptr_t)d_Bt | (uintptr_t)d_C) & 15) { set_error("gemm_tf32: operands must be 16-byte aligned"); return APRB_ERR_INVALID; }
+    // Tile width: the widest BN that still yields enough CTAs to occupy the 148 SMs.
+    const int mt = cdiv(M, GEMM_BM), sms = sm_count();
+    int bn = 64;
+    if (N >= 256 && (long long)mt * cdiv(N, 256) >= sms) bn = 256;
+    else if (N >= 128 && (long long)mt * cdiv(N, 128) >= sms) bn = 128;
+    if (bn == 256) return launch_gemm<256>(d_A, d_Bt, M, N, K, d_rowscale, d_C, st);
+    if (bn == 128) return launch_gemm<128>(d_A, d_Bt, M, N, K, d_rowscale, d_C, st);
+    return launch_gemm<64>(d_A, d_Bt, M, N, K, d_rowscale, d_C, st);
 }
 
 }  // namespace aprb
 
 extern "C" int aprb_linear_tf32(const float* d_x, const float* d_W, int N, int Cin, int Cout, float* d_y, void* stream) {
-    (void)d_x; (void)d_W; (void)N; (void)Cin; (void)Cout; (void)d_y; (void)stream;
-    aprb::set_error("aprb_linear_tf32: tcgen05 path not built");
-    return APRB_ERR_UNSUPPORTED;
+    using namespace aprb;
+    APRB_REQUIRE(N >= 0 && Cin >= 1 && Cout >= 1, "bad shape");
+    if (N == 0) return APRB_OK;
+    APRB_REQUIRE(d_x && d_W && d_y, "null pointer");
+    return gemm_tf32_rowscale(d_x, d_W, N, Cout, Cin, nullptr, d_y, (cudaStream_t)stream);
 }
