@@ -23,7 +23,7 @@ SIGNATURES = {
     "aprb_prof_report": (_i, [C.c_char_p, _sz]),
     "aprb_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "aprb_grid_subsample_ws_bytes": (_sz, [_i, _i, _i]),
-    "aprb_grid_subsample_batch": (_i, [_p, _p, _i, _i, _f, _i, _p, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "aprb_grid_subsample_batch": (_i, [_p, _p, _i, _i, _f, _i, _p, _i, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
     "aprb_radius_neighbors_ws_bytes": (_sz, [_i, _i, _i]),
     "aprb_radius_neighbors_batch": (_i, [_p, _p, _p, _p, _i, _i, _i, _f, _i, _p, _i, _p, _p, _p, _sz, _p]),
     "aprb_kpconv_prepare_weights": (_i, [_p, _i, _i, _i, _p, _p]),
@@ -32,8 +32,9 @@ SIGNATURES = {
     "aprb_max_pool": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "aprb_closest_pool": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "aprb_instnorm_ws_bytes": (_sz, [_i, _i]),
-    "aprb_instnorm_lrelu": (_i, [_p, _i, _i, _f, _f, _p, _i, _p, _p, _sz, _p]),
+    "aprb_instnorm_lrelu": (_i, [_p, _i, _i, _f, _f, _p, _i, _i, _p, _p, _sz, _p]),
     "aprb_linear_tf32": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "aprb_round_tf32": (_i, [_p, _p, _sz, _p]),
 }
 
 _lib = None

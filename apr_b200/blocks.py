@@ -154,7 +154,8 @@ class BatchNormBlock(nn.Module):
 
     def fused(self, x, slope=1.0, residual=None, norm_residual=False):
         if self.use_bn:
-            return ops.instnorm_lrelu(x, slope=slope, residual=residual, norm_residual=norm_residual)
+            return ops.instnorm_lrelu(x, slope=slope, residual=residual, norm_residual=norm_residual,
+                                      round_tf32=(LINEAR_MODE == 'tf32'))
         y = x + self.bias
         if residual is not None:
             y = y + residual
@@ -170,7 +171,12 @@ class BatchNormBlock(nn.Module):
 
 def _linear(mlp, x):
     if LINEAR_MODE == 'tf32' and ops.linear_tf32_supported(x.shape[0], mlp.in_features, mlp.out_features):
-        return ops.linear_tf32(x, mlp.weight)
+        key = (mlp.weight.data_ptr(), mlp.weight._version)
+        cache = getattr(mlp, '_aprb_w_tf32', None)
+        if cache is None or cache[0] != key:                 # TF32-rounded copy, rebuilt when the weight changes
+            cache = (key, ops.round_tf32(mlp.weight))
+            mlp._aprb_w_tf32 = cache
+        return ops.linear_tf32(x, cache[1])
     return nn.functional.linear(x, mlp.weight)
 
 

@@ -60,36 +60,49 @@ int sm_count() {
     return n;
 }
 
-__global__ void offsets_kernel(const int* __restrict__ lens, int B, int* __restrict__ off) {
-    // One block; chunked block scan carrying a running prefix. B is small on the hot path (2 clouds per pair).
-    __shared__ int s_part[256];
-    __shared__ int s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
+__device__ void block_offsets(const int* __restrict__ lens, int B, int* __restrict__ off, int* s_part, int* s_carry) {
+    if (B <= 64) {   // the hot path has B = 2: a sequential prefix by one thread beats a block scan
+        if (threadIdx.x == 0) {
+            int acc = 0;
+            for (int b = 0; b < B; ++b) { off[b] = acc; acc += lens[b]; }
+            off[B] = acc;
+        }
+        return;
+    }
+    if (threadIdx.x == 0) *s_carry = 0;
     __syncthreads();
-    for (int base = 0; base < B; base += blockDim.x) {
+    for (int base = 0; base < B; base += blockDim.x) {   // chunked Hillis-Steele scan carrying a running prefix
         int i = base + threadIdx.x;
         int v = i < B ? lens[i] : 0;
         s_part[threadIdx.x] = v;
         __syncthreads();
-        for (int d = 1; d < blockDim.x; d <<= 1) {  // Hillis-Steele inclusive scan
+        for (int d = 1; d < blockDim.x; d <<= 1) {
             int t = threadIdx.x >= d ? s_part[threadIdx.x - d] : 0;
             __syncthreads();
             s_part[threadIdx.x] += t;
             __syncthreads();
         }
         int incl = s_part[threadIdx.x];
-        int carry = s_carry;
+        int carry = *s_carry;
         if (i < B) off[i] = carry + incl - v;
         __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) s_carry = carry + incl;
+        if (threadIdx.x == blockDim.x - 1) *s_carry = carry + incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) off[B] = s_carry;
+    if (threadIdx.x == 0) off[B] = *s_carry;
 }
 
-__global__ void bbox_init_kernel(int* __restrict__ bbox, int B) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B * 6) bbox[i] = (i % 6) < 3 ? 0x7FFFFFFF : (int)0x80000000;
+__global__ void setup_kernel(const int* __restrict__ lensA, int* __restrict__ offA, const int* __restrict__ lensB,
+                             int* __restrict__ offB, int B, int* __restrict__ bbox, int* __restrict__ zero, int nzero) {
+    __shared__ int s_part[256];
+    __shared__ int s_carry;
+    for (int i = threadIdx.x; i < 6 * B; i += blockDim.x) bbox[i] = (i % 6) < 3 ? 0x7FFFFFFF : (int)0x80000000;
+    for (int i = threadIdx.x; i < nzero; i += blockDim.x) zero[i] = 0;
+    block_offsets(lensA, B, offA, s_part, &s_carry);
+    if (lensB) {
+        __syncthreads();
+        block_offsets(lensB, B, offB, s_part, &s_carry);
+    }
 }
 
 __global__ void bbox_kernel(const float* __restrict__ pts, int N, const int* __restrict__ off, int B,
@@ -150,10 +163,17 @@ int exclusive_scan_i32(const int* d_in, int* d_out, int n, void* d_temp, size_t 
     return APRB_OK;
 }
 
-int sort_pairs_u64_i32(const uint64_t* k_in, uint64_t* k_out, const int* v_in, int* v_out, int n, void* d_temp,
-                       size_t temp_bytes, cudaStream_t st) {
-    ProfScope ps("cub_radix_sort_pairs", st, 10);
+int sort_pairs_i32(const uint64_t* k_in, uint64_t* k_out, const int* v_in, int* v_out, int n, void* d_temp,
+                   size_t temp_bytes, cudaStream_t st) {
+    ProfScope ps("cub_radix_sort_pairs64", st, 10);
     APRB_CUDA_OK(cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, k_in, k_out, v_in, v_out, n, 0, 64, st));
+    return APRB_OK;
+}
+
+int sort_pairs_i32(const uint32_t* k_in, uint32_t* k_out, const int* v_in, int* v_out, int n, void* d_temp,
+                   size_t temp_bytes, cudaStream_t st) {
+    ProfScope ps("cub_radix_sort_pairs32", st, 6);
+    APRB_CUDA_OK(cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, k_in, k_out, v_in, v_out, n, 0, 32, st));
     return APRB_OK;
 }
 

@@ -82,11 +82,11 @@ __device__ __forceinline__ int find_cloud(const int* __restrict__ off, int B, in
     return lo;
 }
 
-// Single-block exclusive prefix of lens[B] -> off[B+1] (any B), plus optional init of a bbox array.
-__global__ void offsets_kernel(const int* __restrict__ lens, int B, int* __restrict__ off);
-
+// Single-block setup: exclusive prefixes lensA[B] -> offA[B+1] and (optional) lensB[B] -> offB[B+1], bbox[B*6] reset to
+// (+max, -max) in ordered-int encoding, and `nzero` ints at `zero` cleared. One launch instead of four.
 // Per-cloud bounding boxes: bbox[b*6 + {0,1,2}] = ordered-int min xyz, {3,4,5} = ordered-int max xyz.
-__global__ void bbox_init_kernel(int* __restrict__ bbox, int B);
+__global__ void setup_kernel(const int* __restrict__ lensA, int* __restrict__ offA, const int* __restrict__ lensB,
+                             int* __restrict__ offB, int B, int* __restrict__ bbox, int* __restrict__ zero, int nzero);
 __global__ void bbox_kernel(const float* __restrict__ pts, int N, const int* __restrict__ off, int B,
                             int* __restrict__ bbox);
 
@@ -94,7 +94,9 @@ __global__ void bbox_kernel(const float* __restrict__ pts, int N, const int* __r
 size_t scan_temp_bytes(int n);
 size_t sort_temp_bytes(int n);
 int exclusive_scan_i32(const int* d_in, int* d_out, int n, void* d_temp, size_t temp_bytes, cudaStream_t st);
-int sort_pairs_u64_i32(const uint64_t* k_in, uint64_t* k_out, const int* v_in, int* v_out, int n, void* d_temp,
-                       size_t temp_bytes, cudaStream_t st);
+int sort_pairs_i32(const uint64_t* k_in, uint64_t* k_out, const int* v_in, int* v_out, int n, void* d_temp,
+                   size_t temp_bytes, cudaStream_t st);
+int sort_pairs_i32(const uint32_t* k_in, uint32_t* k_out, const int* v_in, int* v_out, int n, void* d_temp,
+                   size_t temp_bytes, cudaStream_t st);
 
 }  // namespace aprb

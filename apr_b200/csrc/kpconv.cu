@@ -31,8 +31,35 @@ __global__ void rowsum_pos_kernel(const float* __restrict__ x, int Ns, int C, un
     if (lane == 0) flag[row] = s > 0.f ? 1 : 0;
 }
 
-// Dynamic smem per warp: K*Hp floats of weights + Hp ints of indices (Hp = H rounded up to 32).
-template <typename IdxT, bool ROUND_TF32>
+template <int VEC> struct Vec;
+template <> struct Vec<1> { float v[1]; };
+template <> struct __align__(8) Vec<2> { float v[2]; };
+template <> struct __align__(16) Vec<4> { float v[4]; };
+
+// acc[k][:] += w * xv for every kernel point k set in `mask`; the loop and the switch are warp-uniform (all lanes of a
+// warp work on the same neighbour), so only the influenced kernel points (~1.4 of 15 on average) cost anything.
+template <int VEC>
+__device__ __forceinline__ void kp_accumulate(float (&acc)[KP_MAX_K][VEC], unsigned mask, const float* __restrict__ wrow,
+                                              const Vec<VEC>& xv) {
+    while (mask) {
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float w = wrow[k];
+#define KP_CASE(i) case i: _Pragma("unroll") for (int j = 0; j < VEC; ++j) acc[i][j] = fmaf(w, xv.v[j], acc[i][j]); break;
+        switch (k) {
+            KP_CASE(0) KP_CASE(1) KP_CASE(2) KP_CASE(3) KP_CASE(4) KP_CASE(5) KP_CASE(6) KP_CASE(7)
+            KP_CASE(8) KP_CASE(9) KP_CASE(10) KP_CASE(11) KP_CASE(12) KP_CASE(13) KP_CASE(14) KP_CASE(15)
+        }
+#undef KP_CASE
+    }
+}
+
+// One warp per query. Dynamic smem per warp: Hp*16 floats of influence weights (neighbour-major) + Hp ints of active
+// support indices + Hp ints of (neighbour << 16 | kernel-point mask); Hp = H rounded up to 32.
+// Phase 1 (lanes = neighbours): influence weights, kernel-point masks, neighbor_num, compaction of the neighbours that
+// influence at least one kernel point. Phase 2 (lanes = channels, VEC per lane, slabs of 32*VEC channels): stream the
+// active neighbours' feature rows (two in flight) and accumulate into the <= 16 x VEC register tile.
+template <typename IdxT, int VEC, bool ROUND_TF32>
 __global__ void __launch_bounds__(128)
 kp_weighted_kernel(const float* __restrict__ q, const float* __restrict__ s, const IdxT* __restrict__ idx, int ld,
                    const float* __restrict__ x, const float* __restrict__ kp, const unsigned char* __restrict__ posflag,
@@ -46,78 +73,94 @@ kp_weighted_kernel(const float* __restrict__ q, const float* __restrict__ s, con
     __syncthreads();
     const int n = blockIdx.x * wpb + wib;
     if (n >= Nq) return;
-    float* s_w = s_dyn + (size_t)wib * (K + 1) * Hp;           // [K][Hp]
-    int* s_idx = reinterpret_cast<int*>(s_w + (size_t)K * Hp);  // [Hp]
+    float* s_w = s_dyn + (size_t)wib * Hp * 18;                 // [Hp][16]
+    int* s_si = reinterpret_cast<int*>(s_w + (size_t)Hp * 16);  // [Hp] active support index
+    int* s_hm = s_si + Hp;                                      // [Hp] (h << 16) | mask
     const float qx = q[3 * (size_t)n], qy = q[3 * (size_t)n + 1], qz = q[3 * (size_t)n + 2];
+    const float ext2 = extent * extent, inv_ext = 1.0f / extent;
 
-    int nn = 0;
-    for (int h = lane; h < Hp; h += 32) {
+    int nn = 0, nact = 0;
+    for (int h0 = 0; h0 < Hp; h0 += 32) {
+        const int h = h0 + lane;
         int si = Ns;
         if (h < H) {
-            long long v = (long long)idx[(size_t)n * ld + h];
+            const long long v = (long long)idx[(size_t)n * ld + h];
             si = (v >= 0 && v < Ns) ? (int)v : Ns;
         }
-        s_idx[h] = si;
+        unsigned mask = 0;
         if (si < Ns) {
             nn += posflag[si];
             const float rx = s[3 * (size_t)si] - qx, ry = s[3 * (size_t)si + 1] - qy, rz = s[3 * (size_t)si + 2] - qz;
             for (int k = 0; k < K; ++k) {
                 const float ddx = rx - s_kp[3 * k], ddy = ry - s_kp[3 * k + 1], ddz = rz - s_kp[3 * k + 2];
                 const float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
-                s_w[k * Hp + h] = fmaxf(1.0f - __fdiv_rn(__fsqrt_rn(d2), extent), 0.0f);
+                if (d2 < ext2) {                                 // influence max(0, 1 - d/extent) is non-zero
+                    const float w = 1.0f - sqrtf(d2) * inv_ext;
+                    if (w > 0.f) { s_w[h * 16 + k] = w; mask |= 1u << k; }
+                }
             }
-        } else {
-            for (int k = 0; k < K; ++k) s_w[k * Hp + h] = 0.0f;
         }
+        const unsigned act = __ballot_sync(0xffffffffu, mask != 0);
+        if (mask) {
+            const int pos = nact + __popc(act & ((1u << lane) - 1));
+            s_si[pos] = si;
+            s_hm[pos] = (h << 16) | (int)mask;
+        }
+        nact += __popc(act);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, d);
     if (lane == 0) inv_nn[n] = 1.0f / (float)max(nn, 1);
     __syncwarp();
 
-    // feature slabs of 128 channels: lane owns channels c0 + lane + 32*j, j < 4
     float* wrow = wf + (size_t)n * K * Cin;
-    for (int c0 = 0; c0 < Cin; c0 += 128) {
-        float acc[KP_MAX_K][4];
+    for (int c0 = 0; c0 < Cin; c0 += 32 * VEC) {
+        const int c = c0 + lane * VEC;
+        const bool cvalid = c < Cin;
+        float acc[KP_MAX_K][VEC];
 #pragma unroll
         for (int k = 0; k < KP_MAX_K; ++k)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[k][j] = 0.f;
-        for (int h = 0; h < H; ++h) {
-            const int si = s_idx[h];
-            if (si >= Ns) continue;  // warp-uniform
-            float xv[4];
+            for (int j = 0; j < VEC; ++j) acc[k][j] = 0.f;
+        const float* xc = x + c;
+        int j = 0;
+        for (; j + 1 < nact; j += 2) {                           // two neighbour rows in flight
+            const int si0 = s_si[j], si1 = s_si[j + 1];
+            const int hm0 = s_hm[j], hm1 = s_hm[j + 1];
+            Vec<VEC> x0, x1;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = c0 + lane + 32 * j;
-                xv[j] = c < Cin ? x[(size_t)si * Cin + c] : 0.f;
+            for (int v = 0; v < VEC; ++v) { x0.v[v] = 0.f; x1.v[v] = 0.f; }
+            if (cvalid) {
+                x0 = *reinterpret_cast<const Vec<VEC>*>(xc + (size_t)si0 * Cin);
+                x1 = *reinterpret_cast<const Vec<VEC>*>(xc + (size_t)si1 * Cin);
             }
+            kp_accumulate<VEC>(acc, (unsigned)hm0 & 0xFFFFu, s_w + (hm0 >> 16) * 16, x0);
+            kp_accumulate<VEC>(acc, (unsigned)hm1 & 0xFFFFu, s_w + (hm1 >> 16) * 16, x1);
+        }
+        if (j < nact) {
+            const int si0 = s_si[j], hm0 = s_hm[j];
+            Vec<VEC> x0;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) x0.v[v] = 0.f;
+            if (cvalid) x0 = *reinterpret_cast<const Vec<VEC>*>(xc + (size_t)si0 * Cin);
+            kp_accumulate<VEC>(acc, (unsigned)hm0 & 0xFFFFu, s_w + (hm0 >> 16) * 16, x0);
+        }
+        if (cvalid) {
 #pragma unroll
             for (int k = 0; k < KP_MAX_K; ++k) {
                 if (k < K) {
-                    const float w = s_w[k * Hp + h];  // broadcast
-                    if (w != 0.f) {                   // warp-uniform skip
+                    Vec<VEC> o;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) acc[k][j] = fmaf(w, xv[j], acc[k][j]);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < KP_MAX_K; ++k) {
-            if (k < K) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int c = c0 + lane + 32 * j;
-                    if (c < Cin) {
-                        float v = acc[k][j];
+                    for (int v = 0; v < VEC; ++v) {
+                        float t = acc[k][v];
                         if (ROUND_TF32) {
                             unsigned u;
-                            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-                            v = __uint_as_float(u);
+                            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(t));
+                            t = __uint_as_float(u);
                         }
-                        wrow[(size_t)k * Cin + c] = v;
+                        o.v[v] = t;
                     }
+                    *reinterpret_cast<Vec<VEC>*>(wrow + (size_t)k * Cin + c) = o;
                 }
             }
         }
@@ -194,6 +237,22 @@ extern "C" int aprb_kpconv_prepare_weights(const float* d_W, int K, int Cin, int
     return APRB_OK;
 }
 
+__global__ void round_tf32_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(in[i]));
+    out[i] = __uint_as_float(u);
+}
+
+extern "C" int aprb_round_tf32(const float* d_in, float* d_out, size_t n, void* stream) {
+    APRB_REQUIRE(n == 0 || (d_in && d_out), "null pointer");
+    if (n == 0) return APRB_OK;
+    APRB_TIMED("round_tf32_kernel", (cudaStream_t)stream, 1, (round_tf32_kernel<<<cdiv((long long)n, 256), 256, 0, (cudaStream_t)stream>>>(d_in, d_out, n)));
+    APRB_LAUNCH_OK();
+    return APRB_OK;
+}
+
 extern "C" size_t aprb_kpconv_ws_bytes(int Nq, int Ns, int H, int K, int Cin, int Cout) {
     (void)H; (void)Cout;
     if (Nq < 0 || Ns < 0 || K < 0 || Cin < 0) return 0;
@@ -228,22 +287,27 @@ extern "C" int aprb_kpconv_forward(const float* d_q, const float* d_s, const voi
 
     if (Ns > 0) APRB_TIMED("rowsum_pos_kernel", st, 1, (rowsum_pos_kernel<<<cdiv(Ns, 8), 256, 0, st>>>(d_x, Ns, Cin, flag)));
     const int wpb = 4, Hp = (H + 31) & ~31;
-    size_t smem = (size_t)wpb * (K + 1) * Hp * sizeof(float);
-#define KPW_LAUNCH(IDX, RND)                                                                                         \
+    size_t smem = (size_t)wpb * Hp * 18 * sizeof(float);
+    const bool x16 = ((uintptr_t)d_x % 16 == 0) && ((uintptr_t)wf % 16 == 0);
+    const int vec = (Cin % 4 == 0 && Cin >= 128 && x16) ? 4 : ((Cin % 2 == 0 && Cin >= 64 && x16) ? 2 : 1);
+#define KPW_LAUNCH3(IDX, VEC, RND)                                                                                   \
     do {                                                                                                             \
         if (smem > 48 * 1024)                                                                                        \
-            APRB_CUDA_OK(cudaFuncSetAttribute(kp_weighted_kernel<IDX, RND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        APRB_TIMED("kp_weighted_kernel", st, 1, (kp_weighted_kernel<IDX, RND><<<cdiv(Nq, wpb), wpb * 32, smem, st>>>(             \
+            APRB_CUDA_OK(cudaFuncSetAttribute(kp_weighted_kernel<IDX, VEC, RND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        APRB_TIMED("kp_weighted_kernel", st, 1, (kp_weighted_kernel<IDX, VEC, RND><<<cdiv(Nq, wpb), wpb * 32, smem, st>>>(        \
             d_q, d_s, (const IDX*)d_idx, ld_idx, d_x, d_kp, flag, extent, Nq, Ns, H, K, Cin, wf, inv_nn)));         \
     } while (0)
+#define KPW_LAUNCH(IDX, RND)                                                                                         \
+    do {                                                                                                             \
+        if (vec == 4) KPW_LAUNCH3(IDX, 4, RND); else if (vec == 2) KPW_LAUNCH3(IDX, 2, RND); else KPW_LAUNCH3(IDX, 1, RND); \
+    } while (0)
     if (use_tensor) {
-        if (rows > (size_t)Nq)  // zero the pad rows the tensor path reads
-            APRB_CUDA_OK(cudaMemsetAsync(wf + (size_t)Nq * KC, 0, (rows - Nq) * KC * sizeof(float), st));
         if (idx_is_i64) KPW_LAUNCH(long long, true); else KPW_LAUNCH(int, true);
         APRB_LAUNCH_OK();
         return gemm_tf32_rowscale(wf, d_wprep, Nq, Cout, KC, inv_nn, d_out, st);
     }
     if (idx_is_i64) KPW_LAUNCH(long long, false); else KPW_LAUNCH(int, false);
+#undef KPW_LAUNCH3
 #undef KPW_LAUNCH
     APRB_LAUNCH_OK();
     APRB_TIMED("sgemm_rowscale_kernel", st, 1, (sgemm_rowscale_kernel<<<dim3(cdiv(Cout, 64), cdiv(Nq, 64)), 256, 0, st>>>(wf, d_W, Nq, Cout, KC, inv_nn, d_out)));

@@ -262,9 +262,7 @@ extern "C" int aprb_radius_neighbors_batch(const float* d_q, const float* d_s, c
     carve_nb(c, Nq, Ns > 0 ? Ns : 1, B, &w);
     if (!c.ok()) { set_error("aprb_radius_neighbors_batch: workspace too small (%zu < %zu)", ws_bytes, c.off); return APRB_ERR_WORKSPACE; }
     const int T = 256;
-    APRB_TIMED("offsets_kernel", st, 1, (offsets_kernel<<<1, 256, 0, st>>>(d_qlens, B, w.qoff)));
-    APRB_TIMED("offsets_kernel", st, 1, (offsets_kernel<<<1, 256, 0, st>>>(d_slens, B, w.soff)));
-    APRB_TIMED("bbox_init_kernel", st, 1, (bbox_init_kernel<<<cdiv(6 * B, T), T, 0, st>>>(w.bbox, B)));
+    APRB_TIMED("setup_kernel", st, 1, (setup_kernel<<<1, 256, 0, st>>>(d_qlens, w.qoff, d_slens, w.soff, B, w.bbox, w.total_cells, 1)));
     if (Ns > 0) APRB_TIMED("bbox_kernel", st, 1, (bbox_kernel<<<cdiv(Ns, T), T, 0, st>>>(d_s, Ns, w.soff, B, w.bbox)));
     APRB_TIMED("nb_grid_params_kernel", st, 1, (nb_grid_params_kernel<<<1, 256, 0, st>>>(w.bbox, w.soff, B, radius, w.grids, w.total_cells)));
     APRB_CUDA_OK(cudaMemsetAsync(w.cell_count, 0, sizeof(int) * ((size_t)w.cells_cap + 1), st));

@@ -57,17 +57,27 @@ __global__ void closest_pool_kernel(const float* __restrict__ x, const IdxT* __r
 }
 
 // ---- K6 -------------------------------------------------------------------------------------------------------
-// Pass 1: per (row-chunk, column) Welford partials (count, mean, M2); pass 2: Chan-combine the partials in fixed
-// order (deterministic, no float atomics) -> mean, rstd; pass 3: apply.
-constexpr int NORM_ROWS_PER_CHUNK = 256;
+// Two launches per normalisation: (1) per (row-chunk, column) Welford partials (mean, M2); (2) every block of the apply
+// kernel Chan-combines the partials of its 32 columns in a fixed order (deterministic, no float atomics), then
+// standardises / adds the residual / applies LeakyReLU over its rows. The row-chunk size is picked on the host so that
+// both grids fill the 148 SMs.
+__device__ __forceinline__ void chan_combine(float& am, float& a2, int& an, float bm, float b2, int bn) {
+    if (bn == 0) return;
+    int n = an + bn;
+    float d = bm - am;
+    am += d * ((float)bn / (float)n);
+    a2 += b2 + d * d * ((float)an * (float)bn / (float)n);
+    an = n;
+}
 
-__global__ void norm_partial_kernel(const float* __restrict__ x, int N, int C, float* __restrict__ pmean,
-                                    float* __restrict__ pm2) {
-    // grid: (ceil(C/32), chunks); block: (32, 8). Each thread walks rows r = ty, ty+8, ... of its chunk for column c.
+__global__ void __launch_bounds__(256)
+norm_partial_kernel(const float* __restrict__ x, int N, int C, int rows_per_chunk, float* __restrict__ pmean,
+                    float* __restrict__ pm2) {
+    // grid: (ceil(C/32), chunks); block: (32, 8). Thread (tx, ty) walks rows r0+ty, r0+ty+8, ... of column c.
     __shared__ float s_mean[8][33], s_m2[8][33];
     __shared__ int s_cnt[8][33];
     int c = blockIdx.x * 32 + threadIdx.x;
-    int r0 = blockIdx.y * NORM_ROWS_PER_CHUNK, r1 = min(r0 + NORM_ROWS_PER_CHUNK, N);
+    int r0 = blockIdx.y * rows_per_chunk, r1 = min(r0 + rows_per_chunk, N);
     float mean = 0.f, m2 = 0.f;
     int cnt = 0;
     if (c < C) {
@@ -75,7 +85,7 @@ __global__ void norm_partial_kernel(const float* __restrict__ x, int N, int C, f
             float v = x[(size_t)r * C + c];
             ++cnt;
             float d = v - mean;
-            mean += d / (float)cnt;
+            mean += __fdividef(d, (float)cnt);
             m2 += d * (v - mean);
         }
     }
@@ -84,54 +94,66 @@ __global__ void norm_partial_kernel(const float* __restrict__ x, int N, int C, f
     if (threadIdx.y == 0 && c < C) {
         float am = 0.f, a2 = 0.f;
         int an = 0;
-        for (int k = 0; k < 8; ++k) {
-            int bn = s_cnt[k][threadIdx.x];
-            if (bn == 0) continue;
-            float bm = s_mean[k][threadIdx.x], b2 = s_m2[k][threadIdx.x];
-            int n = an + bn;
-            float d = bm - am;
-            am += d * ((float)bn / (float)n);
-            a2 += b2 + d * d * ((float)an * (float)bn / (float)n);
-            an = n;
-        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) chan_combine(am, a2, an, s_mean[k][threadIdx.x], s_m2[k][threadIdx.x], s_cnt[k][threadIdx.x]);
         pmean[(size_t)blockIdx.y * C + c] = am;
         pm2[(size_t)blockIdx.y * C + c] = a2;
     }
 }
 
-__global__ void norm_finalize_kernel(const float* __restrict__ pmean, const float* __restrict__ pm2, int N, int C,
-                                     int chunks, float eps, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+// combine `chunks` partials of one column; ty strides over chunks, then the 8 ty-partials are combined in order
+__device__ __forceinline__ void block_column_stats(const float* __restrict__ pmean, const float* __restrict__ pm2, int N,
+                                                   int C, int chunks, int rows_per_chunk, float eps, int c,
+                                                   float (*s_a)[33], float (*s_b)[33], int (*s_n)[33],
+                                                   float* s_mean, float* s_rstd) {
     float am = 0.f, a2 = 0.f;
     int an = 0;
-    for (int k = 0; k < chunks; ++k) {
-        int bn = min(NORM_ROWS_PER_CHUNK, N - k * NORM_ROWS_PER_CHUNK);
-        float bm = pmean[(size_t)k * C + c], b2 = pm2[(size_t)k * C + c];
-        int n = an + bn;
-        float d = bm - am;
-        am += d * ((float)bn / (float)n);
-        a2 += b2 + d * d * ((float)an * (float)bn / (float)n);
-        an = n;
+    if (c < C)
+        for (int k = threadIdx.y; k < chunks; k += 8)
+            chan_combine(am, a2, an, pmean[(size_t)k * C + c], pm2[(size_t)k * C + c],
+                         min(rows_per_chunk, N - k * rows_per_chunk));
+    s_a[threadIdx.y][threadIdx.x] = am; s_b[threadIdx.y][threadIdx.x] = a2; s_n[threadIdx.y][threadIdx.x] = an;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+        float m = 0.f, v2 = 0.f;
+        int n = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) chan_combine(m, v2, n, s_a[k][threadIdx.x], s_b[k][threadIdx.x], s_n[k][threadIdx.x]);
+        s_mean[threadIdx.x] = m;
+        s_rstd[threadIdx.x] = rsqrtf(v2 / (float)N + eps);
     }
-    mean_out[c] = am;
-    rstd_out[c] = rsqrtf(a2 / (float)N + eps);
+    __syncthreads();
 }
 
-__global__ void norm_apply_kernel(const float* __restrict__ x, long long total, int C, const float* __restrict__ mean,
-                                  const float* __restrict__ rstd, const float* __restrict__ res,
-                                  const float* __restrict__ rmean, const float* __restrict__ rrstd, float slope,
-                                  float* __restrict__ y) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    int c = (int)(i % C);
-    float v = (x[i] - mean[c]) * rstd[c];
-    if (res) {
-        float r = res[i];
-        if (rmean) r = (r - rmean[c]) * rrstd[c];
-        v += r;
+__global__ void __launch_bounds__(256)
+norm_apply_kernel(const float* __restrict__ x, int N, int C, int chunks, int rows_per_chunk, float eps,
+                  const float* __restrict__ pmean, const float* __restrict__ pm2, const float* __restrict__ res,
+                  const float* __restrict__ rpmean, const float* __restrict__ rpm2, float slope, int rows_per_block,
+                  int round_tf32, float* __restrict__ y) {
+    // grid: (ceil(C/32), row blocks); block (32, 8)
+    __shared__ float s_a[8][33], s_b[8][33];
+    __shared__ int s_n[8][33];
+    __shared__ float s_mean[32], s_rstd[32], s_rmean[32], s_rrstd[32];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    block_column_stats(pmean, pm2, N, C, chunks, rows_per_chunk, eps, c, s_a, s_b, s_n, s_mean, s_rstd);
+    const bool nres = res != nullptr && rpmean != nullptr;
+    if (nres) block_column_stats(rpmean, rpm2, N, C, chunks, rows_per_chunk, eps, c, s_a, s_b, s_n, s_rmean, s_rrstd);
+    if (c >= C) return;
+    const float mean = s_mean[threadIdx.x], rstd = s_rstd[threadIdx.x];
+    const float rmean = nres ? s_rmean[threadIdx.x] : 0.f, rrstd = nres ? s_rrstd[threadIdx.x] : 1.f;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(r0 + rows_per_block, N);
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+        const size_t i = (size_t)r * C + c;
+        float v = (x[i] - mean) * rstd;
+        if (res) v += (res[i] - rmean) * rrstd;
+        v = v >= 0.f ? v : v * slope;
+        if (round_tf32) {   // activations stored TF32-representable: downstream tensor-core GEMMs then read them exactly
+            unsigned u;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+            v = __uint_as_float(u);
+        }
+        y[i] = v;
     }
-    y[i] = v >= 0.f ? v : v * slope;
 }
 
 }  // namespace aprb
@@ -172,41 +194,40 @@ extern "C" int aprb_closest_pool(const float* d_x, const void* d_idx, int idx_is
     return APRB_OK;
 }
 
-extern "C" size_t aprb_instnorm_ws_bytes(int N, int C) {
-    if (N < 0 || C < 0) return 0;
-    size_t chunks = (size_t)cdiv(N > 0 ? N : 1, NORM_ROWS_PER_CHUNK);
-    return 2 * (2 * align256(chunks * C * sizeof(float)) + 2 * align256(C * sizeof(float))) + 256;
+static void norm_plan(int N, int C, int* rows_per_chunk, int* chunks) {
+    // about 2 waves of (column-tile x chunk) blocks, chunks of at least 64 rows, at most 256 chunks
+    int ct = cdiv(C, 32);
+    int want = max(1, (2 * sm_count() + ct - 1) / ct);
+    int ch = min(min(want, 256), max(1, N / 64));
+    int rpc = ((cdiv(N, ch) + 7) / 8) * 8;
+    *rows_per_chunk = rpc;
+    *chunks = cdiv(N, rpc);
 }
 
-static int norm_stats(const float* d_x, int N, int C, float eps, float* pmean, float* pm2, float* mean, float* rstd,
-                      cudaStream_t st) {
-    int chunks = cdiv(N, NORM_ROWS_PER_CHUNK);
-    APRB_TIMED("norm_partial_kernel", st, 1, (norm_partial_kernel<<<dim3(cdiv(C, 32), chunks), dim3(32, 8), 0, st>>>(d_x, N, C, pmean, pm2)));
-    APRB_TIMED("norm_finalize_kernel", st, 1, (norm_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(pmean, pm2, N, C, chunks, eps, mean, rstd)));
-    APRB_LAUNCH_OK();
-    return APRB_OK;
+extern "C" size_t aprb_instnorm_ws_bytes(int N, int C) {
+    if (N < 0 || C < 0) return 0;
+    return 4 * align256((size_t)256 * (C > 0 ? C : 1) * sizeof(float)) + 256;
 }
 
 extern "C" int aprb_instnorm_lrelu(const float* d_x, int N, int C, float eps, float slope, const float* d_residual,
-                                   int norm_residual, float* d_y, void* d_ws, size_t ws_bytes, void* stream) {
+                                   int norm_residual, int round_tf32, float* d_y, void* d_ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     APRB_REQUIRE(N >= 0 && C >= 1, "bad shape");
     if (N == 0) return APRB_OK;
     APRB_REQUIRE(d_x && d_y && d_ws, "null pointer");
     if (ws_bytes < aprb_instnorm_ws_bytes(N, C)) { set_error("aprb_instnorm_lrelu: workspace too small"); return APRB_ERR_WORKSPACE; }
     Carver c(d_ws, ws_bytes);
-    size_t chunks = (size_t)cdiv(N, NORM_ROWS_PER_CHUNK);
-    float* pmean = c.take<float>(chunks * C); float* pm2 = c.take<float>(chunks * C);
-    float* mean = c.take<float>(C); float* rstd = c.take<float>(C);
-    float* rpmean = c.take<float>(chunks * C); float* rpm2 = c.take<float>(chunks * C);
-    float* rmean = c.take<float>(C); float* rrstd = c.take<float>(C);
-    int rc = norm_stats(d_x, N, C, eps, pmean, pm2, mean, rstd, st);
-    if (rc) return rc;
-    bool nr = d_residual && norm_residual;
-    if (nr) { rc = norm_stats(d_residual, N, C, eps, rpmean, rpm2, rmean, rrstd, st); if (rc) return rc; }
-    long long total = (long long)N * C;
-    APRB_TIMED("norm_apply_kernel", st, 1, (norm_apply_kernel<<<cdiv(total, 256), 256, 0, st>>>(d_x, total, C, mean, rstd, d_residual, nr ? rmean : nullptr,
-                                                       nr ? rrstd : nullptr, slope, d_y)));
+    float* pmean = c.take<float>((size_t)256 * C); float* pm2 = c.take<float>((size_t)256 * C);
+    float* rpmean = c.take<float>((size_t)256 * C); float* rpm2 = c.take<float>((size_t)256 * C);
+    int rpc, chunks;
+    norm_plan(N, C, &rpc, &chunks);
+    const dim3 blk(32, 8);
+    const bool nr = d_residual && norm_residual;
+    APRB_TIMED("norm_partial_kernel", st, 1, (norm_partial_kernel<<<dim3(cdiv(C, 32), chunks), blk, 0, st>>>(d_x, N, C, rpc, pmean, pm2)));
+    if (nr) APRB_TIMED("norm_partial_kernel", st, 1, (norm_partial_kernel<<<dim3(cdiv(C, 32), chunks), blk, 0, st>>>(d_residual, N, C, rpc, rpmean, rpm2)));
+    int rpb = rpc;   // same row tiling for the apply pass
+    APRB_TIMED("norm_apply_kernel", st, 1, (norm_apply_kernel<<<dim3(cdiv(C, 32), cdiv(N, rpb)), blk, 0, st>>>(
+        d_x, N, C, chunks, rpc, eps, pmean, pm2, d_residual, nr ? rpmean : nullptr, nr ? rpm2 : nullptr, slope, rpb, round_tf32, d_y)));
     APRB_LAUNCH_OK();
     return APRB_OK;
 }

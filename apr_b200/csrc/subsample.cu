@@ -44,14 +44,16 @@ __global__ void sub_params_kernel(const int* __restrict__ bbox, const int* __res
 
 __device__ __forceinline__ int bitlen(unsigned v) { return 32 - __clz(v); }  // bits to represent v (0 -> 0)
 
+template <typename KeyT>
 __global__ void sub_keys_kernel(const float* __restrict__ pts, int N, const int* __restrict__ off, int B, float dl,
                                 const CloudGrid* __restrict__ grids, const int* __restrict__ gdims,
-                                uint64_t* __restrict__ keys, int* __restrict__ vals, int* __restrict__ status) {
+                                KeyT* __restrict__ keys, int* __restrict__ vals, int* __restrict__ status) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     int bx = bitlen((unsigned)max(gdims[0] - 1, 0)), by = bitlen((unsigned)max(gdims[1] - 1, 0)),
         bz = bitlen((unsigned)max(gdims[2] - 1, 0)), bc = bitlen((unsigned)max(B - 1, 0));
-    if (i == 0 && status && bx + by + bz + bc > 64) *status = 1;
+    // status: 0 = ok, 1 = grid does not fit 64 bits at all, 2 = needs the 64-bit key path (caller re-runs with key_bits=64)
+    if (i == 0 && status) *status = (bx + by + bz + bc > 64) ? 1 : ((bx + by + bz + bc > (int)sizeof(KeyT) * 8) ? 2 : 0);
     int b = find_cloud(off, B, i);
     CloudGrid g = grids[b];
     float px = pts[3 * (size_t)i], py = pts[3 * (size_t)i + 1], pz = pts[3 * (size_t)i + 2];
@@ -65,12 +67,13 @@ __global__ void sub_keys_kernel(const float* __restrict__ pts, int N, const int*
     key = (key << bz) | (uint64_t)iz;
     key = (key << by) | (uint64_t)iy;
     key = (key << bx) | (uint64_t)ix;
-    keys[i] = key;
+    keys[i] = (KeyT)key;
     vals[i] = i;
 }
 
 // flags[i] = 1 iff sorted position i starts a new voxel; flags[N] = 0 (so the exclusive scan's entry N is the total)
-__global__ void sub_flags_kernel(const uint64_t* __restrict__ skeys, int N, int* __restrict__ flags) {
+template <typename KeyT>
+__global__ void sub_flags_kernel(const KeyT* __restrict__ skeys, int N, int* __restrict__ flags) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i > N) return;
     flags[i] = (i < N) && (i == 0 || skeys[i] != skeys[i - 1]);
@@ -109,14 +112,15 @@ __global__ void sub_lens_kernel(const int* __restrict__ pos, const int* __restri
     if (threadIdx.x == 0) *out_M = s_carry;
 }
 
+template <typename KeyT>
 __global__ void sub_emit_kernel(const float* __restrict__ pts, const float* __restrict__ feats, int fdim, int N,
-                                const uint64_t* __restrict__ skeys, const int* __restrict__ svals,
+                                const KeyT* __restrict__ skeys, const int* __restrict__ svals,
                                 const int* __restrict__ pos, const int* __restrict__ off, int B, int max_p,
                                 const int* __restrict__ out_start, float* __restrict__ out_pts,
                                 float* __restrict__ out_feats) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    uint64_t key = skeys[i];
+    KeyT key = skeys[i];
     if (i > 0 && skeys[i - 1] == key) return;  // not a voxel head
     int b = find_cloud(off, B, i);
     int rank = pos[i] - pos[off[b]];            // voxel rank inside its cloud (canonical order)
@@ -183,17 +187,42 @@ extern "C" size_t aprb_grid_subsample_ws_bytes(int N, int B, int fdim) {
     return carve_sub(c, N > 0 ? N : 1, B > 0 ? B : 1, nullptr) + 256;
 }
 
+template <typename KeyT>
+static int run_subsample(const float* d_pts, const int32_t* d_lens, int B, int N, float dl, int max_p, const float* d_feats,
+                         int fdim, float* d_out_pts, int32_t* d_out_lens, int32_t* d_out_M, float* d_out_feats,
+                         int32_t* d_status, SubWs& w, cudaStream_t st) {
+    const int T = 256;
+    KeyT* keys_in = reinterpret_cast<KeyT*>(w.keys_in);
+    KeyT* keys_out = reinterpret_cast<KeyT*>(w.keys_out);
+    APRB_TIMED("setup_kernel", st, 1, (setup_kernel<<<1, 256, 0, st>>>(d_lens, w.off, nullptr, nullptr, B, w.bbox, w.gdims, 4)));
+    APRB_TIMED("bbox_kernel", st, 1, (bbox_kernel<<<cdiv(N, T), T, 0, st>>>(d_pts, N, w.off, B, w.bbox)));
+    APRB_TIMED("sub_params_kernel", st, 1, (sub_params_kernel<<<cdiv(B, T), T, 0, st>>>(w.bbox, w.off, B, dl, w.grids, w.gdims)));
+    APRB_TIMED("sub_keys_kernel", st, 1, (sub_keys_kernel<KeyT><<<cdiv(N, T), T, 0, st>>>(d_pts, N, w.off, B, dl, w.grids, w.gdims, keys_in, w.vals_in, d_status)));
+    APRB_LAUNCH_OK();
+    int rc = sort_pairs_i32(keys_in, keys_out, w.vals_in, w.vals_out, N, w.temp, w.temp_bytes, st);
+    if (rc) return rc;
+    APRB_TIMED("sub_flags_kernel", st, 1, (sub_flags_kernel<KeyT><<<cdiv(N + 1, T), T, 0, st>>>(keys_out, N, w.flags)));
+    rc = exclusive_scan_i32(w.flags, w.pos, N + 1, w.temp, w.temp_bytes, st);
+    if (rc) return rc;
+    APRB_TIMED("sub_lens_kernel", st, 1, (sub_lens_kernel<<<1, 256, 0, st>>>(w.pos, w.off, B, max_p, d_out_lens, w.out_start, d_out_M)));
+    APRB_TIMED("sub_emit_kernel", st, 1, (sub_emit_kernel<KeyT><<<cdiv(N, T), T, 0, st>>>(d_pts, d_feats, fdim, N, keys_out, w.vals_out, w.pos, w.off, B, max_p,
+                                                    w.out_start, d_out_pts, d_out_feats)));
+    APRB_LAUNCH_OK();
+    return APRB_OK;
+}
+
 extern "C" int aprb_grid_subsample_batch(const float* d_pts, const int32_t* d_lens, int B, int N, float dl, int max_p,
                                          const float* d_feats, int fdim, float* d_out_pts, int32_t* d_out_lens,
-                                         int32_t* d_out_M, float* d_out_feats, int32_t* d_status, void* d_ws,
-                                         size_t ws_bytes, void* stream) {
+                                         int32_t* d_out_M, float* d_out_feats, int32_t* d_status, int key_bits,
+                                         void* d_ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     APRB_REQUIRE(B >= 1 && N >= 0, "need B >= 1 and N >= 0");
     APRB_REQUIRE(d_lens && d_out_lens && d_out_M, "null length/output pointer");
     APRB_REQUIRE(dl > 0.f, "sampleDl must be positive");
+    APRB_REQUIRE(key_bits == 32 || key_bits == 64, "key_bits must be 32 or 64");
     APRB_REQUIRE(!(d_feats && (fdim <= 0 || !d_out_feats)), "features given without fdim/out buffer");
-    if (d_status) APRB_CUDA_OK(cudaMemsetAsync(d_status, 0, sizeof(int), st));
     if (N == 0) {
+        if (d_status) APRB_CUDA_OK(cudaMemsetAsync(d_status, 0, sizeof(int), st));
         APRB_CUDA_OK(cudaMemsetAsync(d_out_lens, 0, sizeof(int) * B, st));
         APRB_CUDA_OK(cudaMemsetAsync(d_out_M, 0, sizeof(int), st));
         return APRB_OK;
@@ -203,22 +232,7 @@ extern "C" int aprb_grid_subsample_batch(const float* d_pts, const int32_t* d_le
     SubWs w;
     carve_sub(c, N, B, &w);
     if (!c.ok()) { set_error("aprb_grid_subsample_batch: workspace too small (%zu < %zu)", ws_bytes, c.off); return APRB_ERR_WORKSPACE; }
-    const int T = 256;
-    APRB_TIMED("offsets_kernel", st, 1, (offsets_kernel<<<1, 256, 0, st>>>(d_lens, B, w.off)));
-    APRB_TIMED("bbox_init_kernel", st, 1, (bbox_init_kernel<<<cdiv(6 * B, T), T, 0, st>>>(w.bbox, B)));
-    APRB_CUDA_OK(cudaMemsetAsync(w.gdims, 0, 4 * sizeof(int), st));
-    APRB_TIMED("bbox_kernel", st, 1, (bbox_kernel<<<cdiv(N, T), T, 0, st>>>(d_pts, N, w.off, B, w.bbox)));
-    APRB_TIMED("sub_params_kernel", st, 1, (sub_params_kernel<<<cdiv(B, T), T, 0, st>>>(w.bbox, w.off, B, dl, w.grids, w.gdims)));
-    APRB_TIMED("sub_keys_kernel", st, 1, (sub_keys_kernel<<<cdiv(N, T), T, 0, st>>>(d_pts, N, w.off, B, dl, w.grids, w.gdims, w.keys_in, w.vals_in, d_status)));
-    APRB_LAUNCH_OK();
-    int rc = sort_pairs_u64_i32(w.keys_in, w.keys_out, w.vals_in, w.vals_out, N, w.temp, w.temp_bytes, st);
-    if (rc) return rc;
-    APRB_TIMED("sub_flags_kernel", st, 1, (sub_flags_kernel<<<cdiv(N + 1, T), T, 0, st>>>(w.keys_out, N, w.flags)));
-    rc = exclusive_scan_i32(w.flags, w.pos, N + 1, w.temp, w.temp_bytes, st);
-    if (rc) return rc;
-    APRB_TIMED("sub_lens_kernel", st, 1, (sub_lens_kernel<<<1, 256, 0, st>>>(w.pos, w.off, B, max_p, d_out_lens, w.out_start, d_out_M)));
-    APRB_TIMED("sub_emit_kernel", st, 1, (sub_emit_kernel<<<cdiv(N, T), T, 0, st>>>(d_pts, d_feats, fdim, N, w.keys_out, w.vals_out, w.pos, w.off, B, max_p,
-                                              w.out_start, d_out_pts, d_out_feats)));
-    APRB_LAUNCH_OK();
-    return APRB_OK;
+    if (key_bits == 32)
+        return run_subsample<uint32_t>(d_pts, d_lens, B, N, dl, max_p, d_feats, fdim, d_out_pts, d_out_lens, d_out_M, d_out_feats, d_status, w, st);
+    return run_subsample<uint64_t>(d_pts, d_lens, B, N, dl, max_p, d_feats, fdim, d_out_pts, d_out_lens, d_out_M, d_out_feats, d_status, w, st);
 }

@@ -44,9 +44,10 @@ def _idx(t, name):
 
 
 # --------------------------------------------------------------------------------------------------------------
-def grid_subsample(points, lens, dl, max_p=0, features=None, sync=True):
+def grid_subsample(points, lens, dl, max_p=0, features=None, sync=True, key_bits=32):
     """K1. points [N,3] f32 cuda, lens [B] i32 cuda. Returns (sub_points [M,3], sub_lens [B] i32[, sub_feats]).
-    With sync=False returns the full-capacity buffers plus the device scalar M (no host round trip)."""
+    With sync=False returns the full-capacity buffers plus the device scalars [M, status] (no host round trip).
+    The 32-bit sort key is tried first; a grid that needs more bits is re-run with the 64-bit key."""
     N.require_cuda()
     points, lens = _dev_f32(points, "points"), _dev_i32(lens, "lens")
     n, b = points.shape[0], lens.shape[0]
@@ -63,11 +64,13 @@ def grid_subsample(points, lens, dl, max_p=0, features=None, sync=True):
     ws = _workspace(nbytes, dev)
     rc = N.lib().aprb_grid_subsample_batch(N.ptr(points), N.ptr(lens), b, n, float(dl), int(max_p), N.ptr(feats), fdim,
                                            N.ptr(out), N.ptr(out_lens), N.ptr(m_dev[0:1]), N.ptr(out_f),
-                                           N.ptr(m_dev[1:2]), N.ptr(ws), ws.numel(), N.stream_ptr())
+                                           N.ptr(m_dev[1:2]), int(key_bits), N.ptr(ws), ws.numel(), N.stream_ptr())
     N.check(rc, "aprb_grid_subsample_batch")
     if not sync:
         return (out, out_lens, m_dev) if features is None else (out, out_lens, m_dev, out_f)
     m, status = m_dev.tolist()
+    if status == 2 and key_bits == 32:
+        return grid_subsample(points, lens, dl, max_p, features, sync, key_bits=64)
     if TRACE is not None:
         TRACE.append(("sub", n, m))
     if status != 0:
@@ -162,7 +165,7 @@ def closest_pool(x, inds):
     return out
 
 
-def instnorm_lrelu(x, slope=0.1, residual=None, norm_residual=False, eps=1e-5, out=None):
+def instnorm_lrelu(x, slope=0.1, residual=None, norm_residual=False, eps=1e-5, out=None, round_tf32=False):
     """K6. y = act(standardise_cols(x) [+ residual | + standardise_cols(residual)]); slope=1.0 disables the activation."""
     N.require_cuda()
     xx = _dev_f32(x, "x")
@@ -171,7 +174,7 @@ def instnorm_lrelu(x, slope=0.1, residual=None, norm_residual=False, eps=1e-5, o
     y = out if out is not None else torch.empty_like(xx)
     ws = _workspace(N.lib().aprb_instnorm_ws_bytes(n, c), xx.device)
     rc = N.lib().aprb_instnorm_lrelu(N.ptr(xx), n, c, float(eps), float(slope), N.ptr(res), 1 if norm_residual else 0,
-                                     N.ptr(y), N.ptr(ws), ws.numel(), N.stream_ptr())
+                                     1 if round_tf32 else 0, N.ptr(y), N.ptr(ws), ws.numel(), N.stream_ptr())
     N.check(rc, "aprb_instnorm_lrelu")
     return y
 
@@ -191,3 +194,12 @@ def linear_tf32(x, weight):
     if TRACE is not None:
         TRACE.append(("linear", n, cin, cout))
     return y
+
+
+def round_tf32(t):
+    """Copy of t rounded to TF32 (nearest)."""
+    N.require_cuda()
+    tt = _dev_f32(t.detach(), "t")
+    out = torch.empty_like(tt)
+    N.check(N.lib().aprb_round_tf32(N.ptr(tt), N.ptr(out), tt.numel(), N.stream_ptr()), "aprb_round_tf32")
+    return out

@@ -234,12 +234,14 @@ def run_ours(args):
             ev[i][1].record()
         barrier()
         wall = time.perf_counter() - t0
-        ms = sum(a.elapsed_time(b) for a, b in ev)
-        return ms, wall, _native.launch_count() - l0, r
+        per = [a.elapsed_time(b) for a, b in ev]
+        timed.last_steps = [round(t, 3) for t in per]
+        return sum(per), wall, _native.launch_count() - l0, r
 
     clk = ClockSampler(local)
     clk.start()
     ms_dev, wall_dev, launches, _ = timed(step_dev, args.steps, args.warmup)
+    steps_dev = timed.last_steps
     clocks = clk.stop()
     ms_e2e, wall_e2e, _, io = timed(step_e2e, args.steps, max(args.warmup, 3))
 
@@ -303,7 +305,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(io[0]), "d2h_bytes_per_step": int(io[1]),
                     "ms_per_step": ms_e2e / args.steps},
             "roofline": roof, "kernels": kernels,
-            "wall_ms_per_step": 1e3 * wall_dev / args.steps}
+            "wall_ms_per_step": 1e3 * wall_dev / args.steps, "ms_steps": steps_dev}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cfg_r = kitti_config()

@@ -59,12 +59,13 @@ size_t aprb_grid_subsample_ws_bytes(int N, int B, int fdim);
  * d_out_pts capacity N rows; d_out_lens [B]; d_out_M [1] int32 (device) receives the total row count.
  * Optional: d_feats [N,fdim] -> d_out_feats [<=N,fdim] (per-voxel mean), pass NULL/0 to skip.
  * max_p <= 0 means unlimited (grid_subsampling.cpp:133-134). Asynchronous: read d_out_M / d_out_lens after
- * synchronising `stream`. d_status [1] int32 (device, optional) is set non-zero if the voxel grid does not fit
- * the 64-bit sort key. */
+ * synchronising `stream`. key_bits (32 or 64) is the width of the packed (cloud, iz, iy, ix) sort key: 32 is the fast
+ * path and fits every LiDAR-sized grid. d_status [1] int32 (device, optional) receives 0 = ok, 2 = the grid needs
+ * more than key_bits bits (outputs invalid: call again with key_bits = 64), 1 = it does not fit 64 bits either. */
 int aprb_grid_subsample_batch(const float* d_pts, const int32_t* d_lens, int B, int N, float dl, int max_p,
                               const float* d_feats, int fdim,
                               float* d_out_pts, int32_t* d_out_lens, int32_t* d_out_M, float* d_out_feats,
-                              int32_t* d_status, void* d_ws, size_t ws_bytes, void* stream);
+                              int32_t* d_status, int key_bits, void* d_ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------- K2+K3: batched radius neighbour search ----- */
 size_t aprb_radius_neighbors_ws_bytes(int Nq, int Ns, int B);
@@ -111,15 +112,18 @@ size_t aprb_instnorm_ws_bytes(int N, int C);
 /* y = act( (x - mean_col) * rsqrt(var_col + eps) + (d_residual ? residual : 0) ), statistics per column over all
  * N rows (biased variance), act = LeakyReLU(slope) when slope != 1, identity when slope == 1.
  * norm_residual != 0 additionally standardises the residual with its own column statistics before adding
- * (ResnetBottleneckBlock: unary2 + unary_shortcut, models/blocks.py:672-681). In-place (d_y == d_x) allowed. */
+ * (ResnetBottleneckBlock: unary2 + unary_shortcut, models/blocks.py:672-681). round_tf32 != 0 stores y rounded to
+ * TF32 (nearest), so the tcgen05 GEMMs that consume it read it exactly. In-place (d_y == d_x) allowed. */
 int aprb_instnorm_lrelu(const float* d_x, int N, int C, float eps, float slope,
-                        const float* d_residual, int norm_residual, float* d_y,
+                        const float* d_residual, int norm_residual, int round_tf32, float* d_y,
                         void* d_ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------- Linear (UnaryBlock.mlp) on tcgen05 TF32 ---- */
 /* y[N,Cout] = x[N,Cin] @ W[Cout,Cin]^T (nn.Linear layout, no bias), TF32 operands (round-to-nearest), fp32
  * accumulate in TMEM. Cin % 32 == 0 and Cout % 16 == 0 required, else APRB_ERR_UNSUPPORTED. */
 int aprb_linear_tf32(const float* d_x, const float* d_W, int N, int Cin, int Cout, float* d_y, void* stream);
+/* out[i] = in[i] rounded to TF32 (round to nearest, ties away). Used once per weight update for mlp.weight. */
+int aprb_round_tf32(const float* d_in, float* d_out, size_t n, void* stream);
 
 #ifdef __cplusplus
 }

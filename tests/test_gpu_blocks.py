@@ -154,8 +154,10 @@ def test_encoder_golden_small(cuda, oracle, gold_encoder, mode, tol):
     assert rel(y, torch.from_numpy(g["y_final"])) < tol
 
 
-def test_blocks_vs_oracle_kitti_width(cuda, oracle):
-    """Each block type at KITTI channel widths, fed IDENTICAL inputs on both sides (per-block parity, tensor path on)."""
+@pytest.mark.parametrize("linear_mode", ["fp32", "tf32"])
+def test_blocks_vs_oracle_kitti_width(cuda, oracle, linear_mode):
+    """Each block type at KITTI channel widths, fed IDENTICAL inputs on both sides (per-block parity, tensor path on;
+    unary Linear either cuBLAS fp32 or our tcgen05 TF32 GEMM)."""
     from apr_b200 import synth
     cfg = kitti_config()
     a, b = synth.small_cloud(41, 2600), synth.small_cloud(42, 2400)
@@ -177,9 +179,14 @@ def test_blocks_vs_oracle_kitti_width(cuda, oracle):
             want = blocks_ref.simple_ref(x, cpu, sd, "encoder_blocks.0.", name, layer, extent)
         else:
             want = blocks_ref.resnetb_ref(x, cpu, sd, "encoder_blocks.0.", name, layer, extent)
-        with torch.no_grad():
-            got = blk.to(cuda)(x.to(cuda), gpu)
+        blocks.LINEAR_MODE = linear_mode
+        try:
+            with torch.no_grad():
+                got = blk.to(cuda)(x.to(cuda), gpu)
+        finally:
+            blocks.LINEAR_MODE = 'fp32'
         e = rel(got, want)
+        print(f"{linear_mode} {name} {cin}->{cout}: rel err {e:.2e}")
         worst = max(worst, e)
         assert e < TOL_TF32, f"{name} {cin}->{cout}: rel err {e:.2e}"
     print(f"worst per-block rel err {worst:.2e}")
