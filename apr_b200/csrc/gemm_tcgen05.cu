@@ -99,7 +99,7 @@ struct GemmCfg {
 template <int BN>
 __global__ void __launch_bounds__(192, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-                 const float* __restrict__ rowscale, float* __restrict__ C) {
+                 int kb_per_split, const float* __restrict__ rowscale, float* __restrict__ C) {
     using Cfg = GemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -111,7 +111,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * GEMM_BM, n0 = blockIdx.x * BN;
-    const int num_kb = K / GEMM_BK;
+    // split-K: blockIdx.z owns k-blocks [kb0, kb1); its raw partial tile goes to slice blockIdx.z of C (then C is the
+    // [splits, M, N] partial buffer and rowscale is applied by splitk_reduce_kernel)
+    const int kb0 = blockIdx.z * kb_per_split, kb1 = min(K / GEMM_BK, kb0 + kb_per_split);
+    C += (size_t)blockIdx.z * M * N;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -132,7 +135,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0) {
         if (lane == 0) {                                             // ===== TMA producer =====
             int s = 0; uint32_t ph = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
+            for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);
                 mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::A_BYTES + Cfg::B_BYTES);
                 tma_load_2d(sA + s * Cfg::A_BYTES, &tmA, bar_full + 8 * s, kb * GEMM_BK, m0);
@@ -146,13 +149,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // B=TF32 [10,13)=2, A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
             int s = 0; uint32_t ph = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
+            for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(bar_full + 8 * s, ph);
                 tc_fence_after();
                 const uint64_t da = make_smem_desc(sA + s * Cfg::A_BYTES), db = make_smem_desc(sB + s * Cfg::B_BYTES);
 #pragma unroll
                 for (int k4 = 0; k4 < GEMM_BK / 8; ++k4)             // +32 bytes (>>4 = 2) per K=8 step inside the atom
-                    tc_mma_tf32(tmem_base, da + 2 * k4, db + 2 * k4, idesc, (kb | k4) != 0);
+                    tc_mma_tf32(tmem_base, da + 2 * k4, db + 2 * k4, idesc, ((kb - kb0) | k4) != 0);
                 tc_commit(bar_empty + 8 * s);                        // frees the stage when these MMAs retire
                 if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
             }
@@ -187,6 +190,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
     }
+}
+
+// C[m,n] = (sum_s part[s,m,n]) * rowscale[m]; fixed summation order (deterministic split-K)
+__global__ void splitk_reduce_kernel(const float4* __restrict__ part, int splits, size_t mn4, int n4,
+                                     const float* __restrict__ rowscale, float4* __restrict__ C) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= mn4) return;
+    float4 a = part[i];
+    for (int s = 1; s < splits; ++s) {
+        const float4 b = part[(size_t)s * mn4 + i];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    const float sc = rowscale ? rowscale[i / n4] : 1.0f;
+    C[i] = make_float4(a.x * sc, a.y * sc, a.z * sc, a.w * sc);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
@@ -228,8 +245,8 @@ bool gemm_tf32_supported(int M, int N, int K) {
 }
 
 template <int BN>
-static int launch_gemm(const float* A, const float* Bt, int M, int N, int K, const float* rowscale, float* C,
-                       cudaStream_t st) {
+static int launch_gemm(const float* A, const float* Bt, int M, int N, int K, int splits, int kb_per_split,
+                       const float* rowscale, float* C, cudaStream_t st) {
     CUtensorMap tmA, tmB;
     int rc = make_tmap(&tmA, A, M, K, GEMM_BM);
     if (rc) return rc;
@@ -240,32 +257,64 @@ static int launch_gemm(const float* A, const float* Bt, int M, int N, int K, con
         APRB_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM));
         attr_set = true;
     }
-    dim3 grid(cdiv(N, BN), cdiv(M, GEMM_BM));
-    APRB_TIMED("gemm_tf32_kernel", st, 1, (gemm_tf32_kernel<BN><<<grid, 192, GemmCfg<BN>::SMEM, st>>>(tmA, tmB, M, N, K, rowscale, C)));
+    dim3 grid(cdiv(N, BN), cdiv(M, GEMM_BM), splits);
+    APRB_TIMED("gemm_tf32_kernel", st, 1, (gemm_tf32_kernel<BN><<<grid, 192, GemmCfg<BN>::SMEM, st>>>(tmA, tmB, M, N, K, kb_per_split, rowscale, C)));
     APRB_LAUNCH_OK();
     return APRB_OK;
 }
 
+size_t gemm_tf32_ws_bytes(int M, int N) {   // split-K partial tiles (up to 8 splits), only when split-K can trigger
+    const int bn = N >= 256 ? 256 : (N > 64 ? 128 : 64);
+    if (cdiv(M, GEMM_BM) * cdiv(N, bn) >= sm_count()) return 256;
+    return align256((size_t)8 * M * N * sizeof(float)) + 256;
+}
+
+// d_ws may be NULL (no split-K). Tile width: the widest BN (fewest re-reads of A); split-K fills the SMs when the
+// output grid alone cannot.
 int gemm_tf32_rowscale(const float* d_A, const float* d_Bt, int M, int N, int K, const float* d_rowscale, float* d_C,
-                       cudaStream_t st) {
+                       void* d_ws, size_t ws_bytes, cudaStream_t st) {
     if (!gemm_tf32_supported(M, N, K)) { set_error("gemm_tf32: unsupported shape M=%d N=%d K=%d", M, N, K); return APRB_ERR_UNSUPPORTED; }
     if (((uintptr_t)d_A | (uintptr_t)d_Bt | (uintptr_t)d_C) & 15) { set_error("gemm_tf32: operands must be 16-byte aligned"); return APRB_ERR_INVALID; }
-    // Tile width: the widest BN that still yields enough CTAs to occupy the 148 SMs.
-    const int mt = cdiv(M, GEMM_BM), sms = sm_count();
-    int bn = 64;
-    if (N >= 256 && (long long)mt * cdiv(N, 256) >= sms) bn = 256;
-    else if (N >= 128 && (long long)mt * cdiv(N, 128) >= sms) bn = 128;
-    if (bn == 256) return launch_gemm<256>(d_A, d_Bt, M, N, K, d_rowscale, d_C, st);
-    if (bn == 128) return launch_gemm<128>(d_A, d_Bt, M, N, K, d_rowscale, d_C, st);
-    return launch_gemm<64>(d_A, d_Bt, M, N, K, d_rowscale, d_C, st);
+    const int mt = cdiv(M, GEMM_BM), sms = sm_count(), num_kb = K / GEMM_BK;
+    int bn = N >= 256 ? 256 : (N > 64 ? 128 : 64);
+    int splits = 1;
+    const int tiles = mt * cdiv(N, bn);
+    if (d_ws && tiles < sms) {
+        splits = min(min(sms / tiles, 8), max(1, num_kb / 8));       // >= 8 k-blocks per split
+        while (splits > 1 && (size_t)splits * M * N * sizeof(float) > ws_bytes) --splits;
+    }
+    if (splits <= 1 && tiles < sms / 2) {                            // no split-K possible: fall back to narrower tiles
+        while (bn > 64 && mt * cdiv(N, bn) < sms) bn >>= 1;
+    }
+    int kps = cdiv(num_kb, splits);
+    splits = cdiv(num_kb, kps);
+    float* out = splits > 1 ? (float*)d_ws : d_C;
+    const float* rs = splits > 1 ? nullptr : d_rowscale;
+    int rc;
+    if (bn == 256) rc = launch_gemm<256>(d_A, d_Bt, M, N, K, splits, kps, rs, out, st);
+    else if (bn == 128) rc = launch_gemm<128>(d_A, d_Bt, M, N, K, splits, kps, rs, out, st);
+    else rc = launch_gemm<64>(d_A, d_Bt, M, N, K, splits, kps, rs, out, st);
+    if (rc || splits == 1) return rc;
+    const size_t mn4 = (size_t)M * N / 4;
+    APRB_TIMED("splitk_reduce_kernel", st, 1, (splitk_reduce_kernel<<<cdiv((long long)mn4, 256), 256, 0, st>>>(
+        (const float4*)d_ws, splits, mn4, N / 4, d_rowscale, (float4*)d_C)));
+    APRB_LAUNCH_OK();
+    return APRB_OK;
 }
 
 }  // namespace aprb
 
-extern "C" int aprb_linear_tf32(const float* d_x, const float* d_W, int N, int Cin, int Cout, float* d_y, void* stream) {
+extern "C" size_t aprb_linear_tf32_ws_bytes(int N, int Cin, int Cout) {
+    (void)Cin;
+    if (N < 0 || Cout < 0) return 0;
+    return aprb::gemm_tf32_ws_bytes(N > 0 ? N : 1, Cout > 0 ? Cout : 1);
+}
+
+extern "C" int aprb_linear_tf32(const float* d_x, const float* d_W, int N, int Cin, int Cout, float* d_y, void* d_ws,
+                                size_t ws_bytes, void* stream) {
     using namespace aprb;
     APRB_REQUIRE(N >= 0 && Cin >= 1 && Cout >= 1, "bad shape");
     if (N == 0) return APRB_OK;
     APRB_REQUIRE(d_x && d_W && d_y, "null pointer");
-    return gemm_tf32_rowscale(d_x, d_W, N, Cout, Cin, nullptr, d_y, (cudaStream_t)stream);
+    return gemm_tf32_rowscale(d_x, d_W, N, Cout, Cin, nullptr, d_y, d_ws, ws_bytes, (cudaStream_t)stream);
 }

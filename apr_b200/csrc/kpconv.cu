@@ -15,7 +15,8 @@
 namespace aprb {
 
 int gemm_tf32_rowscale(const float* d_A, const float* d_Bt, int M, int N, int K, const float* d_rowscale, float* d_C,
-                       cudaStream_t st);  // gemm_tcgen05.cu
+                       void* d_ws, size_t ws_bytes, cudaStream_t st);  // gemm_tcgen05.cu
+size_t gemm_tf32_ws_bytes(int M, int N);
 bool gemm_tf32_supported(int M, int N, int K);
 
 constexpr int KP_MAX_K = 16;
@@ -110,11 +111,12 @@ kp_weighted_kernel(const float* __restrict__ q, const float* __restrict__ s, con
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, d);
-    if (lane == 0) inv_nn[n] = 1.0f / (float)max(nn, 1);
+    if (lane == 0 && blockIdx.y == 0) inv_nn[n] = 1.0f / (float)max(nn, 1);
     __syncwarp();
 
     float* wrow = wf + (size_t)n * K * Cin;
-    for (int c0 = 0; c0 < Cin; c0 += 32 * VEC) {
+    // gridDim.y > 1: channel slabs are spread over blockIdx.y (more warps in flight when there are few queries)
+    for (int c0 = blockIdx.y * 32 * VEC; c0 < Cin; c0 += gridDim.y * 32 * VEC) {
         const int c = c0 + lane * VEC;
         const bool cvalid = c < Cin;
         float acc[KP_MAX_K][VEC];
@@ -123,27 +125,22 @@ kp_weighted_kernel(const float* __restrict__ q, const float* __restrict__ s, con
 #pragma unroll
             for (int j = 0; j < VEC; ++j) acc[k][j] = 0.f;
         const float* xc = x + c;
-        int j = 0;
-        for (; j + 1 < nact; j += 2) {                           // two neighbour rows in flight
-            const int si0 = s_si[j], si1 = s_si[j + 1];
-            const int hm0 = s_hm[j], hm1 = s_hm[j + 1];
-            Vec<VEC> x0, x1;
+        for (int j0 = 0; j0 < nact; j0 += 4) {                    // up to four neighbour rows in flight
+            Vec<VEC> xr[4];
+            int hm[4];
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) { x0.v[v] = 0.f; x1.v[v] = 0.f; }
-            if (cvalid) {
-                x0 = *reinterpret_cast<const Vec<VEC>*>(xc + (size_t)si0 * Cin);
-                x1 = *reinterpret_cast<const Vec<VEC>*>(xc + (size_t)si1 * Cin);
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) xr[u].v[v] = 0.f;
+                hm[u] = 0;
+                if (j0 + u < nact) {
+                    hm[u] = s_hm[j0 + u];
+                    if (cvalid) xr[u] = *reinterpret_cast<const Vec<VEC>*>(xc + (size_t)s_si[j0 + u] * Cin);
+                }
             }
-            kp_accumulate<VEC>(acc, (unsigned)hm0 & 0xFFFFu, s_w + (hm0 >> 16) * 16, x0);
-            kp_accumulate<VEC>(acc, (unsigned)hm1 & 0xFFFFu, s_w + (hm1 >> 16) * 16, x1);
-        }
-        if (j < nact) {
-            const int si0 = s_si[j], hm0 = s_hm[j];
-            Vec<VEC> x0;
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) x0.v[v] = 0.f;
-            if (cvalid) x0 = *reinterpret_cast<const Vec<VEC>*>(xc + (size_t)si0 * Cin);
-            kp_accumulate<VEC>(acc, (unsigned)hm0 & 0xFFFFu, s_w + (hm0 >> 16) * 16, x0);
+            for (int u = 0; u < 4; ++u)
+                kp_accumulate<VEC>(acc, (unsigned)hm[u] & 0xFFFFu, s_w + (hm[u] >> 16) * 16, xr[u]);
         }
         if (cvalid) {
 #pragma unroll
@@ -164,6 +161,55 @@ kp_weighted_kernel(const float* __restrict__ q, const float* __restrict__ s, con
                 }
             }
         }
+    }
+}
+
+// Cin == 1 (the first encoder block: one scalar feature per point): lanes = neighbours, the 15 per-kernel-point sums
+// are reduced across the warp with shuffles; no shared memory, no second pass.
+template <typename IdxT>
+__global__ void __launch_bounds__(128)
+kp_weighted_c1_kernel(const float* __restrict__ q, const float* __restrict__ s, const IdxT* __restrict__ idx, int ld,
+                      const float* __restrict__ x, const float* __restrict__ kp, const unsigned char* __restrict__ posflag,
+                      float extent, int Nq, int Ns, int H, int K, float* __restrict__ wf, float* __restrict__ inv_nn) {
+    __shared__ float s_kp[KP_MAX_K * 3];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    if (threadIdx.x < K * 3) s_kp[threadIdx.x] = kp[threadIdx.x];
+    __syncthreads();
+    const int n = blockIdx.x * wpb + wib;
+    if (n >= Nq) return;
+    const float qx = q[3 * (size_t)n], qy = q[3 * (size_t)n + 1], qz = q[3 * (size_t)n + 2];
+    const float ext2 = extent * extent, inv_ext = 1.0f / extent;
+    float acc[KP_MAX_K];
+#pragma unroll
+    for (int k = 0; k < KP_MAX_K; ++k) acc[k] = 0.f;
+    int nn = 0;
+    for (int h = lane; h < H; h += 32) {
+        const long long v = (long long)idx[(size_t)n * ld + h];
+        if (v < 0 || v >= Ns) continue;
+        const int si = (int)v;
+        nn += posflag[si];
+        const float xv = x[si];
+        const float rx = s[3 * (size_t)si] - qx, ry = s[3 * (size_t)si + 1] - qy, rz = s[3 * (size_t)si + 2] - qz;
+#pragma unroll
+        for (int k = 0; k < KP_MAX_K; ++k) {
+            if (k < K) {
+                const float ddx = rx - s_kp[3 * k], ddy = ry - s_kp[3 * k + 1], ddz = rz - s_kp[3 * k + 2];
+                const float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+                if (d2 < ext2) acc[k] = fmaf(fmaxf(1.0f - sqrtf(d2) * inv_ext, 0.f), xv, acc[k]);
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        nn += __shfl_xor_sync(0xffffffffu, nn, d);
+#pragma unroll
+        for (int k = 0; k < KP_MAX_K; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], d);
+    }
+    if (lane == 0) {
+        inv_nn[n] = 1.0f / (float)max(nn, 1);
+#pragma unroll
+        for (int k = 0; k < KP_MAX_K; ++k)
+            if (k < K) wf[(size_t)n * K + k] = acc[k];
     }
 }
 
@@ -254,11 +300,12 @@ extern "C" int aprb_round_tf32(const float* d_in, float* d_out, size_t n, void* 
 }
 
 extern "C" size_t aprb_kpconv_ws_bytes(int Nq, int Ns, int H, int K, int Cin, int Cout) {
-    (void)H; (void)Cout;
+    (void)H;
     if (Nq < 0 || Ns < 0 || K < 0 || Cin < 0) return 0;
     // wf is padded to a multiple of 128 rows so the tensor path can read whole M tiles
     size_t rows = ((size_t)(Nq > 0 ? Nq : 1) + 127) & ~size_t(127);
-    return align256(rows * K * Cin * sizeof(float)) + align256(rows * sizeof(float)) + align256((size_t)Ns + 1) + 256;
+    return align256(rows * K * Cin * sizeof(float)) + align256(rows * sizeof(float)) + align256((size_t)Ns + 1) +
+           gemm_tf32_ws_bytes(Nq > 0 ? Nq : 1, Cout > 0 ? Cout : 1) + 256;
 }
 
 extern "C" int aprb_kpconv_forward(const float* d_q, const float* d_s, const void* d_idx, int idx_is_i64, int ld_idx,
@@ -284,6 +331,8 @@ extern "C" int aprb_kpconv_forward(const float* d_q, const float* d_s, const voi
     float* wf = c.take<float>(rows * KC);
     float* inv_nn = c.take<float>(rows);
     unsigned char* flag = c.take<unsigned char>((size_t)Ns + 1);
+    const size_t gws_bytes = gemm_tf32_ws_bytes(Nq, Cout) - 256;
+    float* gws = c.take<float>(gws_bytes / sizeof(float));
 
     if (Ns > 0) APRB_TIMED("rowsum_pos_kernel", st, 1, (rowsum_pos_kernel<<<cdiv(Ns, 8), 256, 0, st>>>(d_x, Ns, Cin, flag)));
     const int wpb = 4, Hp = (H + 31) & ~31;
@@ -294,7 +343,9 @@ extern "C" int aprb_kpconv_forward(const float* d_q, const float* d_s, const voi
     do {                                                                                                             \
         if (smem > 48 * 1024)                                                                                        \
             APRB_CUDA_OK(cudaFuncSetAttribute(kp_weighted_kernel<IDX, VEC, RND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        APRB_TIMED("kp_weighted_kernel", st, 1, (kp_weighted_kernel<IDX, VEC, RND><<<cdiv(Nq, wpb), wpb * 32, smem, st>>>(        \
+        const int nslabs = cdiv(Cin, 32 * VEC);                                                                      \
+        const int gy = (cdiv(Nq, wpb) < 6 * sm_count()) ? nslabs : 1;                                                \
+        APRB_TIMED("kp_weighted_kernel", st, 1, (kp_weighted_kernel<IDX, VEC, RND><<<dim3(cdiv(Nq, wpb), gy), wpb * 32, smem, st>>>( \
             d_q, d_s, (const IDX*)d_idx, ld_idx, d_x, d_kp, flag, extent, Nq, Ns, H, K, Cin, wf, inv_nn)));         \
     } while (0)
 #define KPW_LAUNCH(IDX, RND)                                                                                         \
@@ -304,9 +355,14 @@ extern "C" int aprb_kpconv_forward(const float* d_q, const float* d_s, const voi
     if (use_tensor) {
         if (idx_is_i64) KPW_LAUNCH(long long, true); else KPW_LAUNCH(int, true);
         APRB_LAUNCH_OK();
-        return gemm_tf32_rowscale(wf, d_wprep, Nq, Cout, KC, inv_nn, d_out, st);
+        return gemm_tf32_rowscale(wf, d_wprep, Nq, Cout, KC, inv_nn, d_out, gws, gws_bytes, st);
     }
-    if (idx_is_i64) KPW_LAUNCH(long long, false); else KPW_LAUNCH(int, false);
+    if (Cin == 1) {
+        if (idx_is_i64) APRB_TIMED("kp_weighted_c1_kernel", st, 1, (kp_weighted_c1_kernel<long long><<<cdiv(Nq, wpb), wpb * 32, 0, st>>>(
+            d_q, d_s, (const long long*)d_idx, ld_idx, d_x, d_kp, flag, extent, Nq, Ns, H, K, wf, inv_nn)));
+        else APRB_TIMED("kp_weighted_c1_kernel", st, 1, (kp_weighted_c1_kernel<int><<<cdiv(Nq, wpb), wpb * 32, 0, st>>>(
+            d_q, d_s, (const int*)d_idx, ld_idx, d_x, d_kp, flag, extent, Nq, Ns, H, K, wf, inv_nn)));
+    } else if (idx_is_i64) KPW_LAUNCH(long long, false); else KPW_LAUNCH(int, false);
 #undef KPW_LAUNCH3
 #undef KPW_LAUNCH
     APRB_LAUNCH_OK();

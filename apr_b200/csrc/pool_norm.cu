@@ -194,6 +194,124 @@ extern "C" int aprb_closest_pool(const float* d_x, const void* d_idx, int idx_is
     return APRB_OK;
 }
 
+// ---- float4 variants (C % 4 == 0, C/4 a power of two <= 256 or a multiple of 256): 16-byte accesses, shifted
+// sums instead of a serial Welford chain, so each thread keeps several independent loads in flight.
+__global__ void __launch_bounds__(256)
+norm_partial4_kernel(const float* __restrict__ x, const float* __restrict__ x2, int N, int C, int W, int rows_per_chunk,
+                     size_t tensor_stride, float* __restrict__ pmean, float* __restrict__ pm2) {
+    if (blockIdx.z == 1) { x = x2; pmean += tensor_stride; pm2 += tensor_stride; }   // second tensor (normalised residual)
+    __shared__ float4 s_s1[256], s_s2[256];
+    __shared__ int s_cnt[256];
+    const int Cq = C >> 2, R = 256 / W;
+    const int tx = threadIdx.x % W, ty = threadIdx.x / W;
+    const int quad = blockIdx.x * W + tx;
+    const int r0 = blockIdx.y * rows_per_chunk, r1 = min(r0 + rows_per_chunk, N);
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1, pv = s1;
+    int cnt = 0;
+    if (quad < Cq) {
+        const float4* xp = reinterpret_cast<const float4*>(x) + quad;
+        pv = xp[(size_t)r0 * Cq];                                  // pivot: first row of the chunk (shifted-data sums)
+#pragma unroll 4
+        for (int r = r0 + ty; r < r1; r += R) {
+            const float4 v = xp[(size_t)r * Cq];
+            const float a = v.x - pv.x, b = v.y - pv.y, c = v.z - pv.z, d = v.w - pv.w;
+            s1.x += a; s1.y += b; s1.z += c; s1.w += d;
+            s2.x = fmaf(a, a, s2.x); s2.y = fmaf(b, b, s2.y); s2.z = fmaf(c, c, s2.z); s2.w = fmaf(d, d, s2.w);
+            ++cnt;
+        }
+    }
+    s_s1[threadIdx.x] = s1; s_s2[threadIdx.x] = s2; s_cnt[threadIdx.x] = cnt;
+    __syncthreads();
+    if (ty == 0 && quad < Cq) {
+        float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1;
+        int n = 0;
+        for (int k = 0; k < R; ++k) {                              // fixed order -> deterministic
+            const float4 b1 = s_s1[k * W + tx], b2 = s_s2[k * W + tx];
+            a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
+            a2.x += b2.x; a2.y += b2.y; a2.z += b2.z; a2.w += b2.w;
+            n += s_cnt[k * W + tx];
+        }
+        const float inv = 1.0f / (float)max(n, 1);
+        float4 mean = make_float4(pv.x + a1.x * inv, pv.y + a1.y * inv, pv.z + a1.z * inv, pv.w + a1.w * inv);
+        float4 m2 = make_float4(fmaxf(a2.x - a1.x * a1.x * inv, 0.f), fmaxf(a2.y - a1.y * a1.y * inv, 0.f),
+                                fmaxf(a2.z - a1.z * a1.z * inv, 0.f), fmaxf(a2.w - a1.w * a1.w * inv, 0.f));
+        reinterpret_cast<float4*>(pmean + (size_t)blockIdx.y * C)[quad] = mean;
+        reinterpret_cast<float4*>(pm2 + (size_t)blockIdx.y * C)[quad] = m2;
+    }
+}
+
+// One warp per column: lanes stride over the chunk partials, then a fixed-shape shuffle tree (deterministic).
+// grid (ceil(C/8), ntensors); block 256. stats layout: [tensor][2][C] = mean, rstd.
+__global__ void __launch_bounds__(256)
+norm_finalize_kernel2(const float* __restrict__ pmean, const float* __restrict__ pm2, int N, int C, int chunks,
+                      int rows_per_chunk, float eps, size_t tensor_stride, float* __restrict__ stats) {
+    const int col = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (col >= C) return;
+    pmean += blockIdx.y * tensor_stride; pm2 += blockIdx.y * tensor_stride;
+    float am = 0.f, a2 = 0.f;
+    int an = 0;
+    for (int k = lane; k < chunks; k += 32)
+        chan_combine(am, a2, an, pmean[(size_t)k * C + col], pm2[(size_t)k * C + col], min(rows_per_chunk, N - k * rows_per_chunk));
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float bm = __shfl_xor_sync(0xffffffffu, am, d), b2 = __shfl_xor_sync(0xffffffffu, a2, d);
+        const int bn = __shfl_xor_sync(0xffffffffu, an, d);
+        // combine (lower lane, upper lane) in that order on both sides so every lane ends with the same value
+        float lm = (lane & d) ? bm : am, l2 = (lane & d) ? b2 : a2; int ln = (lane & d) ? bn : an;
+        const float um = (lane & d) ? am : bm, u2 = (lane & d) ? a2 : b2; const int un = (lane & d) ? an : bn;
+        chan_combine(lm, l2, ln, um, u2, un);
+        am = lm; a2 = l2; an = ln;
+    }
+    if (lane == 0) {
+        stats[(size_t)blockIdx.y * 2 * C + col] = am;
+        stats[(size_t)blockIdx.y * 2 * C + C + col] = rsqrtf(a2 / (float)N + eps);
+    }
+}
+
+__device__ __forceinline__ float act_round(float v, float slope, int round_tf32) {
+    v = v >= 0.f ? v : v * slope;
+    if (round_tf32) {
+        unsigned u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+        v = __uint_as_float(u);
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+norm_apply4_kernel(const float* __restrict__ x, int N, int C, int W, const float* __restrict__ stats,
+                   const float* __restrict__ res, int norm_res, float slope, int rows_per_block, int round_tf32,
+                   float* __restrict__ y) {
+    const int Cq = C >> 2, R = 256 / W;
+    const int tx = threadIdx.x % W, ty = threadIdx.x / W;
+    const int quad = blockIdx.x * W + tx;
+    if (quad >= Cq) return;
+    const float4 mean = reinterpret_cast<const float4*>(stats)[quad];
+    const float4 rstd = reinterpret_cast<const float4*>(stats + C)[quad];
+    float4 rmean = make_float4(0.f, 0.f, 0.f, 0.f), rrstd = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (res && norm_res) {
+        rmean = reinterpret_cast<const float4*>(stats + 2 * (size_t)C)[quad];
+        rrstd = reinterpret_cast<const float4*>(stats + 3 * (size_t)C)[quad];
+    }
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(r0 + rows_per_block, N);
+    const float4* xp = reinterpret_cast<const float4*>(x) + quad;
+    const float4* rp = res ? reinterpret_cast<const float4*>(res) + quad : nullptr;
+    float4* yp = reinterpret_cast<float4*>(y) + quad;
+#pragma unroll 4
+    for (int r = r0 + ty; r < r1; r += R) {
+        const float4 v = xp[(size_t)r * Cq];
+        float4 o = make_float4((v.x - mean.x) * rstd.x, (v.y - mean.y) * rstd.y, (v.z - mean.z) * rstd.z, (v.w - mean.w) * rstd.w);
+        if (rp) {
+            const float4 q = rp[(size_t)r * Cq];
+            o.x += (q.x - rmean.x) * rrstd.x; o.y += (q.y - rmean.y) * rrstd.y;
+            o.z += (q.z - rmean.z) * rrstd.z; o.w += (q.w - rmean.w) * rrstd.w;
+        }
+        o.x = act_round(o.x, slope, round_tf32); o.y = act_round(o.y, slope, round_tf32);
+        o.z = act_round(o.z, slope, round_tf32); o.w = act_round(o.w, slope, round_tf32);
+        yp[(size_t)r * Cq] = o;
+    }
+}
+
 static void norm_plan(int N, int C, int* rows_per_chunk, int* chunks) {
     // about 2 waves of (column-tile x chunk) blocks, chunks of at least 64 rows, at most 256 chunks
     int ct = cdiv(C, 32);
@@ -206,7 +324,7 @@ static void norm_plan(int N, int C, int* rows_per_chunk, int* chunks) {
 
 extern "C" size_t aprb_instnorm_ws_bytes(int N, int C) {
     if (N < 0 || C < 0) return 0;
-    return 4 * align256((size_t)256 * (C > 0 ? C : 1) * sizeof(float)) + 256;
+    return 4 * align256((size_t)256 * (C > 0 ? C : 1) * sizeof(float)) + align256((size_t)4 * (C > 0 ? C : 1) * sizeof(float)) + 512;
 }
 
 extern "C" int aprb_instnorm_lrelu(const float* d_x, int N, int C, float eps, float slope, const float* d_residual,
@@ -217,12 +335,38 @@ extern "C" int aprb_instnorm_lrelu(const float* d_x, int N, int C, float eps, fl
     APRB_REQUIRE(d_x && d_y && d_ws, "null pointer");
     if (ws_bytes < aprb_instnorm_ws_bytes(N, C)) { set_error("aprb_instnorm_lrelu: workspace too small"); return APRB_ERR_WORKSPACE; }
     Carver c(d_ws, ws_bytes);
-    float* pmean = c.take<float>((size_t)256 * C); float* pm2 = c.take<float>((size_t)256 * C);
-    float* rpmean = c.take<float>((size_t)256 * C); float* rpm2 = c.take<float>((size_t)256 * C);
+    // one contiguous block: pmean | rpmean | pm2 | rpm2 | stats  (each 256*C floats; the residual's partials sit one
+    // "tensor stride" (= 2 arrays) after the main tensor's in both the mean and the M2 halves)
+    float* blockp = c.take<float>((size_t)4 * 256 * C + (size_t)4 * C);
+    float* pmean = blockp; float* pm2 = blockp + (size_t)256 * C;
+    float* rpmean = blockp + (size_t)2 * 256 * C; float* rpm2 = blockp + (size_t)3 * 256 * C;
     int rpc, chunks;
+    const bool nr = d_residual && norm_residual;
+    const int Cq = C / 4;
+    const bool aligned = (((uintptr_t)d_x | (uintptr_t)d_y | (uintptr_t)(d_residual ? d_residual : d_x)) & 15) == 0;
+    if (C % 4 == 0 && aligned && ((Cq <= 256 && (Cq & (Cq - 1)) == 0) || Cq % 256 == 0)) {
+        const int W = Cq < 256 ? Cq : 256, gx = cdiv(Cq, W);
+        const int sms = sm_count();
+        // statistics pass: ~4 waves of blocks, chunks of >= 32 rows, <= 256 chunks
+        int ch = min(min(max(1, 4 * sms / (gx * (nr ? 2 : 1))), 256), max(1, N / 32));
+        rpc = cdiv(N, ch);
+        chunks = cdiv(N, rpc);
+        const size_t tstride = (size_t)256 * C;   // pmean/pm2 of the residual live one tensor-stride further (= rpmean/rpm2)
+        float* stats = rpm2 + tstride;            // [2 tensors][mean, rstd][C] (carved below)
+        APRB_TIMED("norm_partial4_kernel", st, 1, (norm_partial4_kernel<<<dim3(gx, chunks, nr ? 2 : 1), 256, 0, st>>>(
+            d_x, d_residual, N, C, W, rpc, 2 * tstride, pmean, pm2)));
+        APRB_TIMED("norm_finalize_kernel2", st, 1, (norm_finalize_kernel2<<<dim3(cdiv(C, 8), nr ? 2 : 1), 256, 0, st>>>(
+            pmean, pm2, N, C, chunks, rpc, eps, 2 * tstride, stats)));
+        // apply pass: its own row tiling, ~6 waves of blocks
+        int rb = min(max(1, 6 * sms / gx), max(1, N / 16));
+        int rpb = cdiv(N, rb);
+        APRB_TIMED("norm_apply4_kernel", st, 1, (norm_apply4_kernel<<<dim3(gx, cdiv(N, rpb)), 256, 0, st>>>(
+            d_x, N, C, W, stats, d_residual, nr ? 1 : 0, slope, rpb, round_tf32, d_y)));
+        APRB_LAUNCH_OK();
+        return APRB_OK;
+    }
     norm_plan(N, C, &rpc, &chunks);
     const dim3 blk(32, 8);
-    const bool nr = d_residual && norm_residual;
     APRB_TIMED("norm_partial_kernel", st, 1, (norm_partial_kernel<<<dim3(cdiv(C, 32), chunks), blk, 0, st>>>(d_x, N, C, rpc, pmean, pm2)));
     if (nr) APRB_TIMED("norm_partial_kernel", st, 1, (norm_partial_kernel<<<dim3(cdiv(C, 32), chunks), blk, 0, st>>>(d_residual, N, C, rpc, rpmean, rpm2)));
     int rpb = rpc;   // same row tiling for the apply pass

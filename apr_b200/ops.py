@@ -190,7 +190,9 @@ def linear_tf32(x, weight):
     n, cin = xx.shape
     cout = w.shape[0]
     y = torch.empty((n, cout), dtype=torch.float32, device=xx.device)
-    N.check(N.lib().aprb_linear_tf32(N.ptr(xx), N.ptr(w), n, cin, cout, N.ptr(y), N.stream_ptr()), "aprb_linear_tf32")
+    ws = _workspace(N.lib().aprb_linear_tf32_ws_bytes(n, cin, cout), xx.device)
+    N.check(N.lib().aprb_linear_tf32(N.ptr(xx), N.ptr(w), n, cin, cout, N.ptr(y), N.ptr(ws), ws.numel(), N.stream_ptr()),
+            "aprb_linear_tf32")
     if TRACE is not None:
         TRACE.append(("linear", n, cin, cout))
     return y

@@ -52,7 +52,11 @@ class ClockSampler:
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.first = index, [], None, 0
+
+    def mark(self):
+        """Rows sampled before this call (warm-up) are ignored."""
+        self.first = len(self.rows)
 
     def start(self):
         try:
@@ -71,6 +75,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        self.rows = self.rows[self.first:] if len(self.rows) > self.first else self.rows
         sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -220,9 +225,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, sampler=None):
+        if sampler is not None:
+            sampler.start()          # forks nvidia-smi: do it BEFORE the warm-up so the fork's page-table churn is absorbed there
         for i in range(warmup):
             fn(i)
+        if sampler is not None:
+            sampler.mark()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
         l0 = _native.launch_count()
@@ -239,8 +248,7 @@ def run_ours(args):
         return sum(per), wall, _native.launch_count() - l0, r
 
     clk = ClockSampler(local)
-    clk.start()
-    ms_dev, wall_dev, launches, _ = timed(step_dev, args.steps, args.warmup)
+    ms_dev, wall_dev, launches, _ = timed(step_dev, args.steps, args.warmup, sampler=clk)
     steps_dev = timed.last_steps
     clocks = clk.stop()
     ms_e2e, wall_e2e, _, io = timed(step_e2e, args.steps, max(args.warmup, 3))

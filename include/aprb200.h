@@ -120,8 +120,11 @@ int aprb_instnorm_lrelu(const float* d_x, int N, int C, float eps, float slope,
 
 /* ---------------------------------------------------------------- Linear (UnaryBlock.mlp) on tcgen05 TF32 ---- */
 /* y[N,Cout] = x[N,Cin] @ W[Cout,Cin]^T (nn.Linear layout, no bias), TF32 operands (round-to-nearest), fp32
- * accumulate in TMEM. Cin % 32 == 0 and Cout % 16 == 0 required, else APRB_ERR_UNSUPPORTED. */
-int aprb_linear_tf32(const float* d_x, const float* d_W, int N, int Cin, int Cout, float* d_y, void* stream);
+ * accumulate in TMEM. Cin % 32 == 0 and Cout % 16 == 0 required, else APRB_ERR_UNSUPPORTED. The workspace (may be
+ * NULL) holds split-K partial tiles when the output grid alone cannot fill the SMs; the reduction order is fixed. */
+size_t aprb_linear_tf32_ws_bytes(int N, int Cin, int Cout);
+int aprb_linear_tf32(const float* d_x, const float* d_W, int N, int Cin, int Cout, float* d_y,
+                     void* d_ws, size_t ws_bytes, void* stream);
 /* out[i] = in[i] rounded to TF32 (round to nearest, ties away). Used once per weight update for mlp.weight. */
 int aprb_round_tf32(const float* d_in, float* d_out, size_t n, void* stream);
 
