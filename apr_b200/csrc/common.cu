@@ -96,7 +96,8 @@ __global__ void setup_kernel(const int* __restrict__ lensA, int* __restrict__ of
                              int* __restrict__ offB, int B, int* __restrict__ bbox, int* __restrict__ zero, int nzero) {
     __shared__ int s_part[256];
     __shared__ int s_carry;
-    for (int i = threadIdx.x; i < 6 * B; i += blockDim.x) bbox[i] = (i % 6) < 3 ? 0x7FFFFFFF : (int)0x80000000;
+    if (bbox)
+        for (int i = threadIdx.x; i < 6 * B; i += blockDim.x) bbox[i] = (i % 6) < 3 ? 0x7FFFFFFF : (int)0x80000000;
     for (int i = threadIdx.x; i < nzero; i += blockDim.x) zero[i] = 0;
     block_offsets(lensA, B, offA, s_part, &s_carry);
     if (lensB) {

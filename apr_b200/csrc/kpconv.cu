@@ -125,22 +125,27 @@ kp_weighted_kernel(const float* __restrict__ q, const float* __restrict__ s, con
 #pragma unroll
             for (int j = 0; j < VEC; ++j) acc[k][j] = 0.f;
         const float* xc = x + c;
-        for (int j0 = 0; j0 < nact; j0 += 4) {                    // up to four neighbour rows in flight
-            Vec<VEC> xr[4];
-            int hm[4];
+        int j = 0;
+        for (; j + 1 < nact; j += 2) {                           // two neighbour rows in flight
+            const int si0 = s_si[j], si1 = s_si[j + 1];
+            const int hm0 = s_hm[j], hm1 = s_hm[j + 1];
+            Vec<VEC> x0, x1;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) xr[u].v[v] = 0.f;
-                hm[u] = 0;
-                if (j0 + u < nact) {
-                    hm[u] = s_hm[j0 + u];
-                    if (cvalid) xr[u] = *reinterpret_cast<const Vec<VEC>*>(xc + (size_t)s_si[j0 + u] * Cin);
-                }
+            for (int v = 0; v < VEC; ++v) { x0.v[v] = 0.f; x1.v[v] = 0.f; }
+            if (cvalid) {
+                x0 = *reinterpret_cast<const Vec<VEC>*>(xc + (size_t)si0 * Cin);
+                x1 = *reinterpret_cast<const Vec<VEC>*>(xc + (size_t)si1 * Cin);
             }
+            kp_accumulate<VEC>(acc, (unsigned)hm0 & 0xFFFFu, s_w + (hm0 >> 16) * 16, x0);
+            kp_accumulate<VEC>(acc, (unsigned)hm1 & 0xFFFFu, s_w + (hm1 >> 16) * 16, x1);
+        }
+        if (j < nact) {
+            const int si0 = s_si[j], hm0 = s_hm[j];
+            Vec<VEC> x0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                kp_accumulate<VEC>(acc, (unsigned)hm[u] & 0xFFFFu, s_w + (hm[u] >> 16) * 16, xr[u]);
+            for (int v = 0; v < VEC; ++v) x0.v[v] = 0.f;
+            if (cvalid) x0 = *reinterpret_cast<const Vec<VEC>*>(xc + (size_t)si0 * Cin);
+            kp_accumulate<VEC>(acc, (unsigned)hm0 & 0xFFFFu, s_w + (hm0 >> 16) * 16, x0);
         }
         if (cvalid) {
 #pragma unroll

@@ -238,31 +238,9 @@ static size_t carve_nb(Carver& c, int Nq, int Ns, int B, NbWs* w) {
 
 using namespace aprb;
 
-extern "C" size_t aprb_radius_neighbors_ws_bytes(int Nq, int Ns, int B) {
-    if (Nq < 0 || Ns < 0 || B < 0) return 0;
-    Carver c(nullptr, 0);
-    return carve_nb(c, Nq, Ns > 0 ? Ns : 1, B > 0 ? B : 1, nullptr) + 256;
-}
-
-extern "C" int aprb_radius_neighbors_batch(const float* d_q, const float* d_s, const int32_t* d_qlens,
-                                           const int32_t* d_slens, int B, int Nq, int Ns, float radius, int width,
-                                           int32_t* d_out_idx, int ld, int32_t* d_counts, int32_t* d_max_count,
-                                           void* d_ws, size_t ws_bytes, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    APRB_REQUIRE(B >= 1 && Nq >= 0 && Ns >= 0, "need B >= 1, Nq >= 0, Ns >= 0");
-    APRB_REQUIRE(d_qlens && d_slens, "null batch-length pointer");
-    APRB_REQUIRE(width >= 1 && width <= 16352, "width must be in [1, 16352]");
-    APRB_REQUIRE(ld >= width, "ld < width");
-    APRB_REQUIRE((long long)Ns * 16 + 64LL * B < 0x7FFFFF00LL, "support set too large for the int32 cell table");
-    if (d_max_count) APRB_CUDA_OK(cudaMemsetAsync(d_max_count, 0, sizeof(int), st));
-    if (Nq == 0) return APRB_OK;
-    APRB_REQUIRE(d_q && d_out_idx && d_ws && (d_s || Ns == 0), "null point/output/workspace pointer");
-    Carver c(d_ws, ws_bytes);
-    NbWs w;
-    carve_nb(c, Nq, Ns > 0 ? Ns : 1, B, &w);
-    if (!c.ok()) { set_error("aprb_radius_neighbors_batch: workspace too small (%zu < %zu)", ws_bytes, c.off); return APRB_ERR_WORKSPACE; }
+static int build_grid(const float* d_s, const int32_t* d_slens, int B, int Ns, float radius, NbWs& w, cudaStream_t st) {
     const int T = 256;
-    APRB_TIMED("setup_kernel", st, 1, (setup_kernel<<<1, 256, 0, st>>>(d_qlens, w.qoff, d_slens, w.soff, B, w.bbox, w.total_cells, 1)));
+    APRB_TIMED("setup_kernel", st, 1, (setup_kernel<<<1, 256, 0, st>>>(d_slens, w.soff, nullptr, nullptr, B, w.bbox, nullptr, 0)));
     if (Ns > 0) APRB_TIMED("bbox_kernel", st, 1, (bbox_kernel<<<cdiv(Ns, T), T, 0, st>>>(d_s, Ns, w.soff, B, w.bbox)));
     APRB_TIMED("nb_grid_params_kernel", st, 1, (nb_grid_params_kernel<<<1, 256, 0, st>>>(w.bbox, w.soff, B, radius, w.grids, w.total_cells)));
     APRB_CUDA_OK(cudaMemsetAsync(w.cell_count, 0, sizeof(int) * ((size_t)w.cells_cap + 1), st));
@@ -271,6 +249,14 @@ extern "C" int aprb_radius_neighbors_batch(const float* d_q, const float* d_s, c
     int rc = exclusive_scan_i32(w.cell_count, w.cell_start, (int)w.cells_cap + 1, w.temp, w.temp_bytes, st);
     if (rc) return rc;
     if (Ns > 0) APRB_TIMED("nb_scatter_kernel", st, 1, (nb_scatter_kernel<<<cdiv(Ns, T), T, 0, st>>>(d_s, Ns, w.cell_of, w.cell_start, w.cell_count, w.sorted)));
+    APRB_LAUNCH_OK();
+    return APRB_OK;
+}
+
+static int query_grid(const float* d_q, const int32_t* d_qlens, int B, int Nq, int Ns, float radius, int width,
+                      int32_t* d_out_idx, int ld, int32_t* d_counts, int32_t* d_max_count, NbWs& w, cudaStream_t st) {
+    // query offsets + reset of the max_count scalar in one tiny launch
+    APRB_TIMED("setup_kernel", st, 1, (setup_kernel<<<1, 256, 0, st>>>(d_qlens, w.qoff, nullptr, nullptr, B, nullptr, d_max_count, d_max_count ? 1 : 0)));
     int cap = 64;
     while (cap < width + 32) cap <<= 1;
     int wpb = 4;  // warps per block
@@ -282,4 +268,65 @@ extern "C" int aprb_radius_neighbors_batch(const float* d_q, const float* d_s, c
                                                         radius, width, cap, d_out_idx, ld, d_counts, d_max_count)));
     APRB_LAUNCH_OK();
     return APRB_OK;
+}
+
+extern "C" size_t aprb_radius_neighbors_ws_bytes(int Nq, int Ns, int B) {
+    if (Nq < 0 || Ns < 0 || B < 0) return 0;
+    Carver c(nullptr, 0);
+    return carve_nb(c, Nq, Ns > 0 ? Ns : 1, B > 0 ? B : 1, nullptr) + 256;
+}
+
+extern "C" size_t aprb_cell_grid_bytes(int Ns, int B) { return aprb_radius_neighbors_ws_bytes(0, Ns, B); }
+
+#define NB_COMMON_CHECKS()                                                                                            \
+    APRB_REQUIRE(B >= 1 && Ns >= 0, "need B >= 1, Ns >= 0");                                                          \
+    APRB_REQUIRE((long long)Ns * 16 + 64LL * B < 0x7FFFFF00LL, "support set too large for the int32 cell table")
+
+extern "C" int aprb_cell_grid_build(const float* d_s, const int32_t* d_slens, int B, int Ns, float radius, void* d_grid,
+                                    size_t grid_bytes, void* stream) {
+    NB_COMMON_CHECKS();
+    APRB_REQUIRE(d_slens && d_grid && (d_s || Ns == 0), "null pointer");
+    APRB_REQUIRE(radius > 0.f, "radius must be positive");
+    Carver c(d_grid, grid_bytes);
+    NbWs w;
+    carve_nb(c, 0, Ns > 0 ? Ns : 1, B, &w);
+    if (!c.ok()) { set_error("aprb_cell_grid_build: grid buffer too small (%zu < %zu)", grid_bytes, c.off); return APRB_ERR_WORKSPACE; }
+    return build_grid(d_s, d_slens, B, Ns, radius, w, (cudaStream_t)stream);
+}
+
+extern "C" int aprb_cell_grid_query(const void* d_grid, size_t grid_bytes, const float* d_q, const int32_t* d_qlens, int B,
+                                    int Nq, int Ns, float radius, int width, int32_t* d_out_idx, int ld,
+                                    int32_t* d_counts, int32_t* d_max_count, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    NB_COMMON_CHECKS();
+    APRB_REQUIRE(Nq >= 0 && d_qlens && d_grid, "bad query arguments");
+    APRB_REQUIRE(width >= 1 && width <= 16352, "width must be in [1, 16352]");
+    APRB_REQUIRE(ld >= width, "ld < width");
+    if (Nq == 0) { if (d_max_count) APRB_CUDA_OK(cudaMemsetAsync(d_max_count, 0, sizeof(int), st)); return APRB_OK; }
+    APRB_REQUIRE(d_q && d_out_idx, "null point/output pointer");
+    Carver c(const_cast<void*>(d_grid), grid_bytes);
+    NbWs w;
+    carve_nb(c, 0, Ns > 0 ? Ns : 1, B, &w);
+    if (!c.ok()) { set_error("aprb_cell_grid_query: grid buffer too small"); return APRB_ERR_WORKSPACE; }
+    return query_grid(d_q, d_qlens, B, Nq, Ns, radius, width, d_out_idx, ld, d_counts, d_max_count, w, st);
+}
+
+extern "C" int aprb_radius_neighbors_batch(const float* d_q, const float* d_s, const int32_t* d_qlens,
+                                           const int32_t* d_slens, int B, int Nq, int Ns, float radius, int width,
+                                           int32_t* d_out_idx, int ld, int32_t* d_counts, int32_t* d_max_count,
+                                           void* d_ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    NB_COMMON_CHECKS();
+    APRB_REQUIRE(Nq >= 0 && d_qlens && d_slens, "null batch-length pointer");
+    APRB_REQUIRE(width >= 1 && width <= 16352, "width must be in [1, 16352]");
+    APRB_REQUIRE(ld >= width, "ld < width");
+    if (Nq == 0) { if (d_max_count) APRB_CUDA_OK(cudaMemsetAsync(d_max_count, 0, sizeof(int), st)); return APRB_OK; }
+    APRB_REQUIRE(d_q && d_out_idx && d_ws && (d_s || Ns == 0), "null point/output/workspace pointer");
+    Carver c(d_ws, ws_bytes);
+    NbWs w;
+    carve_nb(c, Nq, Ns > 0 ? Ns : 1, B, &w);
+    if (!c.ok()) { set_error("aprb_radius_neighbors_batch: workspace too small (%zu < %zu)", ws_bytes, c.off); return APRB_ERR_WORKSPACE; }
+    int rc = build_grid(d_s, d_slens, B, Ns, radius, w, st);
+    if (rc) return rc;
+    return query_grid(d_q, d_qlens, B, Nq, Ns, radius, width, d_out_idx, ld, d_counts, d_max_count, w, st);
 }

@@ -144,26 +144,40 @@ def build_pyramid_device(points, lengths, config, neighborhood_limits, features=
     r_normal = config.first_subsampling_dl * config.conv_radius
     out = dict(points=[], neighbors=[], pools=[], upsamples=[], stack_lengths=[], pool_widths=[])
     empty_i = torch.zeros((0, 1), dtype=torch.int32, device=pts.device)
-    for layer, (has_conv, strided, deform_conv, deform_pool) in enumerate(_pyramid_schedule(config)):
+    sched = list(_pyramid_schedule(config))
+    # One cell list per level, shared by every search whose supports are that level's points: conv(l), pool(l) and the
+    # upsample search of level l-1 (radius 2 r_{l-1} = r_l). Built for the largest radius asked of it.
+    grid = None
+    for layer, (has_conv, strided, deform_conv, deform_pool) in enumerate(sched):
         lim = int(neighborhood_limits[layer])
-        if has_conv:
-            r = r_normal * config.deform_radius / config.conv_radius if deform_conv else r_normal
-            conv_i = ops.radius_neighbors(pts, pts, lens, lens, r, lim)
-        else:
-            conv_i = empty_i
+        r_conv = r_normal * config.deform_radius / config.conv_radius if deform_conv else r_normal
+        r_pool = r_normal * config.deform_radius / config.conv_radius if deform_pool else r_normal
+        need = max(r_conv if has_conv else 0.0, r_pool if strided else 0.0)
+        if grid is None or grid.radius < need:
+            grid = ops.CellGrid(pts, lens, need) if need > 0 else None
+        conv_i = grid.query(pts, lens, r_conv, lim) if has_conv else empty_i
         if strided:
             dl = 2 * r_normal / config.conv_radius
             pool_p, pool_b = ops.grid_subsample(pts, lens, dl)
-            r = r_normal * config.deform_radius / config.conv_radius if deform_pool else r_normal
-            pool_i, _, pool_w = ops.radius_neighbors(pool_p, pts, pool_b, lens, r, lim, want_counts=True)
-            up_i = ops.radius_neighbors(pts, pool_p, lens, pool_b, 2 * r, lim)
+            pool_i, _, pool_w = grid.query(pool_p, pool_b, r_pool, lim, want_counts=True)
+            # grid over the next level's points: serves this level's upsample search and the next level's conv/pool
+            nxt = sched[layer + 1] if layer + 1 < len(sched) else None
+            r_next = 2 * r_normal
+            need_next = 2 * r_pool
+            if nxt is not None:
+                if nxt[0]:
+                    need_next = max(need_next, r_next * config.deform_radius / config.conv_radius if nxt[2] else r_next)
+                if nxt[1]:
+                    need_next = max(need_next, r_next * config.deform_radius / config.conv_radius if nxt[3] else r_next)
+            next_grid = ops.CellGrid(pool_p, pool_b, need_next)
+            up_i = next_grid.query(pts, lens, 2 * r_pool, lim)
         else:
-            pool_i, up_i, pool_w = empty_i, empty_i, None
+            pool_i, up_i, pool_w, next_grid = empty_i, empty_i, None, None
             pool_p = torch.zeros((0, 3), dtype=torch.float32, device=pts.device)
             pool_b = torch.zeros((0,), dtype=torch.int32, device=pts.device)
         out['points'].append(pts); out['neighbors'].append(conv_i); out['pools'].append(pool_i)
         out['upsamples'].append(up_i); out['stack_lengths'].append(lens); out['pool_widths'].append(pool_w)
-        pts, lens = pool_p, pool_b
+        pts, lens, grid = pool_p, pool_b, next_grid
         r_normal *= 2
     out['features'] = features if features is not None else torch.ones((out['points'][0].shape[0], 1),
                                                                      dtype=torch.float32, device=points.device)

@@ -104,6 +104,37 @@ def radius_neighbors(queries, supports, q_lens, s_lens, radius, width, want_coun
     return out
 
 
+class CellGrid:
+    """Cell list over a stacked support set (K2), reusable by several radius queries with radius <= the build radius."""
+
+    def __init__(self, supports, s_lens, radius):
+        N.require_cuda()
+        self.s = _dev_f32(supports, "supports")
+        self.sl = _dev_i32(s_lens, "s_lens")
+        self.ns, self.b, self.radius = self.s.shape[0], self.sl.shape[0], float(radius)
+        nbytes = N.lib().aprb_cell_grid_bytes(self.ns, self.b)
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=self.s.device)
+        N.check(N.lib().aprb_cell_grid_build(N.ptr(self.s), N.ptr(self.sl), self.b, self.ns, self.radius, N.ptr(self.buf),
+                                             self.buf.numel(), N.stream_ptr()), "aprb_cell_grid_build")
+
+    def query(self, queries, q_lens, radius, width, want_counts=False):
+        """Same result as radius_neighbors(queries, supports, q_lens, s_lens, radius, width)."""
+        if float(radius) > self.radius * (1 + 1e-6):
+            raise N.NativeError("CellGrid.query: radius larger than the radius the grid was built for")
+        q, ql = _dev_f32(queries, "queries"), _dev_i32(q_lens, "q_lens")
+        nq, width = q.shape[0], int(width)
+        out = torch.empty((nq, width), dtype=torch.int32, device=q.device)
+        counts = torch.empty(max(nq, 1), dtype=torch.int32, device=q.device) if want_counts else None
+        maxc = torch.zeros(1, dtype=torch.int32, device=q.device) if want_counts else None
+        rc = N.lib().aprb_cell_grid_query(N.ptr(self.buf), self.buf.numel(), N.ptr(q), N.ptr(ql), self.b, nq, self.ns,
+                                          float(radius), width, N.ptr(out), width, N.ptr(counts), N.ptr(maxc),
+                                          N.stream_ptr())
+        N.check(rc, "aprb_cell_grid_query")
+        if TRACE is not None:
+            TRACE.append(("nb", nq, self.ns, width))
+        return (out, counts[:nq], maxc) if want_counts else out
+
+
 def kpconv_prepare_weights(weights):
     """[K,Cin,Cout] f32 -> prepared TF32 K-major operand [Cout, K*Cin]."""
     N.require_cuda()

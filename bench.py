@@ -229,6 +229,7 @@ def run_ours(args):
         if sampler is not None:
             sampler.start()          # forks nvidia-smi: do it BEFORE the warm-up so the fork's page-table churn is absorbed there
         for i in range(warmup):
+            flush.zero_()
             fn(i)
         if sampler is not None:
             sampler.mark()
@@ -345,7 +346,7 @@ def main():
     ap.add_argument("--no-calibrate", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tf32-linear", type=int, default=0, help="allow TF32 in the cuBLAS unary GEMMs (LINEAR_MODE=fp32)")
-    ap.add_argument("--linear-mode", default="", choices=["", "fp32", "tf32"])
+    ap.add_argument("--linear-mode", default="tf32", choices=["fp32", "tf32"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

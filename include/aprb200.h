@@ -81,6 +81,18 @@ int aprb_radius_neighbors_batch(const float* d_q, const float* d_s, const int32_
                                 int32_t* d_out_idx, int ld, int32_t* d_counts, int32_t* d_max_count,
                                 void* d_ws, size_t ws_bytes, void* stream);
 
+/* The same search split in two, so several query sets can share one cell list (in the KPConv pyramid the grid over
+ * P_l with cell r_l serves conv(l) and pool(l); the grid over P_{l+1} with cell 2 r_l serves upsample(l), conv(l+1),
+ * pool(l+1): 4 builds instead of 10). A grid built with `radius` serves any query radius <= that value.
+ * d_grid is an opaque device buffer of aprb_cell_grid_bytes(Ns, B) bytes that must outlive its queries; queries on
+ * one grid must be ordered on one stream (the grid keeps the query offsets). */
+size_t aprb_cell_grid_bytes(int Ns, int B);
+int aprb_cell_grid_build(const float* d_s, const int32_t* d_slens, int B, int Ns, float radius,
+                         void* d_grid, size_t grid_bytes, void* stream);
+int aprb_cell_grid_query(const void* d_grid, size_t grid_bytes, const float* d_q, const int32_t* d_qlens, int B,
+                         int Nq, int Ns, float radius, int width, int32_t* d_out_idx, int ld,
+                         int32_t* d_counts, int32_t* d_max_count, void* stream);
+
 /* ---------------------------------------------------------------- K5: KPConv forward ------------------------- */
 /* Prepared weights: the [K,Cin,Cout] fp32 parameter re-laid as the K-major, TF32-rounded B operand
  * [Cout, K*Cin] used by the tcgen05 contraction. d_wprep has K*Cin*Cout floats. Run once per weight update. */
