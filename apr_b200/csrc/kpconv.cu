@@ -32,6 +32,15 @@ __global__ void rowsum_pos_kernel(const float* __restrict__ x, int Ns, int C, un
     if (lane == 0) flag[row] = s > 0.f ? 1 : 0;
 }
 
+constexpr int KPW_DEPTH = 8;   // neighbour rows in flight per warp (cp.async ring)
+
+template <int VEC>
+__device__ __forceinline__ void cp_async_vec(uint32_t dst, const float* src) {
+    if (VEC == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    else if (VEC == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+
 template <int VEC> struct Vec;
 template <> struct Vec<1> { float v[1]; };
 template <> struct __align__(8) Vec<2> { float v[2]; };
@@ -74,9 +83,10 @@ kp_weighted_kernel(const float* __restrict__ q, const float* __restrict__ s, con
     __syncthreads();
     const int n = blockIdx.x * wpb + wib;
     if (n >= Nq) return;
-    float* s_w = s_dyn + (size_t)wib * Hp * 18;                 // [Hp][16]
+    float* s_w = s_dyn + (size_t)wib * (Hp * 18 + KPW_DEPTH * 32 * VEC);   // [Hp][16]
     int* s_si = reinterpret_cast<int*>(s_w + (size_t)Hp * 16);  // [Hp] active support index
     int* s_hm = s_si + Hp;                                      // [Hp] (h << 16) | mask
+    float* s_ring = reinterpret_cast<float*>(s_hm + Hp);        // [KPW_DEPTH][32][VEC] per-lane cp.async ring
     const float qx = q[3 * (size_t)n], qy = q[3 * (size_t)n + 1], qz = q[3 * (size_t)n + 2];
     const float ext2 = extent * extent, inv_ext = 1.0f / extent;
 
@@ -125,28 +135,29 @@ kp_weighted_kernel(const float* __restrict__ q, const float* __restrict__ s, con
 #pragma unroll
             for (int j = 0; j < VEC; ++j) acc[k][j] = 0.f;
         const float* xc = x + c;
-        int j = 0;
-        for (; j + 1 < nact; j += 2) {                           // two neighbour rows in flight
-            const int si0 = s_si[j], si1 = s_si[j + 1];
-            const int hm0 = s_hm[j], hm1 = s_hm[j + 1];
-            Vec<VEC> x0, x1;
+        // Neighbour rows are staged through a per-lane cp.async ring in shared memory: KPW_DEPTH rows in flight per
+        // warp without holding registers; every lane copies and later reads only its own VEC channels (no cross-lane
+        // hazard, so cp.async.wait_group alone orders the accesses).
+        const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(s_ring + lane * VEC);
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) { x0.v[v] = 0.f; x1.v[v] = 0.f; }
-            if (cvalid) {
-                x0 = *reinterpret_cast<const Vec<VEC>*>(xc + (size_t)si0 * Cin);
-                x1 = *reinterpret_cast<const Vec<VEC>*>(xc + (size_t)si1 * Cin);
+        for (int u = 0; u < KPW_DEPTH; ++u) {
+            if (u < nact && cvalid) cp_async_vec<VEC>(ring0 + u * 32 * VEC * 4, xc + (size_t)s_si[u] * Cin);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        for (int j = 0; j < nact; ++j) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(KPW_DEPTH - 1) : "memory");
+            const int slot = j % KPW_DEPTH;
+            Vec<VEC> xv = *reinterpret_cast<const Vec<VEC>*>(s_ring + (slot * 32 + lane) * VEC);
+            if (!cvalid) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) xv.v[v] = 0.f;
             }
-            kp_accumulate<VEC>(acc, (unsigned)hm0 & 0xFFFFu, s_w + (hm0 >> 16) * 16, x0);
-            kp_accumulate<VEC>(acc, (unsigned)hm1 & 0xFFFFu, s_w + (hm1 >> 16) * 16, x1);
+            const int hm = s_hm[j];
+            if (j + KPW_DEPTH < nact && cvalid) cp_async_vec<VEC>(ring0 + slot * 32 * VEC * 4, xc + (size_t)s_si[j + KPW_DEPTH] * Cin);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            kp_accumulate<VEC>(acc, (unsigned)hm & 0xFFFFu, s_w + (hm >> 16) * 16, xv);
         }
-        if (j < nact) {
-            const int si0 = s_si[j], hm0 = s_hm[j];
-            Vec<VEC> x0;
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) x0.v[v] = 0.f;
-            if (cvalid) x0 = *reinterpret_cast<const Vec<VEC>*>(xc + (size_t)si0 * Cin);
-            kp_accumulate<VEC>(acc, (unsigned)hm0 & 0xFFFFu, s_w + (hm0 >> 16) * 16, x0);
-        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (cvalid) {
 #pragma unroll
             for (int k = 0; k < KP_MAX_K; ++k) {
@@ -341,11 +352,11 @@ extern "C" int aprb_kpconv_forward(const float* d_q, const float* d_s, const voi
 
     if (Ns > 0) APRB_TIMED("rowsum_pos_kernel", st, 1, (rowsum_pos_kernel<<<cdiv(Ns, 8), 256, 0, st>>>(d_x, Ns, Cin, flag)));
     const int wpb = 4, Hp = (H + 31) & ~31;
-    size_t smem = (size_t)wpb * Hp * 18 * sizeof(float);
     const bool x16 = ((uintptr_t)d_x % 16 == 0) && ((uintptr_t)wf % 16 == 0);
     const int vec = (Cin % 4 == 0 && Cin >= 128 && x16) ? 4 : ((Cin % 2 == 0 && Cin >= 64 && x16) ? 2 : 1);
 #define KPW_LAUNCH3(IDX, VEC, RND)                                                                                   \
     do {                                                                                                             \
+        const size_t smem = (size_t)wpb * (Hp * 18 + KPW_DEPTH * 32 * VEC) * sizeof(float);                          \
         if (smem > 48 * 1024)                                                                                        \
             APRB_CUDA_OK(cudaFuncSetAttribute(kp_weighted_kernel<IDX, VEC, RND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         const int nslabs = cdiv(Cin, 32 * VEC);                                                                      \
