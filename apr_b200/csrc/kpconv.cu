@@ -32,44 +32,20 @@ __global__ void rowsum_pos_kernel(const float* __restrict__ x, int Ns, int C, un
     if (lane == 0) flag[row] = s > 0.f ? 1 : 0;
 }
 
-constexpr int KPW_DEPTH = 8;   // neighbour rows in flight per warp (cp.async ring)
-
-template <int VEC>
-__device__ __forceinline__ void cp_async_vec(uint32_t dst, const float* src) {
-    if (VEC == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-    else if (VEC == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-
 template <int VEC> struct Vec;
 template <> struct Vec<1> { float v[1]; };
 template <> struct __align__(8) Vec<2> { float v[2]; };
 template <> struct __align__(16) Vec<4> { float v[4]; };
 
-// acc[k][:] += w * xv for every kernel point k set in `mask`; the loop and the switch are warp-uniform (all lanes of a
-// warp work on the same neighbour), so only the influenced kernel points (~1.4 of 15 on average) cost anything.
-template <int VEC>
-__device__ __forceinline__ void kp_accumulate(float (&acc)[KP_MAX_K][VEC], unsigned mask, const float* __restrict__ wrow,
-                                              const Vec<VEC>& xv) {
-    while (mask) {
-        const int k = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const float w = wrow[k];
-#define KP_CASE(i) case i: _Pragma("unroll") for (int j = 0; j < VEC; ++j) acc[i][j] = fmaf(w, xv.v[j], acc[i][j]); break;
-        switch (k) {
-            KP_CASE(0) KP_CASE(1) KP_CASE(2) KP_CASE(3) KP_CASE(4) KP_CASE(5) KP_CASE(6) KP_CASE(7)
-            KP_CASE(8) KP_CASE(9) KP_CASE(10) KP_CASE(11) KP_CASE(12) KP_CASE(13) KP_CASE(14) KP_CASE(15)
-        }
-#undef KP_CASE
-    }
-}
-
-// One warp per query. Dynamic smem per warp: Hp*16 floats of influence weights (neighbour-major) + Hp ints of active
-// support indices + Hp ints of (neighbour << 16 | kernel-point mask); Hp = H rounded up to 32.
-// Phase 1 (lanes = neighbours): influence weights, kernel-point masks, neighbor_num, compaction of the neighbours that
-// influence at least one kernel point. Phase 2 (lanes = channels, VEC per lane, slabs of 32*VEC channels): stream the
-// active neighbours' feature rows (two in flight) and accumulate into the <= 16 x VEC register tile.
-template <typename IdxT, int VEC, bool ROUND_TF32>
+// One warp per query (stage A+B of KPConv).
+// Phase 1 (lanes = neighbours): relative positions, influence w = max(0, 1 - d/extent) against the K kernel points,
+//   neighbor_num, and — per kernel point — a compacted list of (support index, w) of the neighbours it influences
+//   (ballot compaction; ~5 of H=57 neighbours per kernel point). Dynamic smem per warp: K_MAX lists x Hp x 8 bytes.
+// Phase 2 (lanes = channels): for each kernel point, stream the feature rows of its list (NU rows in flight) and
+//   accumulate w * x into ONE VEC*NJ-wide register tile, then store that kernel point's slice of wf. The kernel point is
+//   a plain loop variable — no per-neighbour dispatch — and a row that influences several kernel points (1.4 on average)
+//   is simply re-read (L1/L2 hit).
+template <typename IdxT, int VEC, int NJ, bool ROUND_TF32>
 __global__ void __launch_bounds__(128)
 kp_weighted_kernel(const float* __restrict__ q, const float* __restrict__ s, const IdxT* __restrict__ idx, int ld,
                    const float* __restrict__ x, const float* __restrict__ kp, const unsigned char* __restrict__ posflag,
@@ -83,14 +59,15 @@ kp_weighted_kernel(const float* __restrict__ q, const float* __restrict__ s, con
     __syncthreads();
     const int n = blockIdx.x * wpb + wib;
     if (n >= Nq) return;
-    float* s_w = s_dyn + (size_t)wib * (Hp * 18 + KPW_DEPTH * 32 * VEC);   // [Hp][16]
-    int* s_si = reinterpret_cast<int*>(s_w + (size_t)Hp * 16);  // [Hp] active support index
-    int* s_hm = s_si + Hp;                                      // [Hp] (h << 16) | mask
-    float* s_ring = reinterpret_cast<float*>(s_hm + Hp);        // [KPW_DEPTH][32][VEC] per-lane cp.async ring
+    int* s_si = reinterpret_cast<int*>(s_dyn) + (size_t)wib * KP_MAX_K * Hp * 2;   // [K_MAX][Hp] support index
+    float* s_lw = reinterpret_cast<float*>(s_si + (size_t)KP_MAX_K * Hp);          // [K_MAX][Hp] influence weight
     const float qx = q[3 * (size_t)n], qy = q[3 * (size_t)n + 1], qz = q[3 * (size_t)n + 2];
     const float ext2 = extent * extent, inv_ext = 1.0f / extent;
 
-    int nn = 0, nact = 0;
+    int nn = 0;
+    int cnt[KP_MAX_K];
+#pragma unroll
+    for (int k = 0; k < KP_MAX_K; ++k) cnt[k] = 0;
     for (int h0 = 0; h0 < Hp; h0 += 32) {
         const int h = h0 + lane;
         int si = Ns;
@@ -98,26 +75,30 @@ kp_weighted_kernel(const float* __restrict__ q, const float* __restrict__ s, con
             const long long v = (long long)idx[(size_t)n * ld + h];
             si = (v >= 0 && v < Ns) ? (int)v : Ns;
         }
-        unsigned mask = 0;
-        if (si < Ns) {
+        float rx = 0.f, ry = 0.f, rz = 0.f;
+        const bool valid = si < Ns;
+        if (valid) {
             nn += posflag[si];
-            const float rx = s[3 * (size_t)si] - qx, ry = s[3 * (size_t)si + 1] - qy, rz = s[3 * (size_t)si + 2] - qz;
-            for (int k = 0; k < K; ++k) {
+            rx = s[3 * (size_t)si] - qx; ry = s[3 * (size_t)si + 1] - qy; rz = s[3 * (size_t)si + 2] - qz;
+        }
+        if (!__any_sync(0xffffffffu, valid)) continue;
+#pragma unroll
+        for (int k = 0; k < KP_MAX_K; ++k) {
+            if (k < K) {
                 const float ddx = rx - s_kp[3 * k], ddy = ry - s_kp[3 * k + 1], ddz = rz - s_kp[3 * k + 2];
                 const float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
-                if (d2 < ext2) {                                 // influence max(0, 1 - d/extent) is non-zero
-                    const float w = 1.0f - sqrtf(d2) * inv_ext;
-                    if (w > 0.f) { s_w[h * 16 + k] = w; mask |= 1u << k; }
+                float w = 0.f;
+                if (valid && d2 < ext2) w = 1.0f - sqrtf(d2) * inv_ext;
+                const bool in = w > 0.f;
+                const unsigned m = __ballot_sync(0xffffffffu, in);
+                if (in) {
+                    const int pos = cnt[k] + __popc(m & ((1u << lane) - 1));
+                    s_si[k * Hp + pos] = si;
+                    s_lw[k * Hp + pos] = w;
                 }
+                cnt[k] += __popc(m);
             }
         }
-        const unsigned act = __ballot_sync(0xffffffffu, mask != 0);
-        if (mask) {
-            const int pos = nact + __popc(act & ((1u << lane) - 1));
-            s_si[pos] = si;
-            s_hm[pos] = (h << 16) | (int)mask;
-        }
-        nact += __popc(act);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, d);
@@ -125,55 +106,61 @@ kp_weighted_kernel(const float* __restrict__ q, const float* __restrict__ s, con
     __syncwarp();
 
     float* wrow = wf + (size_t)n * K * Cin;
-    // gridDim.y > 1: channel slabs are spread over blockIdx.y (more warps in flight when there are few queries)
-    for (int c0 = blockIdx.y * 32 * VEC; c0 < Cin; c0 += gridDim.y * 32 * VEC) {
-        const int c = c0 + lane * VEC;
-        const bool cvalid = c < Cin;
-        float acc[KP_MAX_K][VEC];
+    constexpr int SLAB = 32 * VEC * NJ;
+    constexpr int NU = (VEC * NJ >= 8) ? 2 : 4;                   // rows in flight
+    for (int c0 = blockIdx.y * SLAB; c0 < Cin; c0 += gridDim.y * SLAB) {
 #pragma unroll
-        for (int k = 0; k < KP_MAX_K; ++k)
+        for (int k = 0; k < KP_MAX_K; ++k) {
+            if (k < K) {
+                float acc[NJ][VEC];
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) acc[k][j] = 0.f;
-        const float* xc = x + c;
-        // Neighbour rows are staged through a per-lane cp.async ring in shared memory: KPW_DEPTH rows in flight per
-        // warp without holding registers; every lane copies and later reads only its own VEC channels (no cross-lane
-        // hazard, so cp.async.wait_group alone orders the accesses).
-        const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(s_ring + lane * VEC);
+                for (int j = 0; j < NJ; ++j)
 #pragma unroll
-        for (int u = 0; u < KPW_DEPTH; ++u) {
-            if (u < nact && cvalid) cp_async_vec<VEC>(ring0 + u * 32 * VEC * 4, xc + (size_t)s_si[u] * Cin);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        }
-        for (int j = 0; j < nact; ++j) {
-            asm volatile("cp.async.wait_group %0;" ::"n"(KPW_DEPTH - 1) : "memory");
-            const int slot = j % KPW_DEPTH;
-            Vec<VEC> xv = *reinterpret_cast<const Vec<VEC>*>(s_ring + (slot * 32 + lane) * VEC);
-            if (!cvalid) {
+                    for (int v = 0; v < VEC; ++v) acc[j][v] = 0.f;
+                const int ck = cnt[k];
+                const int* lsi = s_si + k * Hp;
+                const float* lw = s_lw + k * Hp;
+                for (int e0 = 0; e0 < ck; e0 += NU) {
+                    Vec<VEC> xr[NU][NJ];
+                    float w[NU];
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) xv.v[v] = 0.f;
-            }
-            const int hm = s_hm[j];
-            if (j + KPW_DEPTH < nact && cvalid) cp_async_vec<VEC>(ring0 + slot * 32 * VEC * 4, xc + (size_t)s_si[j + KPW_DEPTH] * Cin);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            kp_accumulate<VEC>(acc, (unsigned)hm & 0xFFFFu, s_w + (hm >> 16) * 16, xv);
-        }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (cvalid) {
+                    for (int u = 0; u < NU; ++u) {
+                        const bool on = e0 + u < ck;
+                        w[u] = on ? lw[e0 + u] : 0.f;
+                        const float* row = x + (size_t)(on ? lsi[e0 + u] : lsi[e0]) * Cin + c0 + lane * VEC;
 #pragma unroll
-            for (int k = 0; k < KP_MAX_K; ++k) {
-                if (k < K) {
-                    Vec<VEC> o;
+                        for (int j = 0; j < NJ; ++j) {
+                            if (c0 + lane * VEC + j * 32 * VEC < Cin) xr[u][j] = *reinterpret_cast<const Vec<VEC>*>(row + j * 32 * VEC);
+                            else {
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        float t = acc[k][v];
-                        if (ROUND_TF32) {
-                            unsigned u;
-                            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(t));
-                            t = __uint_as_float(u);
+                                for (int v = 0; v < VEC; ++v) xr[u][j].v[v] = 0.f;
+                            }
                         }
-                        o.v[v] = t;
                     }
-                    *reinterpret_cast<Vec<VEC>*>(wrow + (size_t)k * Cin + c) = o;
+#pragma unroll
+                    for (int u = 0; u < NU; ++u)
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) acc[j][v] = fmaf(w[u], xr[u][j].v[v], acc[j][v]);
+                }
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const int c = c0 + lane * VEC + j * 32 * VEC;
+                    if (c < Cin) {
+                        Vec<VEC> o;
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            float t = acc[j][v];
+                            if (ROUND_TF32) {
+                                unsigned u;
+                                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(t));
+                                t = __uint_as_float(u);
+                            }
+                            o.v[v] = t;
+                        }
+                        *reinterpret_cast<Vec<VEC>*>(wrow + (size_t)k * Cin + c) = o;
+                    }
                 }
             }
         }
@@ -351,22 +338,33 @@ extern "C" int aprb_kpconv_forward(const float* d_q, const float* d_s, const voi
     float* gws = c.take<float>(gws_bytes / sizeof(float));
 
     if (Ns > 0) APRB_TIMED("rowsum_pos_kernel", st, 1, (rowsum_pos_kernel<<<cdiv(Ns, 8), 256, 0, st>>>(d_x, Ns, Cin, flag)));
-    const int wpb = 4, Hp = (H + 31) & ~31;
+    const int Hp = (H + 31) & ~31;
+    const size_t smem_warp = (size_t)KP_MAX_K * Hp * 8;
+    int wpb = 4;
+    while (wpb > 1 && wpb * smem_warp > 160 * 1024) wpb >>= 1;
+    if (smem_warp > 200 * 1024) { set_error("aprb_kpconv_forward: H=%d too large for the shared-memory neighbour lists", H); return APRB_ERR_UNSUPPORTED; }
+    const size_t smem = wpb * smem_warp;
     const bool x16 = ((uintptr_t)d_x % 16 == 0) && ((uintptr_t)wf % 16 == 0);
-    const int vec = (Cin % 4 == 0 && Cin >= 128 && x16) ? 4 : ((Cin % 2 == 0 && Cin >= 64 && x16) ? 2 : 1);
-#define KPW_LAUNCH3(IDX, VEC, RND)                                                                                   \
+    // (VEC, NJ): channels per lane = VEC*NJ, one slab = 32*VEC*NJ channels
+    int vec = 1, nj = 1;
+    if (x16 && Cin % 4 == 0 && Cin >= 128) { vec = 4; nj = Cin >= 512 ? 4 : (Cin >= 256 ? 2 : 1); }
+    else if (x16 && Cin % 2 == 0 && Cin >= 64) { vec = 2; nj = 1; }
+#define KPW_LAUNCH3(IDX, VEC, NJ, RND)                                                                               \
     do {                                                                                                             \
-        const size_t smem = (size_t)wpb * (Hp * 18 + KPW_DEPTH * 32 * VEC) * sizeof(float);                          \
         if (smem > 48 * 1024)                                                                                        \
-            APRB_CUDA_OK(cudaFuncSetAttribute(kp_weighted_kernel<IDX, VEC, RND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        const int nslabs = cdiv(Cin, 32 * VEC);                                                                      \
-        const int gy = (cdiv(Nq, wpb) < 6 * sm_count()) ? nslabs : 1;                                                \
-        APRB_TIMED("kp_weighted_kernel", st, 1, (kp_weighted_kernel<IDX, VEC, RND><<<dim3(cdiv(Nq, wpb), gy), wpb * 32, smem, st>>>( \
+            APRB_CUDA_OK(cudaFuncSetAttribute(kp_weighted_kernel<IDX, VEC, NJ, RND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        const int nslabs = cdiv(Cin, 32 * VEC * NJ);                                                                 \
+        const int gy = (cdiv(Nq, wpb) < 4 * sm_count()) ? nslabs : 1;                                                \
+        APRB_TIMED("kp_weighted_kernel", st, 1, (kp_weighted_kernel<IDX, VEC, NJ, RND><<<dim3(cdiv(Nq, wpb), gy), wpb * 32, smem, st>>>( \
             d_q, d_s, (const IDX*)d_idx, ld_idx, d_x, d_kp, flag, extent, Nq, Ns, H, K, Cin, wf, inv_nn)));         \
     } while (0)
 #define KPW_LAUNCH(IDX, RND)                                                                                         \
     do {                                                                                                             \
-        if (vec == 4) KPW_LAUNCH3(IDX, 4, RND); else if (vec == 2) KPW_LAUNCH3(IDX, 2, RND); else KPW_LAUNCH3(IDX, 1, RND); \
+        if (vec == 4 && nj == 4) KPW_LAUNCH3(IDX, 4, 4, RND);                                                        \
+        else if (vec == 4 && nj == 2) KPW_LAUNCH3(IDX, 4, 2, RND);                                                   \
+        else if (vec == 4) KPW_LAUNCH3(IDX, 4, 1, RND);                                                              \
+        else if (vec == 2) KPW_LAUNCH3(IDX, 2, 1, RND);                                                              \
+        else KPW_LAUNCH3(IDX, 1, 1, RND);                                                                            \
     } while (0)
     if (use_tensor) {
         if (idx_is_i64) KPW_LAUNCH(long long, true); else KPW_LAUNCH(int, true);
@@ -374,9 +372,9 @@ extern "C" int aprb_kpconv_forward(const float* d_q, const float* d_s, const voi
         return gemm_tf32_rowscale(wf, d_wprep, Nq, Cout, KC, inv_nn, d_out, gws, gws_bytes, st);
     }
     if (Cin == 1) {
-        if (idx_is_i64) APRB_TIMED("kp_weighted_c1_kernel", st, 1, (kp_weighted_c1_kernel<long long><<<cdiv(Nq, wpb), wpb * 32, 0, st>>>(
+        if (idx_is_i64) APRB_TIMED("kp_weighted_c1_kernel", st, 1, (kp_weighted_c1_kernel<long long><<<cdiv(Nq, 4), 128, 0, st>>>(
             d_q, d_s, (const long long*)d_idx, ld_idx, d_x, d_kp, flag, extent, Nq, Ns, H, K, wf, inv_nn)));
-        else APRB_TIMED("kp_weighted_c1_kernel", st, 1, (kp_weighted_c1_kernel<int><<<cdiv(Nq, wpb), wpb * 32, 0, st>>>(
+        else APRB_TIMED("kp_weighted_c1_kernel", st, 1, (kp_weighted_c1_kernel<int><<<cdiv(Nq, 4), 128, 0, st>>>(
             d_q, d_s, (const int*)d_idx, ld_idx, d_x, d_kp, flag, extent, Nq, Ns, H, K, wf, inv_nn)));
     } else if (idx_is_i64) KPW_LAUNCH(long long, false); else KPW_LAUNCH(int, false);
 #undef KPW_LAUNCH3

@@ -1,0 +1,333 @@
+// pipeline.cu — native driver of the whole hot path: pyramid (collate) + KFE encoder blocks on one stream.
+//
+// Host-side mirror, in C++, of collate_fn_descriptor (/root/reference/Predator_APR/datasets/dataloader.py:72-198) and of
+// the encoder loop of KPFCNN.forward (models/architectures.py:149-153) with SimpleBlock / ResnetBottleneckBlock.forward
+// (models/blocks.py:581-593, :653-681). Every operation is one of this library's own C-ABI entry points; this file
+// only sequences them, carves one caller-provided arena, and reads the three per-level point counts back through
+// events so the host never waits for the encoder kernels it has already queued.
+#include "common.cuh"
+#include <new>
+#include <vector>
+
+namespace aprb {
+constexpr int KFE_MAX_LEVELS = 8;
+}
+
+struct aprb_kfe {
+    aprb_kfe_config cfg;
+    std::vector<aprb_kfe_block> blocks;
+    cudaEvent_t ev[aprb::KFE_MAX_LEVELS];
+    int* h_counts;  // pinned: per level [M, status, lens[0..B)]
+    int h_counts_cap;
+    // state of the last forward (aprb_kfe_get)
+    int B;
+    int n[aprb::KFE_MAX_LEVELS];
+    const float* pts[aprb::KFE_MAX_LEVELS];
+    const int* lens[aprb::KFE_MAX_LEVELS];
+    const int* conv[aprb::KFE_MAX_LEVELS];
+    const int* pool[aprb::KFE_MAX_LEVELS];
+    const int* up[aprb::KFE_MAX_LEVELS];
+};
+
+using namespace aprb;
+
+namespace {
+
+struct Arena {
+    char* base;
+    size_t off, cap;
+    bool overflow;
+    Arena(void* p, size_t bytes) : base((char*)p), off(0), cap(bytes), overflow(false) {}
+    template <typename T>
+    T* take(size_t n) {
+        size_t bytes = align256(n * sizeof(T));
+        if (off + bytes > cap) { overflow = true; return nullptr; }
+        T* r = (T*)(base + off);
+        off += bytes;
+        return r;
+    }
+    // everything after the persistent allocations is scratch for the op being launched (stream order makes reuse safe)
+    void* scratch() const { return base + off; }
+    size_t scratch_bytes() const { return cap - off; }
+};
+
+#define KFE_OK(expr)            \
+    do {                        \
+        int _rc = (expr);       \
+        if (_rc) return _rc;    \
+    } while (0)
+#define KFE_ALLOC(var, T, n)                                                                     \
+    T* var = A.take<T>(n);                                                                       \
+    if (!var) { set_error("aprb_kfe_forward: arena too small (need > %zu bytes)", A.cap); return APRB_ERR_WORKSPACE; }
+
+int kpconv_call(const aprb_kfe& h, const aprb_kfe_block& b, const float* q, const float* s, const int* idx, int ld,
+                const float* x, int nq, int ns, int H, int cin, int cout, float* out, Arena& A, cudaStream_t st) {
+    size_t need = aprb_kpconv_ws_bytes(nq, ns, H, h.cfg.K, cin, cout);
+    if (A.scratch_bytes() < need) { set_error("aprb_kfe_forward: arena too small for the KPConv workspace"); return APRB_ERR_WORKSPACE; }
+    return aprb_kpconv_forward(q, s, idx, 0, ld, x, b.kp, b.kp_W, b.kp_Wprep, b.extent, nq, ns, H, h.cfg.K, cin, cout, out,
+                               b.kp_Wprep ? 0 : 1, A.scratch(), A.scratch_bytes(), st);
+}
+
+int norm_call(const float* x, int n, int c, float slope, const float* res, int norm_res, float* y, Arena& A, cudaStream_t st) {
+    if (A.scratch_bytes() < aprb_instnorm_ws_bytes(n, c)) { set_error("aprb_kfe_forward: arena too small for the norm workspace"); return APRB_ERR_WORKSPACE; }
+    return aprb_instnorm_lrelu(x, n, c, 1e-5f, slope, res, norm_res, 1, y, A.scratch(), A.scratch_bytes(), st);
+}
+
+int linear_call(const float* x, const float* W, int n, int cin, int cout, float* y, Arena& A, cudaStream_t st) {
+    size_t need = aprb_linear_tf32_ws_bytes(n, cin, cout);
+    void* ws = A.scratch_bytes() >= need ? A.scratch() : nullptr;   // split-K is optional
+    return aprb_linear_tf32(x, W, n, cin, cout, y, ws, ws ? A.scratch_bytes() : 0, st);
+}
+
+// One encoder block. feat [ns_rows, in_dim] -> *out [nq, out_cols]. Temporaries are released when the block returns.
+int run_block(const aprb_kfe& h, const aprb_kfe_block& b, const float* feat, const float** out, int* out_cols, Arena& A,
+              cudaStream_t st) {
+    const int l = b.layer;
+    const int nq = b.strided ? h.n[l + 1] : h.n[l], ns = h.n[l];
+    const float* q = b.strided ? h.pts[l + 1] : h.pts[l];
+    const float* s = h.pts[l];
+    const int* idx = b.strided ? h.pool[l] : h.conv[l];
+    const int H = h.cfg.limits[l];
+    if (b.type == 0) {                                             // SimpleBlock: KPConv -> IN -> LeakyReLU
+        const int cout = b.out_dim / 2;
+        KFE_ALLOC(y, float, (size_t)nq * cout);
+        const size_t mark = A.off;
+        KFE_ALLOC(t, float, (size_t)nq * cout);
+        KFE_OK(kpconv_call(h, b, q, s, idx, H, feat, nq, ns, H, b.in_dim, cout, t, A, st));
+        KFE_OK(norm_call(t, nq, cout, 0.1f, nullptr, 0, y, A, st));
+        A.off = mark;
+        *out = y; *out_cols = cout;
+        return APRB_OK;
+    }
+    const int mid = b.out_dim / 4, cout = b.out_dim;               // ResnetBottleneckBlock
+    KFE_ALLOC(y, float, (size_t)nq * cout);
+    const size_t mark = A.off;
+    const float* x1 = feat;
+    if (b.unary1_W) {                                              // unary1: Linear -> IN -> LeakyReLU
+        KFE_ALLOC(t1, float, (size_t)ns * mid);
+        KFE_OK(linear_call(feat, b.unary1_W, ns, b.in_dim, mid, t1, A, st));
+        KFE_OK(norm_call(t1, ns, mid, 0.1f, nullptr, 0, t1, A, st));
+        x1 = t1;
+    }
+    KFE_ALLOC(t2, float, (size_t)nq * mid);
+    KFE_OK(kpconv_call(h, b, q, s, idx, H, x1, nq, ns, H, mid, mid, t2, A, st));
+    KFE_OK(norm_call(t2, nq, mid, 0.1f, nullptr, 0, t2, A, st));
+    KFE_ALLOC(t3, float, (size_t)nq * cout);
+    KFE_OK(linear_call(t2, b.unary2_W, nq, mid, cout, t3, A, st)); // unary2 (IN folded into the final kernel)
+    const float* sc = feat;
+    if (b.strided) {                                               // shortcut = max_pool(features, pools)
+        KFE_ALLOC(mp, float, (size_t)nq * b.in_dim);
+        KFE_OK(aprb_max_pool(feat, idx, 0, H, nq, ns, H, b.in_dim, nullptr, mp, st));
+        sc = mp;
+    }
+    if (b.shortcut_W) {                                            // LeakyReLU(IN(x3) + IN(Linear(sc)))
+        KFE_ALLOC(t4, float, (size_t)nq * cout);
+        KFE_OK(linear_call(sc, b.shortcut_W, nq, b.in_dim, cout, t4, A, st));
+        KFE_OK(norm_call(t3, nq, cout, 0.1f, t4, 1, y, A, st));
+    } else {                                                       // LeakyReLU(IN(x3) + sc)
+        KFE_OK(norm_call(t3, nq, cout, 0.1f, sc, 0, y, A, st));
+    }
+    A.off = mark;
+    *out = y; *out_cols = cout;
+    return APRB_OK;
+}
+
+__global__ void fill_kernel(float* p, size_t n, float v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}  // namespace
+
+extern "C" int aprb_kfe_create(const aprb_kfe_config* cfg, const aprb_kfe_block* blocks, int nblocks, aprb_kfe** out) {
+    APRB_REQUIRE(cfg && blocks && out && nblocks >= 1, "null argument");
+    APRB_REQUIRE(cfg->num_layers >= 1 && cfg->num_layers <= KFE_MAX_LEVELS, "num_layers out of range");
+    APRB_REQUIRE(cfg->K >= 1 && cfg->K <= 16, "K out of range");
+    for (int i = 0; i < nblocks; ++i) {
+        const aprb_kfe_block& b = blocks[i];
+        APRB_REQUIRE(b.layer >= 0 && b.layer < cfg->num_layers && (!b.strided || b.layer + 1 < cfg->num_layers), "block layer out of range");
+        APRB_REQUIRE(b.kp && b.kp_W, "block without KPConv parameters");
+        if (b.type == 1) {
+            APRB_REQUIRE(b.unary2_W, "resnet block without unary2 weights");
+            const int mid = b.out_dim / 4;
+            bool ok = mid % 32 == 0 && b.out_dim % 16 == 0 && b.in_dim % 32 == 0;
+            if (!ok) { set_error("aprb_kfe_create: block %d dims (%d -> %d) not supported by the tcgen05 Linear", i, b.in_dim, b.out_dim); return APRB_ERR_UNSUPPORTED; }
+        }
+    }
+    aprb_kfe* h = new (std::nothrow) aprb_kfe();
+    APRB_REQUIRE(h, "out of host memory");
+    h->cfg = *cfg;
+    h->blocks.assign(blocks, blocks + nblocks);
+    h->h_counts = nullptr; h->h_counts_cap = 0; h->B = 0;
+    for (int l = 0; l < KFE_MAX_LEVELS; ++l) {
+        h->ev[l] = nullptr; h->n[l] = 0; h->pts[l] = nullptr; h->lens[l] = nullptr; h->conv[l] = h->pool[l] = h->up[l] = nullptr;
+        if (cudaEventCreateWithFlags(&h->ev[l], cudaEventDisableTiming) != cudaSuccess) { set_error("cudaEventCreate failed"); delete h; return APRB_ERR_CUDA; }
+    }
+    *out = h;
+    return APRB_OK;
+}
+
+extern "C" void aprb_kfe_destroy(aprb_kfe* h) {
+    if (!h) return;
+    for (int l = 0; l < KFE_MAX_LEVELS; ++l) if (h->ev[l]) cudaEventDestroy(h->ev[l]);
+    if (h->h_counts) cudaFreeHost(h->h_counts);
+    delete h;
+}
+
+extern "C" size_t aprb_kfe_arena_bytes(const aprb_kfe* h, int N, int B) {
+    if (!h || N < 0 || B < 1) return 0;
+    // Generous closed form (HBM is 180 GB; a KITTI pair needs ~1.2 GB): pyramid + block outputs + the largest
+    // temporaries/scratch, all with the level-0 point count as the bound for every level.
+    size_t n = (size_t)(N > 0 ? N : 1);
+    size_t pyramid = 0, lim = 0;
+    for (int l = 0; l < h->cfg.num_layers; ++l) {
+        lim = (size_t)h->cfg.limits[l];
+        pyramid += 3 * align256(n * lim * 4) + align256(n * 12) + aprb_cell_grid_bytes((int)n, B) + 4096;
+    }
+    size_t feats = 0, worst_tmp = 0;
+    for (const aprb_kfe_block& b : h->blocks) {
+        size_t cout = b.type == 0 ? b.out_dim / 2 : b.out_dim, cin_k = b.type == 0 ? b.in_dim : b.out_dim / 4;
+        feats += align256(n * cout * 4);
+        size_t tmp = n * 4 * (2 * (size_t)(b.out_dim / 4) + 2 * cout + b.in_dim) + 8 * 256;
+        size_t kpw = aprb_kpconv_ws_bytes((int)n, (int)n, (int)lim, h->cfg.K, (int)cin_k, (int)(b.type == 0 ? cout : cin_k));
+        size_t lin = aprb_linear_tf32_ws_bytes((int)n, b.in_dim, (int)cout);
+        size_t scratch = kpw > lin ? kpw : lin;
+        if (tmp + scratch > worst_tmp) worst_tmp = tmp + scratch;
+    }
+    size_t sub = aprb_grid_subsample_ws_bytes((int)n, B, 0);
+    return pyramid + feats + worst_tmp + sub + align256(n * 4) + (1u << 20);
+}
+
+extern "C" int aprb_kfe_forward(aprb_kfe* hp, const float* d_pts, const int32_t* d_lens, const float* d_feats, int N, int B,
+                                void* d_arena, size_t arena_bytes, const float** out_feats, int* out_rows, int* out_cols,
+                                void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    APRB_REQUIRE(hp && d_pts && d_lens && d_arena && out_feats && out_rows && out_cols, "null argument");
+    APRB_REQUIRE(N >= 1 && B >= 1, "need N >= 1 and B >= 1");
+    aprb_kfe& h = *hp;
+    const aprb_kfe_config& cfg = h.cfg;
+    const int L = cfg.num_layers;
+    if (h.h_counts_cap < (2 + B) * KFE_MAX_LEVELS) {
+        if (h.h_counts) cudaFreeHost(h.h_counts);
+        h.h_counts_cap = (2 + B) * KFE_MAX_LEVELS;
+        APRB_CUDA_OK(cudaMallocHost(&h.h_counts, sizeof(int) * h.h_counts_cap));
+    }
+    Arena A(d_arena, arena_bytes);
+    h.B = B;
+    h.n[0] = N; h.pts[0] = d_pts; h.lens[0] = d_lens;
+    for (int l = 0; l < KFE_MAX_LEVELS; ++l) { h.conv[l] = h.pool[l] = h.up[l] = nullptr; if (l) { h.n[l] = 0; h.pts[l] = nullptr; h.lens[l] = nullptr; } }
+
+    const float* x = d_feats;
+    int xc = cfg.in_feats_dim;
+    if (!x) {                                                      // features = ones (datasets/kitti.py:598-599)
+        KFE_ALLOC(ones, float, (size_t)N * xc);
+        APRB_TIMED("fill_kernel", st, 1, (fill_kernel<<<cdiv((long long)N * xc, 256), 256, 0, st>>>(ones, (size_t)N * xc, 1.0f)));
+        x = ones;
+    }
+
+    float r = cfg.first_subsampling_dl * cfg.conv_radius;          // dataloader.py:93
+    void* grid[KFE_MAX_LEVELS] = {nullptr};
+    size_t grid_bytes[KFE_MAX_LEVELS] = {0};
+    size_t bi = 0;                                                  // next encoder block
+    auto run_blocks = [&](int level, int strided) -> int {
+        while (bi < h.blocks.size() && h.blocks[bi].layer == level && (h.blocks[bi].strided != 0) == (strided != 0)) {
+            const float* y = nullptr; int yc = 0;
+            KFE_OK(run_block(h, h.blocks[bi], x, &y, &yc, A, st));
+            x = y; xc = yc; ++bi;
+        }
+        return APRB_OK;
+    };
+
+    for (int l = 0; l < L; ++l) {
+        const int lim = cfg.limits[l];
+        APRB_REQUIRE(lim >= 1, "neighbourhood limit must be >= 1");
+        if (l == 0) {
+            grid_bytes[0] = aprb_cell_grid_bytes(h.n[0], B);
+            grid[0] = A.take<char>(grid_bytes[0]);
+            if (!grid[0]) { set_error("aprb_kfe_forward: arena too small"); return APRB_ERR_WORKSPACE; }
+            KFE_OK(aprb_cell_grid_build(h.pts[0], h.lens[0], B, h.n[0], r, grid[0], grid_bytes[0], st));
+        }
+        KFE_ALLOC(conv, int, (size_t)h.n[l] * lim);
+        KFE_OK(aprb_cell_grid_query(grid[l], grid_bytes[l], h.pts[l], h.lens[l], B, h.n[l], h.n[l], r, lim, conv, lim, nullptr, nullptr, st));
+        h.conv[l] = conv;
+        float* npts = nullptr; int* nlens = nullptr; int* dcnt = nullptr;
+        int* hc = h.h_counts + (2 + B) * l;
+        if (l + 1 < L) {                                           // subsample now, read the count back later
+            npts = A.take<float>((size_t)h.n[l] * 3); nlens = A.take<int>(B); dcnt = A.take<int>(2);
+            if (!npts || !nlens || !dcnt) { set_error("aprb_kfe_forward: arena too small"); return APRB_ERR_WORKSPACE; }
+            const float dl = 2 * r / cfg.conv_radius;              // dataloader.py:138
+            if (A.scratch_bytes() < aprb_grid_subsample_ws_bytes(h.n[l], B, 0)) { set_error("aprb_kfe_forward: arena too small"); return APRB_ERR_WORKSPACE; }
+            KFE_OK(aprb_grid_subsample_batch(h.pts[l], h.lens[l], B, h.n[l], dl, 0, nullptr, 0, npts, nlens, dcnt, nullptr, dcnt + 1, 32,
+                                             A.scratch(), A.scratch_bytes(), st));
+            APRB_CUDA_OK(cudaMemcpyAsync(hc, dcnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            APRB_CUDA_OK(cudaMemcpyAsync(hc + 2, nlens, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+            APRB_CUDA_OK(cudaEventRecord(h.ev[l], st));
+        }
+        KFE_OK(run_blocks(l, 0));                                  // queue this level's non-strided blocks first
+        if (l + 1 < L) {
+            APRB_CUDA_OK(cudaEventSynchronize(h.ev[l]));           // only waits for the subsample, not for the blocks
+            if (hc[1] == 2) {                                      // grid needs the 64-bit key: redo (rare, synchronous)
+                const float dl = 2 * r / cfg.conv_radius;
+                KFE_OK(aprb_grid_subsample_batch(h.pts[l], h.lens[l], B, h.n[l], dl, 0, nullptr, 0, npts, nlens, dcnt, nullptr, dcnt + 1, 64,
+                                                 A.scratch(), A.scratch_bytes(), st));
+                APRB_CUDA_OK(cudaMemcpyAsync(hc, dcnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+                APRB_CUDA_OK(cudaStreamSynchronize(st));
+            }
+            if (hc[1] != 0) { set_error("aprb_kfe_forward: voxel grid of level %d does not fit the sort key", l); return APRB_ERR_UNSUPPORTED; }
+            if (hc[0] < 1) { set_error("aprb_kfe_forward: level %d is empty", l + 1); return APRB_ERR_EMPTY; }
+            h.n[l + 1] = hc[0]; h.pts[l + 1] = npts; h.lens[l + 1] = nlens;
+            KFE_ALLOC(pool, int, (size_t)h.n[l + 1] * lim);
+            KFE_OK(aprb_cell_grid_query(grid[l], grid_bytes[l], npts, nlens, B, h.n[l + 1], h.n[l], r, lim, pool, lim, nullptr, nullptr, st));
+            h.pool[l] = pool;
+            grid_bytes[l + 1] = aprb_cell_grid_bytes(h.n[l + 1], B);
+            grid[l + 1] = A.take<char>(grid_bytes[l + 1]);
+            if (!grid[l + 1]) { set_error("aprb_kfe_forward: arena too small"); return APRB_ERR_WORKSPACE; }
+            KFE_OK(aprb_cell_grid_build(npts, nlens, B, h.n[l + 1], 2 * r, grid[l + 1], grid_bytes[l + 1], st));
+            if (cfg.build_upsamples) {
+                KFE_ALLOC(up, int, (size_t)h.n[l] * lim);
+                KFE_OK(aprb_cell_grid_query(grid[l + 1], grid_bytes[l + 1], h.pts[l], h.lens[l], B, h.n[l], h.n[l + 1], 2 * r, lim, up, lim, nullptr, nullptr, st));
+                h.up[l] = up;
+            }
+            KFE_OK(run_blocks(l, 1));                              // the strided block that closes the level
+        }
+        r *= 2;
+    }
+    if (bi != h.blocks.size()) { set_error("aprb_kfe_forward: %zu block(s) not scheduled (check layer/strided order)", h.blocks.size() - bi); return APRB_ERR_INVALID; }
+    *out_feats = x; *out_rows = h.n[h.blocks.back().strided ? h.blocks.back().layer + 1 : h.blocks.back().layer]; *out_cols = xc;
+    return APRB_OK;
+}
+
+extern "C" int aprb_kfe_forward_host(aprb_kfe* h, const float* h_pts, const int32_t* h_lens, int N, int B, void* d_arena,
+                                     size_t arena_bytes, float* h_out, int h_out_rows_cap, int* out_rows, int* out_cols,
+                                     void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    APRB_REQUIRE(h && h_pts && h_lens && d_arena && h_out && out_rows && out_cols, "null argument");
+    APRB_REQUIRE(N >= 1 && B >= 1, "need N >= 1 and B >= 1");
+    size_t head = align256((size_t)N * 12) + align256((size_t)B * 4);
+    if (arena_bytes <= head) { set_error("aprb_kfe_forward_host: arena too small"); return APRB_ERR_WORKSPACE; }
+    float* d_pts = (float*)d_arena;
+    int* d_lens = (int*)((char*)d_arena + align256((size_t)N * 12));
+    APRB_CUDA_OK(cudaMemcpyAsync(d_pts, h_pts, (size_t)N * 12, cudaMemcpyHostToDevice, st));
+    APRB_CUDA_OK(cudaMemcpyAsync(d_lens, h_lens, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    const float* y = nullptr;
+    KFE_OK(aprb_kfe_forward(h, d_pts, d_lens, nullptr, N, B, (char*)d_arena + head, arena_bytes - head, &y, out_rows, out_cols, st));
+    if (*out_rows > h_out_rows_cap) { set_error("aprb_kfe_forward_host: output has %d rows, buffer holds %d", *out_rows, h_out_rows_cap); return APRB_ERR_WORKSPACE; }
+    APRB_CUDA_OK(cudaMemcpyAsync(h_out, y, (size_t)(*out_rows) * (*out_cols) * sizeof(float), cudaMemcpyDeviceToHost, st));
+    APRB_CUDA_OK(cudaStreamSynchronize(st));
+    return APRB_OK;
+}
+
+extern "C" int aprb_kfe_get(const aprb_kfe* h, int what, int level, const void** d_ptr, int* rows, int* cols) {
+    APRB_REQUIRE(h && d_ptr && rows && cols, "null argument");
+    APRB_REQUIRE(level >= 0 && level < h->cfg.num_layers, "level out of range");
+    const int lim = h->cfg.limits[level];
+    switch (what) {
+        case 0: *d_ptr = h->pts[level]; *rows = h->n[level]; *cols = 3; break;
+        case 1: *d_ptr = h->conv[level]; *rows = h->conv[level] ? h->n[level] : 0; *cols = lim; break;
+        case 2: *d_ptr = h->pool[level]; *rows = h->pool[level] ? h->n[level + 1] : 0; *cols = lim; break;
+        case 3: *d_ptr = h->up[level]; *rows = h->up[level] ? h->n[level] : 0; *cols = lim; break;
+        case 4: *d_ptr = h->lens[level]; *rows = h->B; *cols = 1; break;
+        default: set_error("aprb_kfe_get: unknown selector %d", what); return APRB_ERR_INVALID;
+    }
+    return APRB_OK;
+}

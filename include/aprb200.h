@@ -140,6 +140,56 @@ int aprb_linear_tf32(const float* d_x, const float* d_W, int N, int Cin, int Cou
 /* out[i] = in[i] rounded to TF32 (round to nearest, ties away). Used once per weight update for mlp.weight. */
 int aprb_round_tf32(const float* d_in, float* d_out, size_t n, void* stream);
 
+/* ---------------------------------------------------------------- whole path: pyramid + KFE encoder ---------- */
+/* One call = collate_fn_descriptor (datasets/dataloader.py:72-198: 3 subsamplings + 10 radius searches, cell lists
+ * shared between searches) + the encoder loop of KPFCNN.forward (models/architectures.py:149-153) for one stacked
+ * batch of clouds, driven from native code on one stream: ~3 us of host time per launch instead of a Python call, the
+ * host reads the per-level point counts through events so it never waits for the encoder kernels, and several
+ * handles can run concurrently from several host threads (one stream each). */
+typedef struct {
+    int type;                 /* 0 = SimpleBlock, 1 = ResnetBottleneckBlock                     (blocks.py:539, :596)   */
+    int strided;              /* 'strided' in block_name: queries = next level, indices = pools (blocks.py:583-590)      */
+    int layer;                /* layer_ind                                                                                */
+    int in_dim, out_dim;      /* block dims as passed to block_decider (KPConv runs on out_dim/2 or out_dim/4 channels)   */
+    float radius, extent;     /* KPConv radius / KP_extent of this block                                                  */
+    const float* kp;          /* [K,3]                                                                                    */
+    const float* kp_W;        /* [K,Cin,Cout] raw KPConv weights                                                          */
+    const float* kp_Wprep;    /* prepared [Cout, K*Cin] (aprb_kpconv_prepare_weights) or NULL (fp32 CUDA-core path)       */
+    const float* unary1_W;    /* [out/4, in]  TF32-rounded (aprb_round_tf32), NULL when the block has nn.Identity         */
+    const float* unary2_W;    /* [out, out/4] TF32-rounded                                                                */
+    const float* shortcut_W;  /* [out, in]    TF32-rounded, NULL when in_dim == out_dim                                   */
+} aprb_kfe_block;
+
+typedef struct {
+    int num_layers;           /* pyramid levels (4)                                        configs/train/kitti.yaml:12    */
+    int K;                    /* kernel points (15)                                                                       */
+    float first_subsampling_dl, conv_radius;
+    int limits[8];            /* neighbourhood limit per level (calibrate_neighbors, dataloader.py:200-232)               */
+    int build_upsamples;      /* also run the 3 upsample searches (needed by the decoder; part of the collate)            */
+    int in_feats_dim;         /* 1                                                                                         */
+} aprb_kfe_config;
+
+typedef struct aprb_kfe aprb_kfe;
+
+int aprb_kfe_create(const aprb_kfe_config* cfg, const aprb_kfe_block* blocks, int nblocks, aprb_kfe** out);
+void aprb_kfe_destroy(aprb_kfe* h);
+/* Device arena needed for a stacked batch of at most N points in B clouds. */
+size_t aprb_kfe_arena_bytes(const aprb_kfe* h, int N, int B);
+/* d_pts [N,3] level-0 points (already at first_subsampling_dl), d_lens [B]; d_feats [N,in_feats_dim] or NULL (= ones).
+ * Runs on `stream`, returns after the last kernel is ENQUEUED (it waits only for the three point-count read-backs).
+ * *out_feats receives a device pointer into the arena: encoder output [*out_rows, *out_cols] fp32. */
+int aprb_kfe_forward(aprb_kfe* h, const float* d_pts, const int32_t* d_lens, const float* d_feats, int N, int B,
+                     void* d_arena, size_t arena_bytes, const float** out_feats, int* out_rows, int* out_cols,
+                     void* stream);
+/* Same from HOST buffers (pinned memory recommended): H2D of points/lengths, forward, D2H of the encoder output into
+ * h_out (capacity h_out_rows_cap rows of *out_cols floats); synchronises `stream` before returning. */
+int aprb_kfe_forward_host(aprb_kfe* h, const float* h_pts, const int32_t* h_lens, int N, int B, void* d_arena,
+                          size_t arena_bytes, float* h_out, int h_out_rows_cap, int* out_rows, int* out_cols,
+                          void* stream);
+/* After a forward: pyramid tensors in the arena. what: 0 = points [n,3] f32, 1 = neighbors, 2 = pools, 3 = upsamples
+ * (int32 [n, limit]), 4 = stack lengths [B] i32. Pointers stay valid until the next forward on this handle. */
+int aprb_kfe_get(const aprb_kfe* h, int what, int level, const void** d_ptr, int* rows, int* cols);
+
 #ifdef __cplusplus
 }
 #endif
