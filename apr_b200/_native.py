@@ -39,6 +39,11 @@ SIGNATURES = {
     "aprb_linear_tf32_ws_bytes": (_sz, [_i, _i, _i]),
     "aprb_linear_tf32": (_i, [_p, _p, _i, _i, _i, _p, _p, _sz, _p]),
     "aprb_round_tf32": (_i, [_p, _p, _sz, _p]),
+    "aprb_kfe_create": (_i, [_p, _p, _i, _p]),
+    "aprb_kfe_arena_bytes": (_sz, [_p, _i, _i]),
+    "aprb_kfe_forward": (_i, [_p, _p, _p, _p, _i, _i, _p, _sz, _p, _p, _p, _p]),
+    "aprb_kfe_forward_host": (_i, [_p, _p, _p, _i, _i, _p, _sz, _p, _i, _p, _p, _p]),
+    "aprb_kfe_get": (_i, [_p, _i, _i, _p, _p, _p]),
 }
 
 _lib = None
@@ -61,6 +66,8 @@ def lib():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
+        l.aprb_kfe_destroy.restype = None
+        l.aprb_kfe_destroy.argtypes = [_p]
         _lib = l
     return _lib
 

@@ -1,0 +1,146 @@
+"""Native whole-path runner: pyramid (collate) + KFE encoder blocks in ONE C-ABI call (`aprb_kfe_forward`).
+
+The Python module path (`apr_b200.dataloader.build_pyramid_device` + `apr_b200.architectures.KPFCNNEncoder`) issues
+~250 native calls per pair from Python; this wrapper hands the same schedule to `apr_b200/csrc/pipeline.cu`, which
+sequences the same kernels from C++ (mirror of datasets/dataloader.py:72-198 and models/architectures.py:149-153).
+Several pipelines can run concurrently from several host threads (one CUDA stream each; ctypes releases the GIL).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import blocks, ops
+
+
+class _Block(C.Structure):
+    _fields_ = [("type", C.c_int), ("strided", C.c_int), ("layer", C.c_int), ("in_dim", C.c_int), ("out_dim", C.c_int),
+                ("radius", C.c_float), ("extent", C.c_float), ("kp", C.c_void_p), ("kp_W", C.c_void_p),
+                ("kp_Wprep", C.c_void_p), ("unary1_W", C.c_void_p), ("unary2_W", C.c_void_p), ("shortcut_W", C.c_void_p)]
+
+
+class _Config(C.Structure):
+    _fields_ = [("num_layers", C.c_int), ("K", C.c_int), ("first_subsampling_dl", C.c_float), ("conv_radius", C.c_float),
+                ("limits", C.c_int * 8), ("build_upsamples", C.c_int), ("in_feats_dim", C.c_int)]
+
+
+class KFEPipeline:
+    """encoder: an `apr_b200.architectures.KPFCNNEncoder` on a CUDA device (its parameters are used in place)."""
+
+    def __init__(self, encoder, config, neighborhood_limits, build_upsamples=True, stream=None):
+        N.require_cuda()
+        self.lib = N.lib()
+        self.config = config
+        self.device = next(encoder.parameters()).device
+        self.stream = stream if stream is not None else torch.cuda.current_stream(self.device)
+        self._keep = []                      # tensors whose device memory the native handle points into
+        blks = []
+        with torch.cuda.stream(self.stream):
+            for m in encoder.encoder_blocks:
+                b = _Block()
+                conv = m.KPConv
+                b.type = 0 if isinstance(m, blocks.SimpleBlock) else 1
+                b.strided = 1 if 'strided' in m.block_name else 0
+                b.layer, b.in_dim, b.out_dim = m.layer_ind, m.in_dim, m.out_dim
+                b.radius, b.extent = float(conv.radius), float(conv.KP_extent)
+                kp = conv.kernel_points.detach().float().contiguous()
+                w = conv.weights.detach().float().contiguous()
+                self._keep += [kp, w]
+                b.kp, b.kp_W = kp.data_ptr(), w.data_ptr()
+                if (conv.K * conv.in_channels) % 32 == 0 and conv.out_channels % 16 == 0:
+                    wp = ops.kpconv_prepare_weights(w)
+                    self._keep.append(wp)
+                    b.kp_Wprep = wp.data_ptr()
+                for name in ("unary1", "unary2", "unary_shortcut"):
+                    sub = getattr(m, name, None)
+                    if isinstance(sub, blocks.UnaryBlock):
+                        wt = ops.round_tf32(sub.mlp.weight)
+                        self._keep.append(wt)
+                        setattr(b, {"unary1": "unary1_W", "unary2": "unary2_W", "unary_shortcut": "shortcut_W"}[name],
+                                wt.data_ptr())
+                blks.append(b)
+        cfg = _Config()
+        cfg.num_layers, cfg.K = config.num_layers, config.num_kernel_points
+        cfg.first_subsampling_dl, cfg.conv_radius = config.first_subsampling_dl, config.conv_radius
+        for i, v in enumerate(list(neighborhood_limits)[:8]):
+            cfg.limits[i] = int(v)
+        cfg.build_upsamples = 1 if build_upsamples else 0
+        cfg.in_feats_dim = config.in_feats_dim
+        arr = (_Block * len(blks))(*blks)
+        h = C.c_void_p()
+        N.check(self.lib.aprb_kfe_create(C.byref(cfg), arr, len(blks), C.byref(h)), "aprb_kfe_create")
+        self.handle = h
+        self.arena = None
+        self._out_cols = blks[-1].out_dim if blks[-1].type == 1 else blks[-1].out_dim // 2
+        self._host_out = None
+        self.stream.synchronize()
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.aprb_kfe_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def _ensure_arena(self, n, b):
+        need = self.lib.aprb_kfe_arena_bytes(self.handle, int(n), int(b))
+        if self.arena is None or self.arena.numel() < need:
+            self.arena = torch.empty(int(need * 1.1) + 4096, dtype=torch.uint8, device=self.device)
+        return self.arena
+
+    def _view(self, ptr, rows, cols, dtype):
+        off = ptr - self.arena.data_ptr()
+        nbytes = rows * cols * 4
+        return self.arena[off:off + nbytes].view(dtype).view(rows, cols)
+
+    def forward(self, points, lengths):
+        """points [N,3] f32 cuda, lengths [B] i32 cuda -> encoder output [N_last, C] (a view into the arena, valid until
+        the next forward). Kernels are queued on self.stream; the call returns without waiting for them."""
+        pts, lens = points.float().contiguous(), lengths.int().contiguous()
+        arena = self._ensure_arena(pts.shape[0], lens.shape[0])
+        out, rows, cols = C.c_void_p(), C.c_int(), C.c_int()
+        rc = self.lib.aprb_kfe_forward(self.handle, pts.data_ptr(), lens.data_ptr(), None, pts.shape[0], lens.shape[0],
+                                       arena.data_ptr(), arena.numel(), C.byref(out), C.byref(rows), C.byref(cols),
+                                       C.c_void_p(self.stream.cuda_stream))
+        N.check(rc, "aprb_kfe_forward")
+        self._last_inputs = (pts, lens)
+        return self._view(out.value, rows.value, cols.value, torch.float32)
+
+    def forward_host(self, points, lengths, out=None):
+        """points [N,3] f32 / lengths [B] i32 HOST tensors (pinned recommended) -> encoder output as a pinned host
+        tensor [N_last, C]; does H2D, the whole path and D2H, and synchronises the stream."""
+        pts = points if isinstance(points, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(points, np.float32))
+        lens = lengths if isinstance(lengths, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(lengths, np.int32))
+        pts, lens = pts.float().contiguous(), lens.int().contiguous()
+        n, b = pts.shape[0], lens.shape[0]
+        arena = self._ensure_arena(n, b)
+        if out is None:
+            if self._host_out is None or self._host_out.shape[0] < n:
+                self._host_out = torch.empty((n, self._out_cols), dtype=torch.float32).pin_memory()
+            out = self._host_out
+        rows, cols = C.c_int(), C.c_int()
+        rc = self.lib.aprb_kfe_forward_host(self.handle, pts.data_ptr(), lens.data_ptr(), n, b, arena.data_ptr(),
+                                            arena.numel(), out.data_ptr(), out.shape[0], C.byref(rows), C.byref(cols),
+                                            C.c_void_p(self.stream.cuda_stream))
+        N.check(rc, "aprb_kfe_forward_host")
+        return out[:rows.value]
+
+    def pyramid(self):
+        """The batch dict of the last forward (views into the arena): points, neighbors, pools, upsamples, stack_lengths."""
+        out = dict(points=[], neighbors=[], pools=[], upsamples=[], stack_lengths=[])
+        names = {0: ("points", torch.float32), 1: ("neighbors", torch.int32), 2: ("pools", torch.int32),
+                 3: ("upsamples", torch.int32), 4: ("stack_lengths", torch.int32)}
+        for lvl in range(self.config.num_layers):
+            for what, (key, dt) in names.items():
+                p, r, c = C.c_void_p(), C.c_int(), C.c_int()
+                N.check(self.lib.aprb_kfe_get(self.handle, what, lvl, C.byref(p), C.byref(r), C.byref(c)), "aprb_kfe_get")
+                if not p.value or r.value == 0:
+                    t = torch.zeros((0, max(c.value, 1)), dtype=dt, device=self.device)
+                elif lvl == 0 and what in (0, 4):          # level-0 points / lengths are the caller's own tensors
+                    t = self._last_inputs[0] if what == 0 else self._last_inputs[1].view(-1, 1)
+                else:
+                    t = self._view(p.value, r.value, c.value, dt)
+                out[key].append(t.view(-1) if what == 4 else t)
+        return out

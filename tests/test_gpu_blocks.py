@@ -190,3 +190,50 @@ def test_blocks_vs_oracle_kitti_width(cuda, oracle, linear_mode):
         worst = max(worst, e)
         assert e < TOL_TF32, f"{name} {cin}->{cout}: rel err {e:.2e}"
     print(f"worst per-block rel err {worst:.2e}")
+
+
+def test_native_pipeline_matches_module_path(cuda, oracle):
+    """aprb_kfe_forward (C++ driver: pyramid + encoder in one call) == Python module path, and its pyramid == oracle."""
+    from apr_b200 import dataloader, synth
+    from apr_b200.pipeline import KFEPipeline
+    cfg = kitti_config()
+    a, b = synth.small_cloud(51, 3000), synth.small_cloud(52, 2600)
+    raw = np.concatenate([a, b]); lens = np.array([len(a), len(b)], np.int32)
+    p0, l0 = oracle.subsample_batch(raw, lens, sampleDl=0.3)
+    limits = [30, 31, 32, 33]
+    torch.manual_seed(0); np.random.seed(0)
+    enc = KPFCNNEncoder(cfg).to(cuda).eval()
+    dp, dl_ = _t(p0, cuda), _t(l0, cuda)
+    blocks.LINEAR_MODE = 'tf32'
+    try:
+        want = enc(dataloader.build_pyramid_device(dp, dl_, cfg, limits))
+    finally:
+        blocks.LINEAR_MODE = 'fp32'
+    pipe = KFEPipeline(enc, cfg, limits)
+    got = pipe.forward(dp, dl_)
+    torch.cuda.synchronize()
+    assert got.shape == want.shape
+    assert torch.equal(got, want)                                   # same kernels, same order -> bit-identical
+    ref = collate_ref(p0, l0, cfg, limits, oracle.subsample_batch, oracle.batch_query)
+    pyr = pipe.pyramid()
+    for k in ("points", "neighbors", "pools", "upsamples"):
+        for lvl in range(4):
+            w = ref[k][lvl]
+            d = pyr[k][lvl].cpu().numpy()
+            if w.shape[0] == 0:
+                assert d.shape[0] == 0
+            elif k == "points":
+                assert np.array_equal(d, w)
+            else:
+                assert np.array_equal(d[:, :w.shape[1]], w), (k, lvl)
+    # host-buffer entry point (H2D + path + D2H)
+    host = pipe.forward_host(torch.from_numpy(p0).pin_memory(), torch.from_numpy(l0).pin_memory())
+    assert torch.equal(host, want.cpu())
+    # vs the fp32 CPU oracle end to end (drift over 11 blocks, TF32 tensor path): reported, loose bound
+    cpu = dict(points=[torch.from_numpy(p) for p in ref["points"]], neighbors=[torch.from_numpy(n).long() for n in ref["neighbors"]],
+               pools=[torch.from_numpy(n).long() for n in ref["pools"]], features=torch.ones(len(p0), 1))
+    sd = {k: v.detach().cpu() for k, v in enc.state_dict().items()}
+    y = blocks_ref.encoder_ref(cpu, sd, cfg)
+    e = rel(got, y)
+    print(f"end-of-encoder drift vs fp32 oracle (11 blocks, TF32): {e:.2e}")
+    assert e < 1e-2
