@@ -170,9 +170,30 @@ def algorithmic_work(trace):
     return w, n
 
 
+def encoder_shapes(enc, n_levels):
+    """Op trace [(kind, ...)] of one pass derived from the block list and the per-level point counts."""
+    from apr_b200 import blocks
+    tr = []
+    for m in enc.encoder_blocks:
+        l = m.layer_ind
+        strided = 'strided' in m.block_name
+        nq, ns = (n_levels[l + 1] if strided else n_levels[l]), n_levels[l]
+        c = m.KPConv
+        if isinstance(m, blocks.ResnetBottleneckBlock):
+            if isinstance(m.unary1, blocks.UnaryBlock):
+                tr.append(("linear", ns, m.in_dim, m.out_dim // 4))
+            tr.append(("linear", nq, m.out_dim // 4, m.out_dim))
+            if isinstance(m.unary_shortcut, blocks.UnaryBlock):
+                tr.append(("linear", nq, m.in_dim, m.out_dim))
+        tr.append(("kpconv", nq, ns, None, c.K, c.in_channels, c.out_channels))
+    return tr
+
+
 def run_ours(args):
+    from concurrent.futures import ThreadPoolExecutor
     from apr_b200 import _native, blocks, dataloader, ops
     from apr_b200.architectures import KPFCNNEncoder
+    from apr_b200.pipeline import KFEPipeline
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     _native.require_cuda()
@@ -182,39 +203,54 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     cfg = kitti_config()
-    torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32_linear)
-    if args.linear_mode:
-        blocks.LINEAR_MODE = args.linear_mode
+    blocks.LINEAR_MODE = "tf32"
+    S = max(1, args.streams)
 
-    # ---- inputs: n_pairs distinct pairs per rank, first-level 0.3 m voxelisation done up front (not part of the path)
+    # ---- inputs: distinct pairs per rank, first-level 0.3 m voxelisation done up front (not part of the path)
     pairs_dev, pairs_host = [], []
-    for a, b in raw_pairs(args.pairs, 1000 * rank):
+    for a, b in raw_pairs(max(args.pairs, S), 1000 * rank):
         raw = torch.from_numpy(np.concatenate([a, b])).to(dev)
         lens = torch.tensor([len(a), len(b)], dtype=torch.int32, device=dev)
         p0, l0 = ops.grid_subsample(raw, lens, cfg.first_subsampling_dl)
-        pairs_dev.append((p0.contiguous(), l0))
+        pairs_dev.append((p0.contiguous().clone(), l0.clone()))
         pairs_host.append((p0.cpu().pin_memory(), l0.cpu().pin_memory()))
     torch.manual_seed(0); np.random.seed(0)
     enc = KPFCNNEncoder(cfg).to(dev).eval()
     limits = dataloader.calibrate_neighbors_device(pairs_dev, cfg) if not args.no_calibrate else LIMITS_FALLBACK
     limits = [int(x) for x in limits]
+    torch.cuda.synchronize(dev)
+
+    # ---- S native pipelines, one CUDA stream and one host thread each (aprb_kfe_forward releases the GIL)
+    streams = [torch.cuda.Stream(dev) for _ in range(S)]
+    pipes = [KFEPipeline(enc, cfg, limits, build_upsamples=True, stream=streams[k]) for k in range(S)]
+    pool = ThreadPoolExecutor(max_workers=S) if S > 1 else None
+    main_stream = torch.cuda.current_stream(dev)
+    done_ev = [torch.cuda.Event() for _ in range(S)]
+
+    def fan_out(fn, i):
+        """Run fn(k, pair_index) for the S pipelines concurrently; device-side ordering via events."""
+        start = torch.cuda.Event()
+        start.record(main_stream)
+        def work(k):
+            streams[k].wait_event(start)
+            r = fn(k, (i * S + k))
+            done_ev[k].record(streams[k])
+            return r
+        res = list(pool.map(work, range(S))) if pool else [work(0)]
+        for k in range(S):
+            main_stream.wait_event(done_ev[k])
+        return res
 
     def step_dev(i):
-        p0, l0 = pairs_dev[i % len(pairs_dev)]
-        pyr = dataloader.build_pyramid_device(p0, l0, cfg, limits)
-        return enc(pyr)
-
-    out_host = {}
+        return fan_out(lambda k, j: pipes[k].forward(*pairs_dev[j % len(pairs_dev)]), i)
 
     def step_e2e(i):
-        hp, hl = pairs_host[i % len(pairs_host)]
-        p0 = hp.to(dev, non_blocking=True); l0 = hl.to(dev, non_blocking=True)
-        y = enc(dataloader.build_pyramid_device(p0, l0, cfg, limits))
-        buf = out_host.get(y.shape)
-        if buf is None:
-            buf = out_host[y.shape] = torch.empty(y.shape, dtype=y.dtype).pin_memory()
-        buf.copy_(y, non_blocking=True)
-        return hp.numel() * 4 + hl.numel() * 4, y.numel() * 4
+        def one(k, j):
+            hp, hl = pairs_host[j % len(pairs_host)]
+            y = pipes[k].forward_host(hp, hl)            # H2D + whole path + D2H, synchronises its stream
+            return hp.numel() * 4 + hl.numel() * 4, y.numel() * 4
+        r = fan_out(one, i)
+        return sum(x[0] for x in r), sum(x[1] for x in r)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -239,9 +275,9 @@ def run_ours(args):
         t0 = time.perf_counter()
         for i in range(steps):
             flush.zero_()                                    # L2 flush (256 MiB), outside the timed event pair
-            ev[i][0].record()
+            ev[i][0].record(main_stream)
             r = fn(warmup + i)
-            ev[i][1].record()
+            ev[i][1].record(main_stream)
         barrier()
         wall = time.perf_counter() - t0
         per = [a.elapsed_time(b) for a, b in ev]
@@ -254,62 +290,66 @@ def run_ours(args):
     clocks = clk.stop()
     ms_e2e, wall_e2e, _, io = timed(step_e2e, args.steps, max(args.warmup, 3))
 
-    # ---- per-kernel pass (same steps, CUDA events around every launch on the launching stream) for the roofline
-    ops.TRACE = []
-    _native.prof_enable(True)
+    # ---- per-kernel pass (one stream, CUDA events around every launch on the launching stream) for the roofline
+    _native.prof_enable(True); _native.prof_report()
     for i in range(args.steps):
         flush.zero_()
-        step_dev(args.warmup + i)
+        pipes[0].forward(*pairs_dev[i % len(pairs_dev)])
     prof = _native.prof_report()
     _native.prof_enable(False)
-    trace, ops.TRACE = ops.TRACE, None
-    work, ncalls = algorithmic_work(trace)
+    pyr = pipes[0].pyramid()
+    n_levels = [int(p.shape[0]) for p in pyr["points"]]
+    trace = encoder_shapes(enc, n_levels)
+    kp_flops = sum(2.0 * r[1] * r[4] * r[5] * r[6] for r in trace if r[0] == "kpconv")
+    lin_flops = sum(2.0 * r[1] * r[2] * r[3] for r in trace if r[0] == "linear")
+    # tensor-path flops: KPConv contractions that run on tcgen05 (K*Cin % 32 == 0) + the unary Linear layers
+    tc_flops = sum(2.0 * r[1] * r[4] * r[5] * r[6] for r in trace if r[0] == "kpconv" and (r[4] * r[5]) % 32 == 0) + lin_flops
+    kpw_bytes = sum(4.0 * (r[2] * r[5] + r[1] * r[4] * r[5]) + 4.0 * r[1] * limits[0] + 12.0 * (r[1] + r[2])
+                    for r in trace if r[0] == "kpconv")
 
     if world > 1:
         import torch.distributed as dist
         t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_dev, ms_e2e = t.tolist()
-    clouds = 2.0 * args.steps * world
+    clouds = 2.0 * S * args.steps * world
     value = clouds / (ms_dev * 1e-3)
     e2e = clouds / (ms_e2e * 1e-3)
 
     pk = peaks()
-    mine = {k: v for k, v in prof.items()}
-    top = max(mine.items(), key=lambda kv: kv[1][1]) if mine else (None, (0, 0.0))
-    total_kernel_ms = sum(v[1] for v in mine.values())
-    tensor_names = ("gemm_tf32_kernel", "sgemm_rowscale_kernel")
+    total_kernel_ms = sum(v[1] for v in prof.values())
+    top = max(prof.items(), key=lambda kv: kv[1][1]) if prof else (None, (0, 0.0))
     roof = None
     if top[0] is not None:
         name, (cnt, tot_ms) = top
-        steps = args.steps
-        if name in tensor_names:
+        per_step_s = tot_ms / args.steps * 1e-3
+        share = tot_ms / max(total_kernel_ms, 1e-9)
+        if name in ("gemm_tf32_kernel", "sgemm_rowscale_kernel"):
             peak = pk["bf16"] / 2.0                          # TF32 dense = half the bf16 rate
-            ach = work["kpconv_flops"] / steps / (tot_ms / steps * 1e-3) / 1e12 if tot_ms > 0 else 0.0
-            # the GEMM kernel also serves the unary Linear layers when LINEAR_MODE == 'tf32': count those flops too
-            lin = sum(2.0 * r[1] * r[2] * r[3] for r in trace if r[0] == "linear")
-            ach = (work["kpconv_flops"] + lin) / steps / (tot_ms / steps * 1e-3) / 1e12 if tot_ms > 0 else 0.0
-            roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": ach / peak, "traffic": None,
-                    "note": f"TF32 peak taken as half of {pk['src']} bf16 sustained; share of kernel time "
-                            f"{tot_ms / max(total_kernel_ms, 1e-9):.2f}"}
+            ach = tc_flops / per_step_s / 1e12 if per_step_s > 0 else 0.0
+            roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "traffic": None, "launches_per_step": cnt / args.steps,
+                    "note": f"algorithmic flops = 2*Nq*K*Cin*Cout over the KPConv contractions + 2*N*Cin*Cout over the unary "
+                            f"Linears = {tc_flops / 1e9:.1f} GFLOP/step; TF32 peak = half of {pk['src']} bf16 sustained; "
+                            f"share of kernel time {share:.2f}"}
         else:
-            key = {"kp_weighted_kernel": "kp_weighted_bytes", "nb_query_kernel": "nb_query_bytes"}.get(name)
-            by = work.get(key, 0.0) if key else 0.0
-            ach = by / steps / (tot_ms / steps * 1e-3) / 1e9 if tot_ms > 0 else 0.0
-            roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                    "frac": ach / pk["hbm"], "traffic": None,
-                    "note": f"peak = {pk['src']}; share of kernel time {tot_ms / max(total_kernel_ms, 1e-9):.2f}"}
+            by = kpw_bytes if name == "kp_weighted_kernel" else 0.0
+            ach = by / per_step_s / 1e9 if per_step_s > 0 else 0.0
+            roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                    "traffic": None, "launches_per_step": cnt / args.steps,
+                    "note": f"algorithmic bytes = 4*(Ns*Cin + Nq*K*Cin) + idx + points = {by / 1e6:.0f} MB/step; peak = {pk['src']}; "
+                            f"share of kernel time {share:.2f}"}
     kernels = {k: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps} for k, v in
-               sorted(mine.items(), key=lambda kv: -kv[1][1])[:12]}
+               sorted(prof.items(), key=lambda kv: -kv[1][1])[:14]}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32" if blocks.KPCONV_MODE != 1 else "f32", "data": "synthetic",
-            "config": {"workload": "kitti_pair_kfe_encoder", "pairs_per_step": 1,
-                       "points_stacked": int(pairs_dev[0][0].shape[0]), "limits": limits, "parallelism": f"pairs x{world}",
+            "dtype": "tf32", "data": "synthetic",
+            "config": {"workload": "kitti_pair_kfe_encoder", "pairs_per_step": S, "concurrent_streams": S,
+                       "points_stacked": int(pairs_dev[0][0].shape[0]), "level_points": n_levels, "limits": limits,
+                       "parallelism": f"pairs x{world}", "path": "native (aprb_kfe_forward)",
                        "l2": "flushed between steps (256 MiB memset outside the event pair)",
-                       "linear": blocks.LINEAR_MODE, "kpconv_mode": blocks.KPCONV_MODE},
+                       "kpconv_gflop_per_pair": kp_flops / 1e9, "linear_gflop_per_pair": lin_flops / 1e9},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(io[0]), "d2h_bytes_per_step": int(io[1]),
                     "ms_per_step": ms_e2e / args.steps},
@@ -330,6 +370,8 @@ def run_ours(args):
         line["cpu_baseline"] = None
     if rank == 0:
         print(json.dumps(line))
+    if pool:
+        pool.shutdown()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -345,8 +387,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=3, help="distinct synthetic pairs cycled through (per rank)")
     ap.add_argument("--no-calibrate", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--tf32-linear", type=int, default=0, help="allow TF32 in the cuBLAS unary GEMMs (LINEAR_MODE=fp32)")
-    ap.add_argument("--linear-mode", default="tf32", choices=["fp32", "tf32"])
+    ap.add_argument("--streams", type=int, default=1, help="pairs in flight per GPU (one CUDA stream + host thread each)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

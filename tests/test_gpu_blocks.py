@@ -210,7 +210,7 @@ def test_native_pipeline_matches_module_path(cuda, oracle):
     finally:
         blocks.LINEAR_MODE = 'fp32'
     pipe = KFEPipeline(enc, cfg, limits)
-    got = pipe.forward(dp, dl_)
+    got = pipe.forward(dp, dl_).clone()                             # the result is a view into the arena: copy it
     torch.cuda.synchronize()
     assert got.shape == want.shape
     assert torch.equal(got, want)                                   # same kernels, same order -> bit-identical
