@@ -208,7 +208,9 @@ def run_ours(args):
 
     # ---- inputs: distinct pairs per rank, first-level 0.3 m voxelisation done up front (not part of the path)
     pairs_dev, pairs_host = [], []
-    for a, b in raw_pairs(max(args.pairs, S), 1000 * rank):
+    from apr_b200.shard import shard_indices
+    seeds = shard_indices(max(args.pairs, S) * world, rank, world)      # round-robin over the global pair list
+    for a, b in [synth.pair_raw(sd, "kitti") for sd in seeds]:
         raw = torch.from_numpy(np.concatenate([a, b])).to(dev)
         lens = torch.tensor([len(a), len(b)], dtype=torch.int32, device=dev)
         p0, l0 = ops.grid_subsample(raw, lens, cfg.first_subsampling_dl)
