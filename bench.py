@@ -389,7 +389,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=3, help="distinct synthetic pairs cycled through (per rank)")
     ap.add_argument("--no-calibrate", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=1, help="pairs in flight per GPU (one CUDA stream + host thread each)")
+    ap.add_argument("--streams", type=int, default=8, help="pairs in flight per GPU (one CUDA stream + host thread each)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
