@@ -21,6 +21,7 @@ SIGNATURES = {
     "aprb_launch_count": (C.c_longlong, []),
     "aprb_prof_enable": (_i, [_i]),
     "aprb_prof_report": (_i, [C.c_char_p, _sz]),
+    "aprb_set_option": (_i, [C.c_char_p, _i]),
     "aprb_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "aprb_grid_subsample_ws_bytes": (_sz, [_i, _i, _i]),
     "aprb_grid_subsample_batch": (_i, [_p, _p, _i, _i, _f, _i, _p, _i, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),

@@ -50,6 +50,23 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tma
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mcast(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -96,7 +113,11 @@ struct GemmCfg {
     static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+// CL = thread-block-cluster size along M: the CL CTAs of a cluster compute CL vertically adjacent 128-row tiles of
+// the same BN columns, so they need the SAME B k-blocks: each CTA loads 1/CL of every B tile and TMA-multicasts it to
+// all CTAs of the cluster (L2->SM traffic for B divided by CL). A stage is refilled only after all CL CTAs released it
+// (the MMA warps commit to the "empty" barriers of every CTA in the cluster).
+template <int BN, int CL>
 __global__ void __launch_bounds__(192, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                  int kb_per_split, const float* __restrict__ rowscale, float* __restrict__ C) {
@@ -117,7 +138,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     C += (size_t)blockIdx.z * M * N;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
         mbar_init(bar_tmem, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -129,8 +150,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                                 // peers' barriers are initialised before any multicast
     tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
 
     if (warp == 0) {
         if (lane == 0) {                                             // ===== TMA producer =====
@@ -139,7 +163,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);
                 mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::A_BYTES + Cfg::B_BYTES);
                 tma_load_2d(sA + s * Cfg::A_BYTES, &tmA, bar_full + 8 * s, kb * GEMM_BK, m0);
-                tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, bar_full + 8 * s, kb * GEMM_BK, n0);
+                if (CL == 1) tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, bar_full + 8 * s, kb * GEMM_BK, n0);
+                else tma_load_2d_mcast(sB + s * Cfg::B_BYTES + crank * (BN / CL) * 128, &tmB, bar_full + 8 * s, kb * GEMM_BK,
+                                       n0 + crank * (BN / CL), kMask);
                 if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
             }
         }
@@ -156,7 +182,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                 for (int k4 = 0; k4 < GEMM_BK / 8; ++k4)             // +32 bytes (>>4 = 2) per K=8 step inside the atom
                     tc_mma_tf32(tmem_base, da + 2 * k4, db + 2 * k4, idesc, ((kb - kb0) | k4) != 0);
-                tc_commit(bar_empty + 8 * s);                        // frees the stage when these MMAs retire
+                if (CL == 1) tc_commit(bar_empty + 8 * s);           // frees the stage when these MMAs retire
+                else tc_commit_mcast(bar_empty + 8 * s, kMask);      // ... in every CTA of the cluster
                 if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
             }
             tc_commit(bar_tmem);                                     // accumulator complete
@@ -186,6 +213,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                                 // no CTA exits while a peer may still write to it
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
@@ -244,24 +272,36 @@ bool gemm_tf32_supported(int M, int N, int K) {
     return M >= 1 && N >= 16 && N % 16 == 0 && K >= GEMM_BK && K % GEMM_BK == 0;
 }
 
-template <int BN>
+template <int BN, int CL>
 static int launch_gemm(const float* A, const float* Bt, int M, int N, int K, int splits, int kb_per_split,
                        const float* rowscale, float* C, cudaStream_t st) {
     CUtensorMap tmA, tmB;
     int rc = make_tmap(&tmA, A, M, K, GEMM_BM);
     if (rc) return rc;
-    rc = make_tmap(&tmB, Bt, N, K, BN);
+    rc = make_tmap(&tmB, Bt, N, K, BN / CL);                        // each CTA loads a BN/CL-row slice of the B tile
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        APRB_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM));
+        APRB_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM));
         attr_set = true;
     }
-    dim3 grid(cdiv(N, BN), cdiv(M, GEMM_BM), splits);
-    APRB_TIMED("gemm_tf32_kernel", st, 1, (gemm_tf32_kernel<BN><<<grid, 192, GemmCfg<BN>::SMEM, st>>>(tmA, tmB, M, N, K, kb_per_split, rowscale, C)));
-    APRB_LAUNCH_OK();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cdiv(N, BN), cdiv(cdiv(M, GEMM_BM), CL) * CL, splits);   // grid.y padded to whole clusters
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = GemmCfg<BN>::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = CL; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    {
+        ProfScope ps("gemm_tf32_kernel", st, 1);
+        APRB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, CL>, tmA, tmB, M, N, K, kb_per_split, rowscale, C));
+    }
     return APRB_OK;
 }
+
+int g_gemm_cluster = 1;   // 1 disables the cluster/multicast path (aprb_set_option)
 
 size_t gemm_tf32_ws_bytes(int M, int N) {   // split-K partial tiles (up to 8 splits), only when split-K can trigger
     const int bn = N >= 256 ? 256 : (N > 64 ? 128 : 64);
@@ -291,9 +331,10 @@ int gemm_tf32_rowscale(const float* d_A, const float* d_Bt, int M, int N, int K,
     float* out = splits > 1 ? (float*)d_ws : d_C;
     const float* rs = splits > 1 ? nullptr : d_rowscale;
     int rc;
-    if (bn == 256) rc = launch_gemm<256>(d_A, d_Bt, M, N, K, splits, kps, rs, out, st);
-    else if (bn == 128) rc = launch_gemm<128>(d_A, d_Bt, M, N, K, splits, kps, rs, out, st);
-    else rc = launch_gemm<64>(d_A, d_Bt, M, N, K, splits, kps, rs, out, st);
+    const int cl = (g_gemm_cluster >= 2 && mt >= 2) ? 2 : 1;       // B-tile multicast across 2 vertically adjacent tiles
+    if (bn == 256) rc = cl == 2 ? launch_gemm<256, 2>(d_A, d_Bt, M, N, K, splits, kps, rs, out, st) : launch_gemm<256, 1>(d_A, d_Bt, M, N, K, splits, kps, rs, out, st);
+    else if (bn == 128) rc = cl == 2 ? launch_gemm<128, 2>(d_A, d_Bt, M, N, K, splits, kps, rs, out, st) : launch_gemm<128, 1>(d_A, d_Bt, M, N, K, splits, kps, rs, out, st);
+    else rc = cl == 2 ? launch_gemm<64, 2>(d_A, d_Bt, M, N, K, splits, kps, rs, out, st) : launch_gemm<64, 1>(d_A, d_Bt, M, N, K, splits, kps, rs, out, st);
     if (rc || splits == 1) return rc;
     const size_t mn4 = (size_t)M * N / 4;
     APRB_TIMED("splitk_reduce_kernel", st, 1, (splitk_reduce_kernel<<<cdiv((long long)mn4, 256), 256, 0, st>>>(
@@ -303,6 +344,14 @@ int gemm_tf32_rowscale(const float* d_A, const float* d_Bt, int M, int N, int K,
 }
 
 }  // namespace aprb
+
+extern "C" int aprb_set_option(const char* name, int value) {
+    using namespace aprb;
+    APRB_REQUIRE(name, "null option name");
+    if (strcmp(name, "gemm_cluster") == 0) { g_gemm_cluster = value; return APRB_OK; }
+    set_error("aprb_set_option: unknown option %s", name);
+    return APRB_ERR_INVALID;
+}
 
 extern "C" size_t aprb_linear_tf32_ws_bytes(int N, int Cin, int Cout) {
     (void)Cin;

@@ -47,6 +47,8 @@ long long aprb_launch_count(void);
  * device and writes "kernel_name launches total_ms" lines into buf and clears the records. */
 int aprb_prof_enable(int on);
 int aprb_prof_report(char* buf, size_t cap);
+/* Tuning switches (for A/B measurements): "gemm_cluster" = 1 | 2 (thread-block-cluster size of the tcgen05 GEMM). */
+int aprb_set_option(const char* name, int value);
 /* Device properties the host side sizes grids with (SM count etc.). Returns status. */
 int aprb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

@@ -5,8 +5,11 @@ import torch
 from apr_b200 import ops
 torch.manual_seed(0)
 dev = torch.device("cuda", 0)
+from apr_b200 import _native
+cl = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+_native.check(_native.lib().aprb_set_option(b"gemm_cluster", cl)); print("gemm_cluster =", cl)
 for n, cin, cout in [(128, 32, 64), (128, 64, 64), (256, 128, 128), (1000, 64, 128), (4255, 256, 64), (129, 32, 16),
-                     (1567, 512, 2048), (35000, 960, 64), (1567, 7680, 512)]:
+                     (1567, 512, 2048), (35000, 960, 64), (1567, 7680, 512), (2051, 1024, 2048), (13995, 256, 512), (5471, 3840, 256), (13995, 1920, 128)]:
     x = torch.randn(n, cin, device=dev); w = torch.randn(cout, cin, device=dev) / cin ** 0.5
     y = ops.linear_tf32(x, w)
     torch.cuda.synchronize()
