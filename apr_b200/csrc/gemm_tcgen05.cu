@@ -110,7 +110,7 @@ struct GemmCfg {
     static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
     static constexpr int A_BYTES = GEMM_BM * 128;
     static constexpr int B_BYTES = BN * 128;
-    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 32 * 36 * 4 /*epilogue transpose*/;
 };
 
 // CL = thread-block-cluster size along M: the CL CTAs of a cluster compute CL vertically adjacent 128-row tiles of
@@ -192,23 +192,30 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(bar_tmem, 0);
         tc_fence_after();
         const int quarter = warp & 3;                                // TMEM lane quarter this warp may access
-        const int row = m0 + quarter * 32 + lane;
-        const float sc = (rowscale && row < M) ? rowscale[row] : 1.0f;
-        float* crow = C + (size_t)row * N + n0;
+        const int row_l = quarter * 32 + lane;                       // tile row this thread holds after tcgen05.ld
+        const float sc = (rowscale && m0 + row_l < M) ? rowscale[m0 + row_l] : 1.0f;
+        // Per-warp 32 x 32 transpose buffer (row stride 36 floats: 16-byte aligned, conflict-free float4 phases), so the
+        // global stores are whole 128-byte row segments: lanes 0-7 cover one row's 32 columns, a warp store = 4 rows.
+        float* tbuf = reinterpret_cast<float*>(smem_raw + (bars - raw) + 256) + (size_t)(warp - 2) * 32 * 36;
+        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
             uint32_t v[32];
             tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, v);
-            if (row < M) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    if (n0 + c + j < N) {                            // N % 16 == 0: a float4 is all-in or all-out
-                        float4 o = make_float4(__uint_as_float(v[j]) * sc, __uint_as_float(v[j + 1]) * sc,
-                                               __uint_as_float(v[j + 2]) * sc, __uint_as_float(v[j + 3]) * sc);
-                        *reinterpret_cast<float4*>(crow + c + j) = o;
-                    }
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(tbuf + lane * 36 + j) = make_float4(__uint_as_float(v[j]) * sc, __uint_as_float(v[j + 1]) * sc,
+                                                                              __uint_as_float(v[j + 2]) * sc, __uint_as_float(v[j + 3]) * sc);
+            __syncwarp();
+            if (n0 + c + sub_c < N) {                                // N % 16 == 0: a float4 is all-in or all-out
+#pragma unroll
+                for (int r4 = 0; r4 < 32; r4 += 4) {
+                    const int r = r4 + sub_r, grow = m0 + quarter * 32 + r;
+                    if (grow < M)
+                        *reinterpret_cast<float4*>(C + (size_t)grow * N + n0 + c + sub_c) = *reinterpret_cast<const float4*>(tbuf + r * 36 + sub_c);
                 }
             }
+            __syncwarp();
         }
     }
     tc_fence_before();
