@@ -61,6 +61,7 @@ kp_weighted_kernel(const float* __restrict__ q, const float* __restrict__ s, con
     if (n >= Nq) return;
     int* s_si = reinterpret_cast<int*>(s_dyn) + (size_t)wib * KP_MAX_K * Hp * 2;   // [K_MAX][Hp] support index
     float* s_lw = reinterpret_cast<float*>(s_si + (size_t)KP_MAX_K * Hp);          // [K_MAX][Hp] influence weight
+    int* s_cnt = reinterpret_cast<int*>(s_dyn) + (size_t)wpb * KP_MAX_K * Hp * 2 + wib * KP_MAX_K;   // [K_MAX] list lengths
     const float qx = q[3 * (size_t)n], qy = q[3 * (size_t)n + 1], qz = q[3 * (size_t)n + 2];
     const float ext2 = extent * extent, inv_ext = 1.0f / extent;
 
@@ -93,7 +94,7 @@ kp_weighted_kernel(const float* __restrict__ q, const float* __restrict__ s, con
                 const unsigned m = __ballot_sync(0xffffffffu, in);
                 if (in) {
                     const int pos = cnt[k] + __popc(m & ((1u << lane) - 1));
-                    s_si[k * Hp + pos] = si;
+                    s_si[k * Hp + pos] = si * Cin;              // element offset of the support's feature row
                     s_lw[k * Hp + pos] = w;
                 }
                 cnt[k] += __popc(m);
@@ -103,23 +104,29 @@ kp_weighted_kernel(const float* __restrict__ q, const float* __restrict__ s, con
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, d);
     if (lane == 0 && blockIdx.y == 0) inv_nn[n] = 1.0f / (float)max(nn, 1);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < KP_MAX_K; ++k) s_cnt[k] = cnt[k];
+    }
     __syncwarp();
 
     float* wrow = wf + (size_t)n * K * Cin;
     constexpr int SLAB = 32 * VEC * NJ;
     constexpr int NU = (VEC * NJ >= 8) ? 2 : 4;                   // rows in flight
     for (int c0 = blockIdx.y * SLAB; c0 < Cin; c0 += gridDim.y * SLAB) {
-#pragma unroll
-        for (int k = 0; k < KP_MAX_K; ++k) {
-            if (k < K) {
+        const float* xs = x + c0 + lane * VEC;
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) {                                // runtime loop: small code, stays in the I-cache
+            {
                 float acc[NJ][VEC];
 #pragma unroll
                 for (int j = 0; j < NJ; ++j)
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) acc[j][v] = 0.f;
-                const int ck = cnt[k];
+                const int ck = s_cnt[k];
                 const int* lsi = s_si + k * Hp;
                 const float* lw = s_lw + k * Hp;
+#pragma unroll 1
                 for (int e0 = 0; e0 < ck; e0 += NU) {
                     Vec<VEC> xr[NU][NJ];
                     float w[NU];
@@ -127,7 +134,7 @@ kp_weighted_kernel(const float* __restrict__ q, const float* __restrict__ s, con
                     for (int u = 0; u < NU; ++u) {
                         const bool on = e0 + u < ck;
                         w[u] = on ? lw[e0 + u] : 0.f;
-                        const float* row = x + (size_t)(on ? lsi[e0 + u] : lsi[e0]) * Cin + c0 + lane * VEC;
+                        const float* row = xs + (on ? lsi[e0 + u] : lsi[e0]);
 #pragma unroll
                         for (int j = 0; j < NJ; ++j) {
                             if (c0 + lane * VEC + j * 32 * VEC < Cin) xr[u][j] = *reinterpret_cast<const Vec<VEC>*>(row + j * 32 * VEC);
@@ -319,6 +326,7 @@ extern "C" int aprb_kpconv_forward(const float* d_q, const float* d_s, const voi
     APRB_REQUIRE(Nq >= 0 && Ns >= 0 && H >= 1 && H <= 1024, "need Nq,Ns >= 0 and 1 <= H <= 1024");
     APRB_REQUIRE(K >= 1 && K <= KP_MAX_K && Cin >= 1 && Cout >= 1 && ld_idx >= H, "need 1 <= K <= 16, Cin,Cout >= 1, ld >= H");
     APRB_REQUIRE(extent > 0.f, "extent must be positive");
+    APRB_REQUIRE((long long)Ns * Cin < 0x7FFFFFFFLL, "feature table too large for 32-bit row offsets");
     if (Nq == 0) return APRB_OK;
     APRB_REQUIRE(d_q && d_idx && d_kp && d_out && d_ws && (Ns == 0 || (d_s && d_x)), "null pointer");
     APRB_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
@@ -339,7 +347,7 @@ extern "C" int aprb_kpconv_forward(const float* d_q, const float* d_s, const voi
 
     if (Ns > 0) APRB_TIMED("rowsum_pos_kernel", st, 1, (rowsum_pos_kernel<<<cdiv(Ns, 8), 256, 0, st>>>(d_x, Ns, Cin, flag)));
     const int Hp = (H + 31) & ~31;
-    const size_t smem_warp = (size_t)KP_MAX_K * Hp * 8;
+    const size_t smem_warp = (size_t)KP_MAX_K * Hp * 8 + KP_MAX_K * 4;
     int wpb = 4;
     while (wpb > 1 && wpb * smem_warp > 160 * 1024) wpb >>= 1;
     if (smem_warp > 200 * 1024) { set_error("aprb_kpconv_forward: H=%d too large for the shared-memory neighbour lists", H); return APRB_ERR_UNSUPPORTED; }
