@@ -119,6 +119,10 @@ def run_reference(args):
     if rank != 0:
         return 0                                            # rank 0 alone runs the CPU arm
     cfg = kitti_config()
+    try:                                                    # torchrun exports OMP_NUM_THREADS=1: use every host core
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        torch.set_num_threads(os.cpu_count() or 1)
     ref, kind, pairs, sd = reference_setup(cfg, 2, 0)
     cores = torch.get_num_threads()
     limits = LIMITS_FALLBACK
@@ -360,6 +364,10 @@ def run_ours(args):
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cfg_r = kitti_config()
+        try:
+            torch.set_num_threads(len(os.sched_getaffinity(0)))
+        except Exception:
+            pass
         ref, kind, pairs, sd = reference_setup(cfg_r, 1, 0)
         t0 = time.perf_counter()
         reference_step(ref, None, cfg_r, sd, limits, *pairs[0])
