@@ -134,6 +134,11 @@ def block_decider(block_name, radius, in_dim, out_dim, layer_ind, config):
     raise ValueError('Unknown block name in the architecture definition : ' + block_name)
 
 
+# Super-batched pairs on the module path: {row count of a level: segment offsets [S+1] i32 (ops.segment_offsets)}.
+# Empty = the stacked clouds are one collate, statistics over all rows (the reference, blocks.py:459-468).
+NORM_SEGMENTS = {}
+
+
 class BatchNormBlock(nn.Module):
     """blocks.py:436-473 — despite the name, nn.InstanceNorm1d over ALL rows of the stacked pair (no affine, no
     running stats, eps 1e-5), or a learned bias when use_bn is False. `fused(x, slope, residual, norm_residual)` is
@@ -154,6 +159,9 @@ class BatchNormBlock(nn.Module):
 
     def fused(self, x, slope=1.0, residual=None, norm_residual=False):
         if self.use_bn:
+            if x.shape[1] % 4 == 0:      # two-launch segmented kernels (one segment unless NORM_SEGMENTS says otherwise)
+                return ops.instnorm_lrelu_seg(x, NORM_SEGMENTS.get(x.shape[0]), slope=slope, residual=residual,
+                                              norm_residual=norm_residual, round_tf32=(LINEAR_MODE == 'tf32'))
             return ops.instnorm_lrelu(x, slope=slope, residual=residual, norm_residual=norm_residual,
                                       round_tf32=(LINEAR_MODE == 'tf32'))
         y = x + self.bias

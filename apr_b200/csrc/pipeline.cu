@@ -27,6 +27,8 @@ struct aprb_kfe {
     const int* conv[aprb::KFE_MAX_LEVELS];
     const int* pool[aprb::KFE_MAX_LEVELS];
     const int* up[aprb::KFE_MAX_LEVELS];
+    const int* seg[aprb::KFE_MAX_LEVELS];   // per level: row offsets of the S normalisation segments (S+1 ints), or NULL
+    int S;
 };
 
 using namespace aprb;
@@ -68,9 +70,11 @@ int kpconv_call(const aprb_kfe& h, const aprb_kfe_block& b, const float* q, cons
                                b.kp_Wprep ? 0 : 1, A.scratch(), A.scratch_bytes(), st);
 }
 
-int norm_call(const float* x, int n, int c, float slope, const float* res, int norm_res, float* y, Arena& A, cudaStream_t st) {
-    if (A.scratch_bytes() < aprb_instnorm_ws_bytes(n, c)) { set_error("aprb_kfe_forward: arena too small for the norm workspace"); return APRB_ERR_WORKSPACE; }
-    return aprb_instnorm_lrelu(x, n, c, 1e-5f, slope, res, norm_res, 1, y, A.scratch(), A.scratch_bytes(), st);
+// InstanceNorm over the rows of each collated pair (segment) of level `lvl`
+int norm_call(const aprb_kfe& h, int lvl, const float* x, int n, int c, float slope, const float* res, int norm_res, float* y,
+              Arena& A, cudaStream_t st) {
+    if (A.scratch_bytes() < aprb_instnorm_seg_ws_bytes(n, c, h.S)) { set_error("aprb_kfe_forward: arena too small for the norm workspace"); return APRB_ERR_WORKSPACE; }
+    return aprb_instnorm_lrelu_seg(x, n, c, h.seg[lvl], h.S, 1e-5f, slope, res, norm_res, 1, y, A.scratch(), A.scratch_bytes(), st);
 }
 
 int linear_call(const float* x, const float* W, int n, int cin, int cout, float* y, Arena& A, cudaStream_t st) {
@@ -84,6 +88,7 @@ int run_block(const aprb_kfe& h, const aprb_kfe_block& b, const float* feat, con
               cudaStream_t st) {
     const int l = b.layer;
     const int nq = b.strided ? h.n[l + 1] : h.n[l], ns = h.n[l];
+    const int lq = b.strided ? l + 1 : l;                          // level of the block's output rows
     const float* q = b.strided ? h.pts[l + 1] : h.pts[l];
     const float* s = h.pts[l];
     const int* idx = b.strided ? h.pool[l] : h.conv[l];
@@ -94,7 +99,7 @@ int run_block(const aprb_kfe& h, const aprb_kfe_block& b, const float* feat, con
         const size_t mark = A.off;
         KFE_ALLOC(t, float, (size_t)nq * cout);
         KFE_OK(kpconv_call(h, b, q, s, idx, H, feat, nq, ns, H, b.in_dim, cout, t, A, st));
-        KFE_OK(norm_call(t, nq, cout, 0.1f, nullptr, 0, y, A, st));
+        KFE_OK(norm_call(h, lq, t, nq, cout, 0.1f, nullptr, 0, y, A, st));
         A.off = mark;
         *out = y; *out_cols = cout;
         return APRB_OK;
@@ -106,12 +111,12 @@ int run_block(const aprb_kfe& h, const aprb_kfe_block& b, const float* feat, con
     if (b.unary1_W) {                                              // unary1: Linear -> IN -> LeakyReLU
         KFE_ALLOC(t1, float, (size_t)ns * mid);
         KFE_OK(linear_call(feat, b.unary1_W, ns, b.in_dim, mid, t1, A, st));
-        KFE_OK(norm_call(t1, ns, mid, 0.1f, nullptr, 0, t1, A, st));
+        KFE_OK(norm_call(h, l, t1, ns, mid, 0.1f, nullptr, 0, t1, A, st));
         x1 = t1;
     }
     KFE_ALLOC(t2, float, (size_t)nq * mid);
     KFE_OK(kpconv_call(h, b, q, s, idx, H, x1, nq, ns, H, mid, mid, t2, A, st));
-    KFE_OK(norm_call(t2, nq, mid, 0.1f, nullptr, 0, t2, A, st));
+    KFE_OK(norm_call(h, lq, t2, nq, mid, 0.1f, nullptr, 0, t2, A, st));
     KFE_ALLOC(t3, float, (size_t)nq * cout);
     KFE_OK(linear_call(t2, b.unary2_W, nq, mid, cout, t3, A, st)); // unary2 (IN folded into the final kernel)
     const float* sc = feat;
@@ -123,9 +128,9 @@ int run_block(const aprb_kfe& h, const aprb_kfe_block& b, const float* feat, con
     if (b.shortcut_W) {                                            // LeakyReLU(IN(x3) + IN(Linear(sc)))
         KFE_ALLOC(t4, float, (size_t)nq * cout);
         KFE_OK(linear_call(sc, b.shortcut_W, nq, b.in_dim, cout, t4, A, st));
-        KFE_OK(norm_call(t3, nq, cout, 0.1f, t4, 1, y, A, st));
+        KFE_OK(norm_call(h, lq, t3, nq, cout, 0.1f, t4, 1, y, A, st));
     } else {                                                       // LeakyReLU(IN(x3) + sc)
-        KFE_OK(norm_call(t3, nq, cout, 0.1f, sc, 0, y, A, st));
+        KFE_OK(norm_call(h, lq, t3, nq, cout, 0.1f, sc, 0, y, A, st));
     }
     A.off = mark;
     *out = y; *out_cols = cout;
@@ -158,7 +163,7 @@ extern "C" int aprb_kfe_create(const aprb_kfe_config* cfg, const aprb_kfe_block*
     APRB_REQUIRE(h, "out of host memory");
     h->cfg = *cfg;
     h->blocks.assign(blocks, blocks + nblocks);
-    h->h_counts = nullptr; h->h_counts_cap = 0; h->B = 0;
+    h->h_counts = nullptr; h->h_counts_cap = 0; h->B = 0; h->S = 1;
     for (int l = 0; l < KFE_MAX_LEVELS; ++l) {
         h->ev[l] = nullptr; h->n[l] = 0; h->pts[l] = nullptr; h->lens[l] = nullptr; h->conv[l] = h->pool[l] = h->up[l] = nullptr;
         if (cudaEventCreateWithFlags(&h->ev[l], cudaEventDisableTiming) != cudaSuccess) { set_error("cudaEventCreate failed"); delete h; return APRB_ERR_CUDA; }
@@ -195,7 +200,9 @@ extern "C" size_t aprb_kfe_arena_bytes(const aprb_kfe* h, int N, int B) {
         if (tmp + scratch > worst_tmp) worst_tmp = tmp + scratch;
     }
     size_t sub = aprb_grid_subsample_ws_bytes((int)n, B, 0);
-    return pyramid + feats + worst_tmp + sub + align256(n * 4) + (1u << 20);
+    const int cps = h->cfg.clouds_per_segment > 0 ? h->cfg.clouds_per_segment : B;
+    size_t norm = aprb_instnorm_seg_ws_bytes((int)n, 2048, cdiv(B, cps));
+    return pyramid + feats + worst_tmp + sub + norm + align256(n * 4) + (1u << 20);
 }
 
 extern "C" int aprb_kfe_forward(aprb_kfe* hp, const float* d_pts, const int32_t* d_lens, const float* d_feats, int N, int B,
@@ -215,6 +222,14 @@ extern "C" int aprb_kfe_forward(aprb_kfe* hp, const float* d_pts, const int32_t*
     Arena A(d_arena, arena_bytes);
     h.B = B;
     h.n[0] = N; h.pts[0] = d_pts; h.lens[0] = d_lens;
+    const int cps = cfg.clouds_per_segment > 0 ? cfg.clouds_per_segment : B;
+    h.S = cdiv(B, cps);
+    for (int l = 0; l < KFE_MAX_LEVELS; ++l) h.seg[l] = nullptr;
+    if (h.S > 1) {
+        KFE_ALLOC(seg0, int, (size_t)h.S + 1);
+        KFE_OK(aprb_segment_offsets(d_lens, B, cps, seg0, st));
+        h.seg[0] = seg0;
+    }
     for (int l = 0; l < KFE_MAX_LEVELS; ++l) { h.conv[l] = h.pool[l] = h.up[l] = nullptr; if (l) { h.n[l] = 0; h.pts[l] = nullptr; h.lens[l] = nullptr; } }
 
     const float* x = d_feats;
@@ -276,6 +291,11 @@ extern "C" int aprb_kfe_forward(aprb_kfe* hp, const float* d_pts, const int32_t*
             if (hc[1] != 0) { set_error("aprb_kfe_forward: voxel grid of level %d does not fit the sort key", l); return APRB_ERR_UNSUPPORTED; }
             if (hc[0] < 1) { set_error("aprb_kfe_forward: level %d is empty", l + 1); return APRB_ERR_EMPTY; }
             h.n[l + 1] = hc[0]; h.pts[l + 1] = npts; h.lens[l + 1] = nlens;
+            if (h.S > 1) {
+                KFE_ALLOC(segn, int, (size_t)h.S + 1);
+                KFE_OK(aprb_segment_offsets(nlens, B, cps, segn, st));
+                h.seg[l + 1] = segn;
+            }
             KFE_ALLOC(pool, int, (size_t)h.n[l + 1] * lim);
             KFE_OK(aprb_cell_grid_query(grid[l], grid_bytes[l], npts, nlens, B, h.n[l + 1], h.n[l], r, lim, pool, lim, nullptr, nullptr, st));
             h.pool[l] = pool;

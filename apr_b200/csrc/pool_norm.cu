@@ -375,3 +375,201 @@ extern "C" int aprb_instnorm_lrelu(const float* d_x, int N, int C, float eps, fl
     APRB_LAUNCH_OK();
     return APRB_OK;
 }
+
+// ---- segmented variant (super-batched pairs) ---------------------------------------------------------------------
+// P stacked pairs share every other kernel of the path, but BatchNormBlock (= InstanceNorm over all rows of ONE
+// collated pair, blocks.py:459-468) must keep per-pair statistics: rows [seg_off[s], seg_off[s+1]) form segment s.
+// Two launches: (1) per (segment, chunk, column-quad) shifted-sum partials; (2) every apply block Chan-combines the
+// `ch` partials of its columns in a fixed order (deterministic), then standardises its rows. Segment bounds are read
+// on the device (the host never learns the per-level cloud lengths), chunking is relative to each segment.
+namespace aprb {
+
+__device__ __forceinline__ void chan_combine4(float4& am, float4& a2, int& an, const float4 bm, const float4 b2, int bn) {
+    if (bn <= 0) return;
+    const int n = an + bn;
+    const float fb = (float)bn / (float)n, fab = (float)an * (float)bn / (float)n;
+    float d;
+    d = bm.x - am.x; am.x += d * fb; a2.x += b2.x + d * d * fab;
+    d = bm.y - am.y; am.y += d * fb; a2.y += b2.y + d * d * fab;
+    d = bm.z - am.z; am.z += d * fb; a2.z += b2.z + d * d * fab;
+    d = bm.w - am.w; am.w += d * fb; a2.w += b2.w + d * d * fab;
+    an = n;
+}
+
+// grid (gx, ch, S * nt); block 256 = W quads x R rows
+__global__ void __launch_bounds__(256)
+norm_seg_partial_kernel(const float* __restrict__ x, const float* __restrict__ x2, const int* __restrict__ seg_off, int N,
+                        int C, int W, int ch, int nt, float* __restrict__ pmean, float* __restrict__ pm2) {
+    const int seg = blockIdx.z / nt, t = blockIdx.z - seg * nt;
+    if (t == 1) x = x2;
+    __shared__ float4 s_s1[256], s_s2[256];
+    __shared__ int s_cnt[256];
+    const int Cq = C >> 2, R = 256 / W;
+    const int tx = threadIdx.x % W, ty = threadIdx.x / W;
+    const int quad = blockIdx.x * W + tx;
+    const int a = seg_off ? seg_off[seg] : 0, b = seg_off ? seg_off[seg + 1] : N;
+    const int rpc = (b - a + ch - 1) / ch;
+    const int r0 = a + blockIdx.y * rpc, r1 = min(r0 + rpc, b);
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1, pv = s1;
+    int cnt = 0;
+    if (quad < Cq && r0 < r1) {
+        const float4* xp = reinterpret_cast<const float4*>(x) + quad;
+        pv = xp[(size_t)r0 * Cq];                                  // pivot: first row of the chunk (shifted-data sums)
+#pragma unroll 4
+        for (int r = r0 + ty; r < r1; r += R) {
+            const float4 v = xp[(size_t)r * Cq];
+            const float e = v.x - pv.x, f = v.y - pv.y, g = v.z - pv.z, h = v.w - pv.w;
+            s1.x += e; s1.y += f; s1.z += g; s1.w += h;
+            s2.x = fmaf(e, e, s2.x); s2.y = fmaf(f, f, s2.y); s2.z = fmaf(g, g, s2.z); s2.w = fmaf(h, h, s2.w);
+            ++cnt;
+        }
+    }
+    s_s1[threadIdx.x] = s1; s_s2[threadIdx.x] = s2; s_cnt[threadIdx.x] = cnt;
+    __syncthreads();
+    if (ty == 0 && quad < Cq) {
+        float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1;
+        int n = 0;
+        for (int k = 0; k < R; ++k) {                              // fixed order -> deterministic
+            const float4 b1 = s_s1[k * W + tx], b2 = s_s2[k * W + tx];
+            a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
+            a2.x += b2.x; a2.y += b2.y; a2.z += b2.z; a2.w += b2.w;
+            n += s_cnt[k * W + tx];
+        }
+        const float inv = 1.0f / (float)max(n, 1);
+        const float4 mean = make_float4(pv.x + a1.x * inv, pv.y + a1.y * inv, pv.z + a1.z * inv, pv.w + a1.w * inv);
+        const float4 m2 = make_float4(fmaxf(a2.x - a1.x * a1.x * inv, 0.f), fmaxf(a2.y - a1.y * a1.y * inv, 0.f),
+                                      fmaxf(a2.z - a1.z * a1.z * inv, 0.f), fmaxf(a2.w - a1.w * a1.w * inv, 0.f));
+        const size_t slot = ((size_t)blockIdx.z * ch + blockIdx.y) * C;
+        reinterpret_cast<float4*>(pmean + slot)[quad] = mean;
+        reinterpret_cast<float4*>(pm2 + slot)[quad] = m2;
+    }
+}
+
+// Combine the ch partials of (segment, tensor) for this block's W quads: ty strides over chunks, then the R ty-partials
+// are combined in order by row 0. Result (mean, rstd) in smem.
+__device__ __forceinline__ void seg_block_stats(const float* __restrict__ pmean, const float* __restrict__ pm2, size_t slot0,
+                                                int C, int ch, int a, int b, float eps, int quad, int Cq, int W, int R,
+                                                int tx, int ty, float4* s_a, float4* s_b, int* s_n, float4* s_mean,
+                                                float4* s_rstd) {
+    float4 am = make_float4(0.f, 0.f, 0.f, 0.f), a2 = am;
+    int an = 0;
+    const int rpc = (b - a + ch - 1) / ch;
+    if (quad < Cq)
+        for (int k = ty; k < ch; k += R) {
+            const int cnt = min(rpc, b - a - k * rpc);
+            if (cnt <= 0) continue;
+            chan_combine4(am, a2, an, reinterpret_cast<const float4*>(pmean + slot0 + (size_t)k * C)[quad],
+                          reinterpret_cast<const float4*>(pm2 + slot0 + (size_t)k * C)[quad], cnt);
+        }
+    s_a[threadIdx.x] = am; s_b[threadIdx.x] = a2; s_n[threadIdx.x] = an;
+    __syncthreads();
+    if (ty == 0) {
+        float4 m = make_float4(0.f, 0.f, 0.f, 0.f), v2 = m;
+        int n = 0;
+        for (int k = 0; k < R; ++k) chan_combine4(m, v2, n, s_a[k * W + tx], s_b[k * W + tx], s_n[k * W + tx]);
+        const float inv = 1.0f / (float)max(b - a, 1);
+        s_mean[tx] = m;
+        s_rstd[tx] = make_float4(rsqrtf(v2.x * inv + eps), rsqrtf(v2.y * inv + eps), rsqrtf(v2.z * inv + eps), rsqrtf(v2.w * inv + eps));
+    }
+    __syncthreads();
+}
+
+// grid (gx, rb, S); block 256 = W quads x R rows
+__global__ void __launch_bounds__(256)
+norm_seg_apply_kernel(const float* __restrict__ x, const int* __restrict__ seg_off, int N, int C, int W, int ch, int nt,
+                      float eps, const float* __restrict__ pmean, const float* __restrict__ pm2,
+                      const float* __restrict__ res, float slope, int round_tf32, float* __restrict__ y) {
+    __shared__ float4 s_a[256], s_b[256], s_mean[256], s_rstd[256], s_rmean[256], s_rrstd[256];
+    __shared__ int s_n[256];
+    const int seg = blockIdx.z;
+    const int Cq = C >> 2, R = 256 / W;
+    const int tx = threadIdx.x % W, ty = threadIdx.x / W;
+    const int quad = blockIdx.x * W + tx;
+    const int a = seg_off ? seg_off[seg] : 0, b = seg_off ? seg_off[seg + 1] : N;
+    if (a >= b) return;
+    seg_block_stats(pmean, pm2, ((size_t)seg * nt) * ch * C, C, ch, a, b, eps, quad, Cq, W, R, tx, ty, s_a, s_b, s_n, s_mean, s_rstd);
+    if (nt == 2) seg_block_stats(pmean, pm2, ((size_t)seg * nt + 1) * ch * C, C, ch, a, b, eps, quad, Cq, W, R, tx, ty, s_a, s_b, s_n, s_rmean, s_rrstd);
+    if (quad >= Cq) return;
+    const float4 mean = s_mean[tx], rstd = s_rstd[tx];
+    float4 rmean = make_float4(0.f, 0.f, 0.f, 0.f), rrstd = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (nt == 2) { rmean = s_rmean[tx]; rrstd = s_rrstd[tx]; }
+    const int rpb = (b - a + gridDim.y - 1) / gridDim.y;
+    const int r0 = a + blockIdx.y * rpb, r1 = min(r0 + rpb, b);
+    const float4* xp = reinterpret_cast<const float4*>(x) + quad;
+    const float4* rp = res ? reinterpret_cast<const float4*>(res) + quad : nullptr;
+    float4* yp = reinterpret_cast<float4*>(y) + quad;
+#pragma unroll 4
+    for (int r = r0 + ty; r < r1; r += R) {
+        const float4 v = xp[(size_t)r * Cq];
+        float4 o = make_float4((v.x - mean.x) * rstd.x, (v.y - mean.y) * rstd.y, (v.z - mean.z) * rstd.z, (v.w - mean.w) * rstd.w);
+        if (rp) {
+            const float4 q = rp[(size_t)r * Cq];
+            o.x += (q.x - rmean.x) * rrstd.x; o.y += (q.y - rmean.y) * rrstd.y;
+            o.z += (q.z - rmean.z) * rrstd.z; o.w += (q.w - rmean.w) * rrstd.w;
+        }
+        o.x = act_round(o.x, slope, round_tf32); o.y = act_round(o.y, slope, round_tf32);
+        o.z = act_round(o.z, slope, round_tf32); o.w = act_round(o.w, slope, round_tf32);
+        yp[(size_t)r * Cq] = o;
+    }
+}
+
+// seg_off[s] = first row of segment s = sum of the lengths of the clouds before cloud s*cps (S+1 entries)
+__global__ void seg_offsets_kernel(const int* __restrict__ lens, int B, int cps, int S, int* __restrict__ seg_off) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int acc = 0;
+    for (int b = 0; b < B; ++b) {
+        if (b % cps == 0) seg_off[b / cps] = acc;
+        acc += lens[b];
+    }
+    seg_off[S] = acc;
+}
+
+constexpr int NORM_SEG_MAX_CH = 64;
+
+}  // namespace aprb
+
+extern "C" int aprb_segment_offsets(const int32_t* d_lens, int B, int clouds_per_segment, int32_t* d_seg_off, void* stream) {
+    APRB_REQUIRE(d_lens && d_seg_off && B >= 1 && clouds_per_segment >= 1, "bad argument");
+    const int S = cdiv(B, clouds_per_segment);
+    APRB_TIMED("seg_offsets_kernel", (cudaStream_t)stream, 1, (seg_offsets_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_lens, B, clouds_per_segment, S, d_seg_off)));
+    APRB_LAUNCH_OK();
+    return APRB_OK;
+}
+
+extern "C" size_t aprb_instnorm_seg_ws_bytes(int N, int C, int S) {
+    (void)N;
+    if (C < 1 || S < 1) return 0;
+    return 2 * align256((size_t)2 * S * NORM_SEG_MAX_CH * C * sizeof(float)) + 256;
+}
+
+extern "C" int aprb_instnorm_lrelu_seg(const float* d_x, int N, int C, const int32_t* d_seg_off, int S, float eps,
+                                       float slope, const float* d_residual, int norm_residual, int round_tf32, float* d_y,
+                                       void* d_ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    APRB_REQUIRE(N >= 0 && C >= 1 && S >= 1, "bad shape");
+    APRB_REQUIRE(S == 1 || d_seg_off, "segment offsets required when S > 1");
+    if (N == 0) return APRB_OK;
+    APRB_REQUIRE(d_x && d_y && d_ws, "null pointer");
+    const bool aligned = (((uintptr_t)d_x | (uintptr_t)d_y | (uintptr_t)(d_residual ? d_residual : d_x)) & 15) == 0;
+    if (C % 4 != 0 || !aligned) { set_error("aprb_instnorm_lrelu_seg: needs C %% 4 == 0 and 16-byte aligned tensors"); return APRB_ERR_UNSUPPORTED; }
+    if (ws_bytes < aprb_instnorm_seg_ws_bytes(N, C, S)) { set_error("aprb_instnorm_lrelu_seg: workspace too small"); return APRB_ERR_WORKSPACE; }
+    const int nt = (d_residual && norm_residual) ? 2 : 1;
+    Carver c(d_ws, ws_bytes);
+    float* pmean = c.take<float>((size_t)2 * S * NORM_SEG_MAX_CH * C);
+    float* pm2 = c.take<float>((size_t)2 * S * NORM_SEG_MAX_CH * C);
+    const int Cq = C / 4;
+    int W = 1;
+    while (W < Cq && W < 256) W <<= 1;
+    const int gx = cdiv(Cq, W), sms = sm_count();
+    const int rows_seg = max(1, N / S);
+    // statistics pass: ~4 waves of blocks over all segments, chunks of >= 32 rows
+    int ch = min(min(max(1, 4 * sms / (gx * S * nt)), NORM_SEG_MAX_CH), max(1, rows_seg / 32));
+    APRB_TIMED("norm_seg_partial_kernel", st, 1, (norm_seg_partial_kernel<<<dim3(gx, ch, S * nt), 256, 0, st>>>(
+        d_x, d_residual, d_seg_off, N, C, W, ch, nt, pmean, pm2)));
+    // apply pass: ~6 waves of blocks, >= 16 rows per block
+    int rb = min(max(1, 6 * sms / (gx * S)), max(1, rows_seg / 16));
+    APRB_TIMED("norm_seg_apply_kernel", st, 1, (norm_seg_apply_kernel<<<dim3(gx, rb, S), 256, 0, st>>>(
+        d_x, d_seg_off, N, C, W, ch, nt, eps, pmean, pm2, d_residual, slope, round_tf32, d_y)));
+    APRB_LAUNCH_OK();
+    return APRB_OK;
+}

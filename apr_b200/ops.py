@@ -210,6 +210,36 @@ def instnorm_lrelu(x, slope=0.1, residual=None, norm_residual=False, eps=1e-5, o
     return y
 
 
+def segment_offsets(lens, clouds_per_segment):
+    """Row offsets [S+1] i32 of the normalisation segments (one per collated pair) of a stacked batch."""
+    N.require_cuda()
+    ll = _dev_i32(lens, "lens")
+    b = ll.shape[0]
+    s = (b + clouds_per_segment - 1) // clouds_per_segment
+    out = torch.empty(s + 1, dtype=torch.int32, device=ll.device)
+    N.check(N.lib().aprb_segment_offsets(N.ptr(ll), b, int(clouds_per_segment), N.ptr(out), N.stream_ptr()),
+            "aprb_segment_offsets")
+    return out
+
+
+def instnorm_lrelu_seg(x, seg_off=None, slope=0.1, residual=None, norm_residual=False, eps=1e-5, out=None, round_tf32=False):
+    """K6, segmented: rows [seg_off[s], seg_off[s+1]) are standardised with their own column statistics (one segment per
+    collated pair of a super-batch). seg_off=None is one segment over all rows."""
+    N.require_cuda()
+    xx = _dev_f32(x, "x")
+    n, c = xx.shape
+    res = _dev_f32(residual, "residual") if residual is not None else None
+    so = _dev_i32(seg_off, "seg_off") if seg_off is not None else None
+    nseg = so.shape[0] - 1 if so is not None else 1
+    y = out if out is not None else torch.empty_like(xx)
+    ws = _workspace(N.lib().aprb_instnorm_seg_ws_bytes(n, c, nseg), xx.device)
+    rc = N.lib().aprb_instnorm_lrelu_seg(N.ptr(xx), n, c, N.ptr(so), nseg, float(eps), float(slope), N.ptr(res),
+                                         1 if norm_residual else 0, 1 if round_tf32 else 0, N.ptr(y), N.ptr(ws), ws.numel(),
+                                         N.stream_ptr())
+    N.check(rc, "aprb_instnorm_lrelu_seg")
+    return y
+
+
 def linear_tf32_supported(n, cin, cout):
     return cin % 32 == 0 and cout % 16 == 0 and n > 0
 

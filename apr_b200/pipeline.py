@@ -22,13 +22,18 @@ class _Block(C.Structure):
 
 class _Config(C.Structure):
     _fields_ = [("num_layers", C.c_int), ("K", C.c_int), ("first_subsampling_dl", C.c_float), ("conv_radius", C.c_float),
-                ("limits", C.c_int * 8), ("build_upsamples", C.c_int), ("in_feats_dim", C.c_int)]
+                ("limits", C.c_int * 8), ("build_upsamples", C.c_int), ("in_feats_dim", C.c_int),
+                ("clouds_per_segment", C.c_int)]
 
 
 class KFEPipeline:
-    """encoder: an `apr_b200.architectures.KPFCNNEncoder` on a CUDA device (its parameters are used in place)."""
+    """encoder: an `apr_b200.architectures.KPFCNNEncoder` on a CUDA device (its parameters are used in place).
 
-    def __init__(self, encoder, config, neighborhood_limits, build_upsamples=True, stream=None):
+    clouds_per_segment=0: the stacked clouds of one call are ONE collate (the reference: one pair, dataloader.py:76).
+    clouds_per_segment=2: the call carries P collated pairs stacked (B = 2P clouds); every kernel runs once over the
+    super-batch and BatchNormBlock keeps per-pair statistics, so the result equals P separate calls."""
+
+    def __init__(self, encoder, config, neighborhood_limits, build_upsamples=True, stream=None, clouds_per_segment=0):
         N.require_cuda()
         self.lib = N.lib()
         self.config = config
@@ -67,6 +72,7 @@ class KFEPipeline:
             cfg.limits[i] = int(v)
         cfg.build_upsamples = 1 if build_upsamples else 0
         cfg.in_feats_dim = config.in_feats_dim
+        cfg.clouds_per_segment = int(clouds_per_segment)   # 2 = a super-batch of collated pairs (per-pair InstanceNorm)
         arr = (_Block * len(blks))(*blks)
         h = C.c_void_p()
         N.check(self.lib.aprb_kfe_create(C.byref(cfg), arr, len(blks), C.byref(h)), "aprb_kfe_create")
@@ -117,8 +123,9 @@ class KFEPipeline:
         n, b = pts.shape[0], lens.shape[0]
         arena = self._ensure_arena(n, b)
         if out is None:
-            if self._host_out is None or self._host_out.shape[0] < n:
-                self._host_out = torch.empty((n, self._out_cols), dtype=torch.float32).pin_memory()
+            cap = min(n, max(n // 4, 4096))         # the last level keeps ~6 % of the level-0 rows
+            if self._host_out is None or self._host_out.shape[0] < cap:
+                self._host_out = torch.empty((cap, self._out_cols), dtype=torch.float32).pin_memory()
             out = self._host_out
         rows, cols = C.c_int(), C.c_int()
         rc = self.lib.aprb_kfe_forward_host(self.handle, pts.data_ptr(), lens.data_ptr(), n, b, arena.data_ptr(),

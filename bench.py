@@ -209,26 +209,33 @@ def run_ours(args):
     cfg = kitti_config()
     blocks.LINEAR_MODE = "tf32"
     S = max(1, args.streams)
+    P = max(1, args.batch)                # pairs stacked per aprb_kfe_forward call (super-batch, per-pair InstanceNorm)
 
     # ---- inputs: distinct pairs per rank, first-level 0.3 m voxelisation done up front (not part of the path)
-    pairs_dev, pairs_host = [], []
+    single_dev, pairs_dev, pairs_host = [], [], []
     from apr_b200.shard import shard_indices
-    seeds = shard_indices(max(args.pairs, S) * world, rank, world)      # round-robin over the global pair list
+    n_distinct = max(args.pairs, S, P + 2 if P > 1 else 0)
+    seeds = shard_indices(n_distinct * world, rank, world)              # round-robin over the global pair list
     for a, b in [synth.pair_raw(sd, "kitti") for sd in seeds]:
         raw = torch.from_numpy(np.concatenate([a, b])).to(dev)
         lens = torch.tensor([len(a), len(b)], dtype=torch.int32, device=dev)
         p0, l0 = ops.grid_subsample(raw, lens, cfg.first_subsampling_dl)
-        pairs_dev.append((p0.contiguous().clone(), l0.clone()))
+        single_dev.append((p0.contiguous().clone(), l0.clone()))
+    for j in range(max(args.pairs, S)):                                 # call j carries P distinct pairs, stacked
+        sel = [single_dev[(j + t) % n_distinct] for t in range(P)]
+        p0 = torch.cat([x[0] for x in sel]).contiguous(); l0 = torch.cat([x[1] for x in sel]).contiguous()
+        pairs_dev.append((p0, l0))
         pairs_host.append((p0.cpu().pin_memory(), l0.cpu().pin_memory()))
     torch.manual_seed(0); np.random.seed(0)
     enc = KPFCNNEncoder(cfg).to(dev).eval()
-    limits = dataloader.calibrate_neighbors_device(pairs_dev, cfg) if not args.no_calibrate else LIMITS_FALLBACK
+    limits = dataloader.calibrate_neighbors_device(single_dev, cfg) if not args.no_calibrate else LIMITS_FALLBACK
     limits = [int(x) for x in limits]
     torch.cuda.synchronize(dev)
 
     # ---- S native pipelines, one CUDA stream and one host thread each (aprb_kfe_forward releases the GIL)
     streams = [torch.cuda.Stream(dev) for _ in range(S)]
-    pipes = [KFEPipeline(enc, cfg, limits, build_upsamples=True, stream=streams[k]) for k in range(S)]
+    pipes = [KFEPipeline(enc, cfg, limits, build_upsamples=True, stream=streams[k], clouds_per_segment=2 if P > 1 else 0)
+             for k in range(S)]
     pool = ThreadPoolExecutor(max_workers=S) if S > 1 else None
     main_stream = torch.cuda.current_stream(dev)
     done_ev = [torch.cuda.Event() for _ in range(S)]
@@ -318,7 +325,7 @@ def run_ours(args):
         t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_dev, ms_e2e = t.tolist()
-    clouds = 2.0 * S * args.steps * world
+    clouds = 2.0 * S * P * args.steps * world
     value = clouds / (ms_dev * 1e-3)
     e2e = clouds / (ms_e2e * 1e-3)
 
@@ -336,7 +343,7 @@ def run_ours(args):
             roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "traffic": None, "launches_per_step": cnt / args.steps,
                     "note": f"algorithmic flops = 2*Nq*K*Cin*Cout over the KPConv contractions + 2*N*Cin*Cout over the unary "
-                            f"Linears = {tc_flops / 1e9:.1f} GFLOP/step; TF32 peak = half of {pk['src']} bf16 sustained; "
+                            f"Linears = {tc_flops / 1e9:.1f} GFLOP/call ({P} pair(s)); TF32 peak = half of {pk['src']} bf16 sustained; "
                             f"share of kernel time {share:.2f}"}
         else:
             by = kpw_bytes if name == "kp_weighted_kernel" else 0.0
@@ -351,11 +358,12 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "tf32", "data": "synthetic",
-            "config": {"workload": "kitti_pair_kfe_encoder", "pairs_per_step": S, "concurrent_streams": S,
-                       "points_stacked": int(pairs_dev[0][0].shape[0]), "level_points": n_levels, "limits": limits,
+            "config": {"workload": "kitti_pair_kfe_encoder", "pairs_per_step": S * P, "pairs_per_call": P,
+                       "concurrent_streams": S, "points_stacked": int(pairs_dev[0][0].shape[0]), "level_points": n_levels,
+                       "limits": limits,
                        "parallelism": f"pairs x{world}", "path": "native (aprb_kfe_forward)",
                        "l2": "flushed between steps (256 MiB memset outside the event pair)",
-                       "kpconv_gflop_per_pair": kp_flops / 1e9, "linear_gflop_per_pair": lin_flops / 1e9},
+                       "kpconv_gflop_per_pair": kp_flops / 1e9 / P, "linear_gflop_per_pair": lin_flops / 1e9 / P},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(io[0]), "d2h_bytes_per_step": int(io[1]),
                     "ms_per_step": ms_e2e / args.steps},
@@ -397,7 +405,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=3, help="distinct synthetic pairs cycled through (per rank)")
     ap.add_argument("--no-calibrate", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=8, help="pairs in flight per GPU (one CUDA stream + host thread each)")
+    ap.add_argument("--streams", type=int, default=8, help="calls in flight per GPU (one CUDA stream + host thread each)")
+    ap.add_argument("--batch", type=int, default=1, help="pairs stacked per call (super-batch; per-pair InstanceNorm segments)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

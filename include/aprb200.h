@@ -132,6 +132,16 @@ int aprb_instnorm_lrelu(const float* d_x, int N, int C, float eps, float slope,
                         const float* d_residual, int norm_residual, int round_tf32, float* d_y,
                         void* d_ws, size_t ws_bytes, void* stream);
 
+/* Segmented form for super-batched pairs: rows [d_seg_off[s], d_seg_off[s+1]) (device int32 [S+1]) are normalised with
+ * their own column statistics, i.e. S independent BatchNormBlock calls in two launches. S == 1 with d_seg_off == NULL
+ * is the plain form. Needs C % 4 == 0 and 16-byte aligned tensors. */
+size_t aprb_instnorm_seg_ws_bytes(int N, int C, int S);
+int aprb_instnorm_lrelu_seg(const float* d_x, int N, int C, const int32_t* d_seg_off, int S, float eps, float slope,
+                            const float* d_residual, int norm_residual, int round_tf32, float* d_y,
+                            void* d_ws, size_t ws_bytes, void* stream);
+/* d_seg_off[s] = first stacked row of cloud s * clouds_per_segment; ceil(B / clouds_per_segment) + 1 entries. */
+int aprb_segment_offsets(const int32_t* d_lens, int B, int clouds_per_segment, int32_t* d_seg_off, void* stream);
+
 /* ---------------------------------------------------------------- Linear (UnaryBlock.mlp) on tcgen05 TF32 ---- */
 /* y[N,Cout] = x[N,Cin] @ W[Cout,Cin]^T (nn.Linear layout, no bias), TF32 operands (round-to-nearest), fp32
  * accumulate in TMEM. Cin % 32 == 0 and Cout % 16 == 0 required, else APRB_ERR_UNSUPPORTED. The workspace (may be
@@ -169,6 +179,9 @@ typedef struct {
     int limits[8];            /* neighbourhood limit per level (calibrate_neighbors, dataloader.py:200-232)               */
     int build_upsamples;      /* also run the 3 upsample searches (needed by the decoder; part of the collate)            */
     int in_feats_dim;         /* 1                                                                                         */
+    int clouds_per_segment;   /* super-batching: P collated pairs stacked in one call = B = 2P clouds with 2 here, so that  */
+                              /* BatchNormBlock keeps its per-pair statistics (blocks.py:459-468); 0 = all B clouds are ONE */
+                              /* collate (the reference's own semantics for a single collate_fn_descriptor call)            */
 } aprb_kfe_config;
 
 typedef struct aprb_kfe aprb_kfe;

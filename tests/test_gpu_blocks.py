@@ -123,6 +123,36 @@ def test_instnorm_lrelu_vs_torch(cuda):
     assert (ops.instnorm_lrelu(x.to(cuda), slope=1.0).cpu() - ref).abs().max() < 1e-5
 
 
+def test_instnorm_segmented_vs_torch(cuda):
+    """Segmented InstanceNorm (super-batched pairs): every segment equals a separate BatchNormBlock call."""
+    gen = torch.Generator().manual_seed(4)
+    for lens, c in (([700, 650, 800, 30, 1, 900], 64), ([5000, 4000], 128), ([35000, 31000, 33000, 36000], 64), ([300], 2048)):
+        n = sum(lens)
+        x = torch.randn(n, c, generator=gen) * 2 + torch.linspace(-30, 30, n).unsqueeze(1)   # segment-dependent means
+        r = torch.randn(n, c, generator=gen)
+        off = ops.segment_offsets(torch.tensor(lens, dtype=torch.int32, device=cuda), 1)
+        assert off.cpu().tolist() == [0] + list(np.cumsum(lens))
+        got = ops.instnorm_lrelu_seg(x.to(cuda), off, slope=0.1).cpu()
+        got_r = ops.instnorm_lrelu_seg(x.to(cuda), off, slope=0.1, residual=r.to(cuda), norm_residual=True).cpu()
+        got_p = ops.instnorm_lrelu_seg(x.to(cuda), off, slope=1.0, residual=r.to(cuda)).cpu()
+        a = 0
+        for ln in lens:
+            xs, rs = x[a:a + ln].double(), r[a:a + ln].double()
+            if ln > 1:
+                want = torch.nn.functional.leaky_relu(blocks_ref.instnorm_ref(xs), 0.1).float()
+                assert (got[a:a + ln] - want).abs().max() < 2e-4
+                want = torch.nn.functional.leaky_relu(blocks_ref.instnorm_ref(xs) + blocks_ref.instnorm_ref(rs), 0.1).float()
+                assert (got_r[a:a + ln] - want).abs().max() < 2e-4
+                assert (got_p[a:a + ln] - (blocks_ref.instnorm_ref(xs) + rs).float()).abs().max() < 2e-4
+            a += ln
+    # two clouds per segment (a collated pair), and the unsegmented form == the three-launch kernel's result
+    off = ops.segment_offsets(torch.tensor([10, 20, 30, 40, 50], dtype=torch.int32, device=cuda), 2)
+    assert off.cpu().tolist() == [0, 30, 100, 150]
+    x = torch.randn(4000, 256, generator=gen) + 7
+    a, b = ops.instnorm_lrelu_seg(x.to(cuda), None, slope=0.1).cpu(), ops.instnorm_lrelu(x.to(cuda), slope=0.1).cpu()
+    assert (a - b).abs().max() < 1e-5
+
+
 def _pyramid(oracle, cfg, p0, l0, limits, cuda):
     pyr = collate_ref(p0, l0, cfg, limits, oracle.subsample_batch, oracle.batch_query)
     cpu = dict(points=[torch.from_numpy(p) for p in pyr["points"]],
@@ -237,3 +267,55 @@ def test_native_pipeline_matches_module_path(cuda, oracle):
     e = rel(got, y)
     print(f"end-of-encoder drift vs fp32 oracle (11 blocks, TF32): {e:.2e}")
     assert e < 1e-2
+
+
+def test_native_pipeline_super_batch_equals_separate_pairs(cuda, oracle):
+    """P collated pairs stacked in ONE aprb_kfe_forward call (clouds_per_segment = 2: per-pair InstanceNorm statistics)
+    give, pair by pair, the result of P separate single-pair calls: pyramid bit-exact (indices shifted by the pair's row
+    offset), encoder features equal up to the fp32 reassociation of the norm partial sums."""
+    from apr_b200 import synth
+    from apr_b200.pipeline import KFEPipeline
+    cfg = kitti_config()
+    limits = [30, 31, 32, 33]
+    torch.manual_seed(0); np.random.seed(0)
+    enc = KPFCNNEncoder(cfg).to(cuda).eval()
+    pairs = []
+    for sd, (na, nb) in enumerate([(3000, 2600), (1800, 3300), (2500, 2500)]):
+        a, b = synth.small_cloud(61 + 2 * sd, na), synth.small_cloud(62 + 2 * sd, nb)
+        pairs.append(oracle.subsample_batch(np.concatenate([a, b]), np.array([len(a), len(b)], np.int32), sampleDl=0.3))
+    single = KFEPipeline(enc, cfg, limits)
+    outs, pyrs = [], []
+    for p0, l0 in pairs:
+        outs.append(single.forward(_t(p0, cuda), _t(l0, cuda)).clone())
+        pyrs.append({k: [t.clone() for t in v] for k, v in single.pyramid().items()})
+    torch.cuda.synchronize()
+    batch = KFEPipeline(enc, cfg, limits, clouds_per_segment=2)
+    P0 = np.concatenate([p for p, _ in pairs]); L0 = np.concatenate([l for _, l in pairs])
+    got = batch.forward(_t(P0, cuda), _t(L0, cuda)).clone()
+    pyr = batch.pyramid()
+    torch.cuda.synchronize()
+    assert got.shape[0] == sum(o.shape[0] for o in outs)
+    for lvl in range(4):
+        lens = pyr["stack_lengths"][lvl].cpu().numpy()
+        assert np.array_equal(lens, np.concatenate([p["stack_lengths"][lvl].cpu().numpy() for p in pyrs]))
+        assert torch.equal(pyr["points"][lvl], torch.cat([p["points"][lvl] for p in pyrs]))
+        n_tot = pyr["points"][lvl].shape[0]
+        for key, sup_lvl in (("neighbors", lvl), ("pools", lvl), ("upsamples", lvl + 1)):
+            if pyr[key][lvl].shape[0] == 0:
+                continue
+            ns_tot = pyr["points"][sup_lvl].shape[0]
+            rows = []
+            soff = 0
+            for p in pyrs:
+                t = p[key][lvl].clone()
+                ns = p["points"][sup_lvl].shape[0]
+                t = torch.where(t == ns, torch.full_like(t, ns_tot), t + soff)        # shadow index = stacked total
+                rows.append(t); soff += ns
+            assert torch.equal(pyr[key][lvl], torch.cat(rows)), (key, lvl)
+    a = 0
+    for o in outs:
+        e = rel(got[a:a + o.shape[0]], o)
+        assert e < 2e-5, f"super-batched pair differs from its single-pair run: {e:.2e}"
+        a += o.shape[0]
+    host = batch.forward_host(torch.from_numpy(P0).pin_memory(), torch.from_numpy(L0).pin_memory())
+    assert torch.equal(host, got.cpu())
