@@ -20,6 +20,7 @@ size_t gemm_tf32_ws_bytes(int M, int N);
 bool gemm_tf32_supported(int M, int N, int K);
 
 constexpr int KP_MAX_K = 16;
+int g_kpconv_chunk_mb = 0;   // aprb_set_option("kpconv_chunk_mb"): L2-sized row chunks of the tensor path (0 = off)
 
 // flag[s] = 1 iff sum_c x[s,c] > 0 (one warp per support row; fixed reduction order)
 __global__ void rowsum_pos_kernel(const float* __restrict__ x, int Ns, int C, unsigned char* __restrict__ flag) {
@@ -357,14 +358,15 @@ extern "C" int aprb_kpconv_forward(const float* d_q, const float* d_s, const voi
     int vec = 1, nj = 1;
     if (x16 && Cin % 4 == 0 && Cin >= 128) { vec = 4; nj = Cin >= 512 ? 4 : (Cin >= 256 ? 2 : 1); }
     else if (x16 && Cin % 2 == 0 && Cin >= 64) { vec = 2; nj = 1; }
+    // rows [r0, r0 + nr) of the query set; wf is addressed relative to r0 (the chunked tensor path reuses it)
 #define KPW_LAUNCH3(IDX, VEC, NJ, RND)                                                                               \
     do {                                                                                                             \
         if (smem > 48 * 1024)                                                                                        \
             APRB_CUDA_OK(cudaFuncSetAttribute(kp_weighted_kernel<IDX, VEC, NJ, RND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         const int nslabs = cdiv(Cin, 32 * VEC * NJ);                                                                 \
-        const int gy = (cdiv(Nq, wpb) < 4 * sm_count()) ? nslabs : 1;                                                \
-        APRB_TIMED("kp_weighted_kernel", st, 1, (kp_weighted_kernel<IDX, VEC, NJ, RND><<<dim3(cdiv(Nq, wpb), gy), wpb * 32, smem, st>>>( \
-            d_q, d_s, (const IDX*)d_idx, ld_idx, d_x, d_kp, flag, extent, Nq, Ns, H, K, Cin, wf, inv_nn)));         \
+        const int gy = (cdiv(nr, wpb) < 4 * sm_count()) ? nslabs : 1;                                                \
+        APRB_TIMED("kp_weighted_kernel", st, 1, (kp_weighted_kernel<IDX, VEC, NJ, RND><<<dim3(cdiv(nr, wpb), gy), wpb * 32, smem, st>>>( \
+            d_q + 3 * (size_t)r0, d_s, (const IDX*)d_idx + (size_t)r0 * ld_idx, ld_idx, d_x, d_kp, flag, extent, nr, Ns, H, K, Cin, wf, inv_nn + r0))); \
     } while (0)
 #define KPW_LAUNCH(IDX, RND)                                                                                         \
     do {                                                                                                             \
@@ -375,10 +377,25 @@ extern "C" int aprb_kpconv_forward(const float* d_q, const float* d_s, const voi
         else KPW_LAUNCH3(IDX, 1, 1, RND);                                                                            \
     } while (0)
     if (use_tensor) {
-        if (idx_is_i64) KPW_LAUNCH(long long, true); else KPW_LAUNCH(int, true);
-        APRB_LAUNCH_OK();
-        return gemm_tf32_rowscale(wf, d_wprep, Nq, Cout, KC, inv_nn, d_out, gws, gws_bytes, st);
+        // Row chunks sized so that one chunk of wf (the A operand) stays L2-resident between its producer and the GEMM
+        // that consumes it: with super-batched pairs wf is ~1 GB per layer and would otherwise round-trip through HBM.
+        int chunk_rows = Nq;
+        if (g_kpconv_chunk_mb > 0) {
+            long long rows = ((long long)g_kpconv_chunk_mb << 20) / ((long long)KC * 4);
+            rows = (rows / 128) * 128;
+            if (rows < 128 * 148) rows = 128 * 148;                  // at least one GEMM tile per SM
+            if (rows < Nq) chunk_rows = (int)rows;
+        }
+        for (int r0 = 0; r0 < Nq; r0 += chunk_rows) {
+            const int nr = min(chunk_rows, Nq - r0);
+            if (idx_is_i64) KPW_LAUNCH(long long, true); else KPW_LAUNCH(int, true);
+            APRB_LAUNCH_OK();
+            int rc = gemm_tf32_rowscale(wf, d_wprep, nr, Cout, KC, inv_nn + r0, d_out + (size_t)r0 * Cout, gws, gws_bytes, st);
+            if (rc) return rc;
+        }
+        return APRB_OK;
     }
+    const int r0 = 0, nr = Nq;
     if (Cin == 1) {
         if (idx_is_i64) APRB_TIMED("kp_weighted_c1_kernel", st, 1, (kp_weighted_c1_kernel<long long><<<cdiv(Nq, 4), 128, 0, st>>>(
             d_q, d_s, (const long long*)d_idx, ld_idx, d_x, d_kp, flag, extent, Nq, Ns, H, K, wf, inv_nn)));

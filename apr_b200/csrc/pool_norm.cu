@@ -396,14 +396,18 @@ __device__ __forceinline__ void chan_combine4(float4& am, float4& a2, int& an, c
     an = n;
 }
 
-// grid (gx, ch, S * nt); block 256 = W quads x R rows
+// grid (gx, ch, S * nt); block 256 = W quads x R rows. The LAST block to finish a (segment, tensor, column tile) —
+// a ticket counter decides who is last, never the order of the sum — Chan-combines the ch partials in index order and
+// writes stats[(seg*nt + t)][mean | rstd][C].
 __global__ void __launch_bounds__(256)
 norm_seg_partial_kernel(const float* __restrict__ x, const float* __restrict__ x2, const int* __restrict__ seg_off, int N,
-                        int C, int W, int ch, int nt, float* __restrict__ pmean, float* __restrict__ pm2) {
+                        int C, int W, int ch, int nt, float eps, float* __restrict__ pmean, float* __restrict__ pm2,
+                        int* __restrict__ tickets, float* __restrict__ stats) {
     const int seg = blockIdx.z / nt, t = blockIdx.z - seg * nt;
     if (t == 1) x = x2;
     __shared__ float4 s_s1[256], s_s2[256];
     __shared__ int s_cnt[256];
+    __shared__ int s_last;
     const int Cq = C >> 2, R = 256 / W;
     const int tx = threadIdx.x % W, ty = threadIdx.x / W;
     const int quad = blockIdx.x * W + tx;
@@ -426,6 +430,7 @@ norm_seg_partial_kernel(const float* __restrict__ x, const float* __restrict__ x
     }
     s_s1[threadIdx.x] = s1; s_s2[threadIdx.x] = s2; s_cnt[threadIdx.x] = cnt;
     __syncthreads();
+    const size_t slot0 = (size_t)blockIdx.z * ch * C;
     if (ty == 0 && quad < Cq) {
         float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1;
         int n = 0;
@@ -439,60 +444,59 @@ norm_seg_partial_kernel(const float* __restrict__ x, const float* __restrict__ x
         const float4 mean = make_float4(pv.x + a1.x * inv, pv.y + a1.y * inv, pv.z + a1.z * inv, pv.w + a1.w * inv);
         const float4 m2 = make_float4(fmaxf(a2.x - a1.x * a1.x * inv, 0.f), fmaxf(a2.y - a1.y * a1.y * inv, 0.f),
                                       fmaxf(a2.z - a1.z * a1.z * inv, 0.f), fmaxf(a2.w - a1.w * a1.w * inv, 0.f));
-        const size_t slot = ((size_t)blockIdx.z * ch + blockIdx.y) * C;
-        reinterpret_cast<float4*>(pmean + slot)[quad] = mean;
-        reinterpret_cast<float4*>(pm2 + slot)[quad] = m2;
+        reinterpret_cast<float4*>(pmean + slot0 + (size_t)blockIdx.y * C)[quad] = mean;
+        reinterpret_cast<float4*>(pm2 + slot0 + (size_t)blockIdx.y * C)[quad] = m2;
     }
-}
-
-// Combine the ch partials of (segment, tensor) for this block's W quads: ty strides over chunks, then the R ty-partials
-// are combined in order by row 0. Result (mean, rstd) in smem.
-__device__ __forceinline__ void seg_block_stats(const float* __restrict__ pmean, const float* __restrict__ pm2, size_t slot0,
-                                                int C, int ch, int a, int b, float eps, int quad, int Cq, int W, int R,
-                                                int tx, int ty, float4* s_a, float4* s_b, int* s_n, float4* s_mean,
-                                                float4* s_rstd) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int* tk = tickets + blockIdx.z * gridDim.x + blockIdx.x;
+        const int old = atomicAdd(tk, 1);
+        s_last = (old == ch - 1);
+        if (s_last) *tk = 0;                                       // self-reset for the next use of this workspace
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // ---- finalize: chunk partials combined in chunk order (ty strides, then the R ty-partials in order)
     float4 am = make_float4(0.f, 0.f, 0.f, 0.f), a2 = am;
     int an = 0;
-    const int rpc = (b - a + ch - 1) / ch;
     if (quad < Cq)
         for (int k = ty; k < ch; k += R) {
-            const int cnt = min(rpc, b - a - k * rpc);
-            if (cnt <= 0) continue;
-            chan_combine4(am, a2, an, reinterpret_cast<const float4*>(pmean + slot0 + (size_t)k * C)[quad],
-                          reinterpret_cast<const float4*>(pm2 + slot0 + (size_t)k * C)[quad], cnt);
+            const int c2 = min(rpc, b - a - k * rpc);
+            if (c2 <= 0) continue;
+            chan_combine4(am, a2, an, __ldcg(reinterpret_cast<const float4*>(pmean + slot0 + (size_t)k * C) + quad),
+                          __ldcg(reinterpret_cast<const float4*>(pm2 + slot0 + (size_t)k * C) + quad), c2);
         }
-    s_a[threadIdx.x] = am; s_b[threadIdx.x] = a2; s_n[threadIdx.x] = an;
+    s_s1[threadIdx.x] = am; s_s2[threadIdx.x] = a2; s_cnt[threadIdx.x] = an;
     __syncthreads();
-    if (ty == 0) {
+    if (ty == 0 && quad < Cq) {
         float4 m = make_float4(0.f, 0.f, 0.f, 0.f), v2 = m;
         int n = 0;
-        for (int k = 0; k < R; ++k) chan_combine4(m, v2, n, s_a[k * W + tx], s_b[k * W + tx], s_n[k * W + tx]);
+        for (int k = 0; k < R; ++k) chan_combine4(m, v2, n, s_s1[k * W + tx], s_s2[k * W + tx], s_cnt[k * W + tx]);
         const float inv = 1.0f / (float)max(b - a, 1);
-        s_mean[tx] = m;
-        s_rstd[tx] = make_float4(rsqrtf(v2.x * inv + eps), rsqrtf(v2.y * inv + eps), rsqrtf(v2.z * inv + eps), rsqrtf(v2.w * inv + eps));
+        float* st = stats + (size_t)blockIdx.z * 2 * C;
+        reinterpret_cast<float4*>(st)[quad] = m;
+        reinterpret_cast<float4*>(st + C)[quad] = make_float4(rsqrtf(v2.x * inv + eps), rsqrtf(v2.y * inv + eps),
+                                                              rsqrtf(v2.z * inv + eps), rsqrtf(v2.w * inv + eps));
     }
-    __syncthreads();
 }
 
 // grid (gx, rb, S); block 256 = W quads x R rows
 __global__ void __launch_bounds__(256)
-norm_seg_apply_kernel(const float* __restrict__ x, const int* __restrict__ seg_off, int N, int C, int W, int ch, int nt,
-                      float eps, const float* __restrict__ pmean, const float* __restrict__ pm2,
-                      const float* __restrict__ res, float slope, int round_tf32, float* __restrict__ y) {
-    __shared__ float4 s_a[256], s_b[256], s_mean[256], s_rstd[256], s_rmean[256], s_rrstd[256];
-    __shared__ int s_n[256];
+norm_seg_apply_kernel(const float* __restrict__ x, const int* __restrict__ seg_off, int N, int C, int W, int nt,
+                      const float* __restrict__ stats, const float* __restrict__ res, float slope, int round_tf32,
+                      float* __restrict__ y) {
     const int seg = blockIdx.z;
     const int Cq = C >> 2, R = 256 / W;
     const int tx = threadIdx.x % W, ty = threadIdx.x / W;
     const int quad = blockIdx.x * W + tx;
     const int a = seg_off ? seg_off[seg] : 0, b = seg_off ? seg_off[seg + 1] : N;
-    if (a >= b) return;
-    seg_block_stats(pmean, pm2, ((size_t)seg * nt) * ch * C, C, ch, a, b, eps, quad, Cq, W, R, tx, ty, s_a, s_b, s_n, s_mean, s_rstd);
-    if (nt == 2) seg_block_stats(pmean, pm2, ((size_t)seg * nt + 1) * ch * C, C, ch, a, b, eps, quad, Cq, W, R, tx, ty, s_a, s_b, s_n, s_rmean, s_rrstd);
-    if (quad >= Cq) return;
-    const float4 mean = s_mean[tx], rstd = s_rstd[tx];
+    if (a >= b || quad >= Cq) return;
+    const float* st = stats + (size_t)seg * nt * 2 * C;
+    const float4 mean = reinterpret_cast<const float4*>(st)[quad], rstd = reinterpret_cast<const float4*>(st + C)[quad];
     float4 rmean = make_float4(0.f, 0.f, 0.f, 0.f), rrstd = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (nt == 2) { rmean = s_rmean[tx]; rrstd = s_rrstd[tx]; }
+    if (nt == 2) { rmean = reinterpret_cast<const float4*>(st + 2 * (size_t)C)[quad]; rrstd = reinterpret_cast<const float4*>(st + 3 * (size_t)C)[quad]; }
     const int rpb = (b - a + gridDim.y - 1) / gridDim.y;
     const int r0 = a + blockIdx.y * rpb, r1 = min(r0 + rpb, b);
     const float4* xp = reinterpret_cast<const float4*>(x) + quad;
@@ -539,7 +543,8 @@ extern "C" int aprb_segment_offsets(const int32_t* d_lens, int B, int clouds_per
 extern "C" size_t aprb_instnorm_seg_ws_bytes(int N, int C, int S) {
     (void)N;
     if (C < 1 || S < 1) return 0;
-    return 2 * align256((size_t)2 * S * NORM_SEG_MAX_CH * C * sizeof(float)) + 256;
+    return 2 * align256((size_t)2 * S * NORM_SEG_MAX_CH * C * sizeof(float)) + align256((size_t)4 * S * C * sizeof(float)) +
+           align256((size_t)2 * S * (C / 4 + 1) * sizeof(int)) + 256;
 }
 
 extern "C" int aprb_instnorm_lrelu_seg(const float* d_x, int N, int C, const int32_t* d_seg_off, int S, float eps,
@@ -557,6 +562,8 @@ extern "C" int aprb_instnorm_lrelu_seg(const float* d_x, int N, int C, const int
     Carver c(d_ws, ws_bytes);
     float* pmean = c.take<float>((size_t)2 * S * NORM_SEG_MAX_CH * C);
     float* pm2 = c.take<float>((size_t)2 * S * NORM_SEG_MAX_CH * C);
+    float* stats = c.take<float>((size_t)4 * S * C);
+    int* tickets = c.take<int>((size_t)2 * S * (C / 4 + 1));
     const int Cq = C / 4;
     int W = 1;
     while (W < Cq && W < 256) W <<= 1;
@@ -564,12 +571,13 @@ extern "C" int aprb_instnorm_lrelu_seg(const float* d_x, int N, int C, const int
     const int rows_seg = max(1, N / S);
     // statistics pass: ~4 waves of blocks over all segments, chunks of >= 32 rows
     int ch = min(min(max(1, 4 * sms / (gx * S * nt)), NORM_SEG_MAX_CH), max(1, rows_seg / 32));
+    APRB_CUDA_OK(cudaMemsetAsync(tickets, 0, (size_t)S * nt * gx * sizeof(int), st));
     APRB_TIMED("norm_seg_partial_kernel", st, 1, (norm_seg_partial_kernel<<<dim3(gx, ch, S * nt), 256, 0, st>>>(
-        d_x, d_residual, d_seg_off, N, C, W, ch, nt, pmean, pm2)));
+        d_x, d_residual, d_seg_off, N, C, W, ch, nt, eps, pmean, pm2, tickets, stats)));
     // apply pass: ~6 waves of blocks, >= 16 rows per block
     int rb = min(max(1, 6 * sms / (gx * S)), max(1, rows_seg / 16));
     APRB_TIMED("norm_seg_apply_kernel", st, 1, (norm_seg_apply_kernel<<<dim3(gx, rb, S), 256, 0, st>>>(
-        d_x, d_seg_off, N, C, W, ch, nt, eps, pmean, pm2, d_residual, slope, round_tf32, d_y)));
+        d_x, d_seg_off, N, C, W, nt, stats, d_residual, slope, round_tf32, d_y)));
     APRB_LAUNCH_OK();
     return APRB_OK;
 }

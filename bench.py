@@ -27,9 +27,14 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 from apr_b200 import synth  # noqa: E402
-from apr_b200.config import kitti_config  # noqa: E402
+from apr_b200.config import kitti_config, nuscenes_config  # noqa: E402
 
 METRIC = "KITTI-shaped clouds/sec (subsample+radius+KPConv KFE)"
+WORKLOADS = {   # --workload: (synthetic generator kind, distant pairs, config.workload name)      BASELINE.json configs
+    "kitti": ("kitti", False, "kitti_pair_kfe_encoder"),          # configs[1] (the metric's configuration)
+    "lokitti": ("kitti", True, "lokitti_distant_pair_kfe_encoder"),   # configs[2] pair geometry (pose distance 5-50 m)
+    "nuscenes": ("nusc", False, "nuscenes_pair_kfe_encoder"),     # configs[3]
+}
 UNIT = "clouds/s"
 LIMITS_FALLBACK = [57, 56, 57, 55]       # SURVEY.md §6 (80th percentile), used only if calibration is skipped
 
@@ -206,8 +211,11 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    cfg = kitti_config()
+    cfg = kitti_config() if args.workload != "nuscenes" else nuscenes_config()
     blocks.LINEAR_MODE = "tf32"
+    for kv in args.opt:                                       # A/B switches of the native library (aprb_set_option)
+        k, v = kv.split("=")
+        _native.check(_native.lib().aprb_set_option(k.encode(), int(v)), "aprb_set_option")
     S = max(1, args.streams)
     P = max(1, args.batch)                # pairs stacked per aprb_kfe_forward call (super-batch, per-pair InstanceNorm)
 
@@ -216,7 +224,8 @@ def run_ours(args):
     from apr_b200.shard import shard_indices
     n_distinct = max(args.pairs, S, P + 2 if P > 1 else 0)
     seeds = shard_indices(n_distinct * world, rank, world)              # round-robin over the global pair list
-    for a, b in [synth.pair_raw(sd, "kitti") for sd in seeds]:
+    kind, distant, wl_name = WORKLOADS[args.workload]
+    for a, b in [synth.pair_raw(sd, kind, distant) for sd in seeds]:
         raw = torch.from_numpy(np.concatenate([a, b])).to(dev)
         lens = torch.tensor([len(a), len(b)], dtype=torch.int32, device=dev)
         p0, l0 = ops.grid_subsample(raw, lens, cfg.first_subsampling_dl)
@@ -358,7 +367,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "tf32", "data": "synthetic",
-            "config": {"workload": "kitti_pair_kfe_encoder", "pairs_per_step": S * P, "pairs_per_call": P,
+            "config": {"workload": wl_name, "pairs_per_step": S * P, "pairs_per_call": P,
                        "concurrent_streams": S, "points_stacked": int(pairs_dev[0][0].shape[0]), "level_points": n_levels,
                        "limits": limits,
                        "parallelism": f"pairs x{world}", "path": "native (aprb_kfe_forward)",
@@ -405,8 +414,10 @@ def main():
     ap.add_argument("--pairs", type=int, default=3, help="distinct synthetic pairs cycled through (per rank)")
     ap.add_argument("--no-calibrate", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=8, help="calls in flight per GPU (one CUDA stream + host thread each)")
-    ap.add_argument("--batch", type=int, default=1, help="pairs stacked per call (super-batch; per-pair InstanceNorm segments)")
+    ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS))
+    ap.add_argument("--streams", type=int, default=2, help="calls in flight per GPU (one CUDA stream + host thread each)")
+    ap.add_argument("--batch", type=int, default=8, help="pairs stacked per call (super-batch; per-pair InstanceNorm segments)")
+    ap.add_argument("--opt", action="append", default=[], help="native tuning switch name=value (aprb_set_option)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
