@@ -102,3 +102,104 @@ def encoder_ref(batch, sd, config, return_all=False):
             layer += 1
             r *= 2
     return outs if return_all else x
+
+
+# ---- bottleneck GNN + decoder half of KPFCNN (architectures.py:155-212, models/gcn.py) ------------------------------
+# Restated in the reference's own formulation ([1,C,N] tensors, explicit edge features), which is deliberately NOT the
+# product's factored formulation (apr_b200/gcn.py), so that the comparison checks the algebra as well.
+def _sqdist_ref(a, b):
+    d = -2 * torch.matmul(a, b.t())                                           # lib/utils.py:89-96
+    d = d + torch.sum(a ** 2, dim=-1)[:, None] + torch.sum(b ** 2, dim=-1)[None, :]
+    return torch.clamp(d, min=1e-12)
+
+
+def _graph_feature_ref(coords, feats, k):
+    """coords [N,3], feats [C,N] -> [2C,N,k] = cat(x_i, x_j - x_i) over the k nearest other points (gcn.py:9-35)."""
+    idx = _sqdist_ref(coords, coords).topk(k=k + 1, dim=-1, largest=False, sorted=True)[1][:, 1:]   # [N,k]
+    neigh = feats[:, idx]                                                     # [C,N,k]
+    centre = feats.unsqueeze(-1).expand(-1, -1, k)
+    return torch.cat((centre, neigh - centre), dim=0)
+
+
+def _in2d_lrelu_ref(x, slope=0.2, eps=1e-5):
+    """InstanceNorm2d (no affine) on [C,N,k] + LeakyReLU."""
+    m = x.mean(dim=(1, 2), keepdim=True)
+    v = x.var(dim=(1, 2), unbiased=False, keepdim=True)
+    return F.leaky_relu((x - m) / torch.sqrt(v + eps), slope)
+
+
+def self_attention_ref(coords, feats, sd, prefix, k):
+    """feats [C,N] -> [C,N] (gcn.py:52-79)"""
+    w1 = sd[prefix + 'conv1.weight'].flatten(1); w2 = sd[prefix + 'conv2.weight'].flatten(1); w3 = sd[prefix + 'conv3.weight'].flatten(1)
+    x1 = _in2d_lrelu_ref(torch.einsum('oc,cnk->onk', w1, _graph_feature_ref(coords, feats, k))).max(dim=-1)[0]
+    x2 = _in2d_lrelu_ref(torch.einsum('oc,cnk->onk', w2, _graph_feature_ref(coords, x1, k))).max(dim=-1)[0]
+    x3 = torch.matmul(w3, torch.cat((feats, x1, x2), dim=0)).unsqueeze(-1)
+    return _in2d_lrelu_ref(x3).squeeze(-1)
+
+
+def cross_attention_ref(x, src, sd, prefix, heads):
+    """x [C,N], src [C,M] -> update for x [C,N] (gcn.py:92-129)"""
+    def conv(name, t):
+        return torch.matmul(sd[prefix + name + '.weight'].squeeze(-1), t) + sd[prefix + name + '.bias'][:, None]
+    c = x.shape[0]
+    dim = c // heads
+    q = conv('attn.proj.0', x).view(dim, heads, -1)
+    kk = conv('attn.proj.1', src).view(dim, heads, -1)
+    v = conv('attn.proj.2', src).view(dim, heads, -1)
+    prob = torch.softmax(torch.einsum('dhn,dhm->hnm', q, kk) / dim ** .5, dim=-1)
+    msg = conv('attn.merge', torch.einsum('hnm,dhm->dhn', prob, v).reshape(c, -1))
+    h = conv('mlp.0', torch.cat([x, msg], dim=0))
+    h = (h - h.mean(dim=1, keepdim=True)) / torch.sqrt(h.var(dim=1, unbiased=False, keepdim=True) + 1e-5)   # InstanceNorm1d
+    return conv('mlp.3', F.relu(h))
+
+
+def kpfcnn_ref(batch, sd, config):
+    """Full KPFCNN.forward (architectures.py:137-212) on CPU tensors -> (feats_f, scores_overlap, scores_saliency)."""
+    outs = encoder_ref(batch, sd, config, return_all=True)
+    arch = list(config.architecture)
+    start = next(i for i, b in enumerate(arch) if 'upsample' in b)
+    skips, x_in = [], batch['features']
+    for i, b in enumerate(arch[:start]):                                      # :149-152: the INPUT of every strided block
+        if any(t in b for t in ('pool', 'strided', 'global')):
+            skips.append(x_in)
+        x_in = outs[i]
+    x = outs[-1]
+    n_src = int(batch['stack_lengths'][-1][0])
+    pts = batch['points'][-1]
+    feats = torch.matmul(sd['bottle.weight'].squeeze(-1), x.t()) + sd['bottle.bias'][:, None]      # [C,N] :157-158
+    uncond = feats.t()
+    d0, d1 = feats[:, :n_src], feats[:, n_src:]
+    for li, name in enumerate(config.nets):                                   # gcn.py:194-209
+        p = f'gnn.layers.{li}.'
+        if name == 'self':
+            d0 = self_attention_ref(pts[:n_src], d0, sd, p, config.dgcnn_k)
+            d1 = self_attention_ref(pts[n_src:], d1, sd, p, config.dgcnn_k)
+        else:
+            d0 = d0 + cross_attention_ref(d0, d1, sd, p, config.num_head)
+            d1 = d1 + cross_attention_ref(d1, d0, sd, p, config.num_head)
+    feats = torch.cat([d0, d1], dim=1)
+    feats = torch.matmul(sd['proj_gnn.weight'].squeeze(-1), feats) + sd['proj_gnn.bias'][:, None]
+    scores = (torch.matmul(sd['proj_score.weight'].squeeze(-1), feats) + sd['proj_score.bias'][:, None]).t()   # [N,1]
+    raw = feats.t()
+    fn = F.normalize(raw, p=2, dim=1)
+    inner = fn[:n_src] @ fn[n_src:].t()
+    temp = torch.exp(sd['epsilon']) + 0.03
+    s1 = torch.softmax(inner / temp, dim=1) @ scores[n_src:]
+    s2 = torch.softmax(inner.t() / temp, dim=1) @ scores[:n_src]
+    sal = torch.cat((s1, s2), dim=0)
+    body = raw if config.condition_feature else uncond
+    x = torch.cat([scores, sal, body] if config.add_cross_score else [scores, body], dim=1)
+    layer = sum(1 for b in arch[:start] if 'pool' in b or 'strided' in b)
+    for i, b in enumerate(arch[start:]):                                      # :195-198
+        if i > 0 and 'upsample' in arch[start + i - 1]:
+            x = torch.cat([x, skips.pop()], dim=1)
+        if 'upsample' in b:
+            x = closest_pool_ref(x, batch['upsamples'][layer - 1])
+            layer -= 1
+        elif b == 'last_unary':
+            x = F.linear(x, sd[f'decoder_blocks.{i}.mlp.weight'])
+        else:
+            x = unary_ref(x, sd[f'decoder_blocks.{i}.mlp.weight'])
+    d = config.final_feats_dim
+    clean = lambda s: torch.nan_to_num(torch.clamp(torch.sigmoid(s), 0, 1), nan=0.0, posinf=0.0, neginf=0.0)
+    return F.normalize(x[:, :d], p=2, dim=1), clean(x[:, d]), clean(x[:, d + 1])

@@ -159,6 +159,34 @@ def golden_encoder(O, rarch):
     print(f"  encoder first_feats_dim=128: restatement rel err {err:.2e}")
 
 
+def golden_kpfcnn(O, rarch):
+    """Full KPFCNN forward (encoder + bottleneck GNN + decoder) of the REAL reference on a small pair; pins
+    blocks_ref.kpfcnn_ref and freezes the outputs (small widths so the fixture stays small)."""
+    cfg = kitti_config(first_feats_dim=16, gnn_feats_dim=32, final_feats_dim=8)
+    a, b = small_pair(5, 1500)
+    raw = np.concatenate([a, b]); lens = np.array([len(a), len(b)], np.int32)
+    p0, l0 = O.subsample_batch(raw, lens, sampleDl=0.3)
+    limits = [30, 30, 30, 30]
+    pyr = collate_ref(p0, l0, cfg, limits, O.subsample_batch, O.batch_query)
+    batch = batch_to_torch(pyr)
+    batch['features'] = torch.ones(len(p0), 1)
+    torch.manual_seed(0); np.random.seed(0)
+    model = rarch.KPFCNN(cfg).eval()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        ff, so, ss = model(batch)
+        mf, mo, ms = blocks_ref.kpfcnn_ref(batch, sd, cfg)
+    for name, r, m in (("feats_f", ff, mf), ("scores_overlap", so, mo), ("scores_saliency", ss, ms)):
+        err = ((r - m).norm() / r.norm()).item()
+        assert err < 1e-4, f"kpfcnn_ref {name} != reference ({err})"
+        print(f"  kpfcnn {name}: restatement rel err {err:.2e}")
+    out = {"p0": p0, "l0": l0, "limits": np.array(limits), "feats_f": ff.numpy(), "scores_overlap": so.numpy(),
+           "scores_saliency": ss.numpy()}
+    for k, v in sd.items():
+        out["sd/" + k] = v.numpy()
+    np.savez_compressed(os.path.join(GOLD, "kpfcnn_small.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     O, R = Oracle(), RefL1()
@@ -166,4 +194,5 @@ if __name__ == "__main__":
     rblocks, rarch = import_reference()
     print("KPConv goldens"); golden_kpconv(O, rblocks)
     print("encoder goldens"); golden_encoder(O, rarch)
+    print("KPFCNN goldens"); golden_kpfcnn(O, rarch)
     print("golden fixtures written to", GOLD)

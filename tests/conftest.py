@@ -44,6 +44,11 @@ def gold_encoder():
 
 
 @pytest.fixture(scope="session")
+def gold_kpfcnn():
+    return np.load(os.path.join(GOLD, "kpfcnn_small.npz"))
+
+
+@pytest.fixture(scope="session")
 def cuda():
     import torch
     if not torch.cuda.is_available():

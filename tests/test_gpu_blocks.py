@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from apr_b200 import blocks, ops
-from apr_b200.architectures import KPFCNNEncoder
+from apr_b200.architectures import KPFCNN, KPFCNNEncoder
 from apr_b200.config import kitti_config
 from oracle import blocks_ref
 from oracle.ref import collate_ref
@@ -331,3 +331,57 @@ def test_native_pipeline_super_batch_equals_separate_pairs(cuda, oracle):
         a += o.shape[0]
     host = batch.forward_host(torch.from_numpy(P0).pin_memory(), torch.from_numpy(L0).pin_memory())
     assert torch.equal(host, got.cpu())
+
+
+@pytest.mark.parametrize("mode,tol", [(1, 2e-4), (0, 5e-3)])
+def test_kpfcnn_full_forward_golden(cuda, oracle, gold_kpfcnn, mode, tol):
+    """BASELINE config 3's network: full KPFCNN forward (encoder + bottleneck GNN + decoder) vs the outputs of the REAL
+    reference; the reference's checkpoint keys load with strict=True."""
+    g = gold_kpfcnn
+    cfg = kitti_config(first_feats_dim=16, gnn_feats_dim=32, final_feats_dim=8)
+    pyr = collate_ref(g["p0"], g["l0"], cfg, list(g["limits"]), oracle.subsample_batch, oracle.batch_query)
+    gpu = dict(points=[_t(p, cuda) for p in pyr["points"]], neighbors=[_t(n, cuda).long() for n in pyr["neighbors"]],
+               pools=[_t(n, cuda).long() for n in pyr["pools"]], upsamples=[_t(n, cuda).long() for n in pyr["upsamples"]],
+               stack_lengths=[_t(l, cuda) for l in pyr["stack_lengths"]], features=torch.ones(len(g["p0"]), 1, device=cuda))
+    net = KPFCNN(cfg)
+    net.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd/")}, strict=True)
+    net = net.to(cuda).eval()
+    blocks.KPCONV_MODE = mode
+    try:
+        ff, so, ss = net(gpu)
+    finally:
+        blocks.KPCONV_MODE = 0
+    for got, key in ((ff, "feats_f"), (so, "scores_overlap"), (ss, "scores_saliency")):
+        e = rel(got, torch.from_numpy(g[key]))
+        print(f"KPFCNN {key} (mode {mode}): rel err {e:.2e}")
+        assert got.shape == g[key].shape and e < tol, key
+
+
+def test_kpfcnn_kitti_width_device_pyramid_vs_oracle(cuda, oracle):
+    """Full KPFCNN at the KITTI widths on a small LoKITTI-like pair, pyramid built on the device (collate on the GPU),
+    vs the fp32 CPU restatement of the whole reference forward."""
+    from apr_b200 import dataloader, synth
+    cfg = kitti_config()
+    a = synth.small_cloud(71, 3200)
+    b = synth.small_cloud(71, 3000) + np.array([6.0, 0.5, 0.0], np.float32)          # same scene, shifted sensor
+    p0, l0 = oracle.subsample_batch(np.concatenate([a, b]), np.array([len(a), len(b)], np.int32), sampleDl=0.3)
+    limits = [32, 32, 32, 32]
+    torch.manual_seed(0); np.random.seed(0)
+    net = KPFCNN(cfg).eval()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    ref = collate_ref(p0, l0, cfg, limits, oracle.subsample_batch, oracle.batch_query)
+    cpu = dict(points=[torch.from_numpy(p) for p in ref["points"]], neighbors=[torch.from_numpy(n).long() for n in ref["neighbors"]],
+               pools=[torch.from_numpy(n).long() for n in ref["pools"]], upsamples=[torch.from_numpy(n).long() for n in ref["upsamples"]],
+               stack_lengths=[torch.from_numpy(l) for l in ref["stack_lengths"]], features=torch.ones(len(p0), 1))
+    want = blocks_ref.kpfcnn_ref(cpu, sd, cfg)
+    net = net.to(cuda)
+    pyr = dataloader.build_pyramid_device(_t(p0, cuda), _t(l0, cuda), cfg, limits)
+    blocks.LINEAR_MODE = 'tf32'
+    try:
+        got = net(pyr)
+    finally:
+        blocks.LINEAR_MODE = 'fp32'
+    for gt, wt, name in zip(got, want, ("feats_f", "scores_overlap", "scores_saliency")):
+        e = rel(gt, wt)
+        print(f"KPFCNN kitti width {name}: rel err {e:.2e}")
+        assert gt.shape == wt.shape and e < 2e-2, name
