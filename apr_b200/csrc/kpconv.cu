@@ -271,6 +271,88 @@ sgemm_rowscale_kernel(const float* __restrict__ A, const float* __restrict__ B, 
     }
 }
 
+// ---- training path: data gradient of stage A+B -------------------------------------------------
+// dx[s,:] += sum over (n,h,k) with idx[n,h] == s of w[n,k,h] * dwf[n,k,:]   (the transpose of blocks.py:348-354).
+// One warp per query: the same influence lists as kp_weighted_kernel (recomputed, nothing is stored by the forward),
+// then each kernel point's dwf slice is held in registers and pushed to its list's support rows with red.add.f32.
+template <typename IdxT, int VEC>
+__global__ void __launch_bounds__(128)
+kp_scatter_grad_kernel(const float* __restrict__ q, const float* __restrict__ s, const IdxT* __restrict__ idx, int ld,
+                       const float* __restrict__ kp, float extent, int Nq, int Ns, int H, int K, int Cin,
+                       const float* __restrict__ dwf, float* __restrict__ dx) {
+    extern __shared__ float s_dyn[];
+    __shared__ float s_kp[KP_MAX_K * 3];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int Hp = (H + 31) & ~31;
+    if (threadIdx.x < K * 3) s_kp[threadIdx.x] = kp[threadIdx.x];
+    __syncthreads();
+    const int n = blockIdx.x * wpb + wib;
+    if (n >= Nq) return;
+    int* s_si = reinterpret_cast<int*>(s_dyn) + (size_t)wib * KP_MAX_K * Hp * 2;
+    float* s_lw = reinterpret_cast<float*>(s_si + (size_t)KP_MAX_K * Hp);
+    int* s_cnt = reinterpret_cast<int*>(s_dyn) + (size_t)wpb * KP_MAX_K * Hp * 2 + wib * KP_MAX_K;
+    const float qx = q[3 * (size_t)n], qy = q[3 * (size_t)n + 1], qz = q[3 * (size_t)n + 2];
+    const float ext2 = extent * extent, inv_ext = 1.0f / extent;
+    int cnt[KP_MAX_K];
+#pragma unroll
+    for (int k = 0; k < KP_MAX_K; ++k) cnt[k] = 0;
+    for (int h0 = 0; h0 < Hp; h0 += 32) {
+        const int h = h0 + lane;
+        int si = Ns;
+        if (h < H) {
+            const long long v = (long long)idx[(size_t)n * ld + h];
+            si = (v >= 0 && v < Ns) ? (int)v : Ns;
+        }
+        float rx = 0.f, ry = 0.f, rz = 0.f;
+        const bool valid = si < Ns;
+        if (valid) { rx = s[3 * (size_t)si] - qx; ry = s[3 * (size_t)si + 1] - qy; rz = s[3 * (size_t)si + 2] - qz; }
+        if (!__any_sync(0xffffffffu, valid)) continue;
+#pragma unroll
+        for (int k = 0; k < KP_MAX_K; ++k) {
+            if (k < K) {
+                const float ddx = rx - s_kp[3 * k], ddy = ry - s_kp[3 * k + 1], ddz = rz - s_kp[3 * k + 2];
+                const float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+                float w = 0.f;
+                if (valid && d2 < ext2) w = 1.0f - sqrtf(d2) * inv_ext;
+                const bool in = w > 0.f;
+                const unsigned m = __ballot_sync(0xffffffffu, in);
+                if (in) {
+                    const int pos = cnt[k] + __popc(m & ((1u << lane) - 1));
+                    s_si[k * Hp + pos] = si * Cin;
+                    s_lw[k * Hp + pos] = w;
+                }
+                cnt[k] += __popc(m);
+            }
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < KP_MAX_K; ++k) s_cnt[k] = cnt[k];
+    }
+    __syncwarp();
+    const float* grow = dwf + (size_t)n * K * Cin;
+    for (int c0 = lane * VEC; c0 < Cin; c0 += 32 * VEC) {
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) {
+            const int ck = s_cnt[k];
+            if (ck == 0) continue;
+            float g[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) g[v] = grow[(size_t)k * Cin + c0 + v];
+            for (int e = 0; e < ck; ++e) {
+                const float w = s_lw[k * Hp + e];
+                float* dst = dx + s_si[k * Hp + e] + c0;
+                if (VEC == 4) atomicAdd(reinterpret_cast<float4*>(dst), make_float4(w * g[0], w * g[VEC > 1 ? 1 : 0], w * g[VEC > 2 ? 2 : 0], w * g[VEC > 3 ? 3 : 0]));
+                else {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) atomicAdd(dst + v, w * g[v]);
+                }
+            }
+        }
+    }
+}
+
+
 // W [K,Cin,Cout] -> Wt [Cout, K*Cin] (K-major B operand), rounded to TF32 (round-to-nearest, ties away)
 __global__ void prep_weights_kernel(const float* __restrict__ W, int KC, int Cout, float* __restrict__ Wt) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -306,6 +388,46 @@ extern "C" int aprb_round_tf32(const float* d_in, float* d_out, size_t n, void* 
     APRB_REQUIRE(n == 0 || (d_in && d_out), "null pointer");
     if (n == 0) return APRB_OK;
     APRB_TIMED("round_tf32_kernel", (cudaStream_t)stream, 1, (round_tf32_kernel<<<cdiv((long long)n, 256), 256, 0, (cudaStream_t)stream>>>(d_in, d_out, n)));
+    APRB_LAUNCH_OK();
+    return APRB_OK;
+}
+
+// Launch stage A+B for query rows [r0, r0 + nr): wf rows are written relative to r0, inv_nn at absolute rows.
+static int launch_kp_weighted(const float* d_q, const float* d_s, const void* d_idx, int idx_is_i64, int ld_idx,
+                              const float* d_x, const float* d_kp, const unsigned char* flag, float extent, int r0, int nr,
+                              int Ns, int H, int K, int Cin, bool round_tf32, float* wf, float* inv_nn, cudaStream_t st) {
+    const int Hp = (H + 31) & ~31;
+    const size_t smem_warp = (size_t)KP_MAX_K * Hp * 8 + KP_MAX_K * 4;
+    int wpb = 4;
+    while (wpb > 1 && wpb * smem_warp > 160 * 1024) wpb >>= 1;
+    if (smem_warp > 200 * 1024) { set_error("aprb_kpconv_forward: H=%d too large for the shared-memory neighbour lists", H); return APRB_ERR_UNSUPPORTED; }
+    const size_t smem = wpb * smem_warp;
+    const bool x16 = ((uintptr_t)d_x % 16 == 0) && ((uintptr_t)wf % 16 == 0);
+    // (VEC, NJ): channels per lane = VEC*NJ, one slab = 32*VEC*NJ channels
+    int vec = 1, nj = 1;
+    if (x16 && Cin % 4 == 0 && Cin >= 128) { vec = 4; nj = Cin >= 512 ? 4 : (Cin >= 256 ? 2 : 1); }
+    else if (x16 && Cin % 2 == 0 && Cin >= 64) { vec = 2; nj = 1; }
+#define KPW_LAUNCH3(IDX, VEC, NJ, RND)                                                                               \
+    do {                                                                                                             \
+        if (smem > 48 * 1024)                                                                                        \
+            APRB_CUDA_OK(cudaFuncSetAttribute(kp_weighted_kernel<IDX, VEC, NJ, RND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        const int nslabs = cdiv(Cin, 32 * VEC * NJ);                                                                 \
+        const int gy = (cdiv(nr, wpb) < 4 * sm_count()) ? nslabs : 1;                                                \
+        APRB_TIMED("kp_weighted_kernel", st, 1, (kp_weighted_kernel<IDX, VEC, NJ, RND><<<dim3(cdiv(nr, wpb), gy), wpb * 32, smem, st>>>( \
+            d_q + 3 * (size_t)r0, d_s, (const IDX*)d_idx + (size_t)r0 * ld_idx, ld_idx, d_x, d_kp, flag, extent, nr, Ns, H, K, Cin, wf, inv_nn + r0))); \
+    } while (0)
+#define KPW_LAUNCH(IDX, RND)                                                                                         \
+    do {                                                                                                             \
+        if (vec == 4 && nj == 4) KPW_LAUNCH3(IDX, 4, 4, RND);                                                        \
+        else if (vec == 4 && nj == 2) KPW_LAUNCH3(IDX, 4, 2, RND);                                                   \
+        else if (vec == 4) KPW_LAUNCH3(IDX, 4, 1, RND);                                                              \
+        else if (vec == 2) KPW_LAUNCH3(IDX, 2, 1, RND);                                                              \
+        else KPW_LAUNCH3(IDX, 1, 1, RND);                                                                            \
+    } while (0)
+    if (round_tf32) { if (idx_is_i64) KPW_LAUNCH(long long, true); else KPW_LAUNCH(int, true); }
+    else { if (idx_is_i64) KPW_LAUNCH(long long, false); else KPW_LAUNCH(int, false); }
+#undef KPW_LAUNCH3
+#undef KPW_LAUNCH
     APRB_LAUNCH_OK();
     return APRB_OK;
 }
@@ -347,65 +469,95 @@ extern "C" int aprb_kpconv_forward(const float* d_q, const float* d_s, const voi
     float* gws = c.take<float>(gws_bytes / sizeof(float));
 
     if (Ns > 0) APRB_TIMED("rowsum_pos_kernel", st, 1, (rowsum_pos_kernel<<<cdiv(Ns, 8), 256, 0, st>>>(d_x, Ns, Cin, flag)));
-    const int Hp = (H + 31) & ~31;
-    const size_t smem_warp = (size_t)KP_MAX_K * Hp * 8 + KP_MAX_K * 4;
-    int wpb = 4;
-    while (wpb > 1 && wpb * smem_warp > 160 * 1024) wpb >>= 1;
-    if (smem_warp > 200 * 1024) { set_error("aprb_kpconv_forward: H=%d too large for the shared-memory neighbour lists", H); return APRB_ERR_UNSUPPORTED; }
-    const size_t smem = wpb * smem_warp;
-    const bool x16 = ((uintptr_t)d_x % 16 == 0) && ((uintptr_t)wf % 16 == 0);
-    // (VEC, NJ): channels per lane = VEC*NJ, one slab = 32*VEC*NJ channels
-    int vec = 1, nj = 1;
-    if (x16 && Cin % 4 == 0 && Cin >= 128) { vec = 4; nj = Cin >= 512 ? 4 : (Cin >= 256 ? 2 : 1); }
-    else if (x16 && Cin % 2 == 0 && Cin >= 64) { vec = 2; nj = 1; }
-    // rows [r0, r0 + nr) of the query set; wf is addressed relative to r0 (the chunked tensor path reuses it)
-#define KPW_LAUNCH3(IDX, VEC, NJ, RND)                                                                               \
-    do {                                                                                                             \
-        if (smem > 48 * 1024)                                                                                        \
-            APRB_CUDA_OK(cudaFuncSetAttribute(kp_weighted_kernel<IDX, VEC, NJ, RND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        const int nslabs = cdiv(Cin, 32 * VEC * NJ);                                                                 \
-        const int gy = (cdiv(nr, wpb) < 4 * sm_count()) ? nslabs : 1;                                                \
-        APRB_TIMED("kp_weighted_kernel", st, 1, (kp_weighted_kernel<IDX, VEC, NJ, RND><<<dim3(cdiv(nr, wpb), gy), wpb * 32, smem, st>>>( \
-            d_q + 3 * (size_t)r0, d_s, (const IDX*)d_idx + (size_t)r0 * ld_idx, ld_idx, d_x, d_kp, flag, extent, nr, Ns, H, K, Cin, wf, inv_nn + r0))); \
-    } while (0)
-#define KPW_LAUNCH(IDX, RND)                                                                                         \
-    do {                                                                                                             \
-        if (vec == 4 && nj == 4) KPW_LAUNCH3(IDX, 4, 4, RND);                                                        \
-        else if (vec == 4 && nj == 2) KPW_LAUNCH3(IDX, 4, 2, RND);                                                   \
-        else if (vec == 4) KPW_LAUNCH3(IDX, 4, 1, RND);                                                              \
-        else if (vec == 2) KPW_LAUNCH3(IDX, 2, 1, RND);                                                              \
-        else KPW_LAUNCH3(IDX, 1, 1, RND);                                                                            \
-    } while (0)
     if (use_tensor) {
         // Row chunks sized so that one chunk of wf (the A operand) stays L2-resident between its producer and the GEMM
-        // that consumes it: with super-batched pairs wf is ~1 GB per layer and would otherwise round-trip through HBM.
+        // that consumes it (aprb_set_option("kpconv_chunk_mb"); measured on B200: no gain, off by default).
         int chunk_rows = Nq;
         if (g_kpconv_chunk_mb > 0) {
-            long long rows = ((long long)g_kpconv_chunk_mb << 20) / ((long long)KC * 4);
-            rows = (rows / 128) * 128;
-            if (rows < 128 * 148) rows = 128 * 148;                  // at least one GEMM tile per SM
-            if (rows < Nq) chunk_rows = (int)rows;
+            long long rows_c = ((long long)g_kpconv_chunk_mb << 20) / ((long long)KC * 4);
+            rows_c = (rows_c / 128) * 128;
+            if (rows_c < 128 * 148) rows_c = 128 * 148;              // at least one GEMM tile per SM
+            if (rows_c < Nq) chunk_rows = (int)rows_c;
         }
         for (int r0 = 0; r0 < Nq; r0 += chunk_rows) {
             const int nr = min(chunk_rows, Nq - r0);
-            if (idx_is_i64) KPW_LAUNCH(long long, true); else KPW_LAUNCH(int, true);
-            APRB_LAUNCH_OK();
-            int rc = gemm_tf32_rowscale(wf, d_wprep, nr, Cout, KC, inv_nn + r0, d_out + (size_t)r0 * Cout, gws, gws_bytes, st);
+            int rc = launch_kp_weighted(d_q, d_s, d_idx, idx_is_i64, ld_idx, d_x, d_kp, flag, extent, r0, nr, Ns, H, K, Cin, true, wf, inv_nn, st);
+            if (rc) return rc;
+            rc = gemm_tf32_rowscale(wf, d_wprep, nr, Cout, KC, inv_nn + r0, d_out + (size_t)r0 * Cout, gws, gws_bytes, st);
             if (rc) return rc;
         }
         return APRB_OK;
     }
-    const int r0 = 0, nr = Nq;
     if (Cin == 1) {
         if (idx_is_i64) APRB_TIMED("kp_weighted_c1_kernel", st, 1, (kp_weighted_c1_kernel<long long><<<cdiv(Nq, 4), 128, 0, st>>>(
             d_q, d_s, (const long long*)d_idx, ld_idx, d_x, d_kp, flag, extent, Nq, Ns, H, K, wf, inv_nn)));
         else APRB_TIMED("kp_weighted_c1_kernel", st, 1, (kp_weighted_c1_kernel<int><<<cdiv(Nq, 4), 128, 0, st>>>(
             d_q, d_s, (const int*)d_idx, ld_idx, d_x, d_kp, flag, extent, Nq, Ns, H, K, wf, inv_nn)));
-    } else if (idx_is_i64) KPW_LAUNCH(long long, false); else KPW_LAUNCH(int, false);
-#undef KPW_LAUNCH3
-#undef KPW_LAUNCH
-    APRB_LAUNCH_OK();
+        APRB_LAUNCH_OK();
+    } else {
+        int rc = launch_kp_weighted(d_q, d_s, d_idx, idx_is_i64, ld_idx, d_x, d_kp, flag, extent, 0, Nq, Ns, H, K, Cin, false, wf, inv_nn, st);
+        if (rc) return rc;
+    }
     APRB_TIMED("sgemm_rowscale_kernel", st, 1, (sgemm_rowscale_kernel<<<dim3(cdiv(Cout, 64), cdiv(Nq, 64)), 256, 0, st>>>(wf, d_W, Nq, Cout, KC, inv_nn, d_out)));
+    APRB_LAUNCH_OK();
+    return APRB_OK;
+}
+
+extern "C" size_t aprb_kpconv_weighted_ws_bytes(int Ns) { return Ns < 0 ? 0 : align256((size_t)Ns + 1) + 256; }
+
+extern "C" int aprb_kpconv_weighted(const float* d_q, const float* d_s, const void* d_idx, int idx_is_i64, int ld_idx,
+                                    const float* d_x, const float* d_kp, float extent, int Nq, int Ns, int H, int K, int Cin,
+                                    int round_tf32, float* d_wf, float* d_inv_nn, void* d_ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    APRB_REQUIRE(Nq >= 0 && Ns >= 0 && H >= 1 && H <= 1024, "need Nq,Ns >= 0 and 1 <= H <= 1024");
+    APRB_REQUIRE(K >= 1 && K <= KP_MAX_K && Cin >= 1 && ld_idx >= H && extent > 0.f, "need 1 <= K <= 16, Cin >= 1, ld >= H, extent > 0");
+    APRB_REQUIRE((long long)Ns * Cin < 0x7FFFFFFFLL, "feature table too large for 32-bit row offsets");
+    if (Nq == 0) return APRB_OK;
+    APRB_REQUIRE(d_q && d_idx && d_kp && d_wf && d_inv_nn && d_ws && (Ns == 0 || (d_s && d_x)), "null pointer");
+    if (ws_bytes < aprb_kpconv_weighted_ws_bytes(Ns)) { set_error("aprb_kpconv_weighted: workspace too small"); return APRB_ERR_WORKSPACE; }
+    unsigned char* flag = (unsigned char*)d_ws;
+    if (Ns > 0) APRB_TIMED("rowsum_pos_kernel", st, 1, (rowsum_pos_kernel<<<cdiv(Ns, 8), 256, 0, st>>>(d_x, Ns, Cin, flag)));
+    if (Cin == 1) {
+        if (idx_is_i64) APRB_TIMED("kp_weighted_c1_kernel", st, 1, (kp_weighted_c1_kernel<long long><<<cdiv(Nq, 4), 128, 0, st>>>(
+            d_q, d_s, (const long long*)d_idx, ld_idx, d_x, d_kp, flag, extent, Nq, Ns, H, K, d_wf, d_inv_nn)));
+        else APRB_TIMED("kp_weighted_c1_kernel", st, 1, (kp_weighted_c1_kernel<int><<<cdiv(Nq, 4), 128, 0, st>>>(
+            d_q, d_s, (const int*)d_idx, ld_idx, d_x, d_kp, flag, extent, Nq, Ns, H, K, d_wf, d_inv_nn)));
+        APRB_LAUNCH_OK();
+        return APRB_OK;
+    }
+    return launch_kp_weighted(d_q, d_s, d_idx, idx_is_i64, ld_idx, d_x, d_kp, flag, extent, 0, Nq, Ns, H, K, Cin, round_tf32 != 0,
+                              d_wf, d_inv_nn, st);
+}
+
+extern "C" int aprb_kpconv_backward_data(const float* d_q, const float* d_s, const void* d_idx, int idx_is_i64, int ld_idx,
+                                         const float* d_kp, float extent, int Nq, int Ns, int H, int K, int Cin,
+                                         const float* d_dwf, float* d_dx, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    APRB_REQUIRE(Nq >= 0 && Ns >= 0 && H >= 1 && H <= 1024, "need Nq,Ns >= 0 and 1 <= H <= 1024");
+    APRB_REQUIRE(K >= 1 && K <= KP_MAX_K && Cin >= 1 && ld_idx >= H && extent > 0.f, "need 1 <= K <= 16, Cin >= 1, ld >= H, extent > 0");
+    APRB_REQUIRE((long long)Ns * Cin < 0x7FFFFFFFLL, "feature table too large for 32-bit row offsets");
+    if (Ns == 0) return APRB_OK;
+    APRB_REQUIRE(d_dx, "null pointer");
+    APRB_CUDA_OK(cudaMemsetAsync(d_dx, 0, (size_t)Ns * Cin * sizeof(float), st));
+    if (Nq == 0) return APRB_OK;
+    APRB_REQUIRE(d_q && d_s && d_idx && d_kp && d_dwf, "null pointer");
+    const int Hp = (H + 31) & ~31;
+    const size_t smem_warp = (size_t)KP_MAX_K * Hp * 8 + KP_MAX_K * 4;
+    int wpb = 4;
+    while (wpb > 1 && wpb * smem_warp > 160 * 1024) wpb >>= 1;
+    if (smem_warp > 200 * 1024) { set_error("aprb_kpconv_backward_data: H=%d too large", H); return APRB_ERR_UNSUPPORTED; }
+    const size_t smem = wpb * smem_warp;
+    const bool v4 = Cin % 4 == 0 && ((uintptr_t)d_dwf % 16 == 0) && ((uintptr_t)d_dx % 16 == 0);
+#define KPS_LAUNCH(IDX, VEC)                                                                                          \
+    do {                                                                                                              \
+        if (smem > 48 * 1024)                                                                                         \
+            APRB_CUDA_OK(cudaFuncSetAttribute(kp_scatter_grad_kernel<IDX, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        APRB_TIMED("kp_scatter_grad_kernel", st, 1, (kp_scatter_grad_kernel<IDX, VEC><<<cdiv(Nq, wpb), wpb * 32, smem, st>>>( \
+            d_q, d_s, (const IDX*)d_idx, ld_idx, d_kp, extent, Nq, Ns, H, K, Cin, d_dwf, d_dx)));                      \
+    } while (0)
+    if (idx_is_i64) { if (v4) KPS_LAUNCH(long long, 4); else KPS_LAUNCH(long long, 1); }
+    else { if (v4) KPS_LAUNCH(int, 4); else KPS_LAUNCH(int, 1); }
+#undef KPS_LAUNCH
     APRB_LAUNCH_OK();
     return APRB_OK;
 }

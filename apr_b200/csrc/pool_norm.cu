@@ -56,6 +56,48 @@ __global__ void closest_pool_kernel(const float* __restrict__ x, const IdxT* __r
     out[(size_t)n * C + c] = (s >= 0 && s < Ns) ? x[(size_t)s * C + c] : 0.f;
 }
 
+// Gradient of max_pool (training path): dy[n,c] goes to the FIRST neighbour that attains the maximum (torch.max's
+// index on ties); the shadow row's share is dropped. One thread per (query, channel).
+template <typename IdxT>
+__global__ void max_pool_backward_kernel(const float* __restrict__ x, const IdxT* __restrict__ idx, int ld, int Nq, int Ns,
+                                         int H, int C, const float* __restrict__ dy, float* __restrict__ dx) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)Nq * C) return;
+    int n = (int)(t / C), c = (int)(t % C);
+    const IdxT* row = idx + (size_t)n * ld;
+    float m = -INFINITY;
+    long long arg = Ns;
+    for (int h = 0; h < H; ++h) {
+        long long s = (long long)row[h];
+        const bool real = s >= 0 && s < Ns;
+        const float v = real ? x[(size_t)s * C + c] : 0.f;
+        if (v > m) { m = v; arg = real ? s : Ns; }
+    }
+    if (arg < Ns) atomicAdd(dx + (size_t)arg * C + c, dy[(size_t)n * C + c]);
+}
+
+}  // namespace aprb
+
+using namespace aprb;
+
+extern "C" int aprb_max_pool_backward(const float* d_x, const void* d_idx, int idx_is_i64, int ld_idx, int Nq, int Ns,
+                                      int H, int C, const float* d_dy, float* d_dx, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    APRB_REQUIRE(Nq >= 0 && Ns >= 0 && H >= 1 && C >= 1 && ld_idx >= H, "bad shape");
+    if (Ns == 0) return APRB_OK;
+    APRB_REQUIRE(d_x && d_dx, "null pointer");
+    APRB_CUDA_OK(cudaMemsetAsync(d_dx, 0, (size_t)Ns * C * sizeof(float), st));
+    if (Nq == 0) return APRB_OK;
+    APRB_REQUIRE(d_idx && d_dy, "null pointer");
+    long long total = (long long)Nq * C;
+    if (idx_is_i64) APRB_TIMED("max_pool_backward_kernel", st, 1, (max_pool_backward_kernel<long long><<<cdiv(total, 256), 256, 0, st>>>(d_x, (const long long*)d_idx, ld_idx, Nq, Ns, H, C, d_dy, d_dx)));
+    else APRB_TIMED("max_pool_backward_kernel", st, 1, (max_pool_backward_kernel<int><<<cdiv(total, 256), 256, 0, st>>>(d_x, (const int*)d_idx, ld_idx, Nq, Ns, H, C, d_dy, d_dx)));
+    APRB_LAUNCH_OK();
+    return APRB_OK;
+}
+
+namespace aprb {
+
 // ---- K6 -------------------------------------------------------------------------------------------------------
 // Two launches per normalisation: (1) per (row-chunk, column) Welford partials (mean, M2); (2) every block of the apply
 // kernel Chan-combines the partials of its 32 columns in a fixed order (deterministic, no float atomics), then

@@ -266,3 +266,48 @@ def round_tf32(t):
     out = torch.empty_like(tt)
     N.check(N.lib().aprb_round_tf32(N.ptr(tt), N.ptr(out), tt.numel(), N.stream_ptr()), "aprb_round_tf32")
     return out
+
+
+# ---- training path (stage A+B alone, data gradients) ------------------------------------------------------------------
+def kpconv_weighted(q_pts, s_pts, neighb_inds, x, kernel_points, extent, round_tf32=False):
+    """Stage A+B of KPConv: (wf [Nq, K*Cin], inv_nn [Nq]) — see aprb_kpconv_weighted."""
+    N.require_cuda()
+    q, s, xx = _dev_f32(q_pts, "q_pts"), _dev_f32(s_pts, "s_pts"), _dev_f32(x, "x")
+    kp = _dev_f32(kernel_points.detach(), "kernel_points")
+    idx, is64, ld = _idx(neighb_inds, "neighb_inds")
+    nq, ns, h, k, cin = q.shape[0], s.shape[0], idx.shape[1], kp.shape[0], xx.shape[1]
+    wf = torch.empty((nq, k * cin), dtype=torch.float32, device=q.device)
+    inv_nn = torch.empty(nq, dtype=torch.float32, device=q.device)
+    ws = _workspace(N.lib().aprb_kpconv_weighted_ws_bytes(ns), q.device)
+    rc = N.lib().aprb_kpconv_weighted(N.ptr(q), N.ptr(s), N.ptr(idx), is64, ld, N.ptr(xx), N.ptr(kp), float(extent), nq, ns, h,
+                                      k, cin, 1 if round_tf32 else 0, N.ptr(wf), N.ptr(inv_nn), N.ptr(ws), ws.numel(),
+                                      N.stream_ptr())
+    N.check(rc, "aprb_kpconv_weighted")
+    return wf, inv_nn
+
+
+def kpconv_backward_data(q_pts, s_pts, neighb_inds, kernel_points, extent, dwf, cin):
+    """dx [Ns,Cin] = scatter-add of w[n,k,h] * dwf[n,k,:] over the neighbour lists — see aprb_kpconv_backward_data."""
+    N.require_cuda()
+    q, s, g = _dev_f32(q_pts, "q_pts"), _dev_f32(s_pts, "s_pts"), _dev_f32(dwf, "dwf")
+    kp = _dev_f32(kernel_points.detach(), "kernel_points")
+    idx, is64, ld = _idx(neighb_inds, "neighb_inds")
+    nq, ns, h, k = q.shape[0], s.shape[0], idx.shape[1], kp.shape[0]
+    dx = torch.empty((ns, cin), dtype=torch.float32, device=q.device)
+    rc = N.lib().aprb_kpconv_backward_data(N.ptr(q), N.ptr(s), N.ptr(idx), is64, ld, N.ptr(kp), float(extent), nq, ns, h, k,
+                                           int(cin), N.ptr(g), N.ptr(dx), N.stream_ptr())
+    N.check(rc, "aprb_kpconv_backward_data")
+    return dx
+
+
+def max_pool_backward(x, inds, dy):
+    """Gradient of max_pool w.r.t. x."""
+    N.require_cuda()
+    xx, g = _dev_f32(x, "x"), _dev_f32(dy, "dy")
+    idx, is64, ld = _idx(inds, "inds")
+    nq, h = idx.shape
+    ns, c = xx.shape
+    dx = torch.empty_like(xx)
+    rc = N.lib().aprb_max_pool_backward(N.ptr(xx), N.ptr(idx), is64, ld, nq, ns, h, c, N.ptr(g), N.ptr(dx), N.stream_ptr())
+    N.check(rc, "aprb_max_pool_backward")
+    return dx

@@ -113,10 +113,26 @@ int aprb_kpconv_forward(const float* d_q, const float* d_s, const void* d_idx, i
                         float extent, int Nq, int Ns, int H, int K, int Cin, int Cout,
                         float* d_out, int mode, void* d_ws, size_t ws_bytes, void* stream);
 
+/* Training path. Stage A+B alone: d_wf [Nq, K*Cin] = sum_h w[n,k,h] x[idx[n,h],:] and
+ * d_inv_nn [Nq] = 1 / max(1, neighbor_num) (blocks.py:269-354, :369-371), so that autograd can keep wf for the weight
+ * gradient dW = wf^T (dOut * inv_nn). Workspace: aprb_kpconv_weighted_ws_bytes(Ns). */
+size_t aprb_kpconv_weighted_ws_bytes(int Ns);
+int aprb_kpconv_weighted(const float* d_q, const float* d_s, const void* d_idx, int idx_is_i64, int ld_idx,
+                         const float* d_x, const float* d_kp, float extent, int Nq, int Ns, int H, int K, int Cin,
+                         int round_tf32, float* d_wf, float* d_inv_nn, void* d_ws, size_t ws_bytes, void* stream);
+/* Data gradient of stage A+B: d_dx [Ns,Cin] = scatter-add over the neighbour lists of w[n,k,h] * d_dwf[n,k,:]
+ * (d_dx is zeroed by the call; fp32 red.add, so the summation order is not fixed). */
+int aprb_kpconv_backward_data(const float* d_q, const float* d_s, const void* d_idx, int idx_is_i64, int ld_idx,
+                              const float* d_kp, float extent, int Nq, int Ns, int H, int K, int Cin,
+                              const float* d_dwf, float* d_dx, void* stream);
+
 /* ---------------------------------------------------------------- K4: pooling / upsampling gathers ----------- */
 /* out[n,c] = max_h (x ++ 0)[idx[n,h], c] over h < min(H, *d_width if non-NULL). */
 int aprb_max_pool(const float* d_x, const void* d_idx, int idx_is_i64, int ld_idx, int Nq, int Ns, int H, int C,
                   const int32_t* d_width, float* d_out, void* stream);
+/* Gradient of aprb_max_pool: d_dx [Ns,C] (zeroed by the call) += d_dy[n,c] at the first neighbour attaining the max. */
+int aprb_max_pool_backward(const float* d_x, const void* d_idx, int idx_is_i64, int ld_idx, int Nq, int Ns, int H, int C,
+                           const float* d_dy, float* d_dx, void* stream);
 /* out[n,:] = (x ++ 0)[idx[n,0], :] */
 int aprb_closest_pool(const float* d_x, const void* d_idx, int idx_is_i64, int ld_idx, int Nq, int Ns, int C,
                       float* d_out, void* stream);
