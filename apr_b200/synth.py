@@ -45,10 +45,16 @@ def nusc(seed, pose_x=0.0):
     return lidar(seed, 32, -30.0, 10.0, 1090, 1.84, 70.0, pose_x=pose_x)
 
 
+def pair_pose(seed, distant=False):
+    """Sensor displacement (metres along world x) between the two scans of pair `seed`."""
+    return float(np.random.default_rng(10_000 + seed).uniform(5.0, 50.0 if distant else 20.0))
+
+
 def pair_raw(seed, kind="kitti", distant=False):
-    """Two raw scans of scene `seed`. Ordinary pair: second pose U(5,20) m; distant (LoKITTI-like): U(5,50) m."""
+    """Two raw scans of scene `seed`. Ordinary pair: second pose U(5,20) m; distant (LoKITTI-like): U(5,50) m.
+    Both clouds are in their own sensor frame: world = sensor + (pose_x, 0, 0)."""
     gen = kitti if kind == "kitti" else nusc
-    d = float(np.random.default_rng(10_000 + seed).uniform(5.0, 50.0 if distant else 20.0))
+    d = pair_pose(seed, distant)
     return gen(seed, 0.0), gen(seed, d)
 
 

@@ -405,6 +405,97 @@ def run_ours(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------------ training step
+def run_train(args):
+    """BASELINE configs[4]: one APR training step per rank and step — differentiable KPFCNN forward (our KPConv kernels),
+    NPR generative loss + descriptor/score surrogate, backward (scatter-add data gradients), bucketed NCCL all-reduce
+    overlapped with backward, SGD (lr 0.01, momentum 0.98, wd 1e-6: main.py:66-75). Not the headline metric."""
+    from apr_b200 import _native, dataloader, ops, train
+    from apr_b200.architectures import KPFCNN
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    _native.require_cuda()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = kitti_config()
+    kind, distant, wl_name = WORKLOADS[args.workload]
+    from apr_b200.shard import shard_indices
+    seeds = shard_indices(max(args.pairs, 2) * world, rank, world)
+    items = []
+    for sd in seeds:
+        a, b = synth.pair_raw(sd, kind, distant)
+        d = synth.pair_pose(sd, distant)
+        raw = torch.from_numpy(np.concatenate([a, b])).to(dev)
+        lens = torch.tensor([len(a), len(b)], dtype=torch.int32, device=dev)
+        p0, l0 = ops.grid_subsample(raw, lens, cfg.first_subsampling_dl)
+        apc, apc_l = ops.grid_subsample(raw, lens, 0.2)             # denser 'aggregated' cloud standing in for src/tgt_nghb
+        n_src = int(l0[0])
+        shift = torch.tensor([d, 0.0, 0.0], device=dev)             # tgt sensor frame -> src sensor frame
+        nn_idx = ops.radius_neighbors(p0[:n_src], p0[n_src:] + shift, l0[:1], l0[1:], 0.45, 1)
+        has = nn_idx[:, 0] < (p0.shape[0] - n_src)
+        corr = torch.stack([torch.nonzero(has).flatten(), nn_idx[has, 0].long()], 1)
+        items.append((p0.contiguous(), l0, n_src, corr, apc[:int(apc_l[0])].contiguous(), apc[int(apc_l[0]):].contiguous()))
+    limits = [int(x) for x in dataloader.calibrate_neighbors_device([(it[0], it[1]) for it in items], cfg)]
+    torch.manual_seed(0); np.random.seed(0)
+    net = KPFCNN(cfg).to(dev)
+    head = train.NPRHead(cfg.final_feats_dim, cfg.point_generation_ratio).to(dev)
+    params = [p for p in list(net.parameters()) + list(head.parameters()) if p.requires_grad]
+    red = train.GradBucketReducer(params, bucket_mb=25.0)
+    opt = torch.optim.SGD(params, lr=0.01, momentum=0.98, weight_decay=1e-6)
+    torch.backends.cuda.matmul.allow_tf32 = True                    # the dense contractions run as TF32 library GEMMs
+    losses = []
+
+    def step(i):
+        p0, l0, n_src, corr, apc_s, apc_t = items[i % len(items)]
+        batch = dataloader.build_pyramid_device(p0, l0, cfg, limits)
+        opt.zero_grad(set_to_none=True)
+        ff, so, ss = train.kpfcnn_forward_train(net, batch)
+        loss = train.surrogate_desc_loss(ff[:n_src], ff[n_src:], corr, so, ss, n_src) \
+            + train.npr_loss(head, ff[:n_src], p0[:n_src], apc_s) + train.npr_loss(head, ff[n_src:], p0[n_src:], apc_t)
+        loss.backward()
+        red.finish()
+        opt.step()
+        return loss
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0c = _native.launch_count()
+    e0.record()
+    for i in range(args.steps):
+        losses.append(step(args.warmup + i))
+    e1.record()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    nparam = sum(p.numel() for p in params)
+    if rank == 0:
+        print(json.dumps({"metric": "APR training steps: pairs/sec (KFE + NPR head, fwd+bwd+allreduce+SGD)", "mode": "train",
+                          "value": world * args.steps / (ms * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+                          "config": {"workload": wl_name + "_train", "pairs_per_rank_per_step": 1, "params": nparam,
+                                     "allreduce_bytes_per_step": 4 * nparam if world > 1 else 0, "buckets": len(red.buckets),
+                                     "limits": limits, "points_stacked": int(items[0][0].shape[0])},
+                          "gpu_launches": int(_native.launch_count() - l0c),
+                          "loss_first_last": [float(losses[0]), float(losses[-1])]}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -417,12 +508,16 @@ def main():
     ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS))
     ap.add_argument("--streams", type=int, default=2, help="calls in flight per GPU (one CUDA stream + host thread each)")
     ap.add_argument("--batch", type=int, default=8, help="pairs stacked per call (super-batch; per-pair InstanceNorm segments)")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer = the headline metric (default); train = BASELINE configs[4] training step")
     ap.add_argument("--opt", action="append", default=[], help="native tuning switch name=value (aprb_set_option)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    if args.mode == "train":
+        return run_train(args)
     return run_ours(args)
 
 

@@ -80,19 +80,24 @@ def test_kpfcnn_train_step_gradients_vs_oracle(cuda, oracle, gold_kpfcnn):
     sdr = {k: v.clone().requires_grad_(v.dtype.is_floating_point and 'kernel_points' not in k) for k, v in sd.items()}
     rf, ro, rs = blocks_ref.kpfcnn_ref(cpu, sdr, cfg)
     ((rf * wf_).sum() + (ro * wo).sum() + (rs * ws_).sum()).backward()
-    worst, checked = 0.0, 0
+    gmax = max(v.grad.norm().item() for v in sdr.values() if v.grad is not None)
+    worst, checked, fails = 0.0, 0, []
     for name, p in net.named_parameters():
         if not p.requires_grad:
             continue
         ref = sdr[name].grad
         assert ref is not None and p.grad is not None, name
-        if ref.norm() < 1e-10:
-            continue
-        e = rel(p.grad, ref)
-        worst = max(worst, e); checked += 1
-        assert e < 2e-3, f"{name}: grad rel err {e:.2e}"
-    print(f"KPFCNN parameter gradients: {checked} tensors, worst rel err {worst:.2e}")
-    assert checked > 40
+        # parameters whose gradient is analytically zero (a bias in front of an InstanceNorm) hold only rounding noise
+        # on both sides: bound their absolute size instead of their ratio
+        diff = (p.grad.detach().cpu().double() - ref.double()).norm().item()
+        ok = diff < 2e-3 * ref.norm().item() + 1e-6 * gmax
+        if ref.norm().item() > 1e-5 * gmax:
+            worst = max(worst, diff / ref.norm().item()); checked += 1
+        if not ok:
+            fails.append((name, diff, ref.norm().item()))
+    print(f"KPFCNN parameter gradients: {checked} tensors with non-trivial gradient, worst rel err {worst:.2e}")
+    assert not fails, fails
+    assert checked > 30
 
 
 def test_train_step_runs_and_learns(cuda, oracle):
