@@ -20,6 +20,7 @@ size_t gemm_tf32_ws_bytes(int M, int N);
 bool gemm_tf32_supported(int M, int N, int K);
 
 constexpr int KP_MAX_K = 16;
+int g_kpw_version = 4;       // aprb_set_option("kpw_version"): 3 = per-kernel-point tables (v3), 4 = CSR lists + lane groups
 int g_kpconv_chunk_mb = 0;   // aprb_set_option("kpconv_chunk_mb"): L2-sized row chunks of the tensor path (0 = off)
 
 // flag[s] = 1 iff sum_c x[s,c] > 0 (one warp per support row; fixed reduction order)
@@ -171,6 +172,255 @@ kp_weighted_kernel(const float* __restrict__ q, const float* __restrict__ s, con
                     }
                 }
             }
+        }
+    }
+}
+
+// ---- v4: compact per-row CSR influence lists + lane-group streaming ---------------------------------------------------
+// Same contract as kp_weighted_kernel (Cin % 4 == 0, 16-byte aligned x / wf, H <= 32*NH). What changes is where the
+// instructions go (the v3 kernel was instruction-issue-bound, ~2700 warp instructions per query at Cin = 64):
+//  * phase 1 runs kernel-point-major, so the (element offset, weight) pairs of kernel point k land contiguously after
+//    those of k-1: one CSR row of KPW_ECAP entries + K+1 offsets (1.3 KB) replaces the K x Hp table (8 KB) — 6x the
+//    resident warps; the kernel point is one LDS.128, the square root is sqrt.approx (1 ulp; the weight is linear in it);
+//  * phase 2 splits the warp into 32/LG lane groups that stream DIFFERENT rows: a group of LG lanes covers LG*4*NV
+//    channels with 128-bit loads, so one LDS.64 + one address + NV LDG.128 + 4*NV FFMA serve 32/LG list entries;
+//    lists shorter than the longest of the warp's rows are padded with weight-0 reads of row 0.
+// A row whose list would exceed KPW_ECAP entries (kernel points much closer together than the extent) is evaluated
+// directly by the whole warp (kp_direct_row): ballot over the neighbours, shuffle-broadcast of (offset, weight).
+constexpr int KPW_ECAP = 160;
+constexpr int KPW_SLOT_BYTES = KPW_ECAP * 8 + 80;   // int2 ent[ECAP]; int off[K_MAX+1] (+pad)
+
+__device__ __forceinline__ float sqrt_approx(float v) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float round_tf32(float t) {
+    unsigned u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(t));
+    return __uint_as_float(u);
+}
+
+template <int NH>
+struct RowGeom {          // lanes = neighbours: element offset of the support's feature row and position relative to the query
+    int sio[NH];          // byte offset of the support's feature row, si * Cin * 4 (shadow neighbours: 0, never selected)
+    float rx[NH], ry[NH], rz[NH];   // shadow neighbours sit at x = 3e18: outside every extent
+};
+
+template <typename IdxT, int NH>
+__device__ __forceinline__ int load_row_geom(const float* __restrict__ q, const float* __restrict__ s,
+                                             const IdxT* __restrict__ idx, int ld, const unsigned char* __restrict__ posflag,
+                                             int n, int Ns, int H, int Cin, int lane, RowGeom<NH>& g) {
+    const float qx = q[3 * (size_t)n], qy = q[3 * (size_t)n + 1], qz = q[3 * (size_t)n + 2];
+    int nn = 0;
+#pragma unroll
+    for (int j = 0; j < NH; ++j) {
+        const int h = j * 32 + lane;
+        int si = Ns;
+        if (h < H) {
+            const long long v = (long long)idx[(size_t)n * ld + h];
+            si = (v >= 0 && v < Ns) ? (int)v : Ns;
+        }
+        g.sio[j] = 0;
+        g.rx[j] = 3e18f; g.ry[j] = 0.f; g.rz[j] = 0.f;
+        if (si < Ns) {
+            nn += posflag[si];
+            g.sio[j] = si * Cin * 4;
+            g.rx[j] = s[3 * (size_t)si] - qx; g.ry[j] = s[3 * (size_t)si + 1] - qy; g.rz[j] = s[3 * (size_t)si + 2] - qz;
+        }
+    }
+    return __reduce_add_sync(0xffffffffu, nn);
+}
+
+// influence of kernel point kpk on this lane's neighbour j: w = max(0, 1 - d/extent); in = inside the extent
+template <int NH>
+__device__ __forceinline__ float influence(const RowGeom<NH>& g, int j, const float4 kpk, float ext2, float inv_ext, bool& in) {
+    const float ddx = g.rx[j] - kpk.x, ddy = g.ry[j] - kpk.y, ddz = g.rz[j] - kpk.z;
+    const float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+    in = d2 < ext2;
+    return fmaxf(1.0f - sqrt_approx(d2) * inv_ext, 0.f);
+}
+
+// Overflow path: one row, whole warp, lanes = 4 channels of a 128-channel slab; no lists.
+template <typename IdxT, int NH, bool ROUND_TF32>
+__device__ __noinline__ void kp_direct_row(const float* __restrict__ q, const float* __restrict__ s, const IdxT* __restrict__ idx,
+                                           int ld, const float* __restrict__ x, const float4* s_kp,
+                                           const unsigned char* __restrict__ posflag, float ext2, float inv_ext, int n, int Ns,
+                                           int H, int K, int Cin, float* __restrict__ wrow, int lane) {
+    RowGeom<NH> g;
+    load_row_geom<IdxT, NH>(q, s, idx, ld, posflag, n, Ns, H, Cin, lane, g);
+    for (int c0 = 0; c0 < Cin; c0 += 128) {
+        const int c = c0 + lane * 4;
+        const bool cok = c < Cin;
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) {
+            const float4 kpk = s_kp[k];
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < NH; ++j) {
+                bool in;
+                const float w = influence<NH>(g, j, kpk, ext2, inv_ext, in);
+                unsigned m = __ballot_sync(0xffffffffu, in);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float wb = __shfl_sync(0xffffffffu, w, src);
+                    const int sib = __shfl_sync(0xffffffffu, g.sio[j], src);
+                    if (cok) {
+                        const float4 xr = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(x) + (unsigned)sib + (unsigned)c * 4u);
+                        acc.x = fmaf(wb, xr.x, acc.x); acc.y = fmaf(wb, xr.y, acc.y);
+                        acc.z = fmaf(wb, xr.z, acc.z); acc.w = fmaf(wb, xr.w, acc.w);
+                    }
+                }
+            }
+            if (cok) {
+                if (ROUND_TF32) { acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y); acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w); }
+                *reinterpret_cast<float4*>(wrow + (size_t)k * Cin + c) = acc;
+            }
+        }
+    }
+}
+
+template <typename IdxT, int LG, int NV, int NH, bool FULL, bool ROUND_TF32>
+__global__ void __launch_bounds__(128)
+kp_weighted4_kernel(const float* __restrict__ q, const float* __restrict__ s, const IdxT* __restrict__ idx, int ld,
+                    const float* __restrict__ x, const float* __restrict__ kp, const unsigned char* __restrict__ posflag,
+                    float extent, int Nq, int Ns, int H, int K, int Cin, float* __restrict__ wf,
+                    float* __restrict__ inv_nn) {
+    constexpr int RP = 32 / LG;                  // rows streamed in parallel by one warp
+    constexpr int CH = LG * 4 * NV;              // channels per pass
+    constexpr int NU = NV >= 4 ? 2 : 4;          // list entries in flight per lane group
+    extern __shared__ __align__(16) unsigned char s_rows[];
+    __shared__ float4 s_kp[KP_MAX_K];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    if (threadIdx.x < K) s_kp[threadIdx.x] = make_float4(kp[3 * threadIdx.x], kp[3 * threadIdx.x + 1], kp[3 * threadIdx.x + 2], 0.f);
+    __syncthreads();
+    const int row0 = (blockIdx.x * wpb + wib) * RP;
+    if (row0 >= Nq) return;
+    const float ext2 = extent * extent, inv_ext = 1.0f / extent;
+    unsigned char* wslots = s_rows + (size_t)wib * RP * KPW_SLOT_BYTES;
+    const unsigned ltmask = (1u << lane) - 1u;
+
+    // ---- phase 1: CSR influence lists of the warp's RP rows (whole warp per row, lanes = neighbours) ----
+#pragma unroll 1
+    for (int r = 0; r < RP; ++r) {
+        int2* ent = reinterpret_cast<int2*>(wslots + (size_t)r * KPW_SLOT_BYTES);
+        int* off = reinterpret_cast<int*>(ent + KPW_ECAP);
+        const int n = row0 + r;
+        if (n >= Nq) {
+            if (lane <= KP_MAX_K) off[lane] = 0;
+            continue;
+        }
+        RowGeom<NH> g;
+        const int nn = load_row_geom<IdxT, NH>(q, s, idx, ld, posflag, n, Ns, H, Cin, lane, g);
+        if (lane == 0) inv_nn[n] = 1.0f / (float)max(nn, 1);
+        int run = 0, myoff = 0;
+#pragma unroll
+        for (int k = 0; k < KP_MAX_K; ++k) {
+            if (lane == k) myoff = run;
+            if (k < K) {
+                const float4 kpk = s_kp[k];
+#pragma unroll
+                for (int j = 0; j < NH; ++j) {
+                    bool in;
+                    const float w = influence<NH>(g, j, kpk, ext2, inv_ext, in);
+                    const unsigned m = __ballot_sync(0xffffffffu, in);
+                    const int pos = run + __popc(m & ltmask);
+                    if (in && pos < KPW_ECAP) ent[pos] = make_int2(g.sio[j], __float_as_int(w));
+                    run += __popc(m);
+                }
+            }
+        }
+        if (lane >= K) myoff = run;                    // off[K..K_MAX] = total (unused kernel points have empty lists)
+        if (lane <= KP_MAX_K) off[lane] = myoff;
+    }
+    __syncwarp();
+
+    // ---- phase 2: lane group grp streams row row0 + grp ----
+    // Each lane group runs its OWN trip count (no warp-level primitive inside the loops): shorter lists simply leave
+    // their lanes masked off while the longest one finishes.
+    const int grp = lane / LG, lg = lane % LG;
+    const int n = row0 + grp;
+    const int2* ent = reinterpret_cast<const int2*>(wslots + (size_t)grp * KPW_SLOT_BYTES);
+    const int* off = reinterpret_cast<const int*>(ent + KPW_ECAP);
+    const bool ovf = off[KP_MAX_K] > KPW_ECAP;
+    const bool active = n < Nq && !ovf;
+    const char* xb = reinterpret_cast<const char*>(x);
+    for (int c0 = 0; c0 < Cin; c0 += CH) {
+        const int c = c0 + lg * 4;
+        bool cok[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) cok[j] = FULL || (c + j * LG * 4 < Cin);
+        const char* xbc = xb + (size_t)c * 4u;
+        float* wp = wf + (size_t)n * K * Cin + c;
+        int end = active ? off[0] : 0;
+#pragma unroll 1
+        for (int k = 0; k < K; ++k, wp += Cin) {
+            const int beg = end;
+            end = active ? off[k + 1] : 0;
+            float4 acc[NV];
+#pragma unroll
+            for (int j = 0; j < NV; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            int e = beg;
+#pragma unroll 1
+            for (; e + NU <= end; e += NU) {
+                int2 en[NU];
+                float4 xr[NU][NV];
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
+                    en[u] = ent[e + u];
+                    const char* xe = xbc + (unsigned)en[u].x;
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) {
+                        xr[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (cok[j]) xr[u][j] = __ldg(reinterpret_cast<const float4*>(xe + j * LG * 16));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
+                    const float w = __int_as_float(en[u].y);
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) {
+                        acc[j].x = fmaf(w, xr[u][j].x, acc[j].x); acc[j].y = fmaf(w, xr[u][j].y, acc[j].y);
+                        acc[j].z = fmaf(w, xr[u][j].z, acc[j].z); acc[j].w = fmaf(w, xr[u][j].w, acc[j].w);
+                    }
+                }
+            }
+#pragma unroll 1
+            for (; e < end; ++e) {
+                const int2 en = ent[e];
+                const char* xe = xbc + (unsigned)en.x;
+                const float w = __int_as_float(en.y);
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    if (cok[j]) {
+                        const float4 xr = __ldg(reinterpret_cast<const float4*>(xe + j * LG * 16));
+                        acc[j].x = fmaf(w, xr.x, acc[j].x); acc[j].y = fmaf(w, xr.y, acc[j].y);
+                        acc[j].z = fmaf(w, xr.z, acc[j].z); acc[j].w = fmaf(w, xr.w, acc[j].w);
+                    }
+                }
+            }
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    if (cok[j]) {
+                        float4 o4 = acc[j];
+                        if (ROUND_TF32) { o4.x = round_tf32(o4.x); o4.y = round_tf32(o4.y); o4.z = round_tf32(o4.z); o4.w = round_tf32(o4.w); }
+                        *reinterpret_cast<float4*>(wp + j * LG * 4) = o4;
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    // ---- rows whose lists overflowed: direct evaluation by the whole warp ----
+    if (__any_sync(0xffffffffu, ovf && n < Nq)) {
+#pragma unroll 1
+        for (int r = 0; r < RP; ++r) {
+            const int ovr = __shfl_sync(0xffffffffu, (int)ovf, r * LG);
+            if (ovr && row0 + r < Nq)
+                kp_direct_row<IdxT, NH, ROUND_TF32>(q, s, idx, ld, x, s_kp, posflag, ext2, inv_ext, row0 + r, Ns, H, K, Cin,
+                                                    wf + (size_t)(row0 + r) * K * Cin, lane);
         }
     }
 }
@@ -397,12 +647,43 @@ static int launch_kp_weighted(const float* d_q, const float* d_s, const void* d_
                               const float* d_x, const float* d_kp, const unsigned char* flag, float extent, int r0, int nr,
                               int Ns, int H, int K, int Cin, bool round_tf32, float* wf, float* inv_nn, cudaStream_t st) {
     const int Hp = (H + 31) & ~31;
+    const bool x16 = ((uintptr_t)d_x % 16 == 0) && ((uintptr_t)wf % 16 == 0);
+    if (g_kpw_version >= 4 && x16 && Cin % 4 == 0 && H <= 128 && (long long)Ns * Cin < (1LL << 30)) {
+        // v4: lane-group streaming over compact CSR lists; (LG, NV) by channel count, NH = 32-neighbour groups per row
+        const int nh = H <= 64 ? 2 : 4;
+        const int chs[5] = {32, 64, 128, 256, 512};
+        int cfg = Cin <= 32 ? 0 : (Cin <= 64 ? 1 : (Cin <= 128 ? 2 : (Cin <= 256 ? 3 : 4)));
+        const bool full = Cin % chs[cfg] == 0;
+#define KPW4_LAUNCH(IDX, LG, NV, NH, FULLV, RND)                                                                             \
+        do {                                                                                                          \
+            constexpr int wpb4 = 4;                                                                                   \
+            constexpr int rp = 32 / LG;                                                                               \
+            const size_t smem4 = (size_t)wpb4 * rp * KPW_SLOT_BYTES;                                                  \
+            APRB_TIMED("kp_weighted_kernel", st, 1, (kp_weighted4_kernel<IDX, LG, NV, NH, FULLV, RND><<<cdiv(nr, wpb4 * rp), wpb4 * 32, smem4, st>>>( \
+                d_q + 3 * (size_t)r0, d_s, (const IDX*)d_idx + (size_t)r0 * ld_idx, ld_idx, d_x, d_kp, flag, extent, nr, Ns, H, K, Cin, wf, inv_nn + r0))); \
+        } while (0)
+#define KPW4_CFG(IDX, NH, RND)                                                                                        \
+        do {                                                                                                          \
+            if (cfg == 0) { if (full) KPW4_LAUNCH(IDX, 8, 1, NH, true, RND); else KPW4_LAUNCH(IDX, 8, 1, NH, false, RND); }                                                            \
+            else if (cfg == 1) { if (full) KPW4_LAUNCH(IDX, 16, 1, NH, true, RND); else KPW4_LAUNCH(IDX, 16, 1, NH, false, RND); }                                                      \
+            else if (cfg == 2) { if (full) KPW4_LAUNCH(IDX, 16, 2, NH, true, RND); else KPW4_LAUNCH(IDX, 16, 2, NH, false, RND); }                                                      \
+            else if (cfg == 3) { if (full) KPW4_LAUNCH(IDX, 32, 2, NH, true, RND); else KPW4_LAUNCH(IDX, 32, 2, NH, false, RND); }                                                      \
+            else { if (full) KPW4_LAUNCH(IDX, 32, 4, NH, true, RND); else KPW4_LAUNCH(IDX, 32, 4, NH, false, RND); }                                                                    \
+        } while (0)
+#define KPW4_NH(IDX, RND) do { if (nh == 2) KPW4_CFG(IDX, 2, RND); else KPW4_CFG(IDX, 4, RND); } while (0)
+        if (round_tf32) { if (idx_is_i64) KPW4_NH(long long, true); else KPW4_NH(int, true); }
+        else { if (idx_is_i64) KPW4_NH(long long, false); else KPW4_NH(int, false); }
+#undef KPW4_NH
+#undef KPW4_CFG
+#undef KPW4_LAUNCH
+        APRB_LAUNCH_OK();
+        return APRB_OK;
+    }
     const size_t smem_warp = (size_t)KP_MAX_K * Hp * 8 + KP_MAX_K * 4;
     int wpb = 4;
     while (wpb > 1 && wpb * smem_warp > 160 * 1024) wpb >>= 1;
     if (smem_warp > 200 * 1024) { set_error("aprb_kpconv_forward: H=%d too large for the shared-memory neighbour lists", H); return APRB_ERR_UNSUPPORTED; }
     const size_t smem = wpb * smem_warp;
-    const bool x16 = ((uintptr_t)d_x % 16 == 0) && ((uintptr_t)wf % 16 == 0);
     // (VEC, NJ): channels per lane = VEC*NJ, one slab = 32*VEC*NJ channels
     int vec = 1, nj = 1;
     if (x16 && Cin % 4 == 0 && Cin >= 128) { vec = 4; nj = Cin >= 512 ? 4 : (Cin >= 256 ? 2 : 1); }
@@ -448,7 +729,7 @@ extern "C" int aprb_kpconv_forward(const float* d_q, const float* d_s, const voi
     cudaStream_t st = (cudaStream_t)stream;
     APRB_REQUIRE(Nq >= 0 && Ns >= 0 && H >= 1 && H <= 1024, "need Nq,Ns >= 0 and 1 <= H <= 1024");
     APRB_REQUIRE(K >= 1 && K <= KP_MAX_K && Cin >= 1 && Cout >= 1 && ld_idx >= H, "need 1 <= K <= 16, Cin,Cout >= 1, ld >= H");
-    APRB_REQUIRE(extent > 0.f, "extent must be positive");
+    APRB_REQUIRE(extent > 0.f && extent < 1e15f, "extent must be positive (and below 1e15)");
     APRB_REQUIRE((long long)Ns * Cin < 0x7FFFFFFFLL, "feature table too large for 32-bit row offsets");
     if (Nq == 0) return APRB_OK;
     APRB_REQUIRE(d_q && d_idx && d_kp && d_out && d_ws && (Ns == 0 || (d_s && d_x)), "null pointer");

@@ -57,6 +57,28 @@ def test_kpconv_quirks_vs_oracle(cuda):
     assert torch.all(got[:7] == 0)
 
 
+@pytest.mark.parametrize("cin,h,kp_scale", [(24, 19, 0.4), (64, 57, 0.4), (96, 70, 0.4), (128, 33, 0.4), (256, 40, 0.4),
+                                            (512, 20, 0.4), (64, 40, 0.0), (36, 100, 0.01), (16, 140, 0.4)])
+def test_kpconv_list_kernel_paths(cuda, cin, h, kp_scale):
+    """The CSR-list producer (kp_weighted4_kernel): every lane-group configuration, partial channel slabs, 2 and 4
+    neighbour groups per row, the H > 128 fallback, and rows whose list overflows (kp_scale 0: all 15 kernel points
+    coincide, every neighbour inside the extent influences all of them -> direct path)."""
+    gen = torch.Generator().manual_seed(cin * 1000 + h)
+    ns, nq, cout = 700, 333, 32
+    s = torch.rand(ns, 3, generator=gen) * 1.5
+    q = torch.rand(nq, 3, generator=gen) * 1.5
+    inds = torch.randint(0, ns + 1, (nq, h), generator=gen)
+    inds[:3] = ns
+    x = torch.randn(ns, cin, generator=gen)
+    kp = torch.randn(15, 3, generator=gen) * kp_scale
+    w = torch.randn(15, cin, cout, generator=gen) * 0.1
+    want = blocks_ref.kpconv_ref(q, s, inds, x, kp, w, 0.7)
+    got = ops.kpconv(q.to(cuda), s.to(cuda), inds.to(cuda).int(), x.to(cuda), kp.to(cuda), w.to(cuda), 0.7, mode=1)
+    assert rel(got, want) < TOL_FP32
+    got64 = ops.kpconv(q.to(cuda), s.to(cuda), inds.to(cuda), x.to(cuda), kp.to(cuda), w.to(cuda), 0.7, mode=1)
+    assert torch.equal(got, got64)
+
+
 def test_kpconv_tensor_path_vs_oracle(cuda, gold_kpconv):
     """tcgen05 TF32 contraction (mode 2) on shapes the tensor path accepts."""
     g = gold_kpconv
