@@ -310,10 +310,6 @@ static int launch_gemm(const float* A, const float* Bt, int M, int N, int K, int
 
 extern int g_kpconv_chunk_mb;
 extern int g_kpw_version;
-extern int g_kpw_split;
-extern int g_kpw_rows;
-extern int g_kpw_ring;
-extern int g_kpw_ncb;
 int g_gemm_cluster = 1;   // 1 disables the cluster/multicast path (aprb_set_option)
 
 size_t gemm_tf32_ws_bytes(int M, int N) {   // split-K partial tiles (up to 8 splits), only when split-K can trigger
@@ -364,10 +360,6 @@ extern "C" int aprb_set_option(const char* name, int value) {
     if (strcmp(name, "gemm_cluster") == 0) { g_gemm_cluster = value; return APRB_OK; }
     if (strcmp(name, "kpconv_chunk_mb") == 0) { g_kpconv_chunk_mb = value; return APRB_OK; }
     if (strcmp(name, "kpw_version") == 0) { g_kpw_version = value; return APRB_OK; }
-    if (strcmp(name, "kpw_split") == 0) { g_kpw_split = value; return APRB_OK; }
-    if (strcmp(name, "kpw_rows") == 0) { g_kpw_rows = value; return APRB_OK; }
-    if (strcmp(name, "kpw_ring") == 0) { g_kpw_ring = value; return APRB_OK; }
-    if (strcmp(name, "kpw_ncb") == 0) { g_kpw_ncb = value; return APRB_OK; }
     set_error("aprb_set_option: unknown option %s", name);
     return APRB_ERR_INVALID;
 }

@@ -20,16 +20,11 @@ size_t gemm_tf32_ws_bytes(int M, int N);
 bool gemm_tf32_supported(int M, int N, int K);
 
 constexpr int KP_MAX_K = 16;
-int g_kpw_version = 4;       // aprb_set_option("kpw_version"): 3 = per-kernel-point tables, 4 = CSR lists + lane groups,
-                             // 5 = mma.sync weighting for the tensor path (Cin % 64 == 0), v4 otherwise
-int g_kpw_ring = 0;          // aprb_set_option("kpw_ring"): v5 stages the gathered rows through a cp.async ring (1) or registers (0)
-int g_kpw_ncb = 0;           // aprb_set_option("kpw_ncb"): 8 forces 64-channel slabs in v5 (0 = 128 when Cin % 128 == 0)
-int g_kpw_rows = 0;          // aprb_set_option("kpw_rows"): rows per warp of the v5 kernel (0 = auto)
-int g_kpw_split = 1;         // aprb_set_option("kpw_split"): v5 splits the influence weights hi+lo (fp32-accurate weights)
+int g_kpw_version = 4;       // aprb_set_option("kpw_version"): 3 = per-kernel-point tables, 4 = CSR lists + lane groups
 int g_kpconv_chunk_mb = 0;   // aprb_set_option("kpconv_chunk_mb"): L2-sized row chunks of the tensor path (0 = off)
 
 // flag[s] = 1 iff sum_c x[s,c] > 0 (one warp per support row; fixed reduction order), and the packed support record
-// s4[s] = (x, y, z, flag): the gather kernels fetch a neighbour's position and flag with ONE 128-bit load — a
+// s4[s] = (x, y, z, flag) — with C == 1 (x, y, z, feature) —: the gather kernels fetch a neighbour's position and flag with ONE 128-bit load — a
 // divergent warp load costs one L1 wavefront per distinct line whatever its width, and the three coordinate loads plus
 // the flag byte were 256 of the ~470 LSU wavefronts per query (ncu, round 1).
 __global__ void rowsum_pos_kernel(const float* __restrict__ x, const float* __restrict__ pts, int Ns, int C,
@@ -42,7 +37,8 @@ __global__ void rowsum_pos_kernel(const float* __restrict__ x, const float* __re
     for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
     if (lane == 0) {
         flag[row] = s > 0.f ? 1 : 0;
-        s4[row] = make_float4(pts[3 * (size_t)row], pts[3 * (size_t)row + 1], pts[3 * (size_t)row + 2], s > 0.f ? 1.f : 0.f);
+        s4[row] = make_float4(pts[3 * (size_t)row], pts[3 * (size_t)row + 1], pts[3 * (size_t)row + 2],
+                              C == 1 ? s : (s > 0.f ? 1.f : 0.f));   // Cin == 1: the record carries the feature itself
     }
 }
 
@@ -208,6 +204,10 @@ __device__ __forceinline__ float sqrt_approx(float v) {
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
 }
+// Value whose TRUNCATION to TF32 (what the tensor core does with an fp32 operand) equals round-to-nearest (ties away
+// from zero in magnitude) of t: one integer add instead of the 3-instruction cvt.rna emulation. Exact for finite t;
+// +-inf becomes NaN (a feature table that holds inf is garbage either way).
+__device__ __forceinline__ float pre_round_tf32(float t) { return __uint_as_float(__float_as_uint(t) + 0x1000u); }
 __device__ __forceinline__ float round_tf32(float t) {
     unsigned u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(t));
@@ -218,6 +218,7 @@ template <int NH>
 struct RowGeom {          // lanes = neighbours: element offset of the support's feature row and position relative to the query
     int sio[NH];          // byte offset of the support's feature row, si * Cin * 4 (shadow neighbours: 0, never selected)
     float rx[NH], ry[NH], rz[NH];   // shadow neighbours sit at x = 3e18: outside every extent
+    unsigned any[NH];               // warp ballot: does this group of 32 neighbours hold a valid one (warp-uniform)
 };
 
 template <typename IdxT, int NH>
@@ -242,6 +243,7 @@ __device__ __forceinline__ int load_row_geom(const float* __restrict__ q, const 
             g.sio[j] = si * Cin * 4;
             g.rx[j] = p.x - qx; g.ry[j] = p.y - qy; g.rz[j] = p.z - qz;
         }
+        g.any[j] = __ballot_sync(0xffffffffu, si < Ns);
     }
     return __reduce_add_sync(0xffffffffu, nn);
 }
@@ -272,6 +274,7 @@ __device__ __noinline__ void kp_direct_row(const float* __restrict__ q, const fl
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < NH; ++j) {
+                if (!g.any[j]) continue;
                 bool in;
                 const float w = influence<NH>(g, j, kpk, ext2, inv_ext, in);
                 unsigned m = __ballot_sync(0xffffffffu, in);
@@ -303,7 +306,7 @@ kp_weighted4_kernel(const float* __restrict__ q, const float4* __restrict__ s4, 
                     float* __restrict__ inv_nn) {
     constexpr int RP = 32 / LG;                  // rows streamed in parallel by one warp
     constexpr int CH = LG * 4 * NV;              // channels per pass
-    constexpr int NU = NV >= 4 ? 2 : 4;          // list entries in flight per lane group
+    constexpr int NU = 2;                        // list entries in flight per lane group (lists average ~3 entries)
     extern __shared__ __align__(16) unsigned char s_rows[];
     __shared__ float4 s_kp[KP_MAX_K];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -336,12 +339,14 @@ kp_weighted4_kernel(const float* __restrict__ q, const float4* __restrict__ s4, 
                 const float4 kpk = s_kp[k];
 #pragma unroll
                 for (int j = 0; j < NH; ++j) {
-                    bool in;
-                    const float w = influence<NH>(g, j, kpk, ext2, inv_ext, in);
-                    const unsigned m = __ballot_sync(0xffffffffu, in);
-                    const int pos = run + __popc(m & ltmask);
-                    if (in && pos < KPW_ECAP) ent[pos] = make_int2(g.sio[j], __float_as_int(w));
-                    run += __popc(m);
+                    if (g.any[j]) {                              // neighbours are distance-sorted: the tail group is often all pad
+                        bool in;
+                        const float w = influence<NH>(g, j, kpk, ext2, inv_ext, in);
+                        const unsigned m = __ballot_sync(0xffffffffu, in);
+                        const int pos = run + __popc(m & ltmask);
+                        if (in && pos < KPW_ECAP) ent[pos] = make_int2(g.sio[j], __float_as_int(w));
+                        run += __popc(m);
+                    }
                 }
             }
         }
@@ -419,7 +424,7 @@ kp_weighted4_kernel(const float* __restrict__ q, const float4* __restrict__ s4, 
                 for (int j = 0; j < NV; ++j) {
                     if (cok[j]) {
                         float4 o4 = acc[j];
-                        if (ROUND_TF32) { o4.x = round_tf32(o4.x); o4.y = round_tf32(o4.y); o4.z = round_tf32(o4.z); o4.w = round_tf32(o4.w); }
+                        if (ROUND_TF32) { o4.x = pre_round_tf32(o4.x); o4.y = pre_round_tf32(o4.y); o4.z = pre_round_tf32(o4.z); o4.w = pre_round_tf32(o4.w); }
                         *reinterpret_cast<float4*>(wp + j * LG * 4) = o4;
                     }
                 }
@@ -439,387 +444,17 @@ kp_weighted4_kernel(const float* __restrict__ q, const float4* __restrict__ s4, 
     }
 }
 
-// ---- v5: the weighting stage on the tensor cores (legacy mma.sync path, TF32) ------------------------------------------
-// Per query the weighting is a small dense product wf[K x C] = Wt[K x H] * X[H x C] (Wt = influence weights, X = gathered
-// neighbour rows). With H ~ 56 and ~1.4 non-zero weights per neighbour the dense form does 10x the useful flops, but on
-// mma.sync.m16n8k8 it costs ~450 warp instructions per query where the CUDA-core list walk (v4) needs ~1700, and the
-// kernel was instruction-issue-bound. One warp per query:
-//   * geometry (lanes = neighbours) -> shared: (rx, ry, rz, byte offset of the feature row) per neighbour;
-//   * per block of 8 neighbours: each thread evaluates the 4 influence weights of its A fragment directly in fragment
-//     layout (kernel points groupID and groupID+8, neighbours tig and tig+4) — no ballot, no compaction, no lists;
-//     the B fragment is the gathered rows of neighbours tig / tig+4: NCB/4 128-bit loads each, 128 B contiguous per
-//     8 lanes. Channel c of a 32-channel group sits at MMA column (c/4)%8 of column block c%4 + 4*(c/32), which makes
-//     both the loads and the stores of a thread contiguous;
-//   * weights are split w = hi + lo (two MMAs) so the stage stays fp32-accurate in w; x is rounded to TF32 in registers
-//     (the tensor core would otherwise truncate it) unless the caller guarantees TF32-representable activations.
-// Rounding uses "bits + 0x1000, hardware drops the low 13 bits" (round-half-away in magnitude), exact for finite values.
-// Shadow / out-of-range neighbours read feature row 0 with weight 0.
-__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-__device__ __forceinline__ float kp_influence(const float4 g, const float4 kpk, float inv_ext) {
-    const float ddx = g.x - kpk.x, ddy = g.y - kpk.y, ddz = g.z - kpk.z;
-    const float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
-    return fmaxf(1.0f - sqrt_approx(d2) * inv_ext, 0.f);
-}
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// The gather is latency-bound when done through registers (ncu: 52 % long-scoreboard stalls at 20 warps/SM), so the
-// neighbour rows of an 8-neighbour block travel global -> shared with cp.async through a KPM_STAGES-deep per-warp ring
-// (3 blocks in flight per warp, no registers held), and a warp walks KPM rows back to back with the index / position
-// loads of the NEXT row issued before the block loop of the current one.
-constexpr int KPM_STAGES = 4;
-
-template <int NCB, int NH>
-struct KpmSmem {
-    static constexpr int ROWB = NCB * 32 + 32;          // bytes per gathered row: +32 B pad = conflict-free fragment reads
-    static constexpr int STAGE = 8 * ROWB;
-    static constexpr int GEO = 2 * NH * 32 * 16;        // double-buffered per-row geometry
-    static constexpr int WARP = GEO + KPM_STAGES * STAGE;
-};
-
-template <typename IdxT, int NCB, int NH, bool SPLITW, bool X_EXACT>
-__global__ void __launch_bounds__(128)
-kp_weighted_mma_kernel(const float* __restrict__ q, const float4* __restrict__ s4, const IdxT* __restrict__ idx, int ld,
-                       const float* __restrict__ x, const float* __restrict__ kp,
-                       float extent, int Nq, int Ns, int H, int K, int Cin, int rows_per_warp, float* __restrict__ wf,
-                       float* __restrict__ inv_nn) {
-    using SM = KpmSmem<NCB, NH>;
-    constexpr int SLAB = NCB * 8;                 // channels per pass
-    constexpr int CPR = SLAB / 4;                 // 16-byte chunks per gathered row
-    constexpr int CPL = 8 * CPR / 32;             // chunks per lane per block
-    extern __shared__ __align__(16) unsigned char s_dyn_mma[];
-    __shared__ float4 s_kp[KP_MAX_K];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    if (threadIdx.x < KP_MAX_K)
-        s_kp[threadIdx.x] = threadIdx.x < K ? make_float4(kp[3 * threadIdx.x], kp[3 * threadIdx.x + 1], kp[3 * threadIdx.x + 2], 0.f)
-                                            : make_float4(-3e18f, 0.f, 0.f, 0.f);       // unused rows of the 16-row A tile
-    __syncthreads();
-    const int row_begin = (blockIdx.x * 4 + wib) * rows_per_warp;
-    const int row_end = min(Nq, row_begin + rows_per_warp);
-    if (row_begin >= Nq) return;
-    const float inv_ext = 1.0f / extent;
-    const int gid = lane >> 2, tig = lane & 3;
-    const float4 kpa = s_kp[gid], kpb = s_kp[gid + 8];
-    unsigned char* wsm = s_dyn_mma + (size_t)wib * SM::WARP;
-    float4* geo_buf = reinterpret_cast<float4*>(wsm);
-    const uint32_t ring = smem_addr_u32(wsm + SM::GEO);
-    const char* xb = reinterpret_cast<const char*>(x);
-    const int nslab = Cin / SLAB;
-
-    // ---- row pipeline registers: raw indices of row r+1 (loaded during row r-1... r), positions of row r+1 ----
-    long long raw_next[NH];                       // neighbour indices of the row after the current one
-    auto load_raw = [&](int r, long long (&raw)[NH]) {
-#pragma unroll
-        for (int j = 0; j < NH; ++j) {
-            const int h = j * 32 + lane;
-            raw[j] = (r < row_end && h < H) ? (long long)idx[(size_t)r * ld + h] : (long long)Ns;
-        }
-    };
-    // geometry of row r from its raw indices -> geo_buf[buf]; returns the number of 8-neighbour blocks to visit
-    auto build_geo = [&](int r, const long long (&raw)[NH], int buf) -> int {
-        const float qx = q[3 * (size_t)r], qy = q[3 * (size_t)r + 1], qz = q[3 * (size_t)r + 2];
-        int nn = 0, nblk = 0;
-#pragma unroll
-        for (int j = 0; j < NH; ++j) {
-            const bool valid = raw[j] >= 0 && raw[j] < Ns;
-            float4 g = make_float4(3e18f, 0.f, 0.f, __int_as_float(0));
-            if (valid) {
-                const int si = (int)raw[j];
-                const float4 p = __ldg(s4 + si);
-                nn += p.w > 0.f ? 1 : 0;
-                g = make_float4(p.x - qx, p.y - qy, p.z - qz, __int_as_float(si * Cin * 4));
-            }
-            geo_buf[buf * NH * 32 + j * 32 + lane] = g;
-            const unsigned vm = __ballot_sync(0xffffffffu, valid);
-            if (vm) nblk = j * 4 + ((32 - __clz(vm)) + 7) / 8;
-        }
-        nn = __reduce_add_sync(0xffffffffu, nn);
-        if (lane == 0) inv_nn[r] = 1.0f / (float)max(nn, 1);
-        __syncwarp();
-        return nblk;
-    };
-
-    long long raw_cur[NH];
-    load_raw(row_begin, raw_cur);
-    load_raw(row_begin + 1, raw_next);
-    int nblk = build_geo(row_begin, raw_cur, 0);
-
-    for (int r = row_begin; r < row_end; ++r) {
-        const int buf = (r - row_begin) & 1;
-        const float4* geo = geo_buf + buf * NH * 32;
-#pragma unroll
-        for (int j = 0; j < NH; ++j) raw_cur[j] = raw_next[j];    // indices of row r+1 (arrived by now)
-        load_raw(r + 2, raw_next);                                // in flight during this row's block loop
-
-        // ---- cp.async ring over the (slab, block) sequence of this row ----
-        int pf_hb = 0, pf_c0 = 0, pf_left = nslab * nblk, pf_stage = 0;
-        auto issue_next = [&]() {
-            if (pf_left > 0) {
-                const uint32_t st_base = ring + pf_stage * SM::STAGE;
-#pragma unroll
-                for (int t = 0; t < CPL; ++t) {
-                    const int chunk = t * 32 + lane, nbr = chunk / CPR, col = chunk % CPR;
-                    const unsigned off = (unsigned)__float_as_int(geo[pf_hb * 8 + nbr].w);
-                    cp_async16(st_base + nbr * SM::ROWB + col * 16, xb + off + (size_t)(pf_c0 + col * 4) * 4);
-                }
-                --pf_left;
-                if (++pf_hb == nblk) { pf_hb = 0; pf_c0 += SLAB; }
-                pf_stage = (pf_stage + 1) & (KPM_STAGES - 1);
-            }
-            cp_async_commit();
-        };
-#pragma unroll
-        for (int i = 0; i < KPM_STAGES - 1; ++i) issue_next();
-
-        int stage = 0;
-        for (int c0 = 0; c0 < Cin; c0 += SLAB) {
-            float acc[NCB][4];
-#pragma unroll
-            for (int cb = 0; cb < NCB; ++cb) { acc[cb][0] = 0.f; acc[cb][1] = 0.f; acc[cb][2] = 0.f; acc[cb][3] = 0.f; }
-#pragma unroll 1
-            for (int hb = 0; hb < nblk; ++hb) {
-                cp_async_wait<KPM_STAGES - 2>();
-                __syncwarp();
-                issue_next();
-                const float4 g1 = geo[hb * 8 + tig], g2 = geo[hb * 8 + tig + 4];
-                const unsigned char* st = wsm + SM::GEO + stage * SM::STAGE + gid * 16;
-                stage = (stage + 1) & (KPM_STAGES - 1);
-                float w[4];
-                w[0] = kp_influence(g1, kpa, inv_ext); w[1] = kp_influence(g1, kpb, inv_ext);
-                w[2] = kp_influence(g2, kpa, inv_ext); w[3] = kp_influence(g2, kpb, inv_ext);
-                uint32_t ahi[4], alo[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    if (SPLITW) {
-                        ahi[t] = __float_as_uint(w[t]) & 0xffffe000u;
-                        alo[t] = __float_as_uint(w[t] - __uint_as_float(ahi[t])) + 0x1000u;
-                    } else {
-                        ahi[t] = __float_as_uint(w[t]) + 0x1000u;
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < NCB / 4; ++i) {
-                    const float4 v1 = *reinterpret_cast<const float4*>(st + tig * SM::ROWB + i * 128);
-                    const float4 v2 = *reinterpret_cast<const float4*>(st + (tig + 4) * SM::ROWB + i * 128);
-                    const float bb1[4] = {v1.x, v1.y, v1.z, v1.w};
-                    const float bb2[4] = {v2.x, v2.y, v2.z, v2.w};
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const uint32_t b0 = __float_as_uint(bb1[t]) + (X_EXACT ? 0u : 0x1000u);
-                        const uint32_t b1 = __float_as_uint(bb2[t]) + (X_EXACT ? 0u : 0x1000u);
-                        mma_tf32_16x8x8(acc[i * 4 + t], ahi, b0, b1);
-                        if (SPLITW) mma_tf32_16x8x8(acc[i * 4 + t], alo, b0, b1);
-                    }
-                }
-            }
-            // ---- store: rows k = gid and gid + 8; per 32-channel group i the thread owns channels 8*tig .. 8*tig+7 ----
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int k = gid + half * 8;
-                if (k < K) {
-                    float* wp = wf + (size_t)r * K * Cin + (size_t)k * Cin + c0 + 8 * tig;
-#pragma unroll
-                    for (int i = 0; i < NCB / 4; ++i) {
-#pragma unroll
-                        for (int t = 0; t < 2; ++t) {
-                            float4 o;
-                            o.x = round_tf32(acc[i * 4 + 0][half * 2 + t]); o.y = round_tf32(acc[i * 4 + 1][half * 2 + t]);
-                            o.z = round_tf32(acc[i * 4 + 2][half * 2 + t]); o.w = round_tf32(acc[i * 4 + 3][half * 2 + t]);
-                            *reinterpret_cast<float4*>(wp + i * 32 + t * 4) = o;
-                        }
-                    }
-                }
-            }
-        }
-        // ---- geometry of the next row (its indices were loaded one row ago) ----
-        if (r + 1 < row_end) nblk = build_geo(r + 1, raw_cur, buf ^ 1);
-    }
-}
-
-// Register-pipelined variant of the tensor-core weighting (no shared-memory staging of the gathered rows): the B
-// fragments of block i+1 are loaded (128-bit __ldg straight into fragment layout) before the MMAs of block i, the
-// packed support records of row r+1 are in flight during the whole block loop of row r, and its indices one row
-// earlier still. Fewest LSU wavefronts of all variants (16 per block and 64 channels).
-template <int NCB>
-struct KpFrag {
-    float4 g1, g2;
-    float4 b1[NCB / 4], b2[NCB / 4];
-};
-
-template <typename IdxT, int NCB, int NH, bool SPLITW, bool X_EXACT>
-__global__ void __launch_bounds__(128)
-kp_weighted_mmar_kernel(const float* __restrict__ q, const float4* __restrict__ s4, const IdxT* __restrict__ idx, int ld,
-                        const float* __restrict__ x, const float* __restrict__ kp, float extent, int Nq, int Ns, int H, int K,
-                        int Cin, int rows_per_warp, float* __restrict__ wf, float* __restrict__ inv_nn) {
-    constexpr int SLAB = NCB * 8;
-    __shared__ float4 s_kp[KP_MAX_K];
-    __shared__ float4 s_geo[4][2][NH * 32];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    if (threadIdx.x < KP_MAX_K)
-        s_kp[threadIdx.x] = threadIdx.x < K ? make_float4(kp[3 * threadIdx.x], kp[3 * threadIdx.x + 1], kp[3 * threadIdx.x + 2], 0.f)
-                                            : make_float4(-3e18f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    const int row_begin = (blockIdx.x * 4 + wib) * rows_per_warp;
-    const int row_end = min(Nq, row_begin + rows_per_warp);
-    if (row_begin >= Nq) return;
-    const float inv_ext = 1.0f / extent;
-    const int gid = lane >> 2, tig = lane & 3;
-    const float4 kpa = s_kp[gid], kpb = s_kp[gid + 8];
-    const char* xb = reinterpret_cast<const char*>(x) + (size_t)gid * 16;
-    const int nslab = Cin / SLAB;
-
-    int si_next[NH];                               // validated support indices of the next row (Ns = none)
-    float4 p_next[NH];                             // their packed records, in flight
-    auto load_si = [&](int r, int (&si)[NH]) {
-#pragma unroll
-        for (int j = 0; j < NH; ++j) {
-            const int h = j * 32 + lane;
-            long long v = Ns;
-            if (r < row_end && h < H) v = (long long)idx[(size_t)r * ld + h];
-            si[j] = (v >= 0 && v < Ns) ? (int)v : Ns;
-        }
-    };
-    auto load_p = [&](const int (&si)[NH], float4 (&p)[NH]) {
-#pragma unroll
-        for (int j = 0; j < NH; ++j) {
-            p[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (si[j] < Ns) p[j] = __ldg(s4 + si[j]);
-        }
-    };
-    auto finish_geo = [&](int r, const int (&si)[NH], const float4 (&p)[NH], float4* geo) -> int {
-        const float qx = q[3 * (size_t)r], qy = q[3 * (size_t)r + 1], qz = q[3 * (size_t)r + 2];
-        int nn = 0, nblk = 0;
-#pragma unroll
-        for (int j = 0; j < NH; ++j) {
-            const bool valid = si[j] < Ns;
-            nn += (valid && p[j].w > 0.f) ? 1 : 0;
-            geo[j * 32 + lane] = valid ? make_float4(p[j].x - qx, p[j].y - qy, p[j].z - qz, __int_as_float(si[j] * Cin * 4))
-                                       : make_float4(3e18f, 0.f, 0.f, __int_as_float(0));
-            const unsigned vm = __ballot_sync(0xffffffffu, valid);
-            if (vm) nblk = j * 4 + ((32 - __clz(vm)) + 7) / 8;
-        }
-        nn = __reduce_add_sync(0xffffffffu, nn);
-        if (lane == 0) inv_nn[r] = 1.0f / (float)max(nn, 1);
-        __syncwarp();
-        return nblk;
-    };
-
-    int si_cur[NH];
-    float4 p_cur[NH];
-    load_si(row_begin, si_cur);
-    load_si(row_begin + 1, si_next);
-    load_p(si_cur, p_cur);
-    int nblk = finish_geo(row_begin, si_cur, p_cur, s_geo[wib][0]);
-
-    for (int r = row_begin; r < row_end; ++r) {
-        const int buf = (r - row_begin) & 1;
-        const float4* geo = s_geo[wib][buf];
-#pragma unroll
-        for (int j = 0; j < NH; ++j) si_cur[j] = si_next[j];      // row r+1
-        load_p(si_cur, p_next);                                   // in flight during this row's blocks
-        load_si(r + 2, si_next);
-
-        const int total = nslab * nblk;
-        int pf_hb = 0, pf_c0 = 0, left = total;
-        auto load_next = [&](KpFrag<NCB>& f) {
-            if (left > 0) {
-                f.g1 = geo[pf_hb * 8 + tig]; f.g2 = geo[pf_hb * 8 + tig + 4];
-                const char* r1 = xb + (size_t)pf_c0 * 4 + (unsigned)__float_as_int(f.g1.w);
-                const char* r2 = xb + (size_t)pf_c0 * 4 + (unsigned)__float_as_int(f.g2.w);
-#pragma unroll
-                for (int i = 0; i < NCB / 4; ++i) {
-                    f.b1[i] = __ldg(reinterpret_cast<const float4*>(r1 + i * 128));
-                    f.b2[i] = __ldg(reinterpret_cast<const float4*>(r2 + i * 128));
-                }
-                --left;
-                if (++pf_hb == nblk) { pf_hb = 0; pf_c0 += SLAB; }
-            }
-        };
-        float acc[NCB][4];
-        auto zero_acc = [&]() {
-#pragma unroll
-            for (int cb = 0; cb < NCB; ++cb) { acc[cb][0] = 0.f; acc[cb][1] = 0.f; acc[cb][2] = 0.f; acc[cb][3] = 0.f; }
-        };
-        auto store_acc = [&](int c0) {
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int k = gid + half * 8;
-                if (k < K) {
-                    float* wp = wf + (size_t)r * K * Cin + (size_t)k * Cin + c0 + 8 * tig;
-#pragma unroll
-                    for (int i = 0; i < NCB / 4; ++i) {
-#pragma unroll
-                        for (int t = 0; t < 2; ++t) {
-                            float4 o;
-                            o.x = round_tf32(acc[i * 4 + 0][half * 2 + t]); o.y = round_tf32(acc[i * 4 + 1][half * 2 + t]);
-                            o.z = round_tf32(acc[i * 4 + 2][half * 2 + t]); o.w = round_tf32(acc[i * 4 + 3][half * 2 + t]);
-                            *reinterpret_cast<float4*>(wp + i * 32 + t * 4) = o;
-                        }
-                    }
-                }
-            }
-        };
-        int hb = 0, c0 = 0;
-        auto step = [&](const KpFrag<NCB>& f, KpFrag<NCB>& nxt) {
-            load_next(nxt);
-            float w[4];
-            w[0] = kp_influence(f.g1, kpa, inv_ext); w[1] = kp_influence(f.g1, kpb, inv_ext);
-            w[2] = kp_influence(f.g2, kpa, inv_ext); w[3] = kp_influence(f.g2, kpb, inv_ext);
-            uint32_t ahi[4], alo[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                if (SPLITW) {
-                    ahi[t] = __float_as_uint(w[t]) & 0xffffe000u;
-                    alo[t] = __float_as_uint(w[t] - __uint_as_float(ahi[t])) + 0x1000u;
-                } else {
-                    ahi[t] = __float_as_uint(w[t]) + 0x1000u;
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < NCB / 4; ++i) {
-                const float bb1[4] = {f.b1[i].x, f.b1[i].y, f.b1[i].z, f.b1[i].w};
-                const float bb2[4] = {f.b2[i].x, f.b2[i].y, f.b2[i].z, f.b2[i].w};
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const uint32_t b0 = __float_as_uint(bb1[t]) + (X_EXACT ? 0u : 0x1000u);
-                    const uint32_t b1 = __float_as_uint(bb2[t]) + (X_EXACT ? 0u : 0x1000u);
-                    mma_tf32_16x8x8(acc[i * 4 + t], ahi, b0, b1);
-                    if (SPLITW) mma_tf32_16x8x8(acc[i * 4 + t], alo, b0, b1);
-                }
-            }
-            if (++hb == nblk) { store_acc(c0); zero_acc(); hb = 0; c0 += SLAB; }
-        };
-        zero_acc();
-        KpFrag<NCB> fa, fb;
-        load_next(fa);
-#pragma unroll 1
-        for (int it = 0; it < total; it += 2) {
-            step(fa, fb);
-            if (it + 1 < total) step(fb, fa);
-        }
-        if (nblk == 0)
-            for (int cz = 0; cz < Cin; cz += SLAB) store_acc(cz);   // no neighbour at all: zero row
-        if (r + 1 < row_end) nblk = finish_geo(r + 1, si_cur, p_next, s_geo[wib][buf ^ 1]);
-    }
-}
+// (Round 1 also measured this stage on mma.sync — dense per-query 16 x H x Cin products, three variants. On B200 every
+// legacy HMMA.1688 is charged ~4 LSU data-pipe wavefronts, so that path is LSU-bound at the speed of this kernel or
+// worse: profiles/r01_kp_weighted_variants.txt; the code is in the history at commit "KPConv weighting on mma.sync".)
 
 // Cin == 1 (the first encoder block: one scalar feature per point): lanes = neighbours, the 15 per-kernel-point sums
 // are reduced across the warp with shuffles; no shared memory, no second pass.
 template <typename IdxT>
 __global__ void __launch_bounds__(128)
-kp_weighted_c1_kernel(const float* __restrict__ q, const float* __restrict__ s, const IdxT* __restrict__ idx, int ld,
-                      const float* __restrict__ x, const float* __restrict__ kp, const unsigned char* __restrict__ posflag,
-                      float extent, int Nq, int Ns, int H, int K, float* __restrict__ wf, float* __restrict__ inv_nn) {
+kp_weighted_c1_kernel(const float* __restrict__ q, const float4* __restrict__ s4, const IdxT* __restrict__ idx, int ld,
+                      const float* __restrict__ kp, float extent, int Nq, int Ns, int H, int K, float* __restrict__ wf,
+                      float* __restrict__ inv_nn) {
     __shared__ float s_kp[KP_MAX_K * 3];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     if (threadIdx.x < K * 3) s_kp[threadIdx.x] = kp[threadIdx.x];
@@ -835,25 +470,25 @@ kp_weighted_c1_kernel(const float* __restrict__ q, const float* __restrict__ s, 
     for (int h = lane; h < H; h += 32) {
         const long long v = (long long)idx[(size_t)n * ld + h];
         if (v < 0 || v >= Ns) continue;
-        const int si = (int)v;
-        nn += posflag[si];
-        const float xv = x[si];
-        const float rx = s[3 * (size_t)si] - qx, ry = s[3 * (size_t)si + 1] - qy, rz = s[3 * (size_t)si + 2] - qz;
+        const float4 p = __ldg(s4 + (int)v);           // (x, y, z, feature): with Cin == 1 the packed record carries x itself
+        const float xv = p.w;
+        nn += xv > 0.f ? 1 : 0;
+        const float rx = p.x - qx, ry = p.y - qy, rz = p.z - qz;
 #pragma unroll
         for (int k = 0; k < KP_MAX_K; ++k) {
             if (k < K) {
                 const float ddx = rx - s_kp[3 * k], ddy = ry - s_kp[3 * k + 1], ddz = rz - s_kp[3 * k + 2];
                 const float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
-                if (d2 < ext2) acc[k] = fmaf(fmaxf(1.0f - sqrtf(d2) * inv_ext, 0.f), xv, acc[k]);
+                if (d2 < ext2) acc[k] = fmaf(fmaxf(1.0f - sqrt_approx(d2) * inv_ext, 0.f), xv, acc[k]);
             }
         }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
-        nn += __shfl_xor_sync(0xffffffffu, nn, d);
 #pragma unroll
         for (int k = 0; k < KP_MAX_K; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], d);
     }
+    nn = __reduce_add_sync(0xffffffffu, nn);
     if (lane == 0) {
         inv_nn[n] = 1.0f / (float)max(nn, 1);
 #pragma unroll
@@ -1036,36 +671,6 @@ static int launch_kp_weighted(const float* d_q, const float* d_s, const void* d_
                               int Ns, int H, int K, int Cin, bool round_tf32, float* wf, float* inv_nn, cudaStream_t st) {
     const int Hp = (H + 31) & ~31;
     const bool x16 = ((uintptr_t)d_x % 16 == 0) && ((uintptr_t)wf % 16 == 0);
-    if (g_kpw_version >= 5 && round_tf32 && x16 && Cin % 64 == 0 && H <= 128 && (long long)Ns * Cin < (1LL << 30)) {
-        // v5: weighting on mma.sync (TF32 operands, w split hi+lo, x rounded in registers)
-        const int nh = H <= 64 ? 2 : 4;
-        const bool wide = Cin % 128 == 0 && g_kpw_ncb != 8;
-        // rows walked back to back by one warp: as many as keep >= ~8 CTAs per SM in the grid
-        int rpw = g_kpw_rows > 0 ? g_kpw_rows : 8;
-        while (rpw > 1 && cdiv(nr, 4 * rpw) < 8 * sm_count()) rpw >>= 1;
-#define KPW5_LAUNCH(IDX, NCB, NH, SPL)                                                                                \
-        do {                                                                                                          \
-            if (g_kpw_ring) {                                                                                         \
-                const size_t smem5 = 4 * (size_t)KpmSmem<NCB, NH>::WARP;                                              \
-                APRB_CUDA_OK(cudaFuncSetAttribute(kp_weighted_mma_kernel<IDX, NCB, NH, SPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5)); \
-                APRB_TIMED("kp_weighted_kernel", st, 1, (kp_weighted_mma_kernel<IDX, NCB, NH, SPL, false><<<cdiv(nr, 4 * rpw), 128, smem5, st>>>( \
-                    d_q + 3 * (size_t)r0, s4, (const IDX*)d_idx + (size_t)r0 * ld_idx, ld_idx, d_x, d_kp, extent, nr, Ns, H, K, Cin, rpw, wf, inv_nn + r0))); \
-            } else {                                                                                                  \
-                APRB_TIMED("kp_weighted_kernel", st, 1, (kp_weighted_mmar_kernel<IDX, NCB, NH, SPL, false><<<cdiv(nr, 4 * rpw), 128, 0, st>>>( \
-                    d_q + 3 * (size_t)r0, s4, (const IDX*)d_idx + (size_t)r0 * ld_idx, ld_idx, d_x, d_kp, extent, nr, Ns, H, K, Cin, rpw, wf, inv_nn + r0))); \
-            }                                                                                                         \
-        } while (0)
-#define KPW5_SPL(IDX, NCB, NH) do { if (g_kpw_split) KPW5_LAUNCH(IDX, NCB, NH, true); else KPW5_LAUNCH(IDX, NCB, NH, false); } while (0)
-#define KPW5_NH(IDX, NCB) do { if (nh == 2) KPW5_SPL(IDX, NCB, 2); else KPW5_SPL(IDX, NCB, 4); } while (0)
-#define KPW5_IDX(NCB) do { if (idx_is_i64) KPW5_NH(long long, NCB); else KPW5_NH(int, NCB); } while (0)
-        if (wide) KPW5_IDX(16); else KPW5_IDX(8);
-#undef KPW5_IDX
-#undef KPW5_NH
-#undef KPW5_SPL
-#undef KPW5_LAUNCH
-        APRB_LAUNCH_OK();
-        return APRB_OK;
-    }
     if (g_kpw_version >= 4 && x16 && Cin % 4 == 0 && H <= 128 && (long long)Ns * Cin < (1LL << 30)) {
         // v4: lane-group streaming over compact CSR lists; (LG, NV) by channel count, NH = 32-neighbour groups per row
         const int nh = H <= 64 ? 2 : 4;
@@ -1191,9 +796,9 @@ extern "C" int aprb_kpconv_forward(const float* d_q, const float* d_s, const voi
     }
     if (Cin == 1) {
         if (idx_is_i64) APRB_TIMED("kp_weighted_c1_kernel", st, 1, (kp_weighted_c1_kernel<long long><<<cdiv(Nq, 4), 128, 0, st>>>(
-            d_q, d_s, (const long long*)d_idx, ld_idx, d_x, d_kp, flag, extent, Nq, Ns, H, K, wf, inv_nn)));
+            d_q, s4, (const long long*)d_idx, ld_idx, d_kp, extent, Nq, Ns, H, K, wf, inv_nn)));
         else APRB_TIMED("kp_weighted_c1_kernel", st, 1, (kp_weighted_c1_kernel<int><<<cdiv(Nq, 4), 128, 0, st>>>(
-            d_q, d_s, (const int*)d_idx, ld_idx, d_x, d_kp, flag, extent, Nq, Ns, H, K, wf, inv_nn)));
+            d_q, s4, (const int*)d_idx, ld_idx, d_kp, extent, Nq, Ns, H, K, wf, inv_nn)));
         APRB_LAUNCH_OK();
     } else {
         int rc = launch_kp_weighted(d_q, d_s, d_idx, idx_is_i64, ld_idx, d_x, d_kp, flag, s4, extent, 0, Nq, Ns, H, K, Cin, false, wf, inv_nn, st);
@@ -1223,9 +828,9 @@ extern "C" int aprb_kpconv_weighted(const float* d_q, const float* d_s, const vo
     if (Ns > 0) APRB_TIMED("rowsum_pos_kernel", st, 1, (rowsum_pos_kernel<<<cdiv(Ns, 8), 256, 0, st>>>(d_x, d_s, Ns, Cin, flag, s4)));
     if (Cin == 1) {
         if (idx_is_i64) APRB_TIMED("kp_weighted_c1_kernel", st, 1, (kp_weighted_c1_kernel<long long><<<cdiv(Nq, 4), 128, 0, st>>>(
-            d_q, d_s, (const long long*)d_idx, ld_idx, d_x, d_kp, flag, extent, Nq, Ns, H, K, d_wf, d_inv_nn)));
+            d_q, s4, (const long long*)d_idx, ld_idx, d_kp, extent, Nq, Ns, H, K, d_wf, d_inv_nn)));
         else APRB_TIMED("kp_weighted_c1_kernel", st, 1, (kp_weighted_c1_kernel<int><<<cdiv(Nq, 4), 128, 0, st>>>(
-            d_q, d_s, (const int*)d_idx, ld_idx, d_x, d_kp, flag, extent, Nq, Ns, H, K, d_wf, d_inv_nn)));
+            d_q, s4, (const int*)d_idx, ld_idx, d_kp, extent, Nq, Ns, H, K, d_wf, d_inv_nn)));
         APRB_LAUNCH_OK();
         return APRB_OK;
     }

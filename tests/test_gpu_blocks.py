@@ -79,40 +79,6 @@ def test_kpconv_list_kernel_paths(cuda, cin, h, kp_scale):
     assert torch.equal(got, got64)
 
 
-@pytest.mark.parametrize("cin,h", [(64, 57), (128, 33), (192, 70), (256, 56), (512, 20)])
-def test_kpconv_weighted_mma_vs_lists(cuda, cin, h):
-    """Stage A+B on mma.sync (kp_weighted_mma_kernel, TF32 operands, weights split hi+lo) against the CUDA-core list
-    kernel on the same inputs: with TF32-representable features the two agree to fp32 round-off; with arbitrary fp32
-    features the tensor version rounds x to TF32 (rel. error <= 2^-11 per element)."""
-    from apr_b200 import _native
-    gen = torch.Generator().manual_seed(cin + h)
-    ns, nq = 900, 517
-    s = torch.rand(ns, 3, generator=gen) * 1.5
-    q = torch.rand(nq, 3, generator=gen) * 1.5
-    inds = torch.randint(0, ns + 1, (nq, h), generator=gen)
-    inds[:3] = ns
-    inds[5, : h // 2] = ns                                         # pads in the middle of a row
-    kp = torch.randn(15, 3, generator=gen) * 0.4
-    args = (q.to(cuda), s.to(cuda), inds.to(cuda).int())
-    x = torch.randn(ns, cin, generator=gen).to(cuda)
-    xr = ops.round_tf32(x)
-    setopt = lambda v: _native.check(_native.lib().aprb_set_option(b"kpw_version", v), "aprb_set_option")
-    try:
-        setopt(4)
-        wf4, nn4 = ops.kpconv_weighted(*args, xr, kp.to(cuda), 0.7, round_tf32=True)
-        wf4x, _ = ops.kpconv_weighted(*args, x, kp.to(cuda), 0.7, round_tf32=True)
-        setopt(5)
-        wf5, nn5 = ops.kpconv_weighted(*args, xr, kp.to(cuda), 0.7, round_tf32=True)
-        wf5x, _ = ops.kpconv_weighted(*args, x, kp.to(cuda), 0.7, round_tf32=True)
-    finally:
-        setopt(5)
-    assert torch.equal(nn4, nn5)
-    assert torch.all(wf5[:3] == 0)
-    # both outputs are rounded to TF32 (10-bit mantissa): values that straddle a rounding boundary differ by one TF32 ulp
-    assert rel(wf5, wf4) < 1.5e-4
-    assert rel(wf5x, wf4x) < 4e-4
-
-
 def test_kpconv_tensor_path_vs_oracle(cuda, gold_kpconv):
     """tcgen05 TF32 contraction (mode 2) on shapes the tensor path accepts."""
     g = gold_kpconv
