@@ -107,10 +107,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 
 template <int BN>
 struct GemmCfg {
-    static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int MAX_STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);     // one CTA per SM, deepest ring
+    static constexpr int CO_STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);      // two CTAs per SM (<= 112 KB each)
     static constexpr int A_BYTES = GEMM_BM * 128;
     static constexpr int B_BYTES = BN * 128;
-    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 32 * 36 * 4 /*epilogue transpose*/;
+    // ring + align slack + barriers. The epilogue's transpose buffer (4 warps x 32 x 36 floats = 18 KB) aliases the
+    // A ring: by the time tmem_full fires every TMA write has landed and every MMA that reads the ring has retired.
+    static constexpr int smem(int stages) { return (stages < 2 ? 2 : stages) * (A_BYTES + B_BYTES) + 1024 + 256; }
 };
 
 // CL = thread-block-cluster size along M: the CL CTAs of a cluster compute CL vertically adjacent 128-row tiles of
@@ -118,16 +121,17 @@ struct GemmCfg {
 // all CTAs of the cluster (L2->SM traffic for B divided by CL). A stage is refilled only after all CL CTAs released it
 // (the MMA warps commit to the "empty" barriers of every CTA in the cluster).
 template <int BN, int CL>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 2)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-                 int kb_per_split, const float* __restrict__ rowscale, float* __restrict__ C) {
+                 int kb_per_split, int stages, const float* __restrict__ rowscale, float* __restrict__ C) {
     using Cfg = GemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                    // SWIZZLE_128B tiles need 1024 B alignment
-    const uint32_t sA = base, sB = base + Cfg::STAGES * Cfg::A_BYTES;
-    const uint32_t bars = sB + Cfg::STAGES * Cfg::B_BYTES;           // full[STAGES], empty[STAGES], tmem_full
-    const uint32_t bar_full = bars, bar_empty = bars + 8 * Cfg::STAGES, bar_tmem = bars + 16 * Cfg::STAGES;
+    const int ring = stages < 2 ? 2 : stages;                        // allocated stages (>= 2: room for the epilogue buffer)
+    const uint32_t sA = base, sB = base + ring * Cfg::A_BYTES;
+    const uint32_t bars = sB + ring * Cfg::B_BYTES;                  // full[stages], empty[stages], tmem_full
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * stages, bar_tmem = bars + 16 * stages;
     __shared__ uint32_t s_tmem_base;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -138,7 +142,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     C += (size_t)blockIdx.z * M * N;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
+        for (int s = 0; s < stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
         mbar_init(bar_tmem, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -166,7 +170,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (CL == 1) tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, bar_full + 8 * s, kb * GEMM_BK, n0);
                 else tma_load_2d_mcast(sB + s * Cfg::B_BYTES + crank * (BN / CL) * 128, &tmB, bar_full + 8 * s, kb * GEMM_BK,
                                        n0 + crank * (BN / CL), kMask);
-                if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                if (++s == stages) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -184,7 +188,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tc_mma_tf32(tmem_base, da + 2 * k4, db + 2 * k4, idesc, ((kb - kb0) | k4) != 0);
                 if (CL == 1) tc_commit(bar_empty + 8 * s);           // frees the stage when these MMAs retire
                 else tc_commit_mcast(bar_empty + 8 * s, kMask);      // ... in every CTA of the cluster
-                if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+                if (++s == stages) { s = 0; ph ^= 1; }
             }
             tc_commit(bar_tmem);                                     // accumulator complete
         }
@@ -196,7 +200,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const float sc = (rowscale && m0 + row_l < M) ? rowscale[m0 + row_l] : 1.0f;
         // Per-warp 32 x 32 transpose buffer (row stride 36 floats: 16-byte aligned, conflict-free float4 phases), so the
         // global stores are whole 128-byte row segments: lanes 0-7 cover one row's 32 columns, a warp store = 4 rows.
-        float* tbuf = reinterpret_cast<float*>(smem_raw + (bars - raw) + 256) + (size_t)(warp - 2) * 32 * 36;
+        float* tbuf = reinterpret_cast<float*>(smem_raw + (base - raw)) + (size_t)(warp - 2) * 32 * 36;   // aliases the A ring
         const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
@@ -279,9 +283,20 @@ bool gemm_tf32_supported(int M, int N, int K) {
     return M >= 1 && N >= 16 && N % 16 == 0 && K >= GEMM_BK && K % GEMM_BK == 0;
 }
 
+int g_gemm_costages = 1;  // aprb_set_option("gemm_costages"): shallow rings / several CTAs per SM when the grid allows
+
 template <int BN, int CL>
 static int launch_gemm(const float* A, const float* Bt, int M, int N, int K, int splits, int kb_per_split,
                        const float* rowscale, float* C, cudaStream_t st) {
+    // Ring depth. With at least two tiles per SM in the grid, a shallower ring lets two (or more) CTAs share an SM so
+    // one tile's epilogue (TMEM -> registers -> HBM, the long part of a small-K Linear) overlaps its neighbour's main
+    // loop; otherwise one CTA per SM keeps the deepest ring.
+    const int tiles = cdiv(N, BN) * cdiv(M, GEMM_BM) * splits;
+    int stages = GemmCfg<BN>::MAX_STAGES;
+    // (measured, tools/gemm_bench.py: the 2-stage ring of BN = 256 starves tensor-bound contractions with K >= 1024)
+    if (g_gemm_costages && tiles >= 2 * sm_count() && (BN < 256 || K <= 512)) stages = GemmCfg<BN>::CO_STAGES;
+    stages = min(stages, max(1, kb_per_split));
+    const int smem = GemmCfg<BN>::smem(stages);
     CUtensorMap tmA, tmB;
     int rc = make_tmap(&tmA, A, M, K, GEMM_BM);
     if (rc) return rc;
@@ -289,13 +304,14 @@ static int launch_gemm(const float* A, const float* Bt, int M, int N, int K, int
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        APRB_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM));
+        APRB_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          GemmCfg<BN>::smem(GemmCfg<BN>::MAX_STAGES)));
         attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(cdiv(N, BN), cdiv(cdiv(M, GEMM_BM), CL) * CL, splits);   // grid.y padded to whole clusters
     cfg.blockDim = dim3(192);
-    cfg.dynamicSmemBytes = GemmCfg<BN>::SMEM;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -303,7 +319,7 @@ static int launch_gemm(const float* A, const float* Bt, int M, int N, int K, int
     cfg.attrs = attr; cfg.numAttrs = 1;
     {
         ProfScope ps("gemm_tf32_kernel", st, 1);
-        APRB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, CL>, tmA, tmB, M, N, K, kb_per_split, rowscale, C));
+        APRB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, CL>, tmA, tmB, M, N, K, kb_per_split, stages, rowscale, C));
     }
     return APRB_OK;
 }
@@ -358,6 +374,7 @@ extern "C" int aprb_set_option(const char* name, int value) {
     using namespace aprb;
     APRB_REQUIRE(name, "null option name");
     if (strcmp(name, "gemm_cluster") == 0) { g_gemm_cluster = value; return APRB_OK; }
+    if (strcmp(name, "gemm_costages") == 0) { g_gemm_costages = value; return APRB_OK; }
     if (strcmp(name, "kpconv_chunk_mb") == 0) { g_kpconv_chunk_mb = value; return APRB_OK; }
     if (strcmp(name, "kpw_version") == 0) { g_kpw_version = value; return APRB_OK; }
     set_error("aprb_set_option: unknown option %s", name);
