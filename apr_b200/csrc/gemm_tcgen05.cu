@@ -123,7 +123,8 @@ struct GemmCfg {
 template <int BN, int CL>
 __global__ void __launch_bounds__(192, 2)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-                 int kb_per_split, int stages, const float* __restrict__ rowscale, float* __restrict__ C) {
+                 int kb_per_split, int stages, const float* __restrict__ rowscale, float* __restrict__ C,
+                 float* __restrict__ gstat) {
     using Cfg = GemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -219,6 +220,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         *reinterpret_cast<float4*>(C + (size_t)grow * N + n0 + c + sub_c) = *reinterpret_cast<const float4*>(tbuf + r * 36 + sub_c);
                 }
             }
+            // Column statistics of this warp's 32 rows (one group of the normalisation that follows: aprb_instnorm_*_pre):
+            // lane = column; mean and M2 = sum of squared deviations from that mean, two passes over the transpose buffer.
+            // Only whole groups are recorded; the consumer reads the rows of a ragged last group itself.
+            if (gstat && m0 + quarter * 32 + 32 <= M && n0 + c + lane < N) {
+                float sum = 0.f;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) sum += tbuf[r * 36 + lane];
+                const float mean = sum * (1.0f / 32.0f);
+                float m2 = 0.f;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) { const float d = tbuf[r * 36 + lane] - mean; m2 = fmaf(d, d, m2); }
+                float* gp = gstat + (size_t)((m0 >> 5) + quarter) * 2 * N + n0 + c + lane;
+                gp[0] = mean; gp[N] = m2;
+            }
             __syncwarp();
         }
     }
@@ -287,7 +302,7 @@ int g_gemm_costages = 1;  // aprb_set_option("gemm_costages"): shallow rings / s
 
 template <int BN, int CL>
 static int launch_gemm(const float* A, const float* Bt, int M, int N, int K, int splits, int kb_per_split,
-                       const float* rowscale, float* C, cudaStream_t st) {
+                       const float* rowscale, float* C, float* gstat, cudaStream_t st) {
     // Ring depth. With at least two tiles per SM in the grid, a shallower ring lets two (or more) CTAs share an SM so
     // one tile's epilogue (TMEM -> registers -> HBM, the long part of a small-K Linear) overlaps its neighbour's main
     // loop; otherwise one CTA per SM keeps the deepest ring.
@@ -319,13 +334,14 @@ static int launch_gemm(const float* A, const float* Bt, int M, int N, int K, int
     cfg.attrs = attr; cfg.numAttrs = 1;
     {
         ProfScope ps("gemm_tf32_kernel", st, 1);
-        APRB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, CL>, tmA, tmB, M, N, K, kb_per_split, stages, rowscale, C));
+        APRB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, CL>, tmA, tmB, M, N, K, kb_per_split, stages, rowscale, C, gstat));
     }
     return APRB_OK;
 }
 
 extern int g_kpconv_chunk_mb;
 extern int g_kpw_version;
+extern int g_fuse_stats;
 int g_gemm_cluster = 1;   // 1 disables the cluster/multicast path (aprb_set_option)
 
 size_t gemm_tf32_ws_bytes(int M, int N) {   // split-K partial tiles (up to 8 splits), only when split-K can trigger
@@ -336,8 +352,11 @@ size_t gemm_tf32_ws_bytes(int M, int N) {   // split-K partial tiles (up to 8 sp
 
 // d_ws may be NULL (no split-K). Tile width: the widest BN (fewest re-reads of A); split-K fills the SMs when the
 // output grid alone cannot.
+// d_gstat (optional): per 32-row group column statistics of C, [ceil(M/32)][mean | M2][N], written by the epilogue when the
+// product is finished there (no split-K); *stats_written tells the caller whether it was.
 int gemm_tf32_rowscale(const float* d_A, const float* d_Bt, int M, int N, int K, const float* d_rowscale, float* d_C,
-                       void* d_ws, size_t ws_bytes, cudaStream_t st) {
+                       void* d_ws, size_t ws_bytes, cudaStream_t st, float* d_gstat, int* stats_written) {
+    if (stats_written) *stats_written = 0;
     if (!gemm_tf32_supported(M, N, K)) { set_error("gemm_tf32: unsupported shape M=%d N=%d K=%d", M, N, K); return APRB_ERR_UNSUPPORTED; }
     if (((uintptr_t)d_A | (uintptr_t)d_Bt | (uintptr_t)d_C) & 15) { set_error("gemm_tf32: operands must be 16-byte aligned"); return APRB_ERR_INVALID; }
     const int mt = cdiv(M, GEMM_BM), sms = sm_count(), num_kb = K / GEMM_BK;
@@ -355,11 +374,13 @@ int gemm_tf32_rowscale(const float* d_A, const float* d_Bt, int M, int N, int K,
     splits = cdiv(num_kb, kps);
     float* out = splits > 1 ? (float*)d_ws : d_C;
     const float* rs = splits > 1 ? nullptr : d_rowscale;
+    float* gs = splits > 1 ? nullptr : d_gstat;
+    if (gs && stats_written) *stats_written = 1;
     int rc;
     const int cl = (g_gemm_cluster >= 2 && mt >= 2) ? 2 : 1;       // B-tile multicast across 2 vertically adjacent tiles
-    if (bn == 256) rc = cl == 2 ? launch_gemm<256, 2>(d_A, d_Bt, M, N, K, splits, kps, rs, out, st) : launch_gemm<256, 1>(d_A, d_Bt, M, N, K, splits, kps, rs, out, st);
-    else if (bn == 128) rc = cl == 2 ? launch_gemm<128, 2>(d_A, d_Bt, M, N, K, splits, kps, rs, out, st) : launch_gemm<128, 1>(d_A, d_Bt, M, N, K, splits, kps, rs, out, st);
-    else rc = cl == 2 ? launch_gemm<64, 2>(d_A, d_Bt, M, N, K, splits, kps, rs, out, st) : launch_gemm<64, 1>(d_A, d_Bt, M, N, K, splits, kps, rs, out, st);
+    if (bn == 256) rc = cl == 2 ? launch_gemm<256, 2>(d_A, d_Bt, M, N, K, splits, kps, rs, out, gs, st) : launch_gemm<256, 1>(d_A, d_Bt, M, N, K, splits, kps, rs, out, gs, st);
+    else if (bn == 128) rc = cl == 2 ? launch_gemm<128, 2>(d_A, d_Bt, M, N, K, splits, kps, rs, out, gs, st) : launch_gemm<128, 1>(d_A, d_Bt, M, N, K, splits, kps, rs, out, gs, st);
+    else rc = cl == 2 ? launch_gemm<64, 2>(d_A, d_Bt, M, N, K, splits, kps, rs, out, gs, st) : launch_gemm<64, 1>(d_A, d_Bt, M, N, K, splits, kps, rs, out, gs, st);
     if (rc || splits == 1) return rc;
     const size_t mn4 = (size_t)M * N / 4;
     APRB_TIMED("splitk_reduce_kernel", st, 1, (splitk_reduce_kernel<<<cdiv((long long)mn4, 256), 256, 0, st>>>(
@@ -377,6 +398,7 @@ extern "C" int aprb_set_option(const char* name, int value) {
     if (strcmp(name, "gemm_costages") == 0) { g_gemm_costages = value; return APRB_OK; }
     if (strcmp(name, "kpconv_chunk_mb") == 0) { g_kpconv_chunk_mb = value; return APRB_OK; }
     if (strcmp(name, "kpw_version") == 0) { g_kpw_version = value; return APRB_OK; }
+    if (strcmp(name, "fuse_stats") == 0) { g_fuse_stats = value; return APRB_OK; }
     set_error("aprb_set_option: unknown option %s", name);
     return APRB_ERR_INVALID;
 }
@@ -389,9 +411,21 @@ extern "C" size_t aprb_linear_tf32_ws_bytes(int N, int Cin, int Cout) {
 
 extern "C" int aprb_linear_tf32(const float* d_x, const float* d_W, int N, int Cin, int Cout, float* d_y, void* d_ws,
                                 size_t ws_bytes, void* stream) {
+    return aprb_linear_tf32_stats(d_x, d_W, N, Cin, Cout, d_y, nullptr, nullptr, d_ws, ws_bytes, stream);
+}
+
+extern "C" size_t aprb_group_stats_bytes(int N, int C) {
+    if (N < 0 || C < 1) return 0;
+    return aprb::align256((size_t)aprb::cdiv(N > 0 ? N : 1, 32) * 2 * C * sizeof(float));
+}
+
+extern "C" int aprb_linear_tf32_stats(const float* d_x, const float* d_W, int N, int Cin, int Cout, float* d_y,
+                                      float* d_gstat, int* stats_written, void* d_ws, size_t ws_bytes, void* stream) {
     using namespace aprb;
+    if (stats_written) *stats_written = 0;
     APRB_REQUIRE(N >= 0 && Cin >= 1 && Cout >= 1, "bad shape");
+    APRB_REQUIRE(!d_gstat || stats_written, "stats_written must be given with d_gstat");
     if (N == 0) return APRB_OK;
     APRB_REQUIRE(d_x && d_W && d_y, "null pointer");
-    return gemm_tf32_rowscale(d_x, d_W, N, Cout, Cin, nullptr, d_y, d_ws, ws_bytes, (cudaStream_t)stream);
+    return gemm_tf32_rowscale(d_x, d_W, N, Cout, Cin, nullptr, d_y, d_ws, ws_bytes, (cudaStream_t)stream, d_gstat, stats_written);
 }

@@ -15,7 +15,7 @@
 namespace aprb {
 
 int gemm_tf32_rowscale(const float* d_A, const float* d_Bt, int M, int N, int K, const float* d_rowscale, float* d_C,
-                       void* d_ws, size_t ws_bytes, cudaStream_t st);  // gemm_tcgen05.cu
+                       void* d_ws, size_t ws_bytes, cudaStream_t st, float* d_gstat, int* stats_written);  // gemm_tcgen05.cu
 size_t gemm_tf32_ws_bytes(int M, int N);
 bool gemm_tf32_supported(int M, int N, int K);
 
@@ -750,7 +750,17 @@ extern "C" int aprb_kpconv_forward(const float* d_q, const float* d_s, const voi
                                    const float* d_x, const float* d_kp, const float* d_W, const float* d_wprep,
                                    float extent, int Nq, int Ns, int H, int K, int Cin, int Cout, float* d_out, int mode,
                                    void* d_ws, size_t ws_bytes, void* stream) {
+    return aprb_kpconv_forward_stats(d_q, d_s, d_idx, idx_is_i64, ld_idx, d_x, d_kp, d_W, d_wprep, extent, Nq, Ns, H, K, Cin,
+                                     Cout, d_out, mode, nullptr, nullptr, d_ws, ws_bytes, stream);
+}
+
+extern "C" int aprb_kpconv_forward_stats(const float* d_q, const float* d_s, const void* d_idx, int idx_is_i64, int ld_idx,
+                                         const float* d_x, const float* d_kp, const float* d_W, const float* d_wprep,
+                                         float extent, int Nq, int Ns, int H, int K, int Cin, int Cout, float* d_out, int mode,
+                                         float* d_gstat, int* stats_written, void* d_ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    if (stats_written) *stats_written = 0;
+    APRB_REQUIRE(!d_gstat || stats_written, "stats_written must be given with d_gstat");
     APRB_REQUIRE(Nq >= 0 && Ns >= 0 && H >= 1 && H <= 1024, "need Nq,Ns >= 0 and 1 <= H <= 1024");
     APRB_REQUIRE(K >= 1 && K <= KP_MAX_K && Cin >= 1 && Cout >= 1 && ld_idx >= H, "need 1 <= K <= 16, Cin,Cout >= 1, ld >= H");
     APRB_REQUIRE(extent > 0.f && extent < 1e15f, "extent must be positive (and below 1e15)");
@@ -789,7 +799,9 @@ extern "C" int aprb_kpconv_forward(const float* d_q, const float* d_s, const voi
             const int nr = min(chunk_rows, Nq - r0);
             int rc = launch_kp_weighted(d_q, d_s, d_idx, idx_is_i64, ld_idx, d_x, d_kp, flag, s4, extent, r0, nr, Ns, H, K, Cin, true, wf, inv_nn, st);
             if (rc) return rc;
-            rc = gemm_tf32_rowscale(wf, d_wprep, nr, Cout, KC, inv_nn + r0, d_out + (size_t)r0 * Cout, gws, gws_bytes, st);
+            // group statistics only when the operator is one GEMM over all rows (row chunks would misalign the groups)
+            rc = gemm_tf32_rowscale(wf, d_wprep, nr, Cout, KC, inv_nn + r0, d_out + (size_t)r0 * Cout, gws, gws_bytes, st,
+                                    chunk_rows == Nq ? d_gstat : nullptr, chunk_rows == Nq ? stats_written : nullptr);
             if (rc) return rc;
         }
         return APRB_OK;

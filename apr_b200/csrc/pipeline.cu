@@ -11,6 +11,7 @@
 
 namespace aprb {
 constexpr int KFE_MAX_LEVELS = 8;
+extern int g_fuse_stats;
 }
 
 struct aprb_kfe {
@@ -62,25 +63,36 @@ struct Arena {
     T* var = A.take<T>(n);                                                                       \
     if (!var) { set_error("aprb_kfe_forward: arena too small (need > %zu bytes)", A.cap); return APRB_ERR_WORKSPACE; }
 
+// Group statistics of a GEMM-produced tensor, handed from the producer's epilogue to the normalisation that follows
+// (gs == nullptr: the consumer scans the tensor itself).
+struct GStat {
+    float* buf = nullptr;
+    int written = 0;
+    const float* get() const { return written ? buf : nullptr; }
+};
+
 int kpconv_call(const aprb_kfe& h, const aprb_kfe_block& b, const float* q, const float* s, const int* idx, int ld,
-                const float* x, int nq, int ns, int H, int cin, int cout, float* out, Arena& A, cudaStream_t st) {
+                const float* x, int nq, int ns, int H, int cin, int cout, float* out, GStat* gs, Arena& A, cudaStream_t st) {
     size_t need = aprb_kpconv_ws_bytes(nq, ns, H, h.cfg.K, cin, cout);
     if (A.scratch_bytes() < need) { set_error("aprb_kfe_forward: arena too small for the KPConv workspace"); return APRB_ERR_WORKSPACE; }
-    return aprb_kpconv_forward(q, s, idx, 0, ld, x, b.kp, b.kp_W, b.kp_Wprep, b.extent, nq, ns, H, h.cfg.K, cin, cout, out,
-                               b.kp_Wprep ? 0 : 1, A.scratch(), A.scratch_bytes(), st);
+    return aprb_kpconv_forward_stats(q, s, idx, 0, ld, x, b.kp, b.kp_W, b.kp_Wprep, b.extent, nq, ns, H, h.cfg.K, cin, cout, out,
+                                     b.kp_Wprep ? 0 : 1, gs ? gs->buf : nullptr, gs ? &gs->written : nullptr, A.scratch(),
+                                     A.scratch_bytes(), st);
 }
 
 // InstanceNorm over the rows of each collated pair (segment) of level `lvl`
 int norm_call(const aprb_kfe& h, int lvl, const float* x, int n, int c, float slope, const float* res, int norm_res, float* y,
-              Arena& A, cudaStream_t st) {
+              const GStat* gx, const GStat* gres, Arena& A, cudaStream_t st) {
     if (A.scratch_bytes() < aprb_instnorm_seg_ws_bytes(n, c, h.S)) { set_error("aprb_kfe_forward: arena too small for the norm workspace"); return APRB_ERR_WORKSPACE; }
-    return aprb_instnorm_lrelu_seg(x, n, c, h.seg[lvl], h.S, 1e-5f, slope, res, norm_res, 1, y, A.scratch(), A.scratch_bytes(), st);
+    return aprb_instnorm_lrelu_seg_pre(x, n, c, h.seg[lvl], h.S, 1e-5f, slope, res, norm_res, 1, y, gx ? gx->get() : nullptr,
+                                       gres ? gres->get() : nullptr, A.scratch(), A.scratch_bytes(), st);
 }
 
-int linear_call(const float* x, const float* W, int n, int cin, int cout, float* y, Arena& A, cudaStream_t st) {
+int linear_call(const float* x, const float* W, int n, int cin, int cout, float* y, GStat* gs, Arena& A, cudaStream_t st) {
     size_t need = aprb_linear_tf32_ws_bytes(n, cin, cout);
     void* ws = A.scratch_bytes() >= need ? A.scratch() : nullptr;   // split-K is optional
-    return aprb_linear_tf32(x, W, n, cin, cout, y, ws, ws ? A.scratch_bytes() : 0, st);
+    return aprb_linear_tf32_stats(x, W, n, cin, cout, y, gs ? gs->buf : nullptr, gs ? &gs->written : nullptr, ws,
+                                  ws ? A.scratch_bytes() : 0, st);
 }
 
 // One encoder block. feat [ns_rows, in_dim] -> *out [nq, out_cols]. Temporaries are released when the block returns.
@@ -93,13 +105,20 @@ int run_block(const aprb_kfe& h, const aprb_kfe_block& b, const float* feat, con
     const float* s = h.pts[l];
     const int* idx = b.strided ? h.pool[l] : h.conv[l];
     const int H = h.cfg.limits[l];
+#define KFE_GSTAT(var, rows, cols)                                                                       \
+    GStat var;                                                                                               \
+    if (aprb::g_fuse_stats) {                                                                                \
+        var.buf = (float*)A.take<char>(aprb_group_stats_bytes(rows, cols));                                  \
+        if (!var.buf) { set_error("aprb_kfe_forward: arena too small (need > %zu bytes)", A.cap); return APRB_ERR_WORKSPACE; } \
+    }
     if (b.type == 0) {                                             // SimpleBlock: KPConv -> IN -> LeakyReLU
         const int cout = b.out_dim / 2;
         KFE_ALLOC(y, float, (size_t)nq * cout);
         const size_t mark = A.off;
         KFE_ALLOC(t, float, (size_t)nq * cout);
-        KFE_OK(kpconv_call(h, b, q, s, idx, H, feat, nq, ns, H, b.in_dim, cout, t, A, st));
-        KFE_OK(norm_call(h, lq, t, nq, cout, 0.1f, nullptr, 0, y, A, st));
+        KFE_GSTAT(gt, nq, cout);
+        KFE_OK(kpconv_call(h, b, q, s, idx, H, feat, nq, ns, H, b.in_dim, cout, t, &gt, A, st));
+        KFE_OK(norm_call(h, lq, t, nq, cout, 0.1f, nullptr, 0, y, &gt, nullptr, A, st));
         A.off = mark;
         *out = y; *out_cols = cout;
         return APRB_OK;
@@ -110,15 +129,18 @@ int run_block(const aprb_kfe& h, const aprb_kfe_block& b, const float* feat, con
     const float* x1 = feat;
     if (b.unary1_W) {                                              // unary1: Linear -> IN -> LeakyReLU
         KFE_ALLOC(t1, float, (size_t)ns * mid);
-        KFE_OK(linear_call(feat, b.unary1_W, ns, b.in_dim, mid, t1, A, st));
-        KFE_OK(norm_call(h, l, t1, ns, mid, 0.1f, nullptr, 0, t1, A, st));
+        KFE_GSTAT(g1, ns, mid);
+        KFE_OK(linear_call(feat, b.unary1_W, ns, b.in_dim, mid, t1, &g1, A, st));
+        KFE_OK(norm_call(h, l, t1, ns, mid, 0.1f, nullptr, 0, t1, &g1, nullptr, A, st));
         x1 = t1;
     }
     KFE_ALLOC(t2, float, (size_t)nq * mid);
-    KFE_OK(kpconv_call(h, b, q, s, idx, H, x1, nq, ns, H, mid, mid, t2, A, st));
-    KFE_OK(norm_call(h, lq, t2, nq, mid, 0.1f, nullptr, 0, t2, A, st));
+    KFE_GSTAT(g2, nq, mid);
+    KFE_OK(kpconv_call(h, b, q, s, idx, H, x1, nq, ns, H, mid, mid, t2, &g2, A, st));
+    KFE_OK(norm_call(h, lq, t2, nq, mid, 0.1f, nullptr, 0, t2, &g2, nullptr, A, st));
     KFE_ALLOC(t3, float, (size_t)nq * cout);
-    KFE_OK(linear_call(t2, b.unary2_W, nq, mid, cout, t3, A, st)); // unary2 (IN folded into the final kernel)
+    KFE_GSTAT(g3, nq, cout);
+    KFE_OK(linear_call(t2, b.unary2_W, nq, mid, cout, t3, &g3, A, st)); // unary2 (IN folded into the final kernel)
     const float* sc = feat;
     if (b.strided) {                                               // shortcut = max_pool(features, pools)
         KFE_ALLOC(mp, float, (size_t)nq * b.in_dim);
@@ -127,11 +149,13 @@ int run_block(const aprb_kfe& h, const aprb_kfe_block& b, const float* feat, con
     }
     if (b.shortcut_W) {                                            // LeakyReLU(IN(x3) + IN(Linear(sc)))
         KFE_ALLOC(t4, float, (size_t)nq * cout);
-        KFE_OK(linear_call(sc, b.shortcut_W, nq, b.in_dim, cout, t4, A, st));
-        KFE_OK(norm_call(h, lq, t3, nq, cout, 0.1f, t4, 1, y, A, st));
+        KFE_GSTAT(g4, nq, cout);
+        KFE_OK(linear_call(sc, b.shortcut_W, nq, b.in_dim, cout, t4, &g4, A, st));
+        KFE_OK(norm_call(h, lq, t3, nq, cout, 0.1f, t4, 1, y, &g3, &g4, A, st));
     } else {                                                       // LeakyReLU(IN(x3) + sc)
-        KFE_OK(norm_call(h, lq, t3, nq, cout, 0.1f, sc, 0, y, A, st));
+        KFE_OK(norm_call(h, lq, t3, nq, cout, 0.1f, sc, 0, y, &g3, nullptr, A, st));
     }
+#undef KFE_GSTAT
     A.off = mark;
     *out = y; *out_cols = cout;
     return APRB_OK;
@@ -194,6 +218,7 @@ extern "C" size_t aprb_kfe_arena_bytes(const aprb_kfe* h, int N, int B) {
         size_t cout = b.type == 0 ? b.out_dim / 2 : b.out_dim, cin_k = b.type == 0 ? b.in_dim : b.out_dim / 4;
         feats += align256(n * cout * 4);
         size_t tmp = n * 4 * (2 * (size_t)(b.out_dim / 4) + 2 * cout + b.in_dim) + 8 * 256;
+        tmp += tmp / 16 + 8 * 256;                                  // group statistics: 1/16 of each GEMM output
         size_t kpw = aprb_kpconv_ws_bytes((int)n, (int)n, (int)lim, h->cfg.K, (int)cin_k, (int)(b.type == 0 ? cout : cin_k));
         size_t lin = aprb_linear_tf32_ws_bytes((int)n, b.in_dim, (int)cout);
         size_t scratch = kpw > lin ? kpw : lin;

@@ -443,9 +443,10 @@ __device__ __forceinline__ void chan_combine4(float4& am, float4& a2, int& an, c
 // writes stats[(seg*nt + t)][mean | rstd][C].
 __global__ void __launch_bounds__(256)
 norm_seg_partial_kernel(const float* __restrict__ x, const float* __restrict__ x2, const int* __restrict__ seg_off, int N,
-                        int C, int W, int ch, int nt, float eps, float* __restrict__ pmean, float* __restrict__ pm2,
-                        int* __restrict__ tickets, float* __restrict__ stats) {
-    const int seg = blockIdx.z / nt, t = blockIdx.z - seg * nt;
+                        int C, int W, int ch, int nt, int t_first, int t_count, float eps, float* __restrict__ pmean,
+                        float* __restrict__ pm2, int* __restrict__ tickets, float* __restrict__ stats) {
+    // blockIdx.z = seg * t_count + tt covers tensors t_first .. t_first + t_count - 1 of the nt normalised tensors
+    const int seg = blockIdx.z / t_count, t = t_first + (blockIdx.z - seg * t_count);
     if (t == 1) x = x2;
     __shared__ float4 s_s1[256], s_s2[256];
     __shared__ int s_cnt[256];
@@ -517,7 +518,7 @@ norm_seg_partial_kernel(const float* __restrict__ x, const float* __restrict__ x
         int n = 0;
         for (int k = 0; k < R; ++k) chan_combine4(m, v2, n, s_s1[k * W + tx], s_s2[k * W + tx], s_cnt[k * W + tx]);
         const float inv = 1.0f / (float)max(b - a, 1);
-        float* st = stats + (size_t)blockIdx.z * 2 * C;
+        float* st = stats + (size_t)(seg * nt + t) * 2 * C;
         reinterpret_cast<float4*>(st)[quad] = m;
         reinterpret_cast<float4*>(st + C)[quad] = make_float4(rsqrtf(v2.x * inv + eps), rsqrtf(v2.y * inv + eps),
                                                               rsqrtf(v2.z * inv + eps), rsqrtf(v2.w * inv + eps));
@@ -559,6 +560,69 @@ norm_seg_apply_kernel(const float* __restrict__ x, const int* __restrict__ seg_o
     }
 }
 
+// Statistics from the producer's group partials (GEMM epilogue: per 32-row group mean and M2, see gemm_tcgen05.cu)
+// instead of a pass over the tensor: for segment rows [a, b) the whole groups [ceil(a/32), floor(b/32)) are combined
+// from `gs` (1/16 of the tensor's bytes) and the ragged head / tail rows (< 32 each) are read from the tensor itself, so
+// any segmentation is handled exactly. grid (gx, S * t_count); block 256 = W quads x R lanes over groups; fixed order.
+__global__ void __launch_bounds__(256)
+norm_seg_groups_kernel(const float* __restrict__ x, const float* __restrict__ x2, const float* __restrict__ gs,
+                       const float* __restrict__ gs2, const int* __restrict__ seg_off, int N, int C, int W, int nt,
+                       int t_first, int t_count, float eps, float* __restrict__ stats) {
+    const int seg = blockIdx.y / t_count, t = t_first + (blockIdx.y - seg * t_count);
+    if (t == 1) { x = x2; gs = gs2; }
+    __shared__ float4 s_m[256], s_v[256];
+    __shared__ int s_n[256];
+    const int Cq = C >> 2, R = 256 / W;
+    const int tx = threadIdx.x % W, ty = threadIdx.x / W;
+    const int quad = blockIdx.x * W + tx;
+    const int a = seg_off ? seg_off[seg] : 0, b = seg_off ? seg_off[seg + 1] : N;
+    int g0 = (a + 31) >> 5, g1 = b >> 5;
+    int head_end = g0 << 5, tail_beg = g1 << 5;
+    if (g0 >= g1) { g1 = g0; head_end = b; tail_beg = b; }           // no whole group inside the segment: rows only
+    float4 am = make_float4(0.f, 0.f, 0.f, 0.f), a2 = am;
+    int an = 0;
+    if (quad < Cq) {
+        const float4* xp = reinterpret_cast<const float4*>(x) + quad;
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = a + ty; r < head_end; r += R) chan_combine4(am, a2, an, xp[(size_t)r * Cq], zero, 1);
+        // whole groups all count 32 rows: shifted sums of the group means around the first one this thread sees
+        // (mean = p + S1/G, M2 = sum M2_g + 32 (S2 - S1^2/G)), one Chan combine at the end instead of one per group
+        const float4* gp = reinterpret_cast<const float4*>(gs) + quad;
+        if (g0 + ty < g1) {
+            const float4 pv = __ldcg(gp + (size_t)(g0 + ty) * 2 * Cq);
+            float4 s1 = zero, s2 = zero, sm2 = zero;
+            int G = 0;
+#pragma unroll 8
+            for (int g = g0 + ty; g < g1; g += R) {
+                const float4 m = __ldcg(gp + (size_t)g * 2 * Cq), v = __ldcg(gp + ((size_t)g * 2 + 1) * Cq);
+                const float e = m.x - pv.x, f = m.y - pv.y, gg = m.z - pv.z, hh = m.w - pv.w;
+                s1.x += e; s1.y += f; s1.z += gg; s1.w += hh;
+                s2.x = fmaf(e, e, s2.x); s2.y = fmaf(f, f, s2.y); s2.z = fmaf(gg, gg, s2.z); s2.w = fmaf(hh, hh, s2.w);
+                sm2.x += v.x; sm2.y += v.y; sm2.z += v.z; sm2.w += v.w;
+                ++G;
+            }
+            const float invG = 1.0f / (float)G;
+            const float4 gm = make_float4(pv.x + s1.x * invG, pv.y + s1.y * invG, pv.z + s1.z * invG, pv.w + s1.w * invG);
+            const float4 g2 = make_float4(sm2.x + 32.f * fmaxf(s2.x - s1.x * s1.x * invG, 0.f), sm2.y + 32.f * fmaxf(s2.y - s1.y * s1.y * invG, 0.f),
+                                          sm2.z + 32.f * fmaxf(s2.z - s1.z * s1.z * invG, 0.f), sm2.w + 32.f * fmaxf(s2.w - s1.w * s1.w * invG, 0.f));
+            chan_combine4(am, a2, an, gm, g2, 32 * G);
+        }
+        for (int r = tail_beg + ty; r < b; r += R) chan_combine4(am, a2, an, xp[(size_t)r * Cq], zero, 1);
+    }
+    s_m[threadIdx.x] = am; s_v[threadIdx.x] = a2; s_n[threadIdx.x] = an;
+    __syncthreads();
+    if (ty == 0 && quad < Cq) {
+        float4 m = make_float4(0.f, 0.f, 0.f, 0.f), v2 = m;
+        int n = 0;
+        for (int k = 0; k < R; ++k) chan_combine4(m, v2, n, s_m[k * W + tx], s_v[k * W + tx], s_n[k * W + tx]);
+        const float inv = 1.0f / (float)max(b - a, 1);
+        float* st = stats + (size_t)(seg * nt + t) * 2 * C;
+        reinterpret_cast<float4*>(st)[quad] = m;
+        reinterpret_cast<float4*>(st + C)[quad] = make_float4(rsqrtf(v2.x * inv + eps), rsqrtf(v2.y * inv + eps),
+                                                              rsqrtf(v2.z * inv + eps), rsqrtf(v2.w * inv + eps));
+    }
+}
+
 // seg_off[s] = first row of segment s = sum of the lengths of the clouds before cloud s*cps (S+1 entries)
 __global__ void seg_offsets_kernel(const int* __restrict__ lens, int B, int cps, int S, int* __restrict__ seg_off) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -571,6 +635,7 @@ __global__ void seg_offsets_kernel(const int* __restrict__ lens, int B, int cps,
 }
 
 constexpr int NORM_SEG_MAX_CH = 64;
+int g_fuse_stats = 1;   // aprb_set_option("fuse_stats"): aprb_kfe_forward hands GEMM-epilogue group statistics to the norms
 
 }  // namespace aprb
 
@@ -592,12 +657,21 @@ extern "C" size_t aprb_instnorm_seg_ws_bytes(int N, int C, int S) {
 extern "C" int aprb_instnorm_lrelu_seg(const float* d_x, int N, int C, const int32_t* d_seg_off, int S, float eps,
                                        float slope, const float* d_residual, int norm_residual, int round_tf32, float* d_y,
                                        void* d_ws, size_t ws_bytes, void* stream) {
+    return aprb_instnorm_lrelu_seg_pre(d_x, N, C, d_seg_off, S, eps, slope, d_residual, norm_residual, round_tf32, d_y,
+                                       nullptr, nullptr, d_ws, ws_bytes, stream);
+}
+
+extern "C" int aprb_instnorm_lrelu_seg_pre(const float* d_x, int N, int C, const int32_t* d_seg_off, int S, float eps,
+                                           float slope, const float* d_residual, int norm_residual, int round_tf32,
+                                           float* d_y, const float* d_gstat_x, const float* d_gstat_res, void* d_ws,
+                                           size_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     APRB_REQUIRE(N >= 0 && C >= 1 && S >= 1, "bad shape");
     APRB_REQUIRE(S == 1 || d_seg_off, "segment offsets required when S > 1");
     if (N == 0) return APRB_OK;
     APRB_REQUIRE(d_x && d_y && d_ws, "null pointer");
-    const bool aligned = (((uintptr_t)d_x | (uintptr_t)d_y | (uintptr_t)(d_residual ? d_residual : d_x)) & 15) == 0;
+    const bool aligned = (((uintptr_t)d_x | (uintptr_t)d_y | (uintptr_t)(d_residual ? d_residual : d_x) |
+                           (uintptr_t)(d_gstat_x ? d_gstat_x : d_x) | (uintptr_t)(d_gstat_res ? d_gstat_res : d_x)) & 15) == 0;
     if (C % 4 != 0 || !aligned) { set_error("aprb_instnorm_lrelu_seg: needs C %% 4 == 0 and 16-byte aligned tensors"); return APRB_ERR_UNSUPPORTED; }
     if (ws_bytes < aprb_instnorm_seg_ws_bytes(N, C, S)) { set_error("aprb_instnorm_lrelu_seg: workspace too small"); return APRB_ERR_WORKSPACE; }
     const int nt = (d_residual && norm_residual) ? 2 : 1;
@@ -611,11 +685,26 @@ extern "C" int aprb_instnorm_lrelu_seg(const float* d_x, int N, int C, const int
     while (W < Cq && W < 256) W <<= 1;
     const int gx = cdiv(Cq, W), sms = sm_count();
     const int rows_seg = max(1, N / S);
-    // statistics pass: ~4 waves of blocks over all segments, chunks of >= 32 rows
-    int ch = min(min(max(1, 4 * sms / (gx * S * nt)), NORM_SEG_MAX_CH), max(1, rows_seg / 32));
-    APRB_CUDA_OK(cudaMemsetAsync(tickets, 0, (size_t)S * nt * gx * sizeof(int), st));
-    APRB_TIMED("norm_seg_partial_kernel", st, 1, (norm_seg_partial_kernel<<<dim3(gx, ch, S * nt), 256, 0, st>>>(
-        d_x, d_residual, d_seg_off, N, C, W, ch, nt, eps, pmean, pm2, tickets, stats)));
+    // ---- statistics: from the producer's group partials where given, else one pass over the tensor ----
+    const bool pre[2] = {d_gstat_x != nullptr, nt == 2 && d_gstat_res != nullptr};
+    for (int t0 = 0; t0 < nt;) {                                      // maximal runs of tensors with the same source
+        int t1 = t0 + 1;
+        while (t1 < nt && pre[t1] == pre[t0]) ++t1;
+        const int tc = t1 - t0;
+        if (pre[t0]) {
+            int Wg = 1;
+            while (Wg < Cq && Wg < 8) Wg <<= 1;                       // narrow column tiles: 256 / Wg lanes over the groups
+            APRB_TIMED("norm_seg_groups_kernel", st, 1, (norm_seg_groups_kernel<<<dim3(cdiv(Cq, Wg), S * tc), 256, 0, st>>>(
+                d_x, d_residual, d_gstat_x, d_gstat_res, d_seg_off, N, C, Wg, nt, t0, tc, eps, stats)));
+        } else {
+            // ~4 waves of blocks over all segments, chunks of >= 32 rows
+            int ch = min(min(max(1, 4 * sms / (gx * S * tc)), NORM_SEG_MAX_CH), max(1, rows_seg / 32));
+            APRB_CUDA_OK(cudaMemsetAsync(tickets, 0, (size_t)S * tc * gx * sizeof(int), st));
+            APRB_TIMED("norm_seg_partial_kernel", st, 1, (norm_seg_partial_kernel<<<dim3(gx, ch, S * tc), 256, 0, st>>>(
+                d_x, d_residual, d_seg_off, N, C, W, ch, nt, t0, tc, eps, pmean, pm2, tickets, stats)));
+        }
+        t0 = t1;
+    }
     // apply pass: ~6 waves of blocks, >= 16 rows per block
     int rb = min(max(1, 6 * sms / (gx * S)), max(1, rows_seg / 16));
     APRB_TIMED("norm_seg_apply_kernel", st, 1, (norm_seg_apply_kernel<<<dim3(gx, rb, S), 256, 0, st>>>(

@@ -3,6 +3,8 @@
 These are the stream-ordered building blocks behind the reference-facing modules
 (`apr_b200.cpp_wrappers.*`, `apr_b200.blocks`). torch only allocates memory and provides the current stream.
 """
+import ctypes as C
+
 import torch
 
 from . import _native as N
@@ -146,6 +148,17 @@ def kpconv_prepare_weights(weights):
     return out
 
 
+# Hand the GEMM epilogue's 32-row group statistics of a produced tensor to the InstanceNorm that consumes it (attribute
+# `_aprb_gstat` on the returned tensor; instnorm_lrelu_seg picks it up) — the module-path twin of what aprb_kfe_forward
+# does natively, so both paths run the same kernels in the same order.
+FUSE_STATS = True
+
+
+def _group_stats_buffer(n, c, device):
+    nbytes = N.lib().aprb_group_stats_bytes(int(n), int(c))
+    return torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+
+
 def kpconv(q_pts, s_pts, neighb_inds, x, kernel_points, weights, extent, wprep=None, mode=0):
     """K5. Returns [Nq,Cout] f32."""
     N.require_cuda()
@@ -159,10 +172,15 @@ def kpconv(q_pts, s_pts, neighb_inds, x, kernel_points, weights, extent, wprep=N
     out = torch.empty((nq, cout), dtype=torch.float32, device=q.device)
     nbytes = N.lib().aprb_kpconv_ws_bytes(nq, ns, h, k, cin, cout)
     ws = _workspace(nbytes, q.device)
-    rc = N.lib().aprb_kpconv_forward(N.ptr(q), N.ptr(s), N.ptr(idx), is64, ld, N.ptr(xx), N.ptr(kp), N.ptr(w),
-                                     N.ptr(wprep), float(extent), nq, ns, h, k, cin, cout, N.ptr(out), int(mode),
-                                     N.ptr(ws), ws.numel(), N.stream_ptr())
+    gs = _group_stats_buffer(nq, cout, q.device) if (FUSE_STATS and wprep is not None and mode != 1 and nq > 0) else None
+    written = C.c_int(0)
+    rc = N.lib().aprb_kpconv_forward_stats(N.ptr(q), N.ptr(s), N.ptr(idx), is64, ld, N.ptr(xx), N.ptr(kp), N.ptr(w),
+                                           N.ptr(wprep), float(extent), nq, ns, h, k, cin, cout, N.ptr(out), int(mode),
+                                           N.ptr(gs), C.byref(written) if gs is not None else None,
+                                           N.ptr(ws), ws.numel(), N.stream_ptr())
     N.check(rc, "aprb_kpconv_forward")
+    if written.value:
+        out._aprb_gstat = gs
     if TRACE is not None:
         TRACE.append(("kpconv", nq, ns, h, k, cin, cout))
     return out
@@ -233,9 +251,12 @@ def instnorm_lrelu_seg(x, seg_off=None, slope=0.1, residual=None, norm_residual=
     nseg = so.shape[0] - 1 if so is not None else 1
     y = out if out is not None else torch.empty_like(xx)
     ws = _workspace(N.lib().aprb_instnorm_seg_ws_bytes(n, c, nseg), xx.device)
-    rc = N.lib().aprb_instnorm_lrelu_seg(N.ptr(xx), n, c, N.ptr(so), nseg, float(eps), float(slope), N.ptr(res),
-                                         1 if norm_residual else 0, 1 if round_tf32 else 0, N.ptr(y), N.ptr(ws), ws.numel(),
-                                         N.stream_ptr())
+    # group statistics left on the tensors by the GEMM that produced them (only valid for that very tensor object)
+    gx = getattr(x, "_aprb_gstat", None) if xx is x else None
+    gr = getattr(residual, "_aprb_gstat", None) if (res is not None and res is residual and norm_residual) else None
+    rc = N.lib().aprb_instnorm_lrelu_seg_pre(N.ptr(xx), n, c, N.ptr(so), nseg, float(eps), float(slope), N.ptr(res),
+                                             1 if norm_residual else 0, 1 if round_tf32 else 0, N.ptr(y), N.ptr(gx), N.ptr(gr),
+                                             N.ptr(ws), ws.numel(), N.stream_ptr())
     N.check(rc, "aprb_instnorm_lrelu_seg")
     return y
 
@@ -252,8 +273,13 @@ def linear_tf32(x, weight):
     cout = w.shape[0]
     y = torch.empty((n, cout), dtype=torch.float32, device=xx.device)
     ws = _workspace(N.lib().aprb_linear_tf32_ws_bytes(n, cin, cout), xx.device)
-    N.check(N.lib().aprb_linear_tf32(N.ptr(xx), N.ptr(w), n, cin, cout, N.ptr(y), N.ptr(ws), ws.numel(), N.stream_ptr()),
+    gs = _group_stats_buffer(n, cout, xx.device) if (FUSE_STATS and n > 0) else None
+    written = C.c_int(0)
+    N.check(N.lib().aprb_linear_tf32_stats(N.ptr(xx), N.ptr(w), n, cin, cout, N.ptr(y), N.ptr(gs),
+                                           C.byref(written) if gs is not None else None, N.ptr(ws), ws.numel(), N.stream_ptr()),
             "aprb_linear_tf32")
+    if written.value:
+        y._aprb_gstat = gs
     if TRACE is not None:
         TRACE.append(("linear", n, cin, cout))
     return y

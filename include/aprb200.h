@@ -112,6 +112,17 @@ int aprb_kpconv_forward(const float* d_q, const float* d_s, const void* d_idx, i
                         const float* d_x, const float* d_kp, const float* d_W, const float* d_wprep,
                         float extent, int Nq, int Ns, int H, int K, int Cin, int Cout,
                         float* d_out, int mode, void* d_ws, size_t ws_bytes, void* stream);
+/* Same operator; when d_gstat is given (aprb_group_stats_bytes(Nq, Cout) bytes) and the contraction finishes in one
+ * tcgen05 GEMM, its epilogue also records the column statistics of every whole 32-row group of d_out —
+ * d_gstat[g][0][c] = mean, d_gstat[g][1][c] = sum of squared deviations from that mean, rows [32g, 32g+32) — and sets
+ * *stats_written = 1: the InstanceNorm that follows (models/blocks.py:459-468) then skips its own statistics pass
+ * (aprb_instnorm_lrelu_seg_pre). *stats_written = 0 (fp32 path, split-K, row chunks) means d_gstat was not touched. */
+size_t aprb_group_stats_bytes(int N, int C);
+int aprb_kpconv_forward_stats(const float* d_q, const float* d_s, const void* d_idx, int idx_is_i64, int ld_idx,
+                              const float* d_x, const float* d_kp, const float* d_W, const float* d_wprep,
+                              float extent, int Nq, int Ns, int H, int K, int Cin, int Cout,
+                              float* d_out, int mode, float* d_gstat, int* stats_written,
+                              void* d_ws, size_t ws_bytes, void* stream);
 
 /* Training path. Stage A+B alone: d_wf [Nq, K*Cin] = sum_h w[n,k,h] x[idx[n,h],:] and
  * d_inv_nn [Nq] = 1 / max(1, neighbor_num) (blocks.py:269-354, :369-371), so that autograd can keep wf for the weight
@@ -155,6 +166,12 @@ size_t aprb_instnorm_seg_ws_bytes(int N, int C, int S);
 int aprb_instnorm_lrelu_seg(const float* d_x, int N, int C, const int32_t* d_seg_off, int S, float eps, float slope,
                             const float* d_residual, int norm_residual, int round_tf32, float* d_y,
                             void* d_ws, size_t ws_bytes, void* stream);
+/* Same, with the statistics pass replaced by the producer's group partials where they exist: d_gstat_x for d_x and
+ * d_gstat_res for d_residual (norm_residual != 0), each as written by aprb_linear_tf32_stats / aprb_kpconv_forward_stats
+ * for exactly that tensor, or NULL to scan the tensor. Same result up to fp32 reassociation of the variance sums. */
+int aprb_instnorm_lrelu_seg_pre(const float* d_x, int N, int C, const int32_t* d_seg_off, int S, float eps, float slope,
+                                const float* d_residual, int norm_residual, int round_tf32, float* d_y,
+                                const float* d_gstat_x, const float* d_gstat_res, void* d_ws, size_t ws_bytes, void* stream);
 /* d_seg_off[s] = first stacked row of cloud s * clouds_per_segment; ceil(B / clouds_per_segment) + 1 entries. */
 int aprb_segment_offsets(const int32_t* d_lens, int B, int clouds_per_segment, int32_t* d_seg_off, void* stream);
 
@@ -165,6 +182,9 @@ int aprb_segment_offsets(const int32_t* d_lens, int B, int clouds_per_segment, i
 size_t aprb_linear_tf32_ws_bytes(int N, int Cin, int Cout);
 int aprb_linear_tf32(const float* d_x, const float* d_W, int N, int Cin, int Cout, float* d_y,
                      void* d_ws, size_t ws_bytes, void* stream);
+/* Linear + group statistics of y for the normalisation that follows (see aprb_kpconv_forward_stats). */
+int aprb_linear_tf32_stats(const float* d_x, const float* d_W, int N, int Cin, int Cout, float* d_y,
+                           float* d_gstat, int* stats_written, void* d_ws, size_t ws_bytes, void* stream);
 /* out[i] = in[i] rounded to TF32 (round to nearest, ties away). Used once per weight update for mlp.weight. */
 int aprb_round_tf32(const float* d_in, float* d_out, size_t n, void* stream);
 

@@ -187,6 +187,41 @@ def _pyramid(oracle, cfg, p0, l0, limits, cuda):
     return cpu, gpu
 
 
+def test_instnorm_from_gemm_group_stats(cuda):
+    """Linear on tcgen05 whose epilogue records per-32-row-group column statistics, consumed by the segmented
+    InstanceNorm instead of its own pass over the tensor: equal to the scanning path up to fp32 reassociation, for
+    segment bounds that are unaligned to the groups, shorter than a group, and empty."""
+    gen = torch.Generator().manual_seed(11)
+    for n, cin, cout, bounds in ((5000, 64, 256, [0, 1234, 1250, 1250, 3001, 5000]), (700, 128, 64, [0, 700]),
+                                 (4097, 32, 128, [0, 31, 64, 4097]), (40, 64, 64, [0, 7, 40])):
+        x = (torch.randn(n, cin, generator=gen) * 2 + 0.5).to(cuda)
+        w = (torch.randn(cout, cin, generator=gen) / np.sqrt(cin)).to(cuda)
+        r = (torch.randn(n, cout, generator=gen)).to(cuda)
+        seg = torch.tensor(bounds, dtype=torch.int32, device=cuda)
+        ops.FUSE_STATS = True
+        try:
+            y = ops.linear_tf32(x, w)
+            wrote = hasattr(y, "_aprb_gstat")
+            a = ops.instnorm_lrelu_seg(y, seg, slope=0.1, residual=r, norm_residual=False)
+            y2 = ops.linear_tf32(x, w)
+            b2 = ops.instnorm_lrelu_seg(y, seg, slope=0.1, residual=y2, norm_residual=True)
+        finally:
+            ops.FUSE_STATS = True
+        yc = y.clone()                                               # a clone carries no statistics: scanning path
+        b = ops.instnorm_lrelu_seg(yc, seg, slope=0.1, residual=r, norm_residual=False)
+        b3 = ops.instnorm_lrelu_seg(yc, seg, slope=0.1, residual=y2.clone(), norm_residual=True)
+        assert wrote or n < 128 * 148                                # split-K shapes legitimately skip the statistics
+        assert rel(a, b) < 2e-6, (n, cin, cout, rel(a, b))
+        assert rel(b2, b3) < 2e-6, (n, cin, cout, rel(b2, b3))
+        # and against torch, segment by segment
+        for s0, s1 in zip(bounds[:-1], bounds[1:]):
+            if s1 > s0:
+                ys = yc[s0:s1]
+                ref = (ys - ys.mean(0)) / torch.sqrt(ys.var(0, unbiased=False) + 1e-5) + r[s0:s1]
+                ref = torch.nn.functional.leaky_relu(ref, 0.1)
+                assert rel(a[s0:s1], ref) < 1e-5
+
+
 @pytest.mark.parametrize("mode,tol", [(1, 5e-5), (0, 2e-3)])
 def test_encoder_golden_small(cuda, oracle, gold_encoder, mode, tol):
     """Whole KFE encoder (first_feats_dim=16) vs the REAL reference's output; weights loaded through load_state_dict
