@@ -246,6 +246,153 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
+// ---- persistent variant (no split-K, no cluster) ------------------------------------------------------------------
+// One CTA per SM walks output tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (tile t -> column tile t % num_n fastest,
+// so CTAs that run together share the A rows in L2). The accumulator is double-buffered in TMEM (2 x BN columns):
+// the MMA warp starts tile i+1 in the other buffer while the epilogue warps drain tile i — TMEM -> registers -> smem
+// transpose -> HBM, plus the group statistics — so the epilogue (the long part of a small-K Linear) is off the
+// critical path, the smem ring keeps streaming across tile boundaries, and barrier init / TMEM allocation / tensor-map
+// prefetch are paid once per SM instead of once per tile.
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int BN>
+struct GemmPCfg {
+    static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int A_BYTES = GEMM_BM * 128;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int TBUF = 4 * 32 * 36 * 4;
+    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + TBUF + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
+                            int K, int num_n, int total_tiles, const float* __restrict__ rowscale, float* __restrict__ C,
+                            float* __restrict__ gstat) {
+    using Cfg = GemmPCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t sA = base, sB = base + STAGES * Cfg::A_BYTES;
+    const uint32_t tb = sB + STAGES * Cfg::B_BYTES;                  // epilogue transpose buffers
+    const uint32_t bars = tb + Cfg::TBUF;                            // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES, bar_tfull = bars + 16 * STAGES, bar_tempty = bar_tfull + 16;
+    __shared__ uint32_t s_tmem_base;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = K / GEMM_BK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "n"(2 * BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {                                             // ===== TMA producer =====
+            int s = 0; uint32_t ph = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int m0 = (t / num_n) * GEMM_BM, n0 = (t % num_n) * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::A_BYTES + Cfg::B_BYTES);
+                    tma_load_2d(sA + s * Cfg::A_BYTES, &tmA, bar_full + 8 * s, kb * GEMM_BK, m0);
+                    tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, bar_full + 8 * s, kb * GEMM_BK, n0);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                             // ===== MMA issuer =====
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
+            int s = 0; uint32_t ph = 0;
+            int i = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+                const int ab = i & 1;
+                mbar_wait(bar_tempty + 8 * ab, ((uint32_t)(i >> 1) & 1u) ^ 1u);   // epilogue has drained this buffer
+                tc_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)(ab * BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(bar_full + 8 * s, ph);
+                    tc_fence_after();
+                    const uint64_t da = make_smem_desc(sA + s * Cfg::A_BYTES), db = make_smem_desc(sB + s * Cfg::B_BYTES);
+#pragma unroll
+                    for (int k4 = 0; k4 < GEMM_BK / 8; ++k4)
+                        tc_mma_tf32(acc, da + 2 * k4, db + 2 * k4, idesc, (kb | k4) != 0);
+                    tc_commit(bar_empty + 8 * s);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                tc_commit(bar_tfull + 8 * ab);
+            }
+        }
+    } else {                                                         // ===== epilogue (warps 2..5) =====
+        const int quarter = warp & 3;
+        float* tbuf = reinterpret_cast<float*>(smem_raw + (tb - raw)) + (size_t)(warp - 2) * 32 * 36;
+        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+        int i = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+            const int ab = i & 1;
+            const int m0 = (t / num_n) * GEMM_BM, n0 = (t % num_n) * BN;
+            mbar_wait(bar_tfull + 8 * ab, (uint32_t)(i >> 1) & 1u);
+            tc_fence_after();
+            const int row_l = quarter * 32 + lane;
+            const float sc = (rowscale && m0 + row_l < M) ? rowscale[m0 + row_l] : 1.0f;
+            const bool whole = m0 + quarter * 32 + 32 <= M;
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN + c), v);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(tbuf + lane * 36 + j) = make_float4(__uint_as_float(v[j]) * sc, __uint_as_float(v[j + 1]) * sc,
+                                                                                  __uint_as_float(v[j + 2]) * sc, __uint_as_float(v[j + 3]) * sc);
+                __syncwarp();
+                if (n0 + c + sub_c < N) {
+#pragma unroll
+                    for (int r4 = 0; r4 < 32; r4 += 4) {
+                        const int r = r4 + sub_r, grow = m0 + quarter * 32 + r;
+                        if (grow < M)
+                            *reinterpret_cast<float4*>(C + (size_t)grow * N + n0 + c + sub_c) = *reinterpret_cast<const float4*>(tbuf + r * 36 + sub_c);
+                    }
+                }
+                if (gstat && whole && n0 + c + lane < N) {           // group statistics, as in gemm_tf32_kernel
+                    float sum = 0.f;
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) sum += tbuf[r * 36 + lane];
+                    const float mean = sum * (1.0f / 32.0f);
+                    float m2 = 0.f;
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) { const float d = tbuf[r * 36 + lane] - mean; m2 = fmaf(d, d, m2); }
+                    float* gp = gstat + (size_t)((m0 >> 5) + quarter) * 2 * N + n0 + c + lane;
+                    gp[0] = mean; gp[N] = m2;
+                }
+                __syncwarp();
+            }
+            tc_fence_before();                                       // all tcgen05.ld of this buffer have completed
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * ab);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN));
+    }
+}
+
 // C[m,n] = (sum_s part[s,m,n]) * rowscale[m]; fixed summation order (deterministic split-K)
 __global__ void splitk_reduce_kernel(const float4* __restrict__ part, int splits, size_t mn4, int n4,
                                      const float* __restrict__ rowscale, float4* __restrict__ C) {
@@ -339,6 +486,32 @@ static int launch_gemm(const float* A, const float* Bt, int M, int N, int K, int
     return APRB_OK;
 }
 
+int g_gemm_bn = 0;           // aprb_set_option("gemm_bn"): force the persistent kernel's tile width (0 = by wave count)
+int g_gemm_persistent = 1;   // aprb_set_option("gemm_persistent"): persistent double-buffered kernel when no split-K is needed
+
+template <int BN>
+static int launch_gemm_persistent(const float* A, const float* Bt, int M, int N, int K, const float* rowscale, float* C,
+                                  float* gstat, cudaStream_t st) {
+    CUtensorMap tmA, tmB;
+    int rc = make_tmap(&tmA, A, M, K, GEMM_BM);
+    if (rc) return rc;
+    rc = make_tmap(&tmB, Bt, N, K, BN);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        APRB_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmPCfg<BN>::SMEM));
+        attr_set = true;
+    }
+    const int num_n = cdiv(N, BN), total = num_n * cdiv(M, GEMM_BM);
+    const int grid = min(total, sm_count());
+    {
+        ProfScope ps("gemm_tf32_kernel", st, 1);
+        gemm_tf32_persistent_kernel<BN><<<grid, 192, GemmPCfg<BN>::SMEM, st>>>(tmA, tmB, M, N, K, num_n, total, rowscale, C, gstat);
+    }
+    APRB_LAUNCH_OK();
+    return APRB_OK;
+}
+
 extern int g_kpconv_chunk_mb;
 extern int g_kpw_version;
 extern int g_fuse_stats;
@@ -370,6 +543,23 @@ int gemm_tf32_rowscale(const float* d_A, const float* d_Bt, int M, int N, int K,
     if (splits <= 1 && tiles < sms / 2) {                            // no split-K possible: fall back to narrower tiles
         while (bn > 64 && mt * cdiv(N, bn) < sms) bn >>= 1;
     }
+    if (splits <= 1 && g_gemm_persistent) {
+        // tile width by wave count: cost = ceil(tiles / SMs) * BN / eff(BN) (narrow tiles re-read A and run the tensor
+        // pipe less efficiently, but quantise better on 148 SMs)
+        int best = 0; double best_cost = 1e30;
+        const int cand[3] = {256, 128, 64};
+        const double eff[3] = {1.0, 0.95, 0.80};
+        for (int c = 0; c < 3; ++c) {
+            if (cand[c] > 64 && N < cand[c]) continue;
+            if (g_gemm_bn && cand[c] != g_gemm_bn && !(g_gemm_bn > N && cand[c] == 64)) continue;
+            const double cost = (double)cdiv(mt * cdiv(N, cand[c]), sms) * cand[c] / eff[c];
+            if (cost < best_cost) { best_cost = cost; best = cand[c]; }
+        }
+        if (stats_written && d_gstat) *stats_written = 1;
+        if (best == 256) return launch_gemm_persistent<256>(d_A, d_Bt, M, N, K, d_rowscale, d_C, d_gstat, st);
+        if (best == 128) return launch_gemm_persistent<128>(d_A, d_Bt, M, N, K, d_rowscale, d_C, d_gstat, st);
+        return launch_gemm_persistent<64>(d_A, d_Bt, M, N, K, d_rowscale, d_C, d_gstat, st);
+    }
     int kps = cdiv(num_kb, splits);
     splits = cdiv(num_kb, kps);
     float* out = splits > 1 ? (float*)d_ws : d_C;
@@ -396,6 +586,8 @@ extern "C" int aprb_set_option(const char* name, int value) {
     APRB_REQUIRE(name, "null option name");
     if (strcmp(name, "gemm_cluster") == 0) { g_gemm_cluster = value; return APRB_OK; }
     if (strcmp(name, "gemm_costages") == 0) { g_gemm_costages = value; return APRB_OK; }
+    if (strcmp(name, "gemm_persistent") == 0) { g_gemm_persistent = value; return APRB_OK; }
+    if (strcmp(name, "gemm_bn") == 0) { g_gemm_bn = value; return APRB_OK; }
     if (strcmp(name, "kpconv_chunk_mb") == 0) { g_kpconv_chunk_mb = value; return APRB_OK; }
     if (strcmp(name, "kpw_version") == 0) { g_kpw_version = value; return APRB_OK; }
     if (strcmp(name, "fuse_stats") == 0) { g_fuse_stats = value; return APRB_OK; }
