@@ -29,6 +29,53 @@ __global__ void max_pool_kernel(const float* __restrict__ x, const IdxT* __restr
     *reinterpret_cast<float4*>(out + (size_t)n * C + 4 * gch) = m;
 }
 
+// Warp per query, C = 128 * NV channels (lane owns NV float4): the index row is read once, coalesced, and only the valid
+// neighbours are visited (ballot + shuffle broadcast) — pooling lists are ~half pad — with NV independent 128-bit loads
+// in flight per neighbour. The thread-per-(query, quad) kernel above re-read the row once per quad and walked the pads.
+template <typename IdxT, int NV>
+__global__ void __launch_bounds__(256)
+max_pool_warp_kernel(const float* __restrict__ x, const IdxT* __restrict__ idx, int ld, int Nq, int Ns, int H,
+                     const int* __restrict__ d_width, float* __restrict__ out) {
+    constexpr int C = 128 * NV;
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (n >= Nq) return;
+    const int Hn = d_width ? min(H, *d_width) : H;
+    float4 m[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) m[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    bool any_pad = false;
+    const IdxT* row = idx + (size_t)n * ld;
+    const float4* xb = reinterpret_cast<const float4*>(x) + lane;
+    for (int h0 = 0; h0 < Hn; h0 += 32) {
+        const int h = h0 + lane;
+        long long sv = -1;
+        if (h < Hn) sv = (long long)row[h];
+        const bool valid = sv >= 0 && sv < Ns;
+        unsigned vm = __ballot_sync(0xffffffffu, valid);
+        any_pad |= vm != __ballot_sync(0xffffffffu, h < Hn);
+        const int si = valid ? (int)sv : 0;
+        while (vm) {
+            const int src = __ffs(vm) - 1;
+            vm &= vm - 1;
+            const float4* p = xb + (size_t)__shfl_sync(0xffffffffu, si, src) * (C / 4);
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const float4 v = __ldg(p + j * 32);
+                m[j].x = fmaxf(m[j].x, v.x); m[j].y = fmaxf(m[j].y, v.y); m[j].z = fmaxf(m[j].z, v.z); m[j].w = fmaxf(m[j].w, v.w);
+            }
+        }
+    }
+    float4* op = reinterpret_cast<float4*>(out + (size_t)n * C) + lane;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        if (any_pad) {                                               // the shadow neighbour's all-zero row takes part in the max
+            m[j].x = fmaxf(m[j].x, 0.f); m[j].y = fmaxf(m[j].y, 0.f); m[j].z = fmaxf(m[j].z, 0.f); m[j].w = fmaxf(m[j].w, 0.f);
+        }
+        op[j * 32] = m[j];
+    }
+}
+
 template <typename IdxT>
 __global__ void max_pool_scalar_kernel(const float* __restrict__ x, const IdxT* __restrict__ idx, int ld, int Nq,
                                        int Ns, int H, int C, const int* __restrict__ d_width, float* __restrict__ out) {
@@ -211,6 +258,16 @@ extern "C" int aprb_max_pool(const float* d_x, const void* d_idx, int idx_is_i64
     const int T = 256;
     if (C % 4 == 0 && ((uintptr_t)d_x % 16 == 0) && ((uintptr_t)d_out % 16 == 0)) {
         long long total = (long long)Nq * (C / 4);
+        if (C % 128 == 0 && C <= 1024 && H >= 1) {
+#define MPW(IDX, NV) APRB_TIMED("max_pool_kernel", st, 1, (max_pool_warp_kernel<IDX, NV><<<cdiv(Nq, 8), 256, 0, st>>>(d_x, (const IDX*)d_idx, ld_idx, Nq, Ns, H, d_width, d_out)))
+#define MPW_NV(IDX) do { if (C == 128) MPW(IDX, 1); else if (C == 256) MPW(IDX, 2); else if (C == 384) MPW(IDX, 3); else if (C == 512) MPW(IDX, 4); \
+                         else if (C == 640) MPW(IDX, 5); else if (C == 768) MPW(IDX, 6); else if (C == 896) MPW(IDX, 7); else MPW(IDX, 8); } while (0)
+            if (idx_is_i64) MPW_NV(long long); else MPW_NV(int);
+#undef MPW_NV
+#undef MPW
+            APRB_LAUNCH_OK();
+            return APRB_OK;
+        }
         if (idx_is_i64) APRB_TIMED("max_pool_kernel", st, 1, (max_pool_kernel<long long><<<cdiv(total, T), T, 0, st>>>(d_x, (const long long*)d_idx, ld_idx, Nq, Ns, H, C, d_width, d_out)));
         else APRB_TIMED("max_pool_kernel", st, 1, (max_pool_kernel<int><<<cdiv(total, T), T, 0, st>>>(d_x, (const int*)d_idx, ld_idx, Nq, Ns, H, C, d_width, d_out)));
     } else {

@@ -123,6 +123,17 @@ def test_pools_golden_bit_exact(cuda, gold_kpconv):
     # odd channel count -> scalar kernel
     x = torch.randn(50, 7); inds = torch.randint(0, 51, (20, 9))
     assert torch.equal(ops.max_pool(x.to(cuda), inds.to(cuda)).cpu(), blocks_ref.max_pool_ref(x, inds))
+    # multiples of 128 channels -> warp-per-query kernel (pads anywhere in the row, all-pad rows, H > 32, int64 indices)
+    gen = torch.Generator().manual_seed(3)
+    for c, h in ((128, 9), (256, 56), (512, 33), (1024, 70), (384, 5)):
+        x = torch.randn(300, c, generator=gen)
+        inds = torch.randint(0, 301, (77, h), generator=gen)
+        inds[3] = 300
+        inds[4, : h // 2] = 300
+        want = blocks_ref.max_pool_ref(x, inds)
+        assert torch.equal(ops.max_pool(x.to(cuda), inds.to(cuda).int()).cpu(), want)
+        assert torch.equal(ops.max_pool(x.to(cuda), inds.to(cuda)).cpu(), want)
+        assert torch.equal(ops.max_pool(-x.abs().to(cuda), inds.to(cuda).int()).cpu(), blocks_ref.max_pool_ref(-x.abs(), inds))
 
 
 def test_instnorm_lrelu_vs_torch(cuda):
