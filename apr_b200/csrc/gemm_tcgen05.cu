@@ -14,96 +14,9 @@
 // Operands are fp32 in memory; the tensor core reads them as TF32 (producers round to nearest beforehand where the
 // 1e-3 parity budget needs it), accumulation is fp32 in TMEM. Out-of-range rows/cols are zero-filled by TMA and masked
 // in the epilogue, so M and N need no padding (N % 16 == 0, K % 32 == 0 required).
-#include "common.cuh"
-#include <cuda.h>
+#include "tc_common.cuh"
 
 namespace aprb {
-
-constexpr int GEMM_BM = 128;
-constexpr int GEMM_BK = 32;  // fp32 elements per k-block = 128 bytes = one SWIZZLE_128B row
-
-// ---- PTX wrappers ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Bounded wait: a broken pipeline traps (error at the next sync) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
-        if (spins > (1u << 26)) __trap();
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void tc_commit_mcast(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                            uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
-// start address >> 4 in [0,14), LBO [16,30) (unused for swizzled K-major; 1), SBO = 1024 B (8 rows x 128 B) [32,46),
-// version 1 [46,48), layout SWIZZLE_128B (2) [61,64). The tile base must be 1024-byte aligned.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-    uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
 
 template <int BN>
 struct GemmCfg {
@@ -253,10 +166,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // transpose -> HBM, plus the group statistics — so the epilogue (the long part of a small-K Linear) is off the
 // critical path, the smem ring keeps streaming across tile boundaries, and barrier init / TMEM allocation / tensor-map
 // prefetch are paid once per SM instead of once per tile.
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-
 template <int BN>
 struct GemmPCfg {
     static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
@@ -427,7 +336,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 2-D fp32 row-major [rows, cols] tensor, box = [box_rows, 32 cols], 128B swizzle, zero OOB fill
-static int make_tmap(CUtensorMap* tm, const float* ptr, int rows, int cols, int box_rows) {
+int make_tmap(CUtensorMap* tm, const float* ptr, int rows, int cols, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return APRB_ERR_CUDA; }
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -515,6 +424,7 @@ static int launch_gemm_persistent(const float* A, const float* Bt, int M, int N,
 extern int g_kpconv_chunk_mb;
 extern int g_kpw_version;
 extern int g_fuse_stats;
+extern int g_kpconv_fused;
 int g_gemm_cluster = 1;   // 1 disables the cluster/multicast path (aprb_set_option)
 
 size_t gemm_tf32_ws_bytes(int M, int N) {   // split-K partial tiles (up to 8 splits), only when split-K can trigger
@@ -591,6 +501,7 @@ extern "C" int aprb_set_option(const char* name, int value) {
     if (strcmp(name, "kpconv_chunk_mb") == 0) { g_kpconv_chunk_mb = value; return APRB_OK; }
     if (strcmp(name, "kpw_version") == 0) { g_kpw_version = value; return APRB_OK; }
     if (strcmp(name, "fuse_stats") == 0) { g_fuse_stats = value; return APRB_OK; }
+    if (strcmp(name, "kpconv_fused") == 0) { g_kpconv_fused = value; return APRB_OK; }
     set_error("aprb_set_option: unknown option %s", name);
     return APRB_ERR_INVALID;
 }

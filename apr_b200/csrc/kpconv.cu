@@ -10,16 +10,19 @@
 // warp-uniform, so skipping costs no divergence). wf is written as the [Nq, K*Cin] A operand of stage C.
 // Stage C: [Nq, K*Cin] x [K*Cin, Cout] contraction with the 1/neighbor_num row scale in the epilogue —
 // fp32 CUDA-core tiles here (mode 1); the tcgen05 TF32 path lives in gemm_tcgen05.cu (mode 2).
-#include "common.cuh"
+#include "kpconv_common.cuh"
 
 namespace aprb {
 
 int gemm_tf32_rowscale(const float* d_A, const float* d_Bt, int M, int N, int K, const float* d_rowscale, float* d_C,
                        void* d_ws, size_t ws_bytes, cudaStream_t st, float* d_gstat, int* stats_written);  // gemm_tcgen05.cu
 size_t gemm_tf32_ws_bytes(int M, int N);
+bool kpconv_fused_supported(int H, int K, int Cin, int Cout, long long Ns);   // kpconv_fused.cu
+int kpconv_fused_run(const float* d_q, const float4* s4, const void* d_idx, int idx_is_i64, int ld, const float* d_x,
+                     const float* d_kp, const float* d_wprep, float extent, int Nq, int Ns, int H, int K, int Cin, int Cout,
+                     float* d_out, float* d_gstat, cudaStream_t st);
 bool gemm_tf32_supported(int M, int N, int K);
 
-constexpr int KP_MAX_K = 16;
 int g_kpw_version = 4;       // aprb_set_option("kpw_version"): 3 = per-kernel-point tables, 4 = CSR lists + lane groups
 int g_kpconv_chunk_mb = 0;   // aprb_set_option("kpconv_chunk_mb"): L2-sized row chunks of the tensor path (0 = off)
 
@@ -198,65 +201,6 @@ kp_weighted_kernel(const float* __restrict__ q, const float* __restrict__ s, con
 constexpr int KPW_ECAP = 160;
 constexpr int KPW_SLOT_BYTES = KPW_ECAP * 8 + 80;   // int2 ent[ECAP]; int off[K_MAX+1] (+pad)
 
-__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ float sqrt_approx(float v) {
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-    return r;
-}
-// Value whose TRUNCATION to TF32 (what the tensor core does with an fp32 operand) equals round-to-nearest (ties away
-// from zero in magnitude) of t: one integer add instead of the 3-instruction cvt.rna emulation. Exact for finite t;
-// +-inf becomes NaN (a feature table that holds inf is garbage either way).
-__device__ __forceinline__ float pre_round_tf32(float t) { return __uint_as_float(__float_as_uint(t) + 0x1000u); }
-__device__ __forceinline__ float round_tf32(float t) {
-    unsigned u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(t));
-    return __uint_as_float(u);
-}
-
-template <int NH>
-struct RowGeom {          // lanes = neighbours: element offset of the support's feature row and position relative to the query
-    int sio[NH];          // byte offset of the support's feature row, si * Cin * 4 (shadow neighbours: 0, never selected)
-    float rx[NH], ry[NH], rz[NH];   // shadow neighbours sit at x = 3e18: outside every extent
-    unsigned any[NH];               // warp ballot: does this group of 32 neighbours hold a valid one (warp-uniform)
-};
-
-template <typename IdxT, int NH>
-__device__ __forceinline__ int load_row_geom(const float* __restrict__ q, const float4* __restrict__ s4,
-                                             const IdxT* __restrict__ idx, int ld, int n, int Ns, int H, int Cin, int lane,
-                                             RowGeom<NH>& g) {
-    const float qx = q[3 * (size_t)n], qy = q[3 * (size_t)n + 1], qz = q[3 * (size_t)n + 2];
-    int nn = 0;
-#pragma unroll
-    for (int j = 0; j < NH; ++j) {
-        const int h = j * 32 + lane;
-        int si = Ns;
-        if (h < H) {
-            const long long v = (long long)idx[(size_t)n * ld + h];
-            si = (v >= 0 && v < Ns) ? (int)v : Ns;
-        }
-        g.sio[j] = 0;
-        g.rx[j] = 3e18f; g.ry[j] = 0.f; g.rz[j] = 0.f;
-        if (si < Ns) {
-            const float4 p = __ldg(s4 + si);
-            nn += p.w > 0.f ? 1 : 0;
-            g.sio[j] = si * Cin * 4;
-            g.rx[j] = p.x - qx; g.ry[j] = p.y - qy; g.rz[j] = p.z - qz;
-        }
-        g.any[j] = __ballot_sync(0xffffffffu, si < Ns);
-    }
-    return __reduce_add_sync(0xffffffffu, nn);
-}
-
-// influence of kernel point kpk on this lane's neighbour j: w = max(0, 1 - d/extent); in = inside the extent
-template <int NH>
-__device__ __forceinline__ float influence(const RowGeom<NH>& g, int j, const float4 kpk, float ext2, float inv_ext, bool& in) {
-    const float ddx = g.rx[j] - kpk.x, ddy = g.ry[j] - kpk.y, ddz = g.rz[j] - kpk.z;
-    const float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
-    in = d2 < ext2;
-    return fmaxf(1.0f - sqrt_approx(d2) * inv_ext, 0.f);
-}
-
 // Overflow path: one row, whole warp, lanes = 4 channels of a 128-channel slab; no lists.
 template <typename IdxT, int NH, bool ROUND_TF32>
 __device__ __noinline__ void kp_direct_row(const float* __restrict__ q, const float4* __restrict__ s4, const IdxT* __restrict__ idx,
@@ -331,27 +275,7 @@ kp_weighted4_kernel(const float* __restrict__ q, const float4* __restrict__ s4, 
         RowGeom<NH> g;
         const int nn = load_row_geom<IdxT, NH>(q, s4, idx, ld, n, Ns, H, Cin, lane, g);
         if (lane == 0) inv_nn[n] = 1.0f / (float)max(nn, 1);
-        int run = 0, myoff = 0;
-#pragma unroll
-        for (int k = 0; k < KP_MAX_K; ++k) {
-            if (lane == k) myoff = run;
-            if (k < K) {
-                const float4 kpk = s_kp[k];
-#pragma unroll
-                for (int j = 0; j < NH; ++j) {
-                    if (g.any[j]) {                              // neighbours are distance-sorted: the tail group is often all pad
-                        bool in;
-                        const float w = influence<NH>(g, j, kpk, ext2, inv_ext, in);
-                        const unsigned m = __ballot_sync(0xffffffffu, in);
-                        const int pos = run + __popc(m & ltmask);
-                        if (in && pos < KPW_ECAP) ent[pos] = make_int2(g.sio[j], __float_as_int(w));
-                        run += __popc(m);
-                    }
-                }
-            }
-        }
-        if (lane >= K) myoff = run;                    // off[K..K_MAX] = total (unused kernel points have empty lists)
-        if (lane <= KP_MAX_K) off[lane] = myoff;
+        build_row_list<NH, KPW_ECAP>(g, s_kp, K, ext2, inv_ext, ent, off, lane);
     }
     __syncwarp();
 
@@ -785,6 +709,13 @@ extern "C" int aprb_kpconv_forward_stats(const float* d_q, const float* d_s, con
     float* gws = c.take<float>(gws_bytes / sizeof(float));
 
     if (Ns > 0) APRB_TIMED("rowsum_pos_kernel", st, 1, (rowsum_pos_kernel<<<cdiv(Ns, 8), 256, 0, st>>>(d_x, d_s, Ns, Cin, flag, s4)));
+    if (use_tensor && Ns > 0 && kpconv_fused_supported(H, K, Cin, Cout, Ns) &&
+        ((((uintptr_t)d_x | (uintptr_t)d_out | (uintptr_t)d_wprep | (uintptr_t)(d_gstat ? d_gstat : d_out)) & 15) == 0)) {
+        // one kernel: gather -> influence -> swizzled A tiles in shared memory -> tcgen05 (kpconv_fused.cu)
+        if (d_gstat) *stats_written = 1;
+        return kpconv_fused_run(d_q, s4, d_idx, idx_is_i64, ld_idx, d_x, d_kp, d_wprep, extent, Nq, Ns, H, K, Cin, Cout, d_out,
+                                d_gstat, st);
+    }
     if (use_tensor) {
         // Row chunks sized so that one chunk of wf (the A operand) stays L2-resident between its producer and the GEMM
         // that consumes it (aprb_set_option("kpconv_chunk_mb"); measured on B200: no gain, off by default).

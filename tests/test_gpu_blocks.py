@@ -97,6 +97,53 @@ def test_kpconv_tensor_path_vs_oracle(cuda, gold_kpconv):
         assert e < TOL_TF32, f"Cin={cin} Cout={cout}: rel err {e:.2e}"
 
 
+@pytest.mark.parametrize("cin,h,kp_scale,nq", [(64, 57, 0.4, 1000), (128, 33, 0.4, 517), (64, 20, 0.4, 129), (64, 40, 0.0, 300),
+                                               (128, 64, 0.02, 260)])
+def test_kpconv_fused_kernel_vs_unfused_and_oracle(cuda, cin, h, kp_scale, nq):
+    """kpconv_fused_kernel (gather -> influence -> swizzled A tiles in shared memory -> tcgen05, no [Nq, K*Cin]
+    intermediate) against the two-kernel tensor path and the fp32 oracle: ragged last tile, 1 and 2 neighbour groups,
+    pads inside rows, all-pad rows, rows whose influence list overflows the shared-memory slot (kp_scale ~ 0: every
+    neighbour influences all 15 kernel points -> direct path), int64 indices, and the epilogue's group statistics."""
+    from apr_b200 import _native
+    gen = torch.Generator().manual_seed(cin * 7 + h)
+    ns = 900
+    s = torch.rand(ns, 3, generator=gen) * 1.5
+    q = torch.rand(nq, 3, generator=gen) * 1.5
+    inds = torch.randint(0, ns + 1, (nq, h), generator=gen)
+    inds[:3] = ns
+    inds[5, : h // 2] = ns
+    x = torch.randn(ns, cin, generator=gen)
+    kp = torch.randn(15, 3, generator=gen) * kp_scale
+    w = torch.randn(15, cin, cin, generator=gen) / np.sqrt(15 * cin)
+    want = blocks_ref.kpconv_ref(q, s, inds, x, kp, w, 0.7)
+    dev = [t.to(cuda) for t in (q, s)]
+    wd, xd, kpd = w.to(cuda), x.to(cuda), kp.to(cuda)
+    prep = ops.kpconv_prepare_weights(wd)
+    setopt = lambda v: _native.check(_native.lib().aprb_set_option(b"kpconv_fused", v), "aprb_set_option")
+    try:
+        setopt(0)
+        two = ops.kpconv(*dev, inds.to(cuda).int(), xd, kpd, wd, 0.7, wprep=prep, mode=2)
+        setopt(1)
+        launches = _native.launch_count()
+        one = ops.kpconv(*dev, inds.to(cuda).int(), xd, kpd, wd, 0.7, wprep=prep, mode=2)
+        assert _native.launch_count() - launches == 2            # rowsum/pack + the fused kernel
+        one64 = ops.kpconv(*dev, inds.to(cuda), xd, kpd, wd, 0.7, wprep=prep, mode=2)
+    finally:
+        setopt(0)                                                     # library default (see profiles/r01_kpconv_fused.txt)
+    assert torch.equal(one, one64)
+    assert torch.all(one[:3] == 0)
+    # the fused producer keeps 17 mantissa bits of each influence weight (2^-18 relative): a few A elements then round to
+    # the neighbouring TF32 value (2^-11), hence 1e-4 rather than round-off between the two tensor paths
+    assert rel(one, two) < 1e-4, rel(one, two)
+    assert rel(one, want) < TOL_TF32, rel(one, want)
+    if nq >= 32:                                                      # group statistics written by the fused epilogue
+        gs = one._aprb_gstat.view(-1, 2, cin)
+        g = nq // 32
+        blk = one[: g * 32].view(g, 32, cin)
+        assert rel(gs[:g, 0], blk.mean(1)) < 1e-5
+        assert rel(gs[:g, 1], ((blk - blk.mean(1, keepdim=True)) ** 2).sum(1)) < 1e-4
+
+
 def test_linear_tf32_vs_fp32(cuda):
     gen = torch.Generator().manual_seed(2)
     for n, cin, cout in ((1000, 64, 128), (4255, 256, 64), (129, 32, 16), (1567, 512, 2048)):
