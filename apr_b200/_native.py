@@ -31,6 +31,7 @@ SIGNATURES = {
     "aprb_cell_grid_build": (_i, [_p, _p, _i, _i, _f, _p, _sz, _p]),
     "aprb_cell_grid_query": (_i, [_p, _sz, _p, _p, _i, _i, _i, _f, _i, _p, _i, _p, _p, _p]),
     "aprb_kpconv_prepare_weights": (_i, [_p, _i, _i, _i, _p, _p]),
+    "aprb_kpconv_prepare_weights_f16": (_i, [_p, _i, _i, _i, _p, _p]),
     "aprb_kpconv_ws_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "aprb_kpconv_forward": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _i, _p, _i, _p, _sz, _p]),
     "aprb_kpconv_weighted_ws_bytes": (_sz, [_i]),

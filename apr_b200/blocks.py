@@ -20,6 +20,7 @@ from .kernel_points import load_kernels
 
 # nn.Linear of the unary blocks: 'tf32' = our tcgen05 TF32 GEMM when the shape allows, 'fp32' = cuBLAS fp32 (library)
 LINEAR_MODE = 'fp32'
+KPCONV_F16 = True      # with LINEAR_MODE == 'tf32': KPConv contraction on fp16 operands (ops.kpconv mode 3)
 # KPConv contraction: 0 = auto (tcgen05 TF32 when supported), 1 = fp32 CUDA cores, 2 = force tcgen05
 KPCONV_MODE = 0
 
@@ -98,7 +99,20 @@ class KPConv(nn.Module):
             self._wprep_key = key
         return self._wprep
 
+    def _prepared_f16(self):
+        key = (self.weights.data_ptr(), self.weights._version, self.weights.device)
+        if getattr(self, '_wprep16', None) is None or self._wprep16_key != key:
+            self._wprep16 = ops.kpconv_prepare_weights_f16(self.weights)
+            self._wprep16_key = key
+        return self._wprep16
+
     def forward(self, q_pts, s_pts, neighb_inds, x):
+        # fp16 operands (same mantissa as TF32, half the bytes of the weighted tile) in the regime where every KPConv
+        # input with Cin > 1 is an InstanceNorm output: the TF32 module path (LINEAR_MODE == 'tf32')
+        if (KPCONV_F16 and KPCONV_MODE == 0 and LINEAR_MODE == 'tf32'
+                and ops.kpconv_f16_supported(self.K, self.in_channels, self.out_channels, neighb_inds.shape[1])):
+            return ops.kpconv(q_pts, s_pts, neighb_inds, x, self.kernel_points, self.weights, self.KP_extent,
+                              wprep=self._prepared_f16(), mode=3)
         wprep = None
         if KPCONV_MODE != 1 and (self.K * self.in_channels) % 32 == 0 and self.out_channels % 16 == 0:
             wprep = self._prepared()

@@ -175,7 +175,8 @@ struct GemmPCfg {
     static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + TBUF + 1024 + 256;
 };
 
-template <int BN>
+// F16: operands are fp16 (64 elements per 128-byte k-block, kind::f16) instead of TF32-in-fp32 (32 elements).
+template <int BN, bool F16>
 __global__ void __launch_bounds__(192, 1)
 gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                             int K, int num_n, int total_tiles, const float* __restrict__ rowscale, float* __restrict__ C,
@@ -191,7 +192,8 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES, bar_tfull = bars + 16 * STAGES, bar_tempty = bar_tfull + 16;
     __shared__ uint32_t s_tmem_base;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_kb = K / GEMM_BK;
+    constexpr int BKE = F16 ? 64 : GEMM_BK;                          // elements per 128-byte k-block
+    const int num_kb = K / BKE;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -217,15 +219,17 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(bar_empty + 8 * s, ph ^ 1);
                     mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::A_BYTES + Cfg::B_BYTES);
-                    tma_load_2d(sA + s * Cfg::A_BYTES, &tmA, bar_full + 8 * s, kb * GEMM_BK, m0);
-                    tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, bar_full + 8 * s, kb * GEMM_BK, n0);
+                    tma_load_2d(sA + s * Cfg::A_BYTES, &tmA, bar_full + 8 * s, kb * BKE, m0);
+                    tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, bar_full + 8 * s, kb * BKE, n0);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {                                             // ===== MMA issuer =====
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
+            // instruction descriptor: D = F32; A/B format TF32 (2) or F16 (0); K-major; N >> 3, M >> 4
+            const uint32_t fmt = F16 ? 0u : 2u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
             int s = 0; uint32_t ph = 0;
             int i = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
@@ -238,8 +242,10 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                     tc_fence_after();
                     const uint64_t da = make_smem_desc(sA + s * Cfg::A_BYTES), db = make_smem_desc(sB + s * Cfg::B_BYTES);
 #pragma unroll
-                    for (int k4 = 0; k4 < GEMM_BK / 8; ++k4)
-                        tc_mma_tf32(acc, da + 2 * k4, db + 2 * k4, idesc, (kb | k4) != 0);
+                    for (int k4 = 0; k4 < 4; ++k4) {                  // 4 x 32 bytes of K per 128-byte k-block
+                        if (F16) tc_mma_f16(acc, da + 2 * k4, db + 2 * k4, idesc, (kb | k4) != 0);
+                        else tc_mma_tf32(acc, da + 2 * k4, db + 2 * k4, idesc, (kb | k4) != 0);
+                    }
                     tc_commit(bar_empty + 8 * s);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
@@ -350,6 +356,20 @@ int make_tmap(CUtensorMap* tm, const float* ptr, int rows, int cols, int box_row
     return APRB_OK;
 }
 
+int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return APRB_ERR_CUDA; }
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)ptr, gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(f16) failed (%d) rows=%d cols=%d box_rows=%d", (int)r, rows, cols, box_rows); return APRB_ERR_CUDA; }
+    return APRB_OK;
+}
+
 bool gemm_tf32_supported(int M, int N, int K) {
     return M >= 1 && N >= 16 && N % 16 == 0 && K >= GEMM_BK && K % GEMM_BK == 0;
 }
@@ -398,24 +418,24 @@ static int launch_gemm(const float* A, const float* Bt, int M, int N, int K, int
 int g_gemm_bn = 0;           // aprb_set_option("gemm_bn"): force the persistent kernel's tile width (0 = by wave count)
 int g_gemm_persistent = 1;   // aprb_set_option("gemm_persistent"): persistent double-buffered kernel when no split-K is needed
 
-template <int BN>
-static int launch_gemm_persistent(const float* A, const float* Bt, int M, int N, int K, const float* rowscale, float* C,
+template <int BN, bool F16>
+static int launch_gemm_persistent(const void* A, const void* Bt, int M, int N, int K, const float* rowscale, float* C,
                                   float* gstat, cudaStream_t st) {
     CUtensorMap tmA, tmB;
-    int rc = make_tmap(&tmA, A, M, K, GEMM_BM);
+    int rc = F16 ? make_tmap_f16(&tmA, A, M, K, GEMM_BM) : make_tmap(&tmA, (const float*)A, M, K, GEMM_BM);
     if (rc) return rc;
-    rc = make_tmap(&tmB, Bt, N, K, BN);
+    rc = F16 ? make_tmap_f16(&tmB, Bt, N, K, BN) : make_tmap(&tmB, (const float*)Bt, N, K, BN);
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        APRB_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmPCfg<BN>::SMEM));
+        APRB_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_persistent_kernel<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmPCfg<BN>::SMEM));
         attr_set = true;
     }
     const int num_n = cdiv(N, BN), total = num_n * cdiv(M, GEMM_BM);
     const int grid = min(total, sm_count());
     {
         ProfScope ps("gemm_tf32_kernel", st, 1);
-        gemm_tf32_persistent_kernel<BN><<<grid, 192, GemmPCfg<BN>::SMEM, st>>>(tmA, tmB, M, N, K, num_n, total, rowscale, C, gstat);
+        gemm_tf32_persistent_kernel<BN, F16><<<grid, 192, GemmPCfg<BN>::SMEM, st>>>(tmA, tmB, M, N, K, num_n, total, rowscale, C, gstat);
     }
     APRB_LAUNCH_OK();
     return APRB_OK;
@@ -424,6 +444,7 @@ static int launch_gemm_persistent(const float* A, const float* Bt, int M, int N,
 extern int g_kpconv_chunk_mb;
 extern int g_kpw_version;
 extern int g_fuse_stats;
+extern int g_kpconv_f16;
 extern int g_kpconv_fused;
 int g_gemm_cluster = 1;   // 1 disables the cluster/multicast path (aprb_set_option)
 
@@ -466,9 +487,9 @@ int gemm_tf32_rowscale(const float* d_A, const float* d_Bt, int M, int N, int K,
             if (cost < best_cost) { best_cost = cost; best = cand[c]; }
         }
         if (stats_written && d_gstat) *stats_written = 1;
-        if (best == 256) return launch_gemm_persistent<256>(d_A, d_Bt, M, N, K, d_rowscale, d_C, d_gstat, st);
-        if (best == 128) return launch_gemm_persistent<128>(d_A, d_Bt, M, N, K, d_rowscale, d_C, d_gstat, st);
-        return launch_gemm_persistent<64>(d_A, d_Bt, M, N, K, d_rowscale, d_C, d_gstat, st);
+        if (best == 256) return launch_gemm_persistent<256, false>(d_A, d_Bt, M, N, K, d_rowscale, d_C, d_gstat, st);
+        if (best == 128) return launch_gemm_persistent<128, false>(d_A, d_Bt, M, N, K, d_rowscale, d_C, d_gstat, st);
+        return launch_gemm_persistent<64, false>(d_A, d_Bt, M, N, K, d_rowscale, d_C, d_gstat, st);
     }
     int kps = cdiv(num_kb, splits);
     splits = cdiv(num_kb, kps);
@@ -489,6 +510,30 @@ int gemm_tf32_rowscale(const float* d_A, const float* d_Bt, int M, int N, int K,
     return APRB_OK;
 }
 
+// C[M,N] (fp32) = (A[M,K] @ Bt[N,K]^T) * rowscale[M] with fp16 operands (fp32 accumulation in TMEM): the KPConv
+// contraction when the weighted tile is stored in fp16. Persistent kernel only (no split-K). K % 64 == 0, N % 16 == 0.
+bool gemm_f16_supported(int M, int N, int K) { return M >= 1 && N >= 16 && N % 16 == 0 && K >= 64 && K % 64 == 0; }
+
+int gemm_f16_rowscale(const void* d_A, const void* d_Bt, int M, int N, int K, const float* d_rowscale, float* d_C,
+                      cudaStream_t st, float* d_gstat, int* stats_written) {
+    if (stats_written) *stats_written = 0;
+    if (!gemm_f16_supported(M, N, K)) { set_error("gemm_f16: unsupported shape M=%d N=%d K=%d", M, N, K); return APRB_ERR_UNSUPPORTED; }
+    if (((uintptr_t)d_A | (uintptr_t)d_Bt | (uintptr_t)d_C) & 15) { set_error("gemm_f16: operands must be 16-byte aligned"); return APRB_ERR_INVALID; }
+    const int mt = cdiv(M, GEMM_BM), sms = sm_count();
+    int best = 0; double best_cost = 1e30;
+    const int cand[3] = {256, 128, 64};
+    const double eff[3] = {1.0, 0.95, 0.80};
+    for (int c = 0; c < 3; ++c) {
+        if (cand[c] > 64 && N < cand[c]) continue;
+        const double cost = (double)cdiv(mt * cdiv(N, cand[c]), sms) * cand[c] / eff[c];
+        if (cost < best_cost) { best_cost = cost; best = cand[c]; }
+    }
+    if (stats_written && d_gstat) *stats_written = 1;
+    if (best == 256) return launch_gemm_persistent<256, true>(d_A, d_Bt, M, N, K, d_rowscale, d_C, d_gstat, st);
+    if (best == 128) return launch_gemm_persistent<128, true>(d_A, d_Bt, M, N, K, d_rowscale, d_C, d_gstat, st);
+    return launch_gemm_persistent<64, true>(d_A, d_Bt, M, N, K, d_rowscale, d_C, d_gstat, st);
+}
+
 }  // namespace aprb
 
 extern "C" int aprb_set_option(const char* name, int value) {
@@ -501,6 +546,7 @@ extern "C" int aprb_set_option(const char* name, int value) {
     if (strcmp(name, "kpconv_chunk_mb") == 0) { g_kpconv_chunk_mb = value; return APRB_OK; }
     if (strcmp(name, "kpw_version") == 0) { g_kpw_version = value; return APRB_OK; }
     if (strcmp(name, "fuse_stats") == 0) { g_fuse_stats = value; return APRB_OK; }
+    if (strcmp(name, "kpconv_f16") == 0) { g_kpconv_f16 = value; return APRB_OK; }
     if (strcmp(name, "kpconv_fused") == 0) { g_kpconv_fused = value; return APRB_OK; }
     set_error("aprb_set_option: unknown option %s", name);
     return APRB_ERR_INVALID;

@@ -11,12 +11,16 @@
 // Stage C: [Nq, K*Cin] x [K*Cin, Cout] contraction with the 1/neighbor_num row scale in the epilogue —
 // fp32 CUDA-core tiles here (mode 1); the tcgen05 TF32 path lives in gemm_tcgen05.cu (mode 2).
 #include "kpconv_common.cuh"
+#include <cuda_fp16.h>
 
 namespace aprb {
 
 int gemm_tf32_rowscale(const float* d_A, const float* d_Bt, int M, int N, int K, const float* d_rowscale, float* d_C,
                        void* d_ws, size_t ws_bytes, cudaStream_t st, float* d_gstat, int* stats_written);  // gemm_tcgen05.cu
 size_t gemm_tf32_ws_bytes(int M, int N);
+bool gemm_f16_supported(int M, int N, int K);
+int gemm_f16_rowscale(const void* d_A, const void* d_Bt, int M, int N, int K, const float* d_rowscale, float* d_C,
+                      cudaStream_t st, float* d_gstat, int* stats_written);
 bool kpconv_fused_supported(int H, int K, int Cin, int Cout, long long Ns);   // kpconv_fused.cu
 int kpconv_fused_run(const float* d_q, const float4* s4, const void* d_idx, int idx_is_i64, int ld, const float* d_x,
                      const float* d_kp, const float* d_wprep, float extent, int Nq, int Ns, int H, int K, int Cin, int Cout,
@@ -201,12 +205,20 @@ kp_weighted_kernel(const float* __restrict__ q, const float* __restrict__ s, con
 constexpr int KPW_ECAP = 160;
 constexpr int KPW_SLOT_BYTES = KPW_ECAP * 8 + 80;   // int2 ent[ECAP]; int off[K_MAX+1] (+pad)
 
+// fp16 form of the weighted tile (tensor path with fp16 operands: same 10-bit mantissa as TF32, half the bytes)
+__device__ __forceinline__ void store_half4(__half* dst, const float4 v) {
+    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const unsigned*>(&a); u.y = *reinterpret_cast<const unsigned*>(&b);
+    *reinterpret_cast<uint2*>(dst) = u;
+}
+
 // Overflow path: one row, whole warp, lanes = 4 channels of a 128-channel slab; no lists.
 template <typename IdxT, int NH, bool ROUND_TF32>
 __device__ __noinline__ void kp_direct_row(const float* __restrict__ q, const float4* __restrict__ s4, const IdxT* __restrict__ idx,
                                            int ld, const float* __restrict__ x, const float4* s_kp,
                                            float ext2, float inv_ext, int n, int Ns,
-                                           int H, int K, int Cin, float* __restrict__ wrow, int lane) {
+                                           int H, int K, int Cin, float* __restrict__ wrow, int out16, int lane) {
     RowGeom<NH> g;
     load_row_geom<IdxT, NH>(q, s4, idx, ld, n, Ns, H, Cin, lane, g);
     for (int c0 = 0; c0 < Cin; c0 += 128) {
@@ -235,8 +247,12 @@ __device__ __noinline__ void kp_direct_row(const float* __restrict__ q, const fl
                 }
             }
             if (cok) {
-                if (ROUND_TF32) { acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y); acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w); }
-                *reinterpret_cast<float4*>(wrow + (size_t)k * Cin + c) = acc;
+                if (out16) {
+                    store_half4(reinterpret_cast<__half*>(wrow) + (size_t)k * Cin + c, acc);
+                } else {
+                    if (ROUND_TF32) { acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y); acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w); }
+                    *reinterpret_cast<float4*>(wrow + (size_t)k * Cin + c) = acc;
+                }
             }
         }
     }
@@ -247,7 +263,7 @@ __global__ void __launch_bounds__(128)
 kp_weighted4_kernel(const float* __restrict__ q, const float4* __restrict__ s4, const IdxT* __restrict__ idx, int ld,
                     const float* __restrict__ x, const float* __restrict__ kp,
                     float extent, int Nq, int Ns, int H, int K, int Cin, float* __restrict__ wf,
-                    float* __restrict__ inv_nn) {
+                    float* __restrict__ inv_nn, int out16) {
     constexpr int RP = 32 / LG;                  // rows streamed in parallel by one warp
     constexpr int CH = LG * 4 * NV;              // channels per pass
     constexpr int NU = 2;                        // list entries in flight per lane group (lists average ~3 entries)
@@ -295,10 +311,10 @@ kp_weighted4_kernel(const float* __restrict__ q, const float4* __restrict__ s4, 
 #pragma unroll
         for (int j = 0; j < NV; ++j) cok[j] = FULL || (c + j * LG * 4 < Cin);
         const char* xbc = xb + (size_t)c * 4u;
-        float* wp = wf + (size_t)n * K * Cin + c;
+        size_t wo = (size_t)n * K * Cin + c;                       // element offset of (row n, kernel point k, channel c)
         int end = active ? off[0] : 0;
 #pragma unroll 1
-        for (int k = 0; k < K; ++k, wp += Cin) {
+        for (int k = 0; k < K; ++k, wo += Cin) {
             const int beg = end;
             end = active ? off[k + 1] : 0;
             float4 acc[NV];
@@ -348,8 +364,12 @@ kp_weighted4_kernel(const float* __restrict__ q, const float4* __restrict__ s4, 
                 for (int j = 0; j < NV; ++j) {
                     if (cok[j]) {
                         float4 o4 = acc[j];
-                        if (ROUND_TF32) { o4.x = pre_round_tf32(o4.x); o4.y = pre_round_tf32(o4.y); o4.z = pre_round_tf32(o4.z); o4.w = pre_round_tf32(o4.w); }
-                        *reinterpret_cast<float4*>(wp + j * LG * 4) = o4;
+                        if (out16) {
+                            store_half4(reinterpret_cast<__half*>(wf) + wo + j * LG * 4, o4);
+                        } else {
+                            if (ROUND_TF32) { o4.x = pre_round_tf32(o4.x); o4.y = pre_round_tf32(o4.y); o4.z = pre_round_tf32(o4.z); o4.w = pre_round_tf32(o4.w); }
+                            *reinterpret_cast<float4*>(wf + wo + j * LG * 4) = o4;
+                        }
                     }
                 }
             }
@@ -363,7 +383,8 @@ kp_weighted4_kernel(const float* __restrict__ q, const float4* __restrict__ s4, 
             const int ovr = __shfl_sync(0xffffffffu, (int)ovf, r * LG);
             if (ovr && row0 + r < Nq)
                 kp_direct_row<IdxT, NH, ROUND_TF32>(q, s4, idx, ld, x, s_kp, ext2, inv_ext, row0 + r, Ns, H, K, Cin,
-                                                    wf + (size_t)(row0 + r) * K * Cin, lane);
+                                                    out16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(wf) + (size_t)(row0 + r) * K * Cin)
+                                                          : wf + (size_t)(row0 + r) * K * Cin, out16, lane);
         }
     }
 }
@@ -565,6 +586,22 @@ __global__ void prep_weights_kernel(const float* __restrict__ W, int KC, int Cou
 
 using namespace aprb;
 
+// W [K,Cin,Cout] -> Wt [Cout, K*Cin] in fp16 (round to nearest even): B operand of the fp16-operand contraction (mode 3)
+__global__ void prep_weights_f16_kernel(const float* __restrict__ W, int KC, int Cout, __half* __restrict__ Wt) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)KC * Cout) return;
+    int o = (int)(t / KC), kc = (int)(t % KC);
+    Wt[t] = __float2half_rn(W[(size_t)kc * Cout + o]);
+}
+
+extern "C" int aprb_kpconv_prepare_weights_f16(const float* d_W, int K, int Cin, int Cout, void* d_wprep16, void* stream) {
+    APRB_REQUIRE(d_W && d_wprep16 && K >= 1 && Cin >= 1 && Cout >= 1, "bad argument");
+    long long total = (long long)K * Cin * Cout;
+    APRB_TIMED("prep_weights_kernel", (cudaStream_t)stream, 1, (prep_weights_f16_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(d_W, K * Cin, Cout, (__half*)d_wprep16)));
+    APRB_LAUNCH_OK();
+    return APRB_OK;
+}
+
 extern "C" int aprb_kpconv_prepare_weights(const float* d_W, int K, int Cin, int Cout, float* d_wprep, void* stream) {
     APRB_REQUIRE(d_W && d_wprep && K >= 1 && Cin >= 1 && Cout >= 1, "bad argument");
     long long total = (long long)K * Cin * Cout;
@@ -592,10 +629,14 @@ extern "C" int aprb_round_tf32(const float* d_in, float* d_out, size_t n, void* 
 // Launch stage A+B for query rows [r0, r0 + nr): wf rows are written relative to r0, inv_nn at absolute rows.
 static int launch_kp_weighted(const float* d_q, const float* d_s, const void* d_idx, int idx_is_i64, int ld_idx,
                               const float* d_x, const float* d_kp, const unsigned char* flag, const float4* s4, float extent, int r0, int nr,
-                              int Ns, int H, int K, int Cin, bool round_tf32, float* wf, float* inv_nn, cudaStream_t st) {
+                              int Ns, int H, int K, int Cin, bool round_tf32, float* wf, float* inv_nn, cudaStream_t st, int out16 = 0) {
     const int Hp = (H + 31) & ~31;
     const bool x16 = ((uintptr_t)d_x % 16 == 0) && ((uintptr_t)wf % 16 == 0);
-    if (g_kpw_version >= 4 && x16 && Cin % 4 == 0 && H <= 128 && (long long)Ns * Cin < (1LL << 30)) {
+    if (out16 && !(x16 && Cin % 4 == 0 && H <= 128 && (long long)Ns * Cin < (1LL << 30))) {
+        set_error("aprb_kpconv_forward: fp16 operand path needs Cin %% 4 == 0, H <= 128 and 16-byte aligned features");
+        return APRB_ERR_UNSUPPORTED;
+    }
+    if ((g_kpw_version >= 4 || out16) && x16 && Cin % 4 == 0 && H <= 128 && (long long)Ns * Cin < (1LL << 30)) {
         // v4: lane-group streaming over compact CSR lists; (LG, NV) by channel count, NH = 32-neighbour groups per row
         const int nh = H <= 64 ? 2 : 4;
         const int chs[5] = {32, 64, 128, 256, 512};
@@ -607,7 +648,7 @@ static int launch_kp_weighted(const float* d_q, const float* d_s, const void* d_
             constexpr int rp = 32 / LG;                                                                               \
             const size_t smem4 = (size_t)wpb4 * rp * KPW_SLOT_BYTES;                                                  \
             APRB_TIMED("kp_weighted_kernel", st, 1, (kp_weighted4_kernel<IDX, LG, NV, NH, FULLV, RND><<<cdiv(nr, wpb4 * rp), wpb4 * 32, smem4, st>>>( \
-                d_q + 3 * (size_t)r0, s4, (const IDX*)d_idx + (size_t)r0 * ld_idx, ld_idx, d_x, d_kp, extent, nr, Ns, H, K, Cin, wf, inv_nn + r0))); \
+                d_q + 3 * (size_t)r0, s4, (const IDX*)d_idx + (size_t)r0 * ld_idx, ld_idx, d_x, d_kp, extent, nr, Ns, H, K, Cin, wf, inv_nn + r0, out16))); \
         } while (0)
 #define KPW4_CFG(IDX, NH, RND)                                                                                        \
         do {                                                                                                          \
@@ -691,9 +732,26 @@ extern "C" int aprb_kpconv_forward_stats(const float* d_q, const float* d_s, con
     APRB_REQUIRE((long long)Ns * Cin < 0x7FFFFFFFLL, "feature table too large for 32-bit row offsets");
     if (Nq == 0) return APRB_OK;
     APRB_REQUIRE(d_q && d_idx && d_kp && d_out && d_ws && (Ns == 0 || (d_s && d_x)), "null pointer");
-    APRB_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
+    APRB_REQUIRE(mode >= 0 && mode <= 3, "mode must be 0, 1, 2 or 3");
     if (ws_bytes < aprb_kpconv_ws_bytes(Nq, Ns, H, K, Cin, Cout)) { set_error("aprb_kpconv_forward: workspace too small"); return APRB_ERR_WORKSPACE; }
     const int KC = K * Cin;
+    if (mode == 3) {
+        // tcgen05 with fp16 operands: d_wprep is the fp16 prepared operand (aprb_kpconv_prepare_weights_f16); the weighted
+        // tile is produced in fp16 (same 10-bit mantissa as TF32, half the bytes of the largest tensor of the path).
+        // For features of O(1) magnitude (after InstanceNorm); |sum_h w x| must stay below 65504.
+        APRB_REQUIRE(d_wprep, "mode 3 needs the fp16 prepared weights");
+        if (!gemm_f16_supported(Nq, Cout, KC)) { set_error("aprb_kpconv_forward: fp16 path unsupported for K*Cin=%d Cout=%d", KC, Cout); return APRB_ERR_UNSUPPORTED; }
+        Carver c3(d_ws, ws_bytes);
+        size_t rows3 = ((size_t)Nq + 127) & ~size_t(127);
+        float* wf3 = c3.take<float>(rows3 * KC);                      // same carving as below; holds Nq*KC halves
+        float* inv3 = c3.take<float>(rows3);
+        unsigned char* flag3 = c3.take<unsigned char>((size_t)Ns + 1);
+        float4* s43 = c3.take<float4>((size_t)Ns + 1);
+        if (Ns > 0) APRB_TIMED("rowsum_pos_kernel", st, 1, (rowsum_pos_kernel<<<cdiv(Ns, 8), 256, 0, st>>>(d_x, d_s, Ns, Cin, flag3, s43)));
+        int rc = launch_kp_weighted(d_q, d_s, d_idx, idx_is_i64, ld_idx, d_x, d_kp, flag3, s43, extent, 0, Nq, Ns, H, K, Cin, false, wf3, inv3, st, 1);
+        if (rc) return rc;
+        return gemm_f16_rowscale(wf3, d_wprep, Nq, Cout, KC, inv3, d_out, st, d_gstat, stats_written);
+    }
     bool tensor_ok = d_wprep && gemm_tf32_supported(Nq, Cout, KC);
     if (mode == 2 && !tensor_ok) { set_error("aprb_kpconv_forward: tcgen05 path unsupported for K*Cin=%d Cout=%d", KC, Cout); return APRB_ERR_UNSUPPORTED; }
     bool use_tensor = (mode == 2) || (mode == 0 && tensor_ok);

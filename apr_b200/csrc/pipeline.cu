@@ -12,6 +12,7 @@
 namespace aprb {
 constexpr int KFE_MAX_LEVELS = 8;
 extern int g_fuse_stats;
+extern int g_kpconv_f16;
 }
 
 struct aprb_kfe {
@@ -75,9 +76,10 @@ int kpconv_call(const aprb_kfe& h, const aprb_kfe_block& b, const float* q, cons
                 const float* x, int nq, int ns, int H, int cin, int cout, float* out, GStat* gs, Arena& A, cudaStream_t st) {
     size_t need = aprb_kpconv_ws_bytes(nq, ns, H, h.cfg.K, cin, cout);
     if (A.scratch_bytes() < need) { set_error("aprb_kfe_forward: arena too small for the KPConv workspace"); return APRB_ERR_WORKSPACE; }
-    return aprb_kpconv_forward_stats(q, s, idx, 0, ld, x, b.kp, b.kp_W, b.kp_Wprep, b.extent, nq, ns, H, h.cfg.K, cin, cout, out,
-                                     b.kp_Wprep ? 0 : 1, gs ? gs->buf : nullptr, gs ? &gs->written : nullptr, A.scratch(),
-                                     A.scratch_bytes(), st);
+    const bool f16 = b.kp_Wprep16 && aprb::g_kpconv_f16;
+    return aprb_kpconv_forward_stats(q, s, idx, 0, ld, x, b.kp, b.kp_W, f16 ? (const float*)b.kp_Wprep16 : b.kp_Wprep, b.extent,
+                                     nq, ns, H, h.cfg.K, cin, cout, out, f16 ? 3 : (b.kp_Wprep ? 0 : 1),
+                                     gs ? gs->buf : nullptr, gs ? &gs->written : nullptr, A.scratch(), A.scratch_bytes(), st);
 }
 
 // InstanceNorm over the rows of each collated pair (segment) of level `lvl`

@@ -692,6 +692,7 @@ __global__ void seg_offsets_kernel(const int* __restrict__ lens, int B, int cps,
 }
 
 constexpr int NORM_SEG_MAX_CH = 64;
+int g_kpconv_f16 = 1;   // aprb_set_option("kpconv_f16"): aprb_kfe_forward runs KPConv with fp16 operands where a block provides them
 int g_fuse_stats = 1;   // aprb_set_option("fuse_stats"): aprb_kfe_forward hands GEMM-epilogue group statistics to the norms
 
 }  // namespace aprb

@@ -59,6 +59,15 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// kind::f16: A, B fp16 (or bf16, per the instruction descriptor), K = 16 per instruction (32 bytes, as for TF32)
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                             uint32_t accumulate) {
     asm volatile(
@@ -115,5 +124,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 
 // 2-D fp32 row-major [rows, cols] tensor map, box = [box_rows, 32 cols], 128B swizzle, zero OOB fill (gemm_tcgen05.cu)
 int make_tmap(CUtensorMap* tm, const float* ptr, int rows, int cols, int box_rows);
+// same for fp16 [rows, cols]: box = [box_rows, 64 cols] (128 bytes)
+int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols, int box_rows);
 
 }  // namespace aprb

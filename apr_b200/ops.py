@@ -159,6 +159,21 @@ def _group_stats_buffer(n, c, device):
     return torch.empty(nbytes // 4, dtype=torch.float32, device=device)
 
 
+def kpconv_prepare_weights_f16(weights):
+    """[K,Cin,Cout] f32 -> prepared fp16 K-major operand [Cout, K*Cin] (kpconv mode 3)."""
+    N.require_cuda()
+    w = _dev_f32(weights.detach(), "weights")
+    k, cin, cout = w.shape
+    out = torch.empty((cout, k * cin), dtype=torch.float16, device=w.device)
+    N.check(N.lib().aprb_kpconv_prepare_weights_f16(N.ptr(w), k, cin, cout, N.ptr(out), N.stream_ptr()),
+            "aprb_kpconv_prepare_weights_f16")
+    return out
+
+
+def kpconv_f16_supported(k, cin, cout, h):
+    return (k * cin) % 64 == 0 and cout % 16 == 0 and cin % 4 == 0 and h <= 128
+
+
 def kpconv(q_pts, s_pts, neighb_inds, x, kernel_points, weights, extent, wprep=None, mode=0):
     """K5. Returns [Nq,Cout] f32."""
     N.require_cuda()

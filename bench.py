@@ -531,7 +531,7 @@ def main():
     ap.add_argument("--no-calibrate", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS))
-    ap.add_argument("--streams", type=int, default=2, help="calls in flight per GPU (one CUDA stream + host thread each)")
+    ap.add_argument("--streams", type=int, default=5, help="calls in flight per GPU (one CUDA stream + host thread each)")
     ap.add_argument("--batch", type=int, default=8, help="pairs stacked per call (super-batch; per-pair InstanceNorm segments)")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="infer = the headline metric (default); train = BASELINE configs[4] training step")

@@ -99,6 +99,8 @@ int aprb_cell_grid_query(const void* d_grid, size_t grid_bytes, const float* d_q
 /* Prepared weights: the [K,Cin,Cout] fp32 parameter re-laid as the K-major, TF32-rounded B operand
  * [Cout, K*Cin] used by the tcgen05 contraction. d_wprep has K*Cin*Cout floats. Run once per weight update. */
 int aprb_kpconv_prepare_weights(const float* d_W, int K, int Cin, int Cout, float* d_wprep, void* stream);
+/* fp16 form of the same operand (K*Cin*Cout halves), for mode 3 of aprb_kpconv_forward. */
+int aprb_kpconv_prepare_weights_f16(const float* d_W, int K, int Cin, int Cout, void* d_wprep16, void* stream);
 
 size_t aprb_kpconv_ws_bytes(int Nq, int Ns, int H, int K, int Cin, int Cout);
 
@@ -107,7 +109,9 @@ size_t aprb_kpconv_ws_bytes(int Nq, int Ns, int H, int K, int Cin, int Cout);
  * d_idx is [Nq, ld_idx] int32 (idx_is_i64 == 0) or int64 (idx_is_i64 != 0); only columns [0,H) are read.
  * d_W is the raw [K,Cin,Cout] parameter (used by the fp32 path), d_wprep the prepared operand (tensor path;
  * may be NULL to force the fp32 CUDA-core path). mode: 0 = auto (tensor path when supported), 1 = fp32 CUDA cores,
- * 2 = tcgen05 TF32 (error if unsupported shape). */
+ * 2 = tcgen05 TF32 (error if unsupported shape), 3 = tcgen05 with fp16 operands: d_wprep is then the fp16 operand of
+ * aprb_kpconv_prepare_weights_f16 and the weighted tile is produced in fp16 — the 10-bit mantissa of TF32 at half the
+ * bytes, for features of O(1) magnitude such as InstanceNorm outputs (K*Cin % 64 == 0, Cin % 4 == 0, H <= 128). */
 int aprb_kpconv_forward(const float* d_q, const float* d_s, const void* d_idx, int idx_is_i64, int ld_idx,
                         const float* d_x, const float* d_kp, const float* d_W, const float* d_wprep,
                         float extent, int Nq, int Ns, int H, int K, int Cin, int Cout,
@@ -206,6 +210,8 @@ typedef struct {
     const float* unary1_W;    /* [out/4, in]  TF32-rounded (aprb_round_tf32), NULL when the block has nn.Identity         */
     const float* unary2_W;    /* [out, out/4] TF32-rounded                                                                */
     const float* shortcut_W;  /* [out, in]    TF32-rounded, NULL when in_dim == out_dim                                   */
+    const void* kp_Wprep16;   /* fp16 prepared [Cout, K*Cin] (aprb_kpconv_prepare_weights_f16) or NULL: when set, KPConv  */
+                              /* runs with fp16 operands (mode 3) — its input here is always an InstanceNorm output       */
 } aprb_kfe_block;
 
 typedef struct {

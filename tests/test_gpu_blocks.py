@@ -144,6 +144,28 @@ def test_kpconv_fused_kernel_vs_unfused_and_oracle(cuda, cin, h, kp_scale, nq):
         assert rel(gs[:g, 1], ((blk - blk.mean(1, keepdim=True)) ** 2).sum(1)) < 1e-4
 
 
+def test_kpconv_fp16_operand_path_vs_oracle(cuda, gold_kpconv):
+    """mode 3: the weighted tile and the weights in fp16 (10-bit mantissa like TF32), fp32 accumulation in TMEM."""
+    g = gold_kpconv
+    gen = torch.Generator().manual_seed(19)
+    p0, conv = torch.from_numpy(g["p0"]), torch.from_numpy(g["conv"]).long()
+    for cin, cout in ((64, 64), (128, 128), (64, 256), (256, 256), (36, 48)):
+        x = torch.randn(len(p0), cin, generator=gen)
+        kp = torch.from_numpy(g["c8_kp"])
+        w = torch.randn(15, cin, cout, generator=gen) / np.sqrt(15 * cin)
+        want = blocks_ref.kpconv_ref(p0, p0, conv, x, kp, w, 0.6)
+        wd = w.to(cuda)
+        if not ops.kpconv_f16_supported(15, cin, cout, conv.shape[1]):
+            assert (15 * cin) % 64 != 0
+            continue
+        got = ops.kpconv(p0.to(cuda), p0.to(cuda), conv.to(cuda).int(), x.to(cuda), kp.to(cuda), wd, 0.6,
+                         wprep=ops.kpconv_prepare_weights_f16(wd), mode=3)
+        e = rel(got, want)
+        print(f"kpconv fp16 operands Cin={cin} Cout={cout}: rel err {e:.2e}")
+        assert e < TOL_TF32, f"Cin={cin} Cout={cout}: rel err {e:.2e}"
+        assert hasattr(got, "_aprb_gstat")
+
+
 def test_linear_tf32_vs_fp32(cuda):
     gen = torch.Generator().manual_seed(2)
     for n, cin, cout in ((1000, 64, 128), (4255, 256, 64), (129, 32, 16), (1567, 512, 2048)):
