@@ -445,6 +445,7 @@ extern int g_kpconv_chunk_mb;
 extern int g_kpw_version;
 extern int g_fuse_stats;
 extern int g_kpconv_f16;
+extern int g_act_f16;
 extern int g_kpconv_fused;
 int g_gemm_cluster = 1;   // 1 disables the cluster/multicast path (aprb_set_option)
 
@@ -547,6 +548,7 @@ extern "C" int aprb_set_option(const char* name, int value) {
     if (strcmp(name, "kpw_version") == 0) { g_kpw_version = value; return APRB_OK; }
     if (strcmp(name, "fuse_stats") == 0) { g_fuse_stats = value; return APRB_OK; }
     if (strcmp(name, "kpconv_f16") == 0) { g_kpconv_f16 = value; return APRB_OK; }
+    if (strcmp(name, "act_f16") == 0) { g_act_f16 = value; return APRB_OK; }
     if (strcmp(name, "kpconv_fused") == 0) { g_kpconv_fused = value; return APRB_OK; }
     set_error("aprb_set_option: unknown option %s", name);
     return APRB_ERR_INVALID;
@@ -561,6 +563,17 @@ extern "C" size_t aprb_linear_tf32_ws_bytes(int N, int Cin, int Cout) {
 extern "C" int aprb_linear_tf32(const float* d_x, const float* d_W, int N, int Cin, int Cout, float* d_y, void* d_ws,
                                 size_t ws_bytes, void* stream) {
     return aprb_linear_tf32_stats(d_x, d_W, N, Cin, Cout, d_y, nullptr, nullptr, d_ws, ws_bytes, stream);
+}
+
+extern "C" int aprb_linear_f16_stats(const void* d_x16, const void* d_W16, int N, int Cin, int Cout, float* d_y,
+                                     float* d_gstat, int* stats_written, void* stream) {
+    using namespace aprb;
+    if (stats_written) *stats_written = 0;
+    APRB_REQUIRE(N >= 0 && Cin >= 1 && Cout >= 1, "bad shape");
+    APRB_REQUIRE(!d_gstat || stats_written, "stats_written must be given with d_gstat");
+    if (N == 0) return APRB_OK;
+    APRB_REQUIRE(d_x16 && d_W16 && d_y, "null pointer");
+    return gemm_f16_rowscale(d_x16, d_W16, N, Cout, Cin, nullptr, d_y, (cudaStream_t)stream, d_gstat, stats_written);
 }
 
 extern "C" size_t aprb_group_stats_bytes(int N, int C) {

@@ -35,11 +35,16 @@ int g_kpconv_chunk_mb = 0;   // aprb_set_option("kpconv_chunk_mb"): L2-sized row
 // divergent warp load costs one L1 wavefront per distinct line whatever its width, and the three coordinate loads plus
 // the flag byte were 256 of the ~470 LSU wavefronts per query (ncu, round 1).
 __global__ void rowsum_pos_kernel(const float* __restrict__ x, const float* __restrict__ pts, int Ns, int C,
-                                  unsigned char* __restrict__ flag, float4* __restrict__ s4) {
+                                  unsigned char* __restrict__ flag, float4* __restrict__ s4, int x16) {
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= Ns) return;
     float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += x[(size_t)row * C + c];
+    if (x16) {
+        const __half* xh = reinterpret_cast<const __half*>(x);
+        for (int c = lane; c < C; c += 32) s += __half2float(xh[(size_t)row * C + c]);
+    } else {
+        for (int c = lane; c < C; c += 32) s += x[(size_t)row * C + c];
+    }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
     if (lane == 0) {
@@ -213,14 +218,27 @@ __device__ __forceinline__ void store_half4(__half* dst, const float4 v) {
     *reinterpret_cast<uint2*>(dst) = u;
 }
 
+// 4 consecutive channels of a feature row: fp32 (16 bytes) or fp16 (8 bytes, widened; activations stored in fp16 are
+// TF32-rounded values, so the widening is exact)
+template <bool X16>
+__device__ __forceinline__ float4 ld_feat4(const char* p) {
+    if (X16) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
+
 // Overflow path: one row, whole warp, lanes = 4 channels of a 128-channel slab; no lists.
-template <typename IdxT, int NH, bool ROUND_TF32>
+template <typename IdxT, int NH, bool ROUND_TF32, bool X16>
 __device__ __noinline__ void kp_direct_row(const float* __restrict__ q, const float4* __restrict__ s4, const IdxT* __restrict__ idx,
                                            int ld, const float* __restrict__ x, const float4* s_kp,
                                            float ext2, float inv_ext, int n, int Ns,
                                            int H, int K, int Cin, float* __restrict__ wrow, int out16, int lane) {
     RowGeom<NH> g;
-    load_row_geom<IdxT, NH>(q, s4, idx, ld, n, Ns, H, Cin, lane, g);
+    load_row_geom<IdxT, NH>(q, s4, idx, ld, n, Ns, H, Cin * (X16 ? 2 : 4), lane, g);
     for (int c0 = 0; c0 < Cin; c0 += 128) {
         const int c = c0 + lane * 4;
         const bool cok = c < Cin;
@@ -240,7 +258,7 @@ __device__ __noinline__ void kp_direct_row(const float* __restrict__ q, const fl
                     const float wb = __shfl_sync(0xffffffffu, w, src);
                     const int sib = __shfl_sync(0xffffffffu, g.sio[j], src);
                     if (cok) {
-                        const float4 xr = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(x) + (unsigned)sib + (unsigned)c * 4u);
+                        const float4 xr = ld_feat4<X16>(reinterpret_cast<const char*>(x) + (unsigned)sib + (unsigned)c * (X16 ? 2u : 4u));
                         acc.x = fmaf(wb, xr.x, acc.x); acc.y = fmaf(wb, xr.y, acc.y);
                         acc.z = fmaf(wb, xr.z, acc.z); acc.w = fmaf(wb, xr.w, acc.w);
                     }
@@ -258,7 +276,7 @@ __device__ __noinline__ void kp_direct_row(const float* __restrict__ q, const fl
     }
 }
 
-template <typename IdxT, int LG, int NV, int NH, bool FULL, bool ROUND_TF32>
+template <typename IdxT, int LG, int NV, int NH, bool FULL, bool ROUND_TF32, bool X16>
 __global__ void __launch_bounds__(128)
 kp_weighted4_kernel(const float* __restrict__ q, const float4* __restrict__ s4, const IdxT* __restrict__ idx, int ld,
                     const float* __restrict__ x, const float* __restrict__ kp,
@@ -289,7 +307,7 @@ kp_weighted4_kernel(const float* __restrict__ q, const float4* __restrict__ s4, 
             continue;
         }
         RowGeom<NH> g;
-        const int nn = load_row_geom<IdxT, NH>(q, s4, idx, ld, n, Ns, H, Cin, lane, g);
+        const int nn = load_row_geom<IdxT, NH>(q, s4, idx, ld, n, Ns, H, Cin * (X16 ? 2 : 4), lane, g);
         if (lane == 0) inv_nn[n] = 1.0f / (float)max(nn, 1);
         build_row_list<NH, KPW_ECAP>(g, s_kp, K, ext2, inv_ext, ent, off, lane);
     }
@@ -310,7 +328,8 @@ kp_weighted4_kernel(const float* __restrict__ q, const float4* __restrict__ s4, 
         bool cok[NV];
 #pragma unroll
         for (int j = 0; j < NV; ++j) cok[j] = FULL || (c + j * LG * 4 < Cin);
-        const char* xbc = xb + (size_t)c * 4u;
+        constexpr int ES = X16 ? 2 : 4;                              // bytes per stored feature
+        const char* xbc = xb + (size_t)c * ES;
         size_t wo = (size_t)n * K * Cin + c;                       // element offset of (row n, kernel point k, channel c)
         int end = active ? off[0] : 0;
 #pragma unroll 1
@@ -332,7 +351,7 @@ kp_weighted4_kernel(const float* __restrict__ q, const float4* __restrict__ s4, 
 #pragma unroll
                     for (int j = 0; j < NV; ++j) {
                         xr[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (cok[j]) xr[u][j] = __ldg(reinterpret_cast<const float4*>(xe + j * LG * 16));
+                        if (cok[j]) xr[u][j] = ld_feat4<X16>(xe + j * LG * 4 * ES);
                     }
                 }
 #pragma unroll
@@ -353,7 +372,7 @@ kp_weighted4_kernel(const float* __restrict__ q, const float4* __restrict__ s4, 
 #pragma unroll
                 for (int j = 0; j < NV; ++j) {
                     if (cok[j]) {
-                        const float4 xr = __ldg(reinterpret_cast<const float4*>(xe + j * LG * 16));
+                        const float4 xr = ld_feat4<X16>(xe + j * LG * 4 * ES);
                         acc[j].x = fmaf(w, xr.x, acc[j].x); acc[j].y = fmaf(w, xr.y, acc[j].y);
                         acc[j].z = fmaf(w, xr.z, acc[j].z); acc[j].w = fmaf(w, xr.w, acc[j].w);
                     }
@@ -382,7 +401,7 @@ kp_weighted4_kernel(const float* __restrict__ q, const float4* __restrict__ s4, 
         for (int r = 0; r < RP; ++r) {
             const int ovr = __shfl_sync(0xffffffffu, (int)ovf, r * LG);
             if (ovr && row0 + r < Nq)
-                kp_direct_row<IdxT, NH, ROUND_TF32>(q, s4, idx, ld, x, s_kp, ext2, inv_ext, row0 + r, Ns, H, K, Cin,
+                kp_direct_row<IdxT, NH, ROUND_TF32, X16>(q, s4, idx, ld, x, s_kp, ext2, inv_ext, row0 + r, Ns, H, K, Cin,
                                                     out16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(wf) + (size_t)(row0 + r) * K * Cin)
                                                           : wf + (size_t)(row0 + r) * K * Cin, out16, lane);
         }
@@ -629,37 +648,50 @@ extern "C" int aprb_round_tf32(const float* d_in, float* d_out, size_t n, void* 
 // Launch stage A+B for query rows [r0, r0 + nr): wf rows are written relative to r0, inv_nn at absolute rows.
 static int launch_kp_weighted(const float* d_q, const float* d_s, const void* d_idx, int idx_is_i64, int ld_idx,
                               const float* d_x, const float* d_kp, const unsigned char* flag, const float4* s4, float extent, int r0, int nr,
-                              int Ns, int H, int K, int Cin, bool round_tf32, float* wf, float* inv_nn, cudaStream_t st, int out16 = 0) {
+                              int Ns, int H, int K, int Cin, bool round_tf32, float* wf, float* inv_nn, cudaStream_t st, int out16 = 0, int x16 = 0) {
     const int Hp = (H + 31) & ~31;
-    const bool x16 = ((uintptr_t)d_x % 16 == 0) && ((uintptr_t)wf % 16 == 0);
-    if (out16 && !(x16 && Cin % 4 == 0 && H <= 128 && (long long)Ns * Cin < (1LL << 30))) {
+    const bool al16 = ((uintptr_t)d_x % 16 == 0) && ((uintptr_t)wf % 16 == 0);
+    if (out16 && !(al16 && Cin % 4 == 0 && H <= 128 && (long long)Ns * Cin < (1LL << 30))) {
         set_error("aprb_kpconv_forward: fp16 operand path needs Cin %% 4 == 0, H <= 128 and 16-byte aligned features");
         return APRB_ERR_UNSUPPORTED;
     }
-    if ((g_kpw_version >= 4 || out16) && x16 && Cin % 4 == 0 && H <= 128 && (long long)Ns * Cin < (1LL << 30)) {
+    if ((g_kpw_version >= 4 || out16) && al16 && Cin % 4 == 0 && H <= 128 && (long long)Ns * Cin < (1LL << 30)) {
         // v4: lane-group streaming over compact CSR lists; (LG, NV) by channel count, NH = 32-neighbour groups per row
         const int nh = H <= 64 ? 2 : 4;
         const int chs[5] = {32, 64, 128, 256, 512};
         int cfg = Cin <= 32 ? 0 : (Cin <= 64 ? 1 : (Cin <= 128 ? 2 : (Cin <= 256 ? 3 : 4)));
         const bool full = Cin % chs[cfg] == 0;
-#define KPW4_LAUNCH(IDX, LG, NV, NH, FULLV, RND)                                                                             \
+#define KPW4_LAUNCH(IDX, LG, NV, NH, FULLV, RND, XH)                                                                             \
         do {                                                                                                          \
             constexpr int wpb4 = 4;                                                                                   \
             constexpr int rp = 32 / LG;                                                                               \
             const size_t smem4 = (size_t)wpb4 * rp * KPW_SLOT_BYTES;                                                  \
-            APRB_TIMED("kp_weighted_kernel", st, 1, (kp_weighted4_kernel<IDX, LG, NV, NH, FULLV, RND><<<cdiv(nr, wpb4 * rp), wpb4 * 32, smem4, st>>>( \
+            APRB_TIMED("kp_weighted_kernel", st, 1, (kp_weighted4_kernel<IDX, LG, NV, NH, FULLV, RND, XH><<<cdiv(nr, wpb4 * rp), wpb4 * 32, smem4, st>>>( \
                 d_q + 3 * (size_t)r0, s4, (const IDX*)d_idx + (size_t)r0 * ld_idx, ld_idx, d_x, d_kp, extent, nr, Ns, H, K, Cin, wf, inv_nn + r0, out16))); \
         } while (0)
 #define KPW4_CFG(IDX, NH, RND)                                                                                        \
         do {                                                                                                          \
-            if (cfg == 0) { if (full) KPW4_LAUNCH(IDX, 8, 1, NH, true, RND); else KPW4_LAUNCH(IDX, 8, 1, NH, false, RND); }                                                            \
-            else if (cfg == 1) { if (full) KPW4_LAUNCH(IDX, 16, 1, NH, true, RND); else KPW4_LAUNCH(IDX, 16, 1, NH, false, RND); }                                                      \
-            else if (cfg == 2) { if (full) KPW4_LAUNCH(IDX, 16, 2, NH, true, RND); else KPW4_LAUNCH(IDX, 16, 2, NH, false, RND); }                                                      \
-            else if (cfg == 3) { if (full) KPW4_LAUNCH(IDX, 32, 2, NH, true, RND); else KPW4_LAUNCH(IDX, 32, 2, NH, false, RND); }                                                      \
-            else { if (full) KPW4_LAUNCH(IDX, 32, 4, NH, true, RND); else KPW4_LAUNCH(IDX, 32, 4, NH, false, RND); }                                                                    \
+            if (cfg == 0) { if (full) KPW4_LAUNCH(IDX, 8, 1, NH, true, RND, false); else KPW4_LAUNCH(IDX, 8, 1, NH, false, RND, false); }                                                            \
+            else if (cfg == 1) { if (full) KPW4_LAUNCH(IDX, 16, 1, NH, true, RND, false); else KPW4_LAUNCH(IDX, 16, 1, NH, false, RND, false); }                                                      \
+            else if (cfg == 2) { if (full) KPW4_LAUNCH(IDX, 16, 2, NH, true, RND, false); else KPW4_LAUNCH(IDX, 16, 2, NH, false, RND, false); }                                                      \
+            else if (cfg == 3) { if (full) KPW4_LAUNCH(IDX, 32, 2, NH, true, RND, false); else KPW4_LAUNCH(IDX, 32, 2, NH, false, RND, false); }                                                      \
+            else { if (full) KPW4_LAUNCH(IDX, 32, 4, NH, true, RND, false); else KPW4_LAUNCH(IDX, 32, 4, NH, false, RND, false); }                                                                    \
         } while (0)
 #define KPW4_NH(IDX, RND) do { if (nh == 2) KPW4_CFG(IDX, 2, RND); else KPW4_CFG(IDX, 4, RND); } while (0)
-        if (round_tf32) { if (idx_is_i64) KPW4_NH(long long, true); else KPW4_NH(int, true); }
+        if (x16) {
+            // fp16 features in, fp16 weighted tile out (the native pipeline's activation format): int32 indices, whole slabs
+            if (idx_is_i64 || !full || !out16) { set_error("aprb_kpconv_forward: fp16 features need int32 indices and Cin %% %d == 0", chs[cfg]); return APRB_ERR_UNSUPPORTED; }
+#define KPW4_X16(NH)                                                                                                  \
+            do {                                                                                                      \
+                if (cfg == 0) KPW4_LAUNCH(int, 8, 1, NH, true, false, true);                                          \
+                else if (cfg == 1) KPW4_LAUNCH(int, 16, 1, NH, true, false, true);                                    \
+                else if (cfg == 2) KPW4_LAUNCH(int, 16, 2, NH, true, false, true);                                    \
+                else if (cfg == 3) KPW4_LAUNCH(int, 32, 2, NH, true, false, true);                                    \
+                else KPW4_LAUNCH(int, 32, 4, NH, true, false, true);                                                  \
+            } while (0)
+            if (nh == 2) KPW4_X16(2); else KPW4_X16(4);
+#undef KPW4_X16
+        } else if (round_tf32) { if (idx_is_i64) KPW4_NH(long long, true); else KPW4_NH(int, true); }
         else { if (idx_is_i64) KPW4_NH(long long, false); else KPW4_NH(int, false); }
 #undef KPW4_NH
 #undef KPW4_CFG
@@ -674,8 +706,8 @@ static int launch_kp_weighted(const float* d_q, const float* d_s, const void* d_
     const size_t smem = wpb * smem_warp;
     // (VEC, NJ): channels per lane = VEC*NJ, one slab = 32*VEC*NJ channels
     int vec = 1, nj = 1;
-    if (x16 && Cin % 4 == 0 && Cin >= 128) { vec = 4; nj = Cin >= 512 ? 4 : (Cin >= 256 ? 2 : 1); }
-    else if (x16 && Cin % 2 == 0 && Cin >= 64) { vec = 2; nj = 1; }
+    if (al16 && Cin % 4 == 0 && Cin >= 128) { vec = 4; nj = Cin >= 512 ? 4 : (Cin >= 256 ? 2 : 1); }
+    else if (al16 && Cin % 2 == 0 && Cin >= 64) { vec = 2; nj = 1; }
 #define KPW_LAUNCH3(IDX, VEC, NJ, RND)                                                                               \
     do {                                                                                                             \
         if (smem > 48 * 1024)                                                                                        \
@@ -732,10 +764,11 @@ extern "C" int aprb_kpconv_forward_stats(const float* d_q, const float* d_s, con
     APRB_REQUIRE((long long)Ns * Cin < 0x7FFFFFFFLL, "feature table too large for 32-bit row offsets");
     if (Nq == 0) return APRB_OK;
     APRB_REQUIRE(d_q && d_idx && d_kp && d_out && d_ws && (Ns == 0 || (d_s && d_x)), "null pointer");
-    APRB_REQUIRE(mode >= 0 && mode <= 3, "mode must be 0, 1, 2 or 3");
+    APRB_REQUIRE(mode >= 0 && mode <= 4, "mode must be 0 .. 4");
     if (ws_bytes < aprb_kpconv_ws_bytes(Nq, Ns, H, K, Cin, Cout)) { set_error("aprb_kpconv_forward: workspace too small"); return APRB_ERR_WORKSPACE; }
     const int KC = K * Cin;
-    if (mode == 3) {
+    if (mode == 3 || mode == 4) {
+        const int x16 = mode == 4;                                    // mode 4: d_x itself is fp16 [Ns, Cin]
         // tcgen05 with fp16 operands: d_wprep is the fp16 prepared operand (aprb_kpconv_prepare_weights_f16); the weighted
         // tile is produced in fp16 (same 10-bit mantissa as TF32, half the bytes of the largest tensor of the path).
         // For features of O(1) magnitude (after InstanceNorm); |sum_h w x| must stay below 65504.
@@ -747,8 +780,8 @@ extern "C" int aprb_kpconv_forward_stats(const float* d_q, const float* d_s, con
         float* inv3 = c3.take<float>(rows3);
         unsigned char* flag3 = c3.take<unsigned char>((size_t)Ns + 1);
         float4* s43 = c3.take<float4>((size_t)Ns + 1);
-        if (Ns > 0) APRB_TIMED("rowsum_pos_kernel", st, 1, (rowsum_pos_kernel<<<cdiv(Ns, 8), 256, 0, st>>>(d_x, d_s, Ns, Cin, flag3, s43)));
-        int rc = launch_kp_weighted(d_q, d_s, d_idx, idx_is_i64, ld_idx, d_x, d_kp, flag3, s43, extent, 0, Nq, Ns, H, K, Cin, false, wf3, inv3, st, 1);
+        if (Ns > 0) APRB_TIMED("rowsum_pos_kernel", st, 1, (rowsum_pos_kernel<<<cdiv(Ns, 8), 256, 0, st>>>(d_x, d_s, Ns, Cin, flag3, s43, x16)));
+        int rc = launch_kp_weighted(d_q, d_s, d_idx, idx_is_i64, ld_idx, d_x, d_kp, flag3, s43, extent, 0, Nq, Ns, H, K, Cin, false, wf3, inv3, st, 1, x16);
         if (rc) return rc;
         return gemm_f16_rowscale(wf3, d_wprep, Nq, Cout, KC, inv3, d_out, st, d_gstat, stats_written);
     }
@@ -766,7 +799,7 @@ extern "C" int aprb_kpconv_forward_stats(const float* d_q, const float* d_s, con
     const size_t gws_bytes = gemm_tf32_ws_bytes(Nq, Cout) - 256;
     float* gws = c.take<float>(gws_bytes / sizeof(float));
 
-    if (Ns > 0) APRB_TIMED("rowsum_pos_kernel", st, 1, (rowsum_pos_kernel<<<cdiv(Ns, 8), 256, 0, st>>>(d_x, d_s, Ns, Cin, flag, s4)));
+    if (Ns > 0) APRB_TIMED("rowsum_pos_kernel", st, 1, (rowsum_pos_kernel<<<cdiv(Ns, 8), 256, 0, st>>>(d_x, d_s, Ns, Cin, flag, s4, 0)));
     if (use_tensor && Ns > 0 && kpconv_fused_supported(H, K, Cin, Cout, Ns) &&
         ((((uintptr_t)d_x | (uintptr_t)d_out | (uintptr_t)d_wprep | (uintptr_t)(d_gstat ? d_gstat : d_out)) & 15) == 0)) {
         // one kernel: gather -> influence -> swizzled A tiles in shared memory -> tcgen05 (kpconv_fused.cu)
@@ -826,7 +859,7 @@ extern "C" int aprb_kpconv_weighted(const float* d_q, const float* d_s, const vo
     if (ws_bytes < aprb_kpconv_weighted_ws_bytes(Ns)) { set_error("aprb_kpconv_weighted: workspace too small"); return APRB_ERR_WORKSPACE; }
     unsigned char* flag = (unsigned char*)d_ws;
     float4* s4 = (float4*)((char*)d_ws + align256((size_t)Ns + 1));
-    if (Ns > 0) APRB_TIMED("rowsum_pos_kernel", st, 1, (rowsum_pos_kernel<<<cdiv(Ns, 8), 256, 0, st>>>(d_x, d_s, Ns, Cin, flag, s4)));
+    if (Ns > 0) APRB_TIMED("rowsum_pos_kernel", st, 1, (rowsum_pos_kernel<<<cdiv(Ns, 8), 256, 0, st>>>(d_x, d_s, Ns, Cin, flag, s4, 0)));
     if (Cin == 1) {
         if (idx_is_i64) APRB_TIMED("kp_weighted_c1_kernel", st, 1, (kp_weighted_c1_kernel<long long><<<cdiv(Nq, 4), 128, 0, st>>>(
             d_q, s4, (const long long*)d_idx, ld_idx, d_kp, extent, Nq, Ns, H, K, d_wf, d_inv_nn)));

@@ -26,14 +26,14 @@ __device__ __forceinline__ float round_tf32(float t) {
 
 template <int NH>
 struct RowGeom {          // lanes = neighbours: element offset of the support's feature row and position relative to the query
-    int sio[NH];          // byte offset of the support's feature row, si * Cin * 4 (shadow neighbours: 0, never selected)
+    int sio[NH];          // byte offset of the support's feature row, si * row_bytes (shadow neighbours: 0, never selected)
     float rx[NH], ry[NH], rz[NH];   // shadow neighbours sit at x = 3e18: outside every extent
     unsigned any[NH];               // warp ballot: does this group of 32 neighbours hold a valid one (warp-uniform)
 };
 
 template <typename IdxT, int NH>
 __device__ __forceinline__ int load_row_geom(const float* __restrict__ q, const float4* __restrict__ s4,
-                                             const IdxT* __restrict__ idx, int ld, int n, int Ns, int H, int Cin, int lane,
+                                             const IdxT* __restrict__ idx, int ld, int n, int Ns, int H, int row_bytes, int lane,
                                              RowGeom<NH>& g) {
     const float qx = q[3 * (size_t)n], qy = q[3 * (size_t)n + 1], qz = q[3 * (size_t)n + 2];
     int nn = 0;
@@ -50,7 +50,7 @@ __device__ __forceinline__ int load_row_geom(const float* __restrict__ q, const 
         if (si < Ns) {
             const float4 p = __ldg(s4 + si);
             nn += p.w > 0.f ? 1 : 0;
-            g.sio[j] = si * Cin * 4;
+            g.sio[j] = si * row_bytes;
             g.rx[j] = p.x - qx; g.ry[j] = p.y - qy; g.rz[j] = p.z - qz;
         }
         g.any[j] = __ballot_sync(0xffffffffu, si < Ns);

@@ -78,7 +78,7 @@ __device__ __noinline__ float4 kpf_direct_slice(const float* __restrict__ q, con
                                                 const float4 kpk, float ext2, float inv_ext, int n, int Ns, int H, int Cin,
                                                 int lane) {
     RowGeom<NH> g;
-    load_row_geom<IdxT, NH>(q, s4, idx, ld, n, Ns, H, Cin, lane, g);
+    load_row_geom<IdxT, NH>(q, s4, idx, ld, n, Ns, H, Cin * 4, lane, g);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < NH; ++j) {

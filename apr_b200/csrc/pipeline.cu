@@ -13,6 +13,7 @@ namespace aprb {
 constexpr int KFE_MAX_LEVELS = 8;
 extern int g_fuse_stats;
 extern int g_kpconv_f16;
+extern int g_act_f16;
 }
 
 struct aprb_kfe {
@@ -31,6 +32,10 @@ struct aprb_kfe {
     const int* up[aprb::KFE_MAX_LEVELS];
     const int* seg[aprb::KFE_MAX_LEVELS];   // per level: row offsets of the S normalisation segments (S+1 ints), or NULL
     int S;
+    // fp16 activation mode: fp16 copies of the unary weights, owned by the handle (cudaMalloc at create), per block
+    // [unary1, unary2, shortcut]; act16_ok = every block fits the fp16 kernels' shape constraints
+    std::vector<void*> w16;
+    bool act16_ok;
 };
 
 using namespace aprb;
@@ -163,6 +168,95 @@ int run_block(const aprb_kfe& h, const aprb_kfe_block& b, const float* feat, con
     return APRB_OK;
 }
 
+// ---- fp16 activation mode -------------------------------------------------------------------------------------------
+// Every normalised activation (the output of an InstanceNorm + LeakyReLU, already rounded to TF32's 10-bit mantissa) is
+// stored in fp16 — exact for these values — so it costs half the bytes to write, to gather in KPConv / max-pool and to
+// stream into the tensor cores (kind::f16). GEMM outputs, which feed the statistics, stay fp32.
+int norm16_call(const aprb_kfe& h, int lvl, const float* x, int n, int c, const void* res, int res16, int norm_res, void* y,
+                int out16, const GStat* gx, const GStat* gres, Arena& A, cudaStream_t st) {
+    if (A.scratch_bytes() < aprb_instnorm_seg_ws_bytes(n, c, h.S)) { set_error("aprb_kfe_forward: arena too small for the norm workspace"); return APRB_ERR_WORKSPACE; }
+    return aprb_instnorm_lrelu_seg_f16(x, n, c, h.seg[lvl], h.S, 1e-5f, 0.1f, res, res16, norm_res, 1, y, out16,
+                                       gx ? gx->get() : nullptr, gres ? gres->get() : nullptr, A.scratch(), A.scratch_bytes(), st);
+}
+
+int run_block16(const aprb_kfe& h, size_t bi, const void* feat, bool feat16, bool last, const void** out, int* out_cols,
+                Arena& A, cudaStream_t st) {
+    const aprb_kfe_block& b = h.blocks[bi];
+    const int l = b.layer;
+    const int nq = b.strided ? h.n[l + 1] : h.n[l], ns = h.n[l];
+    const int lq = b.strided ? l + 1 : l;
+    const float* q = b.strided ? h.pts[l + 1] : h.pts[l];
+    const float* s = h.pts[l];
+    const int* idx = b.strided ? h.pool[l] : h.conv[l];
+    const int H = h.cfg.limits[l];
+    const int out16 = last ? 0 : 1;
+#define KFE_GSTAT(var, rows, cols)                                                                       \
+    GStat var;                                                                                               \
+    if (aprb::g_fuse_stats) {                                                                                \
+        var.buf = (float*)A.take<char>(aprb_group_stats_bytes(rows, cols));                                  \
+        if (!var.buf) { set_error("aprb_kfe_forward: arena too small (need > %zu bytes)", A.cap); return APRB_ERR_WORKSPACE; } \
+    }
+    if (b.type == 0) {                                             // SimpleBlock on the raw fp32 input features
+        if (feat16) { set_error("aprb_kfe_forward: SimpleBlock after the first block is not supported in fp16 mode"); return APRB_ERR_UNSUPPORTED; }
+        const int cout = b.out_dim / 2;
+        KFE_ALLOC(y, float, (size_t)nq * cout);
+        const size_t mark = A.off;
+        KFE_ALLOC(t, float, (size_t)nq * cout);
+        KFE_GSTAT(gt, nq, cout);
+        KFE_OK(kpconv_call(h, b, q, s, idx, H, (const float*)feat, nq, ns, H, b.in_dim, cout, t, &gt, A, st));
+        KFE_OK(norm16_call(h, lq, t, nq, cout, nullptr, 0, 0, y, out16, &gt, nullptr, A, st));
+        A.off = mark;
+        *out = y; *out_cols = cout;
+        return APRB_OK;
+    }
+    if (!feat16) { set_error("aprb_kfe_forward: fp16 mode expects fp16 features at a resnet block"); return APRB_ERR_UNSUPPORTED; }
+    const int mid = b.out_dim / 4, cout = b.out_dim;
+    void* const* w16 = &h.w16[bi * 3];
+    KFE_ALLOC(y, float, (size_t)nq * cout);                        // fp32-sized: holds fp16 or (last block) fp32
+    const size_t mark = A.off;
+    const void* x1 = feat;
+    if (b.unary1_W) {
+        KFE_ALLOC(t1raw, float, (size_t)ns * mid);
+        KFE_ALLOC(t1, float, (size_t)ns * mid / 2 + 8);
+        KFE_GSTAT(g1, ns, mid);
+        KFE_OK(aprb_linear_f16_stats(feat, w16[0], ns, b.in_dim, mid, t1raw, g1.buf, g1.buf ? &g1.written : nullptr, st));
+        KFE_OK(norm16_call(h, l, t1raw, ns, mid, nullptr, 0, 0, t1, 1, &g1, nullptr, A, st));
+        x1 = t1;
+    }
+    KFE_ALLOC(t2raw, float, (size_t)nq * mid);
+    KFE_ALLOC(t2, float, (size_t)nq * mid / 2 + 8);
+    KFE_GSTAT(g2, nq, mid);
+    {
+        size_t need = aprb_kpconv_ws_bytes(nq, ns, H, h.cfg.K, mid, mid);
+        if (A.scratch_bytes() < need) { set_error("aprb_kfe_forward: arena too small for the KPConv workspace"); return APRB_ERR_WORKSPACE; }
+        KFE_OK(aprb_kpconv_forward_stats(q, s, idx, 0, H, (const float*)x1, b.kp, b.kp_W, (const float*)b.kp_Wprep16, b.extent, nq, ns,
+                                         H, h.cfg.K, mid, mid, t2raw, 4, g2.buf, g2.buf ? &g2.written : nullptr, A.scratch(),
+                                         A.scratch_bytes(), st));
+    }
+    KFE_OK(norm16_call(h, lq, t2raw, nq, mid, nullptr, 0, 0, t2, 1, &g2, nullptr, A, st));
+    KFE_ALLOC(t3, float, (size_t)nq * cout);
+    KFE_GSTAT(g3, nq, cout);
+    KFE_OK(aprb_linear_f16_stats(t2, w16[1], nq, mid, cout, t3, g3.buf, g3.buf ? &g3.written : nullptr, st));
+    const void* sc = feat;
+    if (b.strided) {
+        KFE_ALLOC(mp, float, (size_t)nq * b.in_dim / 2 + 8);
+        KFE_OK(aprb_max_pool_f16(feat, idx, H, nq, ns, H, b.in_dim, mp, st));
+        sc = mp;
+    }
+    if (b.shortcut_W) {
+        KFE_ALLOC(t4, float, (size_t)nq * cout);
+        KFE_GSTAT(g4, nq, cout);
+        KFE_OK(aprb_linear_f16_stats(sc, w16[2], nq, b.in_dim, cout, t4, g4.buf, g4.buf ? &g4.written : nullptr, st));
+        KFE_OK(norm16_call(h, lq, t3, nq, cout, t4, 0, 1, y, out16, &g3, &g4, A, st));
+    } else {
+        KFE_OK(norm16_call(h, lq, t3, nq, cout, sc, 1, 0, y, out16, &g3, nullptr, A, st));
+    }
+#undef KFE_GSTAT
+    A.off = mark;
+    *out = y; *out_cols = cout;
+    return APRB_OK;
+}
+
 __global__ void fill_kernel(float* p, size_t n, float v) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -194,12 +288,41 @@ extern "C" int aprb_kfe_create(const aprb_kfe_config* cfg, const aprb_kfe_block*
         h->ev[l] = nullptr; h->n[l] = 0; h->pts[l] = nullptr; h->lens[l] = nullptr; h->conv[l] = h->pool[l] = h->up[l] = nullptr;
         if (cudaEventCreateWithFlags(&h->ev[l], cudaEventDisableTiming) != cudaSuccess) { set_error("cudaEventCreate failed"); delete h; return APRB_ERR_CUDA; }
     }
+    // fp16 activation mode: shape constraints of the fp16 kernels, and fp16 copies of the unary weights
+    h->act16_ok = nblocks >= 2 && blocks[0].type == 0;
+    for (int i = 1; i < nblocks && h->act16_ok; ++i) {
+        const aprb_kfe_block& b = blocks[i];
+        const int mid = b.out_dim / 4;
+        const bool slab_ok = mid == 64 || mid == 128 || mid == 256 || mid % 512 == 0;     // producer slabs hold whole rows
+        h->act16_ok = b.type == 1 && b.kp_Wprep16 && b.in_dim % 64 == 0 && mid % 64 == 0 && b.out_dim % 16 == 0 && slab_ok &&
+                      (!b.strided || (b.in_dim % 128 == 0 && b.in_dim <= 1024)) && cfg->limits[b.layer] <= 128;
+    }
+    h->w16.assign((size_t)nblocks * 3, nullptr);
+    if (h->act16_ok) {
+        for (int i = 1; i < nblocks; ++i) {
+            const aprb_kfe_block& b = blocks[i];
+            const float* src[3] = {b.unary1_W, b.unary2_W, b.shortcut_W};
+            const size_t cnt[3] = {(size_t)(b.out_dim / 4) * b.in_dim, (size_t)b.out_dim * (b.out_dim / 4), (size_t)b.out_dim * b.in_dim};
+            for (int j = 0; j < 3; ++j) {
+                if (!src[j]) continue;
+                void* p = nullptr;
+                if (cudaMalloc(&p, cnt[j] * 2) != cudaSuccess || aprb_f32_to_f16(src[j], p, cnt[j], nullptr) != APRB_OK) {
+                    set_error("aprb_kfe_create: fp16 weight copy failed");
+                    aprb_kfe_destroy(h);
+                    return APRB_ERR_CUDA;
+                }
+                h->w16[(size_t)i * 3 + j] = p;
+            }
+        }
+        if (cudaStreamSynchronize(nullptr) != cudaSuccess) { set_error("aprb_kfe_create: sync failed"); aprb_kfe_destroy(h); return APRB_ERR_CUDA; }
+    }
     *out = h;
     return APRB_OK;
 }
 
 extern "C" void aprb_kfe_destroy(aprb_kfe* h) {
     if (!h) return;
+    for (void* p : h->w16) if (p) cudaFree(p);
     for (int l = 0; l < KFE_MAX_LEVELS; ++l) if (h->ev[l]) cudaEventDestroy(h->ev[l]);
     if (h->h_counts) cudaFreeHost(h->h_counts);
     delete h;
@@ -261,6 +384,8 @@ extern "C" int aprb_kfe_forward(aprb_kfe* hp, const float* d_pts, const int32_t*
 
     const float* x = d_feats;
     int xc = cfg.in_feats_dim;
+    const bool act16 = aprb::g_act_f16 && aprb::g_kpconv_f16 && h.act16_ok;
+    bool x_is16 = false;
     if (!x) {                                                      // features = ones (datasets/kitti.py:598-599)
         KFE_ALLOC(ones, float, (size_t)N * xc);
         APRB_TIMED("fill_kernel", st, 1, (fill_kernel<<<cdiv((long long)N * xc, 256), 256, 0, st>>>(ones, (size_t)N * xc, 1.0f)));
@@ -274,7 +399,14 @@ extern "C" int aprb_kfe_forward(aprb_kfe* hp, const float* d_pts, const int32_t*
     auto run_blocks = [&](int level, int strided) -> int {
         while (bi < h.blocks.size() && h.blocks[bi].layer == level && (h.blocks[bi].strided != 0) == (strided != 0)) {
             const float* y = nullptr; int yc = 0;
-            KFE_OK(run_block(h, h.blocks[bi], x, &y, &yc, A, st));
+            if (act16) {
+                const void* y16 = nullptr;
+                const bool last = bi + 1 == h.blocks.size();
+                KFE_OK(run_block16(h, bi, x, x_is16, last, &y16, &yc, A, st));
+                y = (const float*)y16; x_is16 = !last;
+            } else {
+                KFE_OK(run_block(h, h.blocks[bi], x, &y, &yc, A, st));
+            }
             x = y; xc = yc; ++bi;
         }
         return APRB_OK;

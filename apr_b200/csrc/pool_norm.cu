@@ -6,8 +6,24 @@
 // eps 1e-5, biased variance, no affine, no running stats) fused with the LeakyReLU(0.1) / residual add that follow it
 // in UnaryBlock (:496-510), SimpleBlock (:592) and ResnetBottleneckBlock (:669-681).
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace aprb {
+
+// 4 channels stored in fp16 (8 bytes) <-> float4. Activations kept in fp16 are TF32-rounded values (10-bit mantissa):
+// the narrowing is exact for magnitudes in fp16's normal range.
+__device__ __forceinline__ float4 load_half4(const __half* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void store_half4(__half* p, const float4 v) {
+    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const unsigned*>(&a); u.y = *reinterpret_cast<const unsigned*>(&b);
+    *reinterpret_cast<uint2*>(p) = u;
+}
 
 template <typename IdxT>
 __global__ void max_pool_kernel(const float* __restrict__ x, const IdxT* __restrict__ idx, int ld, int Nq, int Ns,
@@ -32,7 +48,7 @@ __global__ void max_pool_kernel(const float* __restrict__ x, const IdxT* __restr
 // Warp per query, C = 128 * NV channels (lane owns NV float4): the index row is read once, coalesced, and only the valid
 // neighbours are visited (ballot + shuffle broadcast) — pooling lists are ~half pad — with NV independent 128-bit loads
 // in flight per neighbour. The thread-per-(query, quad) kernel above re-read the row once per quad and walked the pads.
-template <typename IdxT, int NV>
+template <typename IdxT, int NV, bool H16>
 __global__ void __launch_bounds__(256)
 max_pool_warp_kernel(const float* __restrict__ x, const IdxT* __restrict__ idx, int ld, int Nq, int Ns, int H,
                      const int* __restrict__ d_width, float* __restrict__ out) {
@@ -46,7 +62,8 @@ max_pool_warp_kernel(const float* __restrict__ x, const IdxT* __restrict__ idx, 
     for (int j = 0; j < NV; ++j) m[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     bool any_pad = false;
     const IdxT* row = idx + (size_t)n * ld;
-    const float4* xb = reinterpret_cast<const float4*>(x) + lane;
+    const float4* xb = reinterpret_cast<const float4*>(x) + lane;                       // fp32 rows: C/4 float4
+    const __half* xh = reinterpret_cast<const __half*>(x) + lane * 4;                   // fp16 rows: C halves
     for (int h0 = 0; h0 < Hn; h0 += 32) {
         const int h = h0 + lane;
         long long sv = -1;
@@ -58,10 +75,11 @@ max_pool_warp_kernel(const float* __restrict__ x, const IdxT* __restrict__ idx, 
         while (vm) {
             const int src = __ffs(vm) - 1;
             vm &= vm - 1;
-            const float4* p = xb + (size_t)__shfl_sync(0xffffffffu, si, src) * (C / 4);
+            const size_t srow = (size_t)__shfl_sync(0xffffffffu, si, src);
+            const float4* p = xb + srow * (C / 4);
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
-                const float4 v = __ldg(p + j * 32);
+                const float4 v = H16 ? load_half4(xh + srow * C + j * 128) : __ldg(p + j * 32);
                 m[j].x = fmaxf(m[j].x, v.x); m[j].y = fmaxf(m[j].y, v.y); m[j].z = fmaxf(m[j].z, v.z); m[j].w = fmaxf(m[j].w, v.w);
             }
         }
@@ -72,7 +90,8 @@ max_pool_warp_kernel(const float* __restrict__ x, const IdxT* __restrict__ idx, 
         if (any_pad) {                                               // the shadow neighbour's all-zero row takes part in the max
             m[j].x = fmaxf(m[j].x, 0.f); m[j].y = fmaxf(m[j].y, 0.f); m[j].z = fmaxf(m[j].z, 0.f); m[j].w = fmaxf(m[j].w, 0.f);
         }
-        op[j * 32] = m[j];
+        if (H16) store_half4(reinterpret_cast<__half*>(out) + (size_t)n * C + lane * 4 + j * 128, m[j]);
+        else op[j * 32] = m[j];
     }
 }
 
@@ -259,7 +278,7 @@ extern "C" int aprb_max_pool(const float* d_x, const void* d_idx, int idx_is_i64
     if (C % 4 == 0 && ((uintptr_t)d_x % 16 == 0) && ((uintptr_t)d_out % 16 == 0)) {
         long long total = (long long)Nq * (C / 4);
         if (C % 128 == 0 && C <= 1024 && H >= 1) {
-#define MPW(IDX, NV) APRB_TIMED("max_pool_kernel", st, 1, (max_pool_warp_kernel<IDX, NV><<<cdiv(Nq, 8), 256, 0, st>>>(d_x, (const IDX*)d_idx, ld_idx, Nq, Ns, H, d_width, d_out)))
+#define MPW(IDX, NV) APRB_TIMED("max_pool_kernel", st, 1, (max_pool_warp_kernel<IDX, NV, false><<<cdiv(Nq, 8), 256, 0, st>>>(d_x, (const IDX*)d_idx, ld_idx, Nq, Ns, H, d_width, d_out)))
 #define MPW_NV(IDX) do { if (C == 128) MPW(IDX, 1); else if (C == 256) MPW(IDX, 2); else if (C == 384) MPW(IDX, 3); else if (C == 512) MPW(IDX, 4); \
                          else if (C == 640) MPW(IDX, 5); else if (C == 768) MPW(IDX, 6); else if (C == 896) MPW(IDX, 7); else MPW(IDX, 8); } while (0)
             if (idx_is_i64) MPW_NV(long long); else MPW_NV(int);
@@ -275,6 +294,35 @@ extern "C" int aprb_max_pool(const float* d_x, const void* d_idx, int idx_is_i64
         if (idx_is_i64) APRB_TIMED("max_pool_scalar_kernel", st, 1, (max_pool_scalar_kernel<long long><<<cdiv(total, T), T, 0, st>>>(d_x, (const long long*)d_idx, ld_idx, Nq, Ns, H, C, d_width, d_out)));
         else APRB_TIMED("max_pool_scalar_kernel", st, 1, (max_pool_scalar_kernel<int><<<cdiv(total, T), T, 0, st>>>(d_x, (const int*)d_idx, ld_idx, Nq, Ns, H, C, d_width, d_out)));
     }
+    APRB_LAUNCH_OK();
+    return APRB_OK;
+}
+
+extern "C" int aprb_max_pool_f16(const void* d_x16, const int32_t* d_idx, int ld_idx, int Nq, int Ns, int H, int C,
+                                 void* d_out16, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    APRB_REQUIRE(Nq >= 0 && Ns >= 0 && H >= 1 && C >= 128 && C % 128 == 0 && C <= 1024 && ld_idx >= H, "need C in {128, ..., 1024}, H >= 1");
+    if (Nq == 0) return APRB_OK;
+    APRB_REQUIRE(d_idx && d_out16 && (d_x16 || Ns == 0), "null pointer");
+#define MPH(NV) APRB_TIMED("max_pool_kernel", st, 1, (max_pool_warp_kernel<int, NV, true><<<cdiv(Nq, 8), 256, 0, st>>>((const float*)d_x16, d_idx, ld_idx, Nq, Ns, H, nullptr, (float*)d_out16)))
+    switch (C / 128) {
+        case 1: MPH(1); break; case 2: MPH(2); break; case 3: MPH(3); break; case 4: MPH(4); break;
+        case 5: MPH(5); break; case 6: MPH(6); break; case 7: MPH(7); break; default: MPH(8); break;
+    }
+#undef MPH
+    APRB_LAUNCH_OK();
+    return APRB_OK;
+}
+
+__global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2half_rn(in[i]);
+}
+
+extern "C" int aprb_f32_to_f16(const float* d_in, void* d_out16, size_t n, void* stream) {
+    APRB_REQUIRE(n == 0 || (d_in && d_out16), "null pointer");
+    if (n == 0) return APRB_OK;
+    APRB_TIMED("f32_to_f16_kernel", (cudaStream_t)stream, 1, (f32_to_f16_kernel<<<cdiv((long long)n, 256), 256, 0, (cudaStream_t)stream>>>(d_in, (__half*)d_out16, n)));
     APRB_LAUNCH_OK();
     return APRB_OK;
 }
@@ -586,7 +634,7 @@ norm_seg_partial_kernel(const float* __restrict__ x, const float* __restrict__ x
 __global__ void __launch_bounds__(256)
 norm_seg_apply_kernel(const float* __restrict__ x, const int* __restrict__ seg_off, int N, int C, int W, int nt,
                       const float* __restrict__ stats, const float* __restrict__ res, float slope, int round_tf32,
-                      float* __restrict__ y) {
+                      float* __restrict__ y, int res16, int out16) {
     const int seg = blockIdx.z;
     const int Cq = C >> 2, R = 256 / W;
     const int tx = threadIdx.x % W, ty = threadIdx.x / W;
@@ -607,13 +655,14 @@ norm_seg_apply_kernel(const float* __restrict__ x, const int* __restrict__ seg_o
         const float4 v = xp[(size_t)r * Cq];
         float4 o = make_float4((v.x - mean.x) * rstd.x, (v.y - mean.y) * rstd.y, (v.z - mean.z) * rstd.z, (v.w - mean.w) * rstd.w);
         if (rp) {
-            const float4 q = rp[(size_t)r * Cq];
+            const float4 q = res16 ? load_half4(reinterpret_cast<const __half*>(res) + ((size_t)r * Cq + quad) * 4) : rp[(size_t)r * Cq];
             o.x += (q.x - rmean.x) * rrstd.x; o.y += (q.y - rmean.y) * rrstd.y;
             o.z += (q.z - rmean.z) * rrstd.z; o.w += (q.w - rmean.w) * rrstd.w;
         }
         o.x = act_round(o.x, slope, round_tf32); o.y = act_round(o.y, slope, round_tf32);
         o.z = act_round(o.z, slope, round_tf32); o.w = act_round(o.w, slope, round_tf32);
-        yp[(size_t)r * Cq] = o;
+        if (out16) store_half4(reinterpret_cast<__half*>(y) + ((size_t)r * Cq + quad) * 4, o);
+        else yp[(size_t)r * Cq] = o;
     }
 }
 
@@ -692,6 +741,7 @@ __global__ void seg_offsets_kernel(const int* __restrict__ lens, int B, int cps,
 }
 
 constexpr int NORM_SEG_MAX_CH = 64;
+int g_act_f16 = 1;      // aprb_set_option("act_f16"): aprb_kfe_forward stores normalised activations in fp16 (needs kpconv_f16)
 int g_kpconv_f16 = 1;   // aprb_set_option("kpconv_f16"): aprb_kfe_forward runs KPConv with fp16 operands where a block provides them
 int g_fuse_stats = 1;   // aprb_set_option("fuse_stats"): aprb_kfe_forward hands GEMM-epilogue group statistics to the norms
 
@@ -723,7 +773,19 @@ extern "C" int aprb_instnorm_lrelu_seg_pre(const float* d_x, int N, int C, const
                                            float slope, const float* d_residual, int norm_residual, int round_tf32,
                                            float* d_y, const float* d_gstat_x, const float* d_gstat_res, void* d_ws,
                                            size_t ws_bytes, void* stream) {
+    return aprb_instnorm_lrelu_seg_f16(d_x, N, C, d_seg_off, S, eps, slope, d_residual, 0, norm_residual, round_tf32, d_y, 0,
+                                       d_gstat_x, d_gstat_res, d_ws, ws_bytes, stream);
+}
+
+extern "C" int aprb_instnorm_lrelu_seg_f16(const float* d_x, int N, int C, const int32_t* d_seg_off, int S, float eps,
+                                           float slope, const void* d_residual_v, int residual_is_f16, int norm_residual,
+                                           int round_tf32, void* d_y_v, int out_is_f16, const float* d_gstat_x,
+                                           const float* d_gstat_res, void* d_ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    const float* d_residual = (const float*)d_residual_v;
+    float* d_y = (float*)d_y_v;
+    APRB_REQUIRE(!(residual_is_f16 && norm_residual), "a residual that is standardised itself must be fp32 (a GEMM output)");
+    APRB_REQUIRE(!(out_is_f16 && (const void*)d_x == d_y_v), "fp16 output cannot alias the fp32 input");
     APRB_REQUIRE(N >= 0 && C >= 1 && S >= 1, "bad shape");
     APRB_REQUIRE(S == 1 || d_seg_off, "segment offsets required when S > 1");
     if (N == 0) return APRB_OK;
@@ -766,7 +828,7 @@ extern "C" int aprb_instnorm_lrelu_seg_pre(const float* d_x, int N, int C, const
     // apply pass: ~6 waves of blocks, >= 16 rows per block
     int rb = min(max(1, 6 * sms / (gx * S)), max(1, rows_seg / 16));
     APRB_TIMED("norm_seg_apply_kernel", st, 1, (norm_seg_apply_kernel<<<dim3(gx, rb, S), 256, 0, st>>>(
-        d_x, d_seg_off, N, C, W, nt, stats, d_residual, slope, round_tf32, d_y)));
+        d_x, d_seg_off, N, C, W, nt, stats, d_residual, slope, round_tf32, d_y, residual_is_f16, out_is_f16)));
     APRB_LAUNCH_OK();
     return APRB_OK;
 }

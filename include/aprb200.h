@@ -111,7 +111,8 @@ size_t aprb_kpconv_ws_bytes(int Nq, int Ns, int H, int K, int Cin, int Cout);
  * may be NULL to force the fp32 CUDA-core path). mode: 0 = auto (tensor path when supported), 1 = fp32 CUDA cores,
  * 2 = tcgen05 TF32 (error if unsupported shape), 3 = tcgen05 with fp16 operands: d_wprep is then the fp16 operand of
  * aprb_kpconv_prepare_weights_f16 and the weighted tile is produced in fp16 — the 10-bit mantissa of TF32 at half the
- * bytes, for features of O(1) magnitude such as InstanceNorm outputs (K*Cin % 64 == 0, Cin % 4 == 0, H <= 128). */
+ * bytes, for features of O(1) magnitude such as InstanceNorm outputs (K*Cin % 64 == 0, Cin % 4 == 0, H <= 128).
+ * 4 = as 3, and d_x itself is fp16 [Ns, Cin] (int32 indices, Cin a multiple of the producer's 32/64/128/256/512 slab). */
 int aprb_kpconv_forward(const float* d_q, const float* d_s, const void* d_idx, int idx_is_i64, int ld_idx,
                         const float* d_x, const float* d_kp, const float* d_W, const float* d_wprep,
                         float extent, int Nq, int Ns, int H, int K, int Cin, int Cout,
@@ -176,6 +177,21 @@ int aprb_instnorm_lrelu_seg(const float* d_x, int N, int C, const int32_t* d_seg
 int aprb_instnorm_lrelu_seg_pre(const float* d_x, int N, int C, const int32_t* d_seg_off, int S, float eps, float slope,
                                 const float* d_residual, int norm_residual, int round_tf32, float* d_y,
                                 const float* d_gstat_x, const float* d_gstat_res, void* d_ws, size_t ws_bytes, void* stream);
+/* fp16 activation storage (aprb_kfe_forward keeps every normalised activation in fp16: the values are TF32-rounded, so
+ * nothing is lost, and each such tensor costs half the HBM bytes to write, gather and feed to the tensor cores):
+ * the same normalisation with an optional fp16 residual (a plain residual only) and an optional fp16 output. d_x is
+ * always the fp32 output of a GEMM. */
+int aprb_instnorm_lrelu_seg_f16(const float* d_x, int N, int C, const int32_t* d_seg_off, int S, float eps, float slope,
+                                const void* d_residual, int residual_is_f16, int norm_residual, int round_tf32,
+                                void* d_y, int out_is_f16, const float* d_gstat_x, const float* d_gstat_res,
+                                void* d_ws, size_t ws_bytes, void* stream);
+/* max_pool on fp16 features (C a multiple of 128, <= 1024; int32 indices). */
+int aprb_max_pool_f16(const void* d_x16, const int32_t* d_idx, int ld_idx, int Nq, int Ns, int H, int C,
+                      void* d_out16, void* stream);
+/* y (fp32) = x16 @ W16^T with fp16 operands on tcgen05 (Cin % 64 == 0, Cout % 16 == 0) + group statistics of y. */
+int aprb_linear_f16_stats(const void* d_x16, const void* d_W16, int N, int Cin, int Cout, float* d_y,
+                          float* d_gstat, int* stats_written, void* stream);
+int aprb_f32_to_f16(const float* d_in, void* d_out16, size_t n, void* stream);
 /* d_seg_off[s] = first stacked row of cloud s * clouds_per_segment; ceil(B / clouds_per_segment) + 1 entries. */
 int aprb_segment_offsets(const int32_t* d_lens, int B, int clouds_per_segment, int32_t* d_seg_off, void* stream);
 

@@ -381,7 +381,20 @@ def test_native_pipeline_matches_module_path(cuda, oracle):
     got = pipe.forward(dp, dl_).clone()                             # the result is a view into the arena: copy it
     torch.cuda.synchronize()
     assert got.shape == want.shape
-    assert torch.equal(got, want)                                   # same kernels, same order -> bit-identical
+    # The native path keeps normalised activations in fp16 (exact: they are TF32-rounded) and runs every contraction with
+    # kind::f16; the module path keeps them in fp32 and runs the Linears with kind::tf32. Same operand values, different
+    # accumulation grouping inside the tensor core (K = 16 vs 8 per instruction): fp32 round-off, which a TF32 re-rounding
+    # of a stored activation occasionally turns into 2^-11 — the same drift class as super-batched vs single pairs.
+    e_paths = rel(got, want)
+    print(f"native (fp16 activations) vs module path (fp32 activations): {e_paths:.2e}")
+    assert e_paths < 5e-3
+    from apr_b200 import _native
+    try:                                                            # fp32 activations + TF32 Linears natively: bit-identical
+        _native.check(_native.lib().aprb_set_option(b"act_f16", 0), "aprb_set_option")
+        got32 = pipe.forward(dp, dl_).clone()
+    finally:
+        _native.check(_native.lib().aprb_set_option(b"act_f16", 1), "aprb_set_option")
+    assert torch.equal(got32, want)                                 # same kernels, same order -> bit-identical
     ref = collate_ref(p0, l0, cfg, limits, oracle.subsample_batch, oracle.batch_query)
     pyr = pipe.pyramid()
     for k in ("points", "neighbors", "pools", "upsamples"):
@@ -396,7 +409,7 @@ def test_native_pipeline_matches_module_path(cuda, oracle):
                 assert np.array_equal(d[:, :w.shape[1]], w), (k, lvl)
     # host-buffer entry point (H2D + path + D2H)
     host = pipe.forward_host(torch.from_numpy(p0).pin_memory(), torch.from_numpy(l0).pin_memory())
-    assert torch.equal(host, want.cpu())
+    assert torch.equal(host, got.cpu())
     # vs the fp32 CPU oracle end to end (drift over 11 blocks, TF32 tensor path): reported, loose bound
     cpu = dict(points=[torch.from_numpy(p) for p in ref["points"]], neighbors=[torch.from_numpy(n).long() for n in ref["neighbors"]],
                pools=[torch.from_numpy(n).long() for n in ref["pools"]], features=torch.ones(len(p0), 1))
