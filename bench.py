@@ -362,6 +362,20 @@ def run_ours(args):
     e2e = clouds / (ms_e2e * 1e-3)
 
     pk = peaks()
+    opts = dict(kv.split("=") for kv in args.opt)
+    f16_mode = int(opts.get("act_f16", 1)) != 0 and int(opts.get("kpconv_f16", 1)) != 0
+
+    def traffic_of(kernel):
+        """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this
+        workload (profiles/r01_traffic.json), or None when no capture covers the kernel / the options differ."""
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as f:
+                t = json.load(f)
+            ok = t.get("workload") == wl_name and t.get("pairs_per_call") == P and not args.opt
+            return float(t["kernels"][kernel]["dram_bytes_per_launch"]) if ok and kernel in t.get("kernels", {}) else None
+        except Exception:
+            return None
+
     total_kernel_ms = sum(v[1] for v in prof.values())
     top = max(prof.items(), key=lambda kv: kv[1][1]) if prof else (None, (0, 0.0))
     roof = None
@@ -370,18 +384,20 @@ def run_ours(args):
         per_step_s = tot_ms / args.steps * 1e-3
         share = tot_ms / max(total_kernel_ms, 1e-9)
         if name in ("gemm_tf32_kernel", "sgemm_rowscale_kernel"):
-            peak = pk["bf16"] / 2.0                          # TF32 dense = half the bf16 rate
+            # fp16 operands (default: act_f16 = kpconv_f16 = 1) run at the bf16/fp16 dense rate, TF32 at half of it
+            peak = pk["bf16"] if f16_mode else pk["bf16"] / 2.0
             ach = tc_flops / per_step_s / 1e12 if per_step_s > 0 else 0.0
             roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": None, "launches_per_step": cnt / args.steps,
+                    "traffic": traffic_of(name), "launches_per_step": cnt / args.steps,
                     "note": f"algorithmic flops = 2*Nq*K*Cin*Cout over the KPConv contractions + 2*N*Cin*Cout over the unary "
-                            f"Linears = {tc_flops / 1e9:.1f} GFLOP/call ({P} pair(s)); TF32 peak = half of {pk['src']} bf16 sustained; "
-                            f"share of kernel time {share:.2f}"}
+                            f"Linears = {tc_flops / 1e9:.1f} GFLOP/call ({P} pair(s)); peak = {pk['src']} bf16 sustained"
+                            f"{'' if f16_mode else ' / 2 (TF32)'}; the HBM-bound launches of this kernel (levels 0-1) are read in "
+                            f"profiles/; share of kernel time {share:.2f}"}
         else:
             by = kpw_bytes if name == "kp_weighted_kernel" else 0.0
             ach = by / per_step_s / 1e9 if per_step_s > 0 else 0.0
             roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-                    "traffic": None, "launches_per_step": cnt / args.steps,
+                    "traffic": traffic_of(name), "launches_per_step": cnt / args.steps,
                     "note": f"algorithmic bytes = 4*(Ns*Cin + Nq*K*Cin) + idx + points = {by / 1e6:.0f} MB/step; peak = {pk['src']}; "
                             f"share of kernel time {share:.2f}"}
     kernels = {k: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps} for k, v in
@@ -389,12 +405,16 @@ def run_ours(args):
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32", "data": "synthetic",
+            "dtype": "f16" if f16_mode else "tf32", "data": "synthetic",
             "config": {"workload": wl_name, "pairs_per_step": S * P, "pairs_per_call": P,
                        "concurrent_streams": S, "points_stacked": int(pairs_dev[0][0].shape[0]), "level_points": n_levels,
                        "limits": limits,
                        "parallelism": f"pairs x{world}", "path": "native (aprb_kfe_forward)",
                        "l2": "flushed between steps (256 MiB memset outside the event pair)",
+                       "precision": ("fp16 operands (10-bit mantissa, as TF32) with fp32 accumulation in TMEM for every contraction; "
+                                     "normalised activations stored in fp16 (exact: they are TF32-rounded); neighbour search, "
+                                     "subsampling, influence weights, statistics in fp32/integer") if f16_mode else
+                                    "TF32 operands, fp32 accumulation; activations fp32",
                        "kpconv_gflop_per_pair": kp_flops / 1e9 / P, "linear_gflop_per_pair": lin_flops / 1e9 / P},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(io[0]), "d2h_bytes_per_step": int(io[1]),
