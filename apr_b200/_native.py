@@ -58,6 +58,7 @@ SIGNATURES = {
     "aprb_round_tf32": (_i, [_p, _p, _sz, _p]),
     "aprb_kfe_create": (_i, [_p, _p, _i, _p]),
     "aprb_kfe_arena_bytes": (_sz, [_p, _i, _i]),
+    "aprb_kfe_arena_bytes_est": (_sz, [_p, _i, _i, _f]),
     "aprb_kfe_forward": (_i, [_p, _p, _p, _p, _i, _i, _p, _sz, _p, _p, _p, _p]),
     "aprb_kfe_forward_host": (_i, [_p, _p, _p, _i, _i, _p, _sz, _p, _i, _p, _p, _p]),
     "aprb_kfe_get": (_i, [_p, _i, _i, _p, _p, _p]),

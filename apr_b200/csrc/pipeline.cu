@@ -328,32 +328,47 @@ extern "C" void aprb_kfe_destroy(aprb_kfe* h) {
     delete h;
 }
 
-extern "C" size_t aprb_kfe_arena_bytes(const aprb_kfe* h, int N, int B) {
+// Arena size when level l holds at most N * ratio^l points (ratio in (0, 1]; 1 = the unconditional bound: a grid
+// subsampling never returns more points than it was given).
+extern "C" size_t aprb_kfe_arena_bytes_est(const aprb_kfe* h, int N, int B, float ratio) {
     if (!h || N < 0 || B < 1) return 0;
-    // Generous closed form (HBM is 180 GB; a KITTI pair needs ~1.2 GB): pyramid + block outputs + the largest
-    // temporaries/scratch, all with the level-0 point count as the bound for every level.
-    size_t n = (size_t)(N > 0 ? N : 1);
-    size_t pyramid = 0, lim = 0;
-    for (int l = 0; l < h->cfg.num_layers; ++l) {
-        lim = (size_t)h->cfg.limits[l];
+    if (!(ratio > 0.f) || ratio > 1.f) ratio = 1.f;
+    const int L = h->cfg.num_layers;
+    size_t nl[KFE_MAX_LEVELS + 1];
+    double f = 1.0;
+    for (int l = 0; l <= KFE_MAX_LEVELS; ++l) {
+        size_t v = (size_t)((double)(N > 0 ? N : 1) * f) + 256;     // + slack for tiny clouds
+        nl[l] = v < (size_t)(N > 0 ? N : 1) ? v : (size_t)(N > 0 ? N : 1);
+        f *= ratio;
+    }
+    size_t pyramid = 0;
+    for (int l = 0; l < L; ++l) {
+        const size_t lim = (size_t)h->cfg.limits[l], n = nl[l];
         pyramid += 3 * align256(n * lim * 4) + align256(n * 12) + aprb_cell_grid_bytes((int)n, B) + 4096;
     }
     size_t feats = 0, worst_tmp = 0;
     for (const aprb_kfe_block& b : h->blocks) {
+        const size_t ns = nl[b.layer], nq = b.strided ? nl[b.layer + 1] : ns;          // support / query rows of the block
+        const size_t lim = (size_t)h->cfg.limits[b.layer];
         size_t cout = b.type == 0 ? b.out_dim / 2 : b.out_dim, cin_k = b.type == 0 ? b.in_dim : b.out_dim / 4;
-        feats += align256(n * cout * 4);
-        size_t tmp = n * 4 * (2 * (size_t)(b.out_dim / 4) + 2 * cout + b.in_dim) + 8 * 256;
+        feats += align256(nq * cout * 4);
+        size_t tmp = ns * 4 * (2 * (size_t)(b.out_dim / 4) + b.in_dim) + nq * 4 * (2 * (size_t)(b.out_dim / 4) + 2 * cout + b.in_dim) + 16 * 256;
         tmp += tmp / 16 + 8 * 256;                                  // group statistics: 1/16 of each GEMM output
-        size_t kpw = aprb_kpconv_ws_bytes((int)n, (int)n, (int)lim, h->cfg.K, (int)cin_k, (int)(b.type == 0 ? cout : cin_k));
-        size_t lin = aprb_linear_tf32_ws_bytes((int)n, b.in_dim, (int)cout);
+        size_t kpw = aprb_kpconv_ws_bytes((int)nq, (int)ns, (int)lim, h->cfg.K, (int)cin_k, (int)(b.type == 0 ? cout : cin_k));
+        size_t lin = aprb_linear_tf32_ws_bytes((int)ns, b.in_dim, (int)cout);
         size_t scratch = kpw > lin ? kpw : lin;
         if (tmp + scratch > worst_tmp) worst_tmp = tmp + scratch;
     }
-    size_t sub = aprb_grid_subsample_ws_bytes((int)n, B, 0);
+    size_t sub = aprb_grid_subsample_ws_bytes((int)nl[0], B, 0);
     const int cps = h->cfg.clouds_per_segment > 0 ? h->cfg.clouds_per_segment : B;
-    size_t norm = aprb_instnorm_seg_ws_bytes((int)n, 2048, cdiv(B, cps));
-    return pyramid + feats + worst_tmp + sub + norm + align256(n * 4) + (1u << 20);
+    size_t norm = aprb_instnorm_seg_ws_bytes((int)nl[0], 2048, cdiv(B, cps));
+    return pyramid + feats + worst_tmp + sub + norm + align256(nl[0] * 4) + (1u << 20);
 }
+
+// Unconditional bound (every level as large as level 0): 27 GB for a super-batch of 8 KITTI pairs. Callers that can
+// retry use aprb_kfe_arena_bytes_est(ratio ~ 0.6; measured level ratios are 0.40-0.42) and fall back to this on
+// APRB_ERR_WORKSPACE — aprb_kfe_forward checks every carve and never writes past the arena.
+extern "C" size_t aprb_kfe_arena_bytes(const aprb_kfe* h, int N, int B) { return aprb_kfe_arena_bytes_est(h, N, B, 1.0f); }
 
 extern "C" int aprb_kfe_forward(aprb_kfe* hp, const float* d_pts, const int32_t* d_lens, const float* d_feats, int N, int B,
                                 void* d_arena, size_t arena_bytes, const float** out_feats, int* out_rows, int* out_cols,

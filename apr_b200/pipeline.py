@@ -95,11 +95,26 @@ class KFEPipeline:
         except Exception:
             pass
 
-    def _ensure_arena(self, n, b):
-        need = self.lib.aprb_kfe_arena_bytes(self.handle, int(n), int(b))
+    LEVEL_RATIO = 0.6   # arena sized for level l <= N * 0.6^l points (measured 0.40-0.42); grown to the bound on demand
+
+    def _ensure_arena(self, n, b, full=False):
+        if full:
+            need = self.lib.aprb_kfe_arena_bytes(self.handle, int(n), int(b))
+        else:
+            need = self.lib.aprb_kfe_arena_bytes_est(self.handle, int(n), int(b), C.c_float(self.LEVEL_RATIO))
         if self.arena is None or self.arena.numel() < need:
-            self.arena = torch.empty(int(need * 1.1) + 4096, dtype=torch.uint8, device=self.device)
+            self.arena = None                                       # release before growing
+            self.arena = torch.empty(int(need * 1.05) + 4096, dtype=torch.uint8, device=self.device)
         return self.arena
+
+    def _call(self, fn, n, b):
+        """fn(arena) -> status; retried once with the unconditional arena bound when a level outgrew the estimate
+        (the native driver checks every carve and returns APRB_ERR_WORKSPACE before writing past the arena)."""
+        rc = fn(self._ensure_arena(n, b))
+        if rc == -2:
+            torch.cuda.current_stream(self.device).synchronize(); self.stream.synchronize()
+            rc = fn(self._ensure_arena(n, b, full=True))
+        return rc
 
     def _view(self, ptr, rows, cols, dtype):
         off = ptr - self.arena.data_ptr()
@@ -110,11 +125,10 @@ class KFEPipeline:
         """points [N,3] f32 cuda, lengths [B] i32 cuda -> encoder output [N_last, C] (a view into the arena, valid until
         the next forward). Kernels are queued on self.stream; the call returns without waiting for them."""
         pts, lens = points.float().contiguous(), lengths.int().contiguous()
-        arena = self._ensure_arena(pts.shape[0], lens.shape[0])
         out, rows, cols = C.c_void_p(), C.c_int(), C.c_int()
-        rc = self.lib.aprb_kfe_forward(self.handle, pts.data_ptr(), lens.data_ptr(), None, pts.shape[0], lens.shape[0],
-                                       arena.data_ptr(), arena.numel(), C.byref(out), C.byref(rows), C.byref(cols),
-                                       C.c_void_p(self.stream.cuda_stream))
+        rc = self._call(lambda arena: self.lib.aprb_kfe_forward(
+            self.handle, pts.data_ptr(), lens.data_ptr(), None, pts.shape[0], lens.shape[0], arena.data_ptr(), arena.numel(),
+            C.byref(out), C.byref(rows), C.byref(cols), C.c_void_p(self.stream.cuda_stream)), pts.shape[0], lens.shape[0])
         N.check(rc, "aprb_kfe_forward")
         self._last_inputs = (pts, lens)
         return self._view(out.value, rows.value, cols.value, torch.float32)
@@ -126,16 +140,15 @@ class KFEPipeline:
         lens = lengths if isinstance(lengths, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(lengths, np.int32))
         pts, lens = pts.float().contiguous(), lens.int().contiguous()
         n, b = pts.shape[0], lens.shape[0]
-        arena = self._ensure_arena(n, b)
         if out is None:
             cap = min(n, max(n // 4, 4096))         # the last level keeps ~6 % of the level-0 rows
             if self._host_out is None or self._host_out.shape[0] < cap:
                 self._host_out = torch.empty((cap, self._out_cols), dtype=torch.float32).pin_memory()
             out = self._host_out
         rows, cols = C.c_int(), C.c_int()
-        rc = self.lib.aprb_kfe_forward_host(self.handle, pts.data_ptr(), lens.data_ptr(), n, b, arena.data_ptr(),
-                                            arena.numel(), out.data_ptr(), out.shape[0], C.byref(rows), C.byref(cols),
-                                            C.c_void_p(self.stream.cuda_stream))
+        rc = self._call(lambda arena: self.lib.aprb_kfe_forward_host(
+            self.handle, pts.data_ptr(), lens.data_ptr(), n, b, arena.data_ptr(), arena.numel(), out.data_ptr(), out.shape[0],
+            C.byref(rows), C.byref(cols), C.c_void_p(self.stream.cuda_stream)), n, b)
         N.check(rc, "aprb_kfe_forward_host")
         return out[:rows.value]
 

@@ -248,6 +248,9 @@ int aprb_kfe_create(const aprb_kfe_config* cfg, const aprb_kfe_block* blocks, in
 void aprb_kfe_destroy(aprb_kfe* h);
 /* Device arena needed for a stacked batch of at most N points in B clouds. */
 size_t aprb_kfe_arena_bytes(const aprb_kfe* h, int N, int B);
+/* Same with level l bounded by N * ratio^l points (measured 0.40-0.42 per level; 1 = the unconditional bound above).
+ * aprb_kfe_forward returns APRB_ERR_WORKSPACE, without writing past the arena, if a level turns out larger. */
+size_t aprb_kfe_arena_bytes_est(const aprb_kfe* h, int N, int B, float ratio);
 /* d_pts [N,3] level-0 points (already at first_subsampling_dl), d_lens [B]; d_feats [N,in_feats_dim] or NULL (= ones).
  * Runs on `stream`, returns after the last kernel is ENQUEUED (it waits only for the three point-count read-backs).
  * *out_feats receives a device pointer into the arena: encoder output [*out_rows, *out_cols] fp32. */

@@ -420,6 +420,30 @@ def test_native_pipeline_matches_module_path(cuda, oracle):
     assert e < 1e-2
 
 
+def test_native_pipeline_arena_estimate_and_fallback(cuda):
+    """The arena is sized for level sizes N * 0.6^l; a pyramid that shrinks less (here: estimate forced to 0.05) makes
+    the native driver return APRB_ERR_WORKSPACE before writing past the arena, and the call is retried with the
+    unconditional bound: same result either way."""
+    from apr_b200 import synth
+    from apr_b200.pipeline import KFEPipeline
+    cfg = kitti_config()
+    a, b = synth.small_cloud(71, 2500), synth.small_cloud(72, 2300)
+    raw = torch.from_numpy(np.concatenate([a, b])).to(cuda)
+    lens = torch.tensor([len(a), len(b)], dtype=torch.int32, device=cuda)
+    p0, l0 = ops.grid_subsample(raw, lens, 0.3)
+    torch.manual_seed(0); np.random.seed(0)
+    enc = KPFCNNEncoder(cfg).to(cuda).eval()
+    ref_pipe = KFEPipeline(enc, cfg, [30, 31, 32, 33])
+    want = ref_pipe.forward(p0, l0).clone()
+    est_bytes = ref_pipe.arena.numel()
+    tight = KFEPipeline(enc, cfg, [30, 31, 32, 33])
+    tight.LEVEL_RATIO = 0.05
+    got = tight.forward(p0, l0).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    assert tight.arena.numel() > est_bytes                           # it had to grow to the unconditional bound
+
+
 def test_native_pipeline_super_batch_equals_separate_pairs(cuda, oracle):
     """P collated pairs stacked in ONE aprb_kfe_forward call (clouds_per_segment = 2: per-pair InstanceNorm statistics)
     give, pair by pair, the result of P separate single-pair calls: pyramid bit-exact (indices shifted by the pair's row
