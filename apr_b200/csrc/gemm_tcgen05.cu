@@ -446,6 +446,8 @@ extern int g_kpw_version;
 extern int g_fuse_stats;
 extern int g_kpconv_f16;
 extern int g_act_f16;
+extern int g_dbg_skip_d2h;
+extern int g_host_zero_copy;
 extern int g_kpconv_fused;
 int g_gemm_cluster = 1;   // 1 disables the cluster/multicast path (aprb_set_option)
 
@@ -549,6 +551,8 @@ extern "C" int aprb_set_option(const char* name, int value) {
     if (strcmp(name, "fuse_stats") == 0) { g_fuse_stats = value; return APRB_OK; }
     if (strcmp(name, "kpconv_f16") == 0) { g_kpconv_f16 = value; return APRB_OK; }
     if (strcmp(name, "act_f16") == 0) { g_act_f16 = value; return APRB_OK; }
+    if (strcmp(name, "dbg_skip_d2h") == 0) { g_dbg_skip_d2h = value; return APRB_OK; }
+    if (strcmp(name, "host_zero_copy") == 0) { g_host_zero_copy = value; return APRB_OK; }
     if (strcmp(name, "kpconv_fused") == 0) { g_kpconv_fused = value; return APRB_OK; }
     set_error("aprb_set_option: unknown option %s", name);
     return APRB_ERR_INVALID;

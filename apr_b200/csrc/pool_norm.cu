@@ -741,6 +741,8 @@ __global__ void seg_offsets_kernel(const int* __restrict__ lens, int B, int cps,
 }
 
 constexpr int NORM_SEG_MAX_CH = 64;
+int g_dbg_skip_d2h = 0;
+int g_host_zero_copy = 0;   // aprb_set_option("host_zero_copy"): async host output stored by the last kernel itself (measured slower: 1991 vs 2393 clouds/s)
 int g_act_f16 = 1;      // aprb_set_option("act_f16"): aprb_kfe_forward stores normalised activations in fp16 (needs kpconv_f16)
 int g_kpconv_f16 = 1;   // aprb_set_option("kpconv_f16"): aprb_kfe_forward runs KPConv with fp16 operands where a block provides them
 int g_fuse_stats = 1;   // aprb_set_option("fuse_stats"): aprb_kfe_forward hands GEMM-epilogue group statistics to the norms

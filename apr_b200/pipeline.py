@@ -152,6 +152,24 @@ class KFEPipeline:
         N.check(rc, "aprb_kfe_forward_host")
         return out[:rows.value]
 
+    def forward_host_async(self, points, lengths, out):
+        """Like forward_host, but returns as soon as the call is queued: (view of `out`, ticket). The encoder output
+        lands in `out` (pinned host tensor [>= N_last, C]) through a side stream while the next call — which must use a
+        different `out` — already runs; `wait_host(ticket)` blocks until this call's output is complete. At most two
+        calls in flight per pipeline."""
+        pts, lens = points.float().contiguous(), lengths.int().contiguous()
+        n, b = pts.shape[0], lens.shape[0]
+        rows, cols, ticket = C.c_int(), C.c_int(), C.c_int()
+        rc = self._call(lambda arena: self.lib.aprb_kfe_forward_host_async(
+            self.handle, pts.data_ptr(), lens.data_ptr(), n, b, arena.data_ptr(), arena.numel(), out.data_ptr(), out.shape[0],
+            C.byref(rows), C.byref(cols), C.byref(ticket), C.c_void_p(self.stream.cuda_stream)), n, b)
+        N.check(rc, "aprb_kfe_forward_host_async")
+        self._last_host_inputs = (pts, lens)                         # keep the host buffers alive until the copy ran
+        return out[:rows.value], ticket.value
+
+    def wait_host(self, ticket):
+        N.check(self.lib.aprb_kfe_wait_host(self.handle, int(ticket)), "aprb_kfe_wait_host")
+
     def pyramid(self):
         """The batch dict of the last forward (views into the arena): points, neighbors, pools, upsamples, stack_lengths."""
         out = dict(points=[], neighbors=[], pools=[], upsamples=[], stack_lengths=[])

@@ -262,6 +262,14 @@ int aprb_kfe_forward(aprb_kfe* h, const float* d_pts, const int32_t* d_lens, con
 int aprb_kfe_forward_host(aprb_kfe* h, const float* h_pts, const int32_t* h_lens, int N, int B, void* d_arena,
                           size_t arena_bytes, float* h_out, int h_out_rows_cap, int* out_rows, int* out_cols,
                           void* stream);
+/* Asynchronous form of the same call: returns once everything is queued. The final block writes into one of two device
+ * buffers owned by the handle and a side stream copies it to h_out when the path is done, so the next call (other
+ * buffer, other host buffer) can be queued and run while this output is still crossing PCIe. aprb_kfe_wait_host(h, t)
+ * blocks until the copy of the call that returned ticket t has landed. At most two calls in flight per handle. */
+int aprb_kfe_forward_host_async(aprb_kfe* h, const float* h_pts, const int32_t* h_lens, int N, int B, void* d_arena,
+                                size_t arena_bytes, float* h_out, int h_out_rows_cap, int* out_rows, int* out_cols,
+                                int* ticket, void* stream);
+int aprb_kfe_wait_host(aprb_kfe* h, int ticket);
 /* After a forward: pyramid tensors in the arena. what: 0 = points [n,3] f32, 1 = neighbors, 2 = pools, 3 = upsamples
  * (int32 [n, limit]), 4 = stack lengths [B] i32. Pointers stay valid until the next forward on this handle. */
 int aprb_kfe_get(const aprb_kfe* h, int what, int level, const void** d_ptr, int* rows, int* cols);

@@ -408,8 +408,20 @@ def test_native_pipeline_matches_module_path(cuda, oracle):
             else:
                 assert np.array_equal(d[:, :w.shape[1]], w), (k, lvl)
     # host-buffer entry point (H2D + path + D2H)
-    host = pipe.forward_host(torch.from_numpy(p0).pin_memory(), torch.from_numpy(l0).pin_memory())
+    hp, hl = torch.from_numpy(p0).pin_memory(), torch.from_numpy(l0).pin_memory()
+    host = pipe.forward_host(hp, hl)
     assert torch.equal(host, got.cpu())
+    # asynchronous host entry point: two calls in flight, results awaited one call later, ping-pong device/host buffers
+    bufs = [torch.empty((got.shape[0] + 7, got.shape[1]), dtype=torch.float32).pin_memory() for _ in range(2)]
+    pending = []
+    for c in range(5):
+        y, ticket = pipe.forward_host_async(hp, hl, bufs[c & 1])
+        if pending:
+            pipe.wait_host(pending[1])
+            assert torch.equal(pending[0], got.cpu())
+        pending = (y, ticket)
+    pipe.wait_host(pending[1])
+    assert torch.equal(pending[0], got.cpu())
     # vs the fp32 CPU oracle end to end (drift over 11 blocks, TF32 tensor path): reported, loose bound
     cpu = dict(points=[torch.from_numpy(p) for p in ref["points"]], neighbors=[torch.from_numpy(n).long() for n in ref["neighbors"]],
                pools=[torch.from_numpy(n).long() for n in ref["pools"]], features=torch.ones(len(p0), 1))
