@@ -18,6 +18,17 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl refere
 import torch
 import torch.nn.functional as F
 
+# The oracle is the fp32 statement of the reference: pin the CPU (oneDNN) backends to IEEE fp32 — a host whose oneDNN
+# defaults to a reduced-precision fp32 math mode would otherwise move the yardstick itself by ~1e-4. CUDA settings are
+# not touched.
+for _mod in ("torch.backends.mkldnn", "torch.backends.mkldnn.matmul", "torch.backends.mkldnn.conv"):
+    try:
+        _m = eval(_mod)
+        if hasattr(_m, "fp32_precision"):
+            _m.fp32_precision = "ieee"
+    except Exception:
+        pass
+
 
 def kpconv_ref(q_pts, s_pts, inds, x, kernel_points, weights, extent):
     inds = inds.long()
