@@ -54,6 +54,9 @@ SIGNATURES = {
     "aprb_instnorm_lrelu_seg_f16": (_i, [_p, _i, _i, _p, _i, _f, _f, _p, _i, _i, _i, _p, _i, _p, _p, _p, _sz, _p]),
     "aprb_max_pool_f16": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "aprb_linear_f16_stats": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
+    "aprb_linear_f16_stats_ragged": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _i, _p]),
+    "aprb_instnorm_seg_stats": (_i, [_p, _p, _i, _i, _p, _i, _f, _p, _p, _p, _p]),
+    "aprb_linear_f16_norm_apply": (_i, [_p, _p, _i, _i, _i, _p, _p, _i, _p, _p, _i, _p, _f, _p, _i, _p]),
     "aprb_f32_to_f16": (_i, [_p, _p, _sz, _p]),
     "aprb_round_tf32": (_i, [_p, _p, _sz, _p]),
     "aprb_kfe_create": (_i, [_p, _p, _i, _p]),

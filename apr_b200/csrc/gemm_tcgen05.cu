@@ -15,6 +15,7 @@
 // 1e-3 parity budget needs it), accumulation is fp32 in TMEM. Out-of-range rows/cols are zero-filled by TMA and masked
 // in the epilogue, so M and N need no padding (N % 16 == 0, K % 32 == 0 required).
 #include "tc_common.cuh"
+#include <cuda_fp16.h>
 
 namespace aprb {
 
@@ -308,6 +309,307 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     }
 }
 
+
+// ---- recompute path: GEMM whose epilogue IS the normalisation -------------------------------------------------------
+// For the small-K Linears that end a ResnetBottleneckBlock (unary2: C/4 -> C, shortcut: C_in -> C; blocks.py:669-681) the
+// fp32 output is the largest tensor of the block and exists only to be standardised: written (4C bytes/row), read
+// back by the normalisation (4C) and rewritten in fp16 (2C). Recomputing the product is cheaper than that round trip.
+// gemm_nrm_f16_kernel runs twice:
+//   STATS : the contraction, of which only the per-32-row-group column statistics (mean, M2) leave the SM — plus the
+//           rows the normalisation must read from the tensor itself: the ragged last group and the groups that
+//           straddle a segment boundary seg_off[1..S-1];
+//   apply : the contraction again — bit-identical accumulators: same operands, same K order — finished as
+//             y = LeakyReLU( (acc - mean) * rstd  +  shortcut )      shortcut = fp16 residual rows, or, DUAL, a second
+//           product (x_sc @ W_sc^T - rmean) * rrstd accumulated by the same CTA in a second TMEM buffer,
+//           rounded to the 10-bit mantissa and stored in fp16 (fp32 for the encoder's final output).
+// These products have K = 64..1024, so a tile's main loop is short and the kernel lives in its epilogue: 8 epilogue
+// warps (two per TMEM lane quarter, 64 of the tile's 128 columns each) instead of the 4 of the general kernel, the
+// residual rows of a tile prefetched into registers before the accumulator is awaited, and statistics summed in four
+// independent chains. BN = 128; TMEM holds 2 (double buffer) x 1 or 2 accumulators = 256 / 512 columns.
+struct NrmArgs {
+    int M, N;
+    int nkb_main, nkb_sc;            // k-blocks (64 fp16) of the main product and of the shortcut product (0: none)
+    int num_n, total_tiles;
+    const int* seg_off;              // S + 1 row offsets of the normalisation segments, or NULL (one segment)
+    int S;
+    // STATS
+    float* gstat;                    // [ceil(M/32)][mean | M2][N]
+    float* C;                        // fp32 [M, N]: receives the ragged / straddling groups only
+    // apply
+    const float* stats;              // [S][nt][mean | rstd][N], nt = 1 + DUAL (tensor 0 = main, 1 = shortcut product)
+    const __half* res;               // optional plain fp16 residual [M, N]
+    float slope;
+    void* out;
+    int out16;
+};
+
+struct GemmNCfg {
+    static constexpr int BN = 128;
+    static constexpr int STAGES = 5;
+    static constexpr int A_BYTES = GEMM_BM * 128;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int EPI_WARPS = 8;
+    static constexpr int TBUF = EPI_WARPS * 32 * 36 * 4;
+    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + TBUF + 1024 + 256;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+};
+
+__device__ __forceinline__ float nrm_act_round(float v, float slope) {
+    v = v >= 0.f ? v : v * slope;
+    unsigned u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    return __uint_as_float(u);
+}
+
+template <bool DUAL, bool STATS>
+__global__ void __launch_bounds__(GemmNCfg::THREADS, 1)
+gemm_nrm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const NrmArgs p) {
+    using Cfg = GemmNCfg;
+    constexpr int BN = Cfg::BN, STAGES = Cfg::STAGES;
+    constexpr int ACC = DUAL ? 2 * BN : BN;                          // TMEM columns per tile (main | shortcut)
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t sA = base, sB = base + STAGES * Cfg::A_BYTES;
+    const uint32_t tb = sB + STAGES * Cfg::B_BYTES;
+    const uint32_t bars = tb + Cfg::TBUF;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES, bar_tfull = bars + 16 * STAGES, bar_tempty = bar_tfull + 16;
+    __shared__ uint32_t s_tmem_base;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int M = p.M, N = p.N;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, Cfg::EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        if (DUAL) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB2) : "memory");
+        }
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "n"(2 * ACC));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {                                             // ===== TMA producer =====
+            int s = 0; uint32_t ph = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const int m0 = (t / p.num_n) * GEMM_BM, n0 = (t % p.num_n) * BN;
+                if (DUAL)
+                    for (int kb = 0; kb < p.nkb_sc; ++kb) {
+                        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                        mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::A_BYTES + Cfg::B_BYTES);
+                        tma_load_2d(sA + s * Cfg::A_BYTES, &tmA2, bar_full + 8 * s, kb * 64, m0);
+                        tma_load_2d(sB + s * Cfg::B_BYTES, &tmB2, bar_full + 8 * s, kb * 64, n0);
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
+                    }
+                for (int kb = 0; kb < p.nkb_main; ++kb) {
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::A_BYTES + Cfg::B_BYTES);
+                    tma_load_2d(sA + s * Cfg::A_BYTES, &tmA, bar_full + 8 * s, kb * 64, m0);
+                    tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, bar_full + 8 * s, kb * 64, n0);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                             // ===== MMA issuer =====
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);   // F16 x F16 -> F32
+            int s = 0; uint32_t ph = 0;
+            int i = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
+                const int ab = i & 1;
+                mbar_wait(bar_tempty + 8 * ab, ((uint32_t)(i >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t acc_main = tmem_base + (uint32_t)(ab * ACC), acc_sc = acc_main + BN;
+                if (DUAL)
+                    for (int kb = 0; kb < p.nkb_sc; ++kb) {
+                        mbar_wait(bar_full + 8 * s, ph);
+                        tc_fence_after();
+                        const uint64_t da = make_smem_desc(sA + s * Cfg::A_BYTES), db = make_smem_desc(sB + s * Cfg::B_BYTES);
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) tc_mma_f16(acc_sc, da + 2 * k4, db + 2 * k4, idesc, (kb | k4) != 0);
+                        tc_commit(bar_empty + 8 * s);
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
+                    }
+                for (int kb = 0; kb < p.nkb_main; ++kb) {
+                    mbar_wait(bar_full + 8 * s, ph);
+                    tc_fence_after();
+                    const uint64_t da = make_smem_desc(sA + s * Cfg::A_BYTES), db = make_smem_desc(sB + s * Cfg::B_BYTES);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) tc_mma_f16(acc_main, da + 2 * k4, db + 2 * k4, idesc, (kb | k4) != 0);
+                    tc_commit(bar_empty + 8 * s);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                tc_commit(bar_tfull + 8 * ab);
+            }
+        }
+    } else {                                                         // ===== epilogue (warps 2..9) =====
+        const int quarter = warp & 3;                                // TMEM lane quarter this warp may read
+        const int chalf = (warp - 2) >> 2;                           // which 64 of the tile's 128 columns
+        float* tbuf = reinterpret_cast<float*>(smem_raw + (tb - raw)) + (size_t)(warp - 2) * 32 * 36;
+        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+        constexpr int NT = DUAL ? 2 : 1;
+        int i = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
+            const int ab = i & 1;
+            const int m0 = (t / p.num_n) * GEMM_BM, n0 = (t % p.num_n) * BN;
+            const int g0 = m0 + quarter * 32;                        // first row of this warp's 32-row group
+            const float* stp = nullptr;
+            bool store = true, whole = true;
+            uint2 rq[2][8];
+            if (STATS) {
+                whole = g0 + 32 <= M;
+                if (whole) {                                         // straddles: some segment starts in (g0, g0 + 31]
+                    bool hit = false;
+                    for (int s0 = 1; s0 < p.S; s0 += 32) {
+                        const int s = s0 + lane;
+                        const int o = (s < p.S && p.seg_off) ? p.seg_off[s] : -1;
+                        hit |= (o > g0 && o <= g0 + 31);
+                    }
+                    store = __any_sync(0xffffffffu, hit);
+                }
+            } else {
+                // this thread's accumulator row and the normalisation segment it belongs to
+                const int row = min(g0 + lane, M - 1);
+                const int seg = (p.seg_off && p.S > 1) ? find_cloud(p.seg_off, p.S, row) : 0;
+                stp = p.stats + (size_t)seg * NT * 2 * N + n0;
+                if (!DUAL && p.res) {                                // residual rows of the tile: in flight before the wait
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int c = chalf * 64 + cc * 32;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int grow = g0 + k * 4 + sub_r;
+                            rq[cc][k] = (grow < M && n0 + c + sub_c < N)
+                                            ? __ldg(reinterpret_cast<const uint2*>(p.res + (size_t)grow * N + n0 + c + sub_c))
+                                            : make_uint2(0u, 0u);
+                        }
+                    }
+                }
+            }
+            mbar_wait(bar_tfull + 8 * ab, (uint32_t)(i >> 1) & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c = chalf * 64 + cc * 32;
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * ACC + c), v);
+                if (STATS) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(tbuf + lane * 36 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                                      __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                } else if (DUAL) {
+                    uint32_t w[32];
+                    tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * ACC + BN + c), w);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (n0 + c + j < N) {
+                            const float4 mean = __ldg(reinterpret_cast<const float4*>(stp + c + j));
+                            const float4 rstd = __ldg(reinterpret_cast<const float4*>(stp + N + c + j));
+                            const float4 rmean = __ldg(reinterpret_cast<const float4*>(stp + 2 * (size_t)N + c + j));
+                            const float4 rrstd = __ldg(reinterpret_cast<const float4*>(stp + 3 * (size_t)N + c + j));
+                            o.x = fmaf(__uint_as_float(w[j]) - rmean.x, rrstd.x, (__uint_as_float(v[j]) - mean.x) * rstd.x);
+                            o.y = fmaf(__uint_as_float(w[j + 1]) - rmean.y, rrstd.y, (__uint_as_float(v[j + 1]) - mean.y) * rstd.y);
+                            o.z = fmaf(__uint_as_float(w[j + 2]) - rmean.z, rrstd.z, (__uint_as_float(v[j + 2]) - mean.z) * rstd.z);
+                            o.w = fmaf(__uint_as_float(w[j + 3]) - rmean.w, rrstd.w, (__uint_as_float(v[j + 3]) - mean.w) * rstd.w);
+                        }
+                        *reinterpret_cast<float4*>(tbuf + lane * 36 + j) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (n0 + c + j < N) {
+                            const float4 mean = __ldg(reinterpret_cast<const float4*>(stp + c + j));
+                            const float4 rstd = __ldg(reinterpret_cast<const float4*>(stp + N + c + j));
+                            o.x = (__uint_as_float(v[j]) - mean.x) * rstd.x;
+                            o.y = (__uint_as_float(v[j + 1]) - mean.y) * rstd.y;
+                            o.z = (__uint_as_float(v[j + 2]) - mean.z) * rstd.z;
+                            o.w = (__uint_as_float(v[j + 3]) - mean.w) * rstd.w;
+                        }
+                        *reinterpret_cast<float4*>(tbuf + lane * 36 + j) = o;
+                    }
+                }
+                __syncwarp();
+                if (STATS) {
+                    if (store && n0 + c + sub_c < N) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int r = k * 4 + sub_r, grow = g0 + r;
+                            if (grow < M)
+                                *reinterpret_cast<float4*>(p.C + (size_t)grow * N + n0 + c + sub_c) = *reinterpret_cast<const float4*>(tbuf + r * 36 + sub_c);
+                        }
+                    }
+                    if (whole && n0 + c + lane < N) {                // lane = column: four independent chains over the rows
+                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                        for (int r = 0; r < 32; r += 4) {
+                            s0 += tbuf[r * 36 + lane]; s1 += tbuf[(r + 1) * 36 + lane];
+                            s2 += tbuf[(r + 2) * 36 + lane]; s3 += tbuf[(r + 3) * 36 + lane];
+                        }
+                        const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / 32.0f);
+                        float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+                        for (int r = 0; r < 32; r += 4) {
+                            const float d0 = tbuf[r * 36 + lane] - mean, d1 = tbuf[(r + 1) * 36 + lane] - mean;
+                            const float d2 = tbuf[(r + 2) * 36 + lane] - mean, d3 = tbuf[(r + 3) * 36 + lane] - mean;
+                            q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+                        }
+                        float* gp = p.gstat + (size_t)(g0 >> 5) * 2 * N + n0 + c + lane;
+                        gp[0] = mean; gp[N] = (q0 + q1) + (q2 + q3);
+                    }
+                } else if (n0 + c + sub_c < N) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int r = k * 4 + sub_r, grow = g0 + r;
+                        if (grow < M) {
+                            float4 o = *reinterpret_cast<const float4*>(tbuf + r * 36 + sub_c);
+                            const size_t e = (size_t)grow * N + n0 + c + sub_c;
+                            if (!DUAL && p.res) {
+                                const float2 q0 = __half22float2(*reinterpret_cast<const __half2*>(&rq[cc][k].x));
+                                const float2 q1 = __half22float2(*reinterpret_cast<const __half2*>(&rq[cc][k].y));
+                                o.x += q0.x; o.y += q0.y; o.z += q1.x; o.w += q1.y;
+                            }
+                            o.x = nrm_act_round(o.x, p.slope); o.y = nrm_act_round(o.y, p.slope);
+                            o.z = nrm_act_round(o.z, p.slope); o.w = nrm_act_round(o.w, p.slope);
+                            if (p.out16) {
+                                const __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+                                uint2 u;
+                                u.x = *reinterpret_cast<const uint32_t*>(&h0); u.y = *reinterpret_cast<const uint32_t*>(&h1);
+                                *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + e) = u;
+                            } else {
+                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + e) = o;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * ab);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * ACC));
+    }
+}
+
 // C[m,n] = (sum_s part[s,m,n]) * rowscale[m]; fixed summation order (deterministic split-K)
 __global__ void splitk_reduce_kernel(const float4* __restrict__ part, int splits, size_t mn4, int n4,
                                      const float* __restrict__ rowscale, float4* __restrict__ C) {
@@ -449,6 +751,7 @@ extern int g_act_f16;
 extern int g_dbg_skip_d2h;
 extern int g_host_zero_copy;
 extern int g_kpconv_fused;
+extern int g_gemm_apply;
 int g_gemm_cluster = 1;   // 1 disables the cluster/multicast path (aprb_set_option)
 
 size_t gemm_tf32_ws_bytes(int M, int N) {   // split-K partial tiles (up to 8 splits), only when split-K can trigger
@@ -537,6 +840,69 @@ int gemm_f16_rowscale(const void* d_A, const void* d_Bt, int M, int N, int K, co
     return launch_gemm_persistent<64, true>(d_A, d_Bt, M, N, K, d_rowscale, d_C, d_gstat, st);
 }
 
+template <bool DUAL, bool STATS>
+static int launch_gemm_nrm(const void* A, const void* Bt, int K, const void* A2, const void* Bt2, int K2, NrmArgs p,
+                           cudaStream_t st) {
+    constexpr int BN = GemmNCfg::BN;
+    CUtensorMap tmA, tmB, tmA2, tmB2;
+    int rc = make_tmap_f16(&tmA, A, p.M, K, GEMM_BM);
+    if (rc) return rc;
+    rc = make_tmap_f16(&tmB, Bt, p.N, K, BN);
+    if (rc) return rc;
+    tmA2 = tmA; tmB2 = tmB;
+    if (DUAL) {
+        rc = make_tmap_f16(&tmA2, A2, p.M, K2, GEMM_BM);
+        if (rc) return rc;
+        rc = make_tmap_f16(&tmB2, Bt2, p.N, K2, BN);
+        if (rc) return rc;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        APRB_CUDA_OK(cudaFuncSetAttribute(gemm_nrm_f16_kernel<DUAL, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmNCfg::SMEM));
+        attr_set = true;
+    }
+    p.nkb_main = K / 64; p.nkb_sc = DUAL ? K2 / 64 : 0;
+    p.num_n = cdiv(p.N, BN); p.total_tiles = p.num_n * cdiv(p.M, GEMM_BM);
+    const int grid = min(p.total_tiles, sm_count());
+    {
+        ProfScope ps(STATS ? "gemm_nrm_stats_kernel" : "gemm_nrm_apply_kernel", st, 1);
+        gemm_nrm_f16_kernel<DUAL, STATS><<<grid, GemmNCfg::THREADS, GemmNCfg::SMEM, st>>>(tmA, tmB, tmA2, tmB2, p);
+    }
+    APRB_LAUNCH_OK();
+    return APRB_OK;
+}
+
+// Statistics pass of the recompute path: group statistics of A @ Bt^T; d_C receives the ragged / straddling groups only.
+int gemm_stats_f16(const void* d_A, const void* d_Bt, int M, int N, int K, const int* d_seg_off, int S, float* d_gstat,
+                   float* d_C, cudaStream_t st) {
+    if (!gemm_f16_supported(M, N, K) || N % 4 != 0) { set_error("gemm_stats_f16: unsupported shape M=%d N=%d K=%d", M, N, K); return APRB_ERR_UNSUPPORTED; }
+    if (((uintptr_t)d_A | (uintptr_t)d_Bt | (uintptr_t)d_C | (uintptr_t)d_gstat) & 15) { set_error("gemm_stats_f16: operands must be 16-byte aligned"); return APRB_ERR_INVALID; }
+    NrmArgs p = {};
+    p.M = M; p.N = N; p.seg_off = d_seg_off; p.S = S; p.gstat = d_gstat; p.C = d_C;
+    return launch_gemm_nrm<false, true>(d_A, d_Bt, K, nullptr, nullptr, 0, p, st);
+}
+
+// y = LeakyReLU((A @ Bt^T - mean) * rstd + shortcut), see gemm_nrm_f16_kernel. A2 / Bt2 (optional): the shortcut is a
+// second product standardised with stats tensor 1; res16 (optional, exclusive with A2): plain fp16 residual rows.
+int gemm_apply_f16(const void* d_A, const void* d_Bt, int M, int N, int K, const void* d_A2, const void* d_Bt2, int K2,
+                   const int* d_seg_off, int S, const float* d_stats, const void* d_res16, float slope, void* d_out,
+                   int out16, cudaStream_t st) {
+    if (!gemm_f16_supported(M, N, K) || N % 4 != 0 || (d_A2 && (K2 < 64 || K2 % 64 != 0))) {
+        set_error("gemm_apply_f16: unsupported shape M=%d N=%d K=%d K2=%d", M, N, K, K2);
+        return APRB_ERR_UNSUPPORTED;
+    }
+    if (((uintptr_t)d_A | (uintptr_t)d_Bt | (uintptr_t)d_out | (uintptr_t)d_stats | (uintptr_t)(d_A2 ? d_A2 : d_A) |
+         (uintptr_t)(d_Bt2 ? d_Bt2 : d_Bt) | (uintptr_t)(d_res16 ? d_res16 : d_A)) & 15) {
+        set_error("gemm_apply_f16: operands must be 16-byte aligned");
+        return APRB_ERR_INVALID;
+    }
+    NrmArgs p = {};
+    p.M = M; p.N = N; p.seg_off = d_seg_off; p.S = S; p.stats = d_stats; p.res = (const __half*)d_res16; p.slope = slope;
+    p.out = d_out; p.out16 = out16;
+    if (d_A2) return launch_gemm_nrm<true, false>(d_A, d_Bt, K, d_A2, d_Bt2, K2, p, st);
+    return launch_gemm_nrm<false, false>(d_A, d_Bt, K, nullptr, nullptr, 0, p, st);
+}
+
 }  // namespace aprb
 
 extern "C" int aprb_set_option(const char* name, int value) {
@@ -554,6 +920,7 @@ extern "C" int aprb_set_option(const char* name, int value) {
     if (strcmp(name, "dbg_skip_d2h") == 0) { g_dbg_skip_d2h = value; return APRB_OK; }
     if (strcmp(name, "host_zero_copy") == 0) { g_host_zero_copy = value; return APRB_OK; }
     if (strcmp(name, "kpconv_fused") == 0) { g_kpconv_fused = value; return APRB_OK; }
+    if (strcmp(name, "gemm_apply") == 0) { g_gemm_apply = value; return APRB_OK; }
     set_error("aprb_set_option: unknown option %s", name);
     return APRB_ERR_INVALID;
 }
@@ -578,6 +945,31 @@ extern "C" int aprb_linear_f16_stats(const void* d_x16, const void* d_W16, int N
     if (N == 0) return APRB_OK;
     APRB_REQUIRE(d_x16 && d_W16 && d_y, "null pointer");
     return gemm_f16_rowscale(d_x16, d_W16, N, Cout, Cin, nullptr, d_y, (cudaStream_t)stream, d_gstat, stats_written);
+}
+
+extern "C" int aprb_linear_f16_stats_ragged(const void* d_x16, const void* d_W16, int N, int Cin, int Cout, float* d_y,
+                                            float* d_gstat, const int32_t* d_seg_off, int S, void* stream) {
+    using namespace aprb;
+    APRB_REQUIRE(N >= 0 && Cin >= 1 && Cout >= 1 && S >= 1, "bad shape");
+    APRB_REQUIRE(S == 1 || d_seg_off, "segment offsets required when S > 1");
+    if (N == 0) return APRB_OK;
+    APRB_REQUIRE(d_x16 && d_W16 && d_y && d_gstat, "null pointer");
+    return gemm_stats_f16(d_x16, d_W16, N, Cout, Cin, d_seg_off, S, d_gstat, d_y, (cudaStream_t)stream);
+}
+
+extern "C" int aprb_linear_f16_norm_apply(const void* d_x16, const void* d_W16, int N, int Cin, int Cout,
+                                          const void* d_sc16, const void* d_Wsc16, int Csc, const void* d_res16,
+                                          const int32_t* d_seg_off, int S, const float* d_stats, float slope, void* d_y,
+                                          int out_is_f16, void* stream) {
+    using namespace aprb;
+    APRB_REQUIRE(N >= 0 && Cin >= 1 && Cout >= 1 && S >= 1, "bad shape");
+    APRB_REQUIRE(S == 1 || d_seg_off, "segment offsets required when S > 1");
+    APRB_REQUIRE((d_sc16 == nullptr) == (d_Wsc16 == nullptr), "shortcut operand and weights go together");
+    APRB_REQUIRE(!(d_sc16 && d_res16), "either a shortcut product or a plain residual, not both");
+    if (N == 0) return APRB_OK;
+    APRB_REQUIRE(d_x16 && d_W16 && d_y && d_stats, "null pointer");
+    return gemm_apply_f16(d_x16, d_W16, N, Cout, Cin, d_sc16, d_Wsc16, Csc, d_seg_off, S, d_stats, d_res16, slope, d_y,
+                          out_is_f16, (cudaStream_t)stream);
 }
 
 extern "C" size_t aprb_group_stats_bytes(int N, int C) {

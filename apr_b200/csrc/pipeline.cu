@@ -16,6 +16,7 @@ extern int g_kpconv_f16;
 extern int g_act_f16;
 extern int g_dbg_skip_d2h;
 extern int g_host_zero_copy;
+extern int g_gemm_apply;
 }
 
 struct aprb_kfe {
@@ -261,13 +262,38 @@ int run_block16(const aprb_kfe& h, size_t bi, const void* feat, bool feat16, boo
     KFE_OK(norm16_call(h, lq, t2raw, nq, mid, nullptr, 0, 0, t2, 1, &g2, nullptr, A, st));
     KFE_ALLOC(t3, float, (size_t)nq * cout);
     KFE_GSTAT(g3, nq, cout);
-    KFE_OK(aprb_linear_f16_stats(t2, w16[1], nq, mid, cout, t3, g3.buf, g3.buf ? &g3.written : nullptr, st));
     const void* sc = feat;
     if (b.strided) {
         KFE_ALLOC(mp, float, (size_t)nq * b.in_dim / 2 + 8);
         KFE_OK(aprb_max_pool_f16(feat, idx, H, nq, ns, H, b.in_dim, mp, st));
         sc = mp;
     }
+    // Measured per block shape (tools/nrm_bench.py, profiles/r01_nrm_recompute.txt): recomputing wins while the products
+    // are HBM-bound (1.15-1.41x for K_main + K_shortcut <= 1024) and loses once the repeated contraction is the cost
+    // (0.86x at 512 + 1024 -> 2048, the last shortcut block): those keep the stored path.
+    const int k_total = mid + (b.shortcut_W ? b.in_dim : 0);
+    if (aprb::g_gemm_apply && g3.buf && (k_total <= 1024 || aprb::g_gemm_apply > 1)) {
+        // Recompute path (include/aprb200.h, aprb_linear_f16_norm_apply): the [nq, cout] fp32 outputs of unary2 and of the
+        // shortcut Linear are never materialised — statistics pass, per-segment mean / rstd, then the contraction again
+        // with the normalisation, the shortcut and the activation in its epilogue. t3 / t4 only receive the ragged rows.
+        const int nt = b.shortcut_W ? 2 : 1;
+        KFE_OK(aprb_linear_f16_stats_ragged(t2, w16[1], nq, mid, cout, t3, g3.buf, h.seg[lq], h.S, st));
+        float* t4 = nullptr; GStat g4;
+        if (b.shortcut_W) {
+            t4 = A.take<float>((size_t)nq * cout);
+            g4.buf = (float*)A.take<char>(aprb_group_stats_bytes(nq, cout));
+            if (!t4 || !g4.buf) { set_error("aprb_kfe_forward: arena too small (need > %zu bytes)", A.cap); return APRB_ERR_WORKSPACE; }
+            KFE_OK(aprb_linear_f16_stats_ragged(sc, w16[2], nq, b.in_dim, cout, t4, g4.buf, h.seg[lq], h.S, st));
+        }
+        KFE_ALLOC(stt, float, (size_t)h.S * nt * 2 * cout);
+        KFE_OK(aprb_instnorm_seg_stats(t3, t4, nq, cout, h.seg[lq], h.S, 1e-5f, g3.buf, g4.buf, stt, st));
+        KFE_OK(aprb_linear_f16_norm_apply(t2, w16[1], nq, mid, cout, b.shortcut_W ? sc : nullptr, b.shortcut_W ? w16[2] : nullptr,
+                                          b.in_dim, b.shortcut_W ? nullptr : sc, h.seg[lq], h.S, stt, 0.1f, y, out16, st));
+        A.off = mark;
+        *out = y; *out_cols = cout;
+        return APRB_OK;
+    }
+    KFE_OK(aprb_linear_f16_stats(t2, w16[1], nq, mid, cout, t3, g3.buf, g3.buf ? &g3.written : nullptr, st));
     if (b.shortcut_W) {
         KFE_ALLOC(t4, float, (size_t)nq * cout);
         KFE_GSTAT(g4, nq, cout);

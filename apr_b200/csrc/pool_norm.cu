@@ -746,6 +746,7 @@ int g_host_zero_copy = 0;   // aprb_set_option("host_zero_copy"): async host out
 int g_act_f16 = 1;      // aprb_set_option("act_f16"): aprb_kfe_forward stores normalised activations in fp16 (needs kpconv_f16)
 int g_kpconv_f16 = 1;   // aprb_set_option("kpconv_f16"): aprb_kfe_forward runs KPConv with fp16 operands where a block provides them
 int g_fuse_stats = 1;   // aprb_set_option("fuse_stats"): aprb_kfe_forward hands GEMM-epilogue group statistics to the norms
+int g_gemm_apply = 1;   // aprb_set_option("gemm_apply"): unary2 / shortcut Linears are recomputed with the normalisation in the epilogue
 
 }  // namespace aprb
 
@@ -762,6 +763,27 @@ extern "C" size_t aprb_instnorm_seg_ws_bytes(int N, int C, int S) {
     if (C < 1 || S < 1) return 0;
     return 2 * align256((size_t)2 * S * NORM_SEG_MAX_CH * C * sizeof(float)) + align256((size_t)4 * S * C * sizeof(float)) +
            align256((size_t)2 * S * (C / 4 + 1) * sizeof(int)) + 256;
+}
+
+// Statistics only: d_stats[seg][t][mean | rstd][C] (t = 0 for d_x, 1 for d_x2 when given) from the producers' group
+// partials; the tensors themselves are read only at the ragged rows of each segment (aprb_linear_f16_stats_ragged wrote
+// exactly those). Consumed by aprb_linear_f16_norm_apply.
+extern "C" int aprb_instnorm_seg_stats(const float* d_x, const float* d_x2, int N, int C, const int32_t* d_seg_off, int S,
+                                       float eps, const float* d_gstat_x, const float* d_gstat_x2, float* d_stats,
+                                       void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    APRB_REQUIRE(N >= 0 && C >= 4 && C % 4 == 0 && S >= 1, "bad shape (C % 4 == 0)");
+    APRB_REQUIRE(S == 1 || d_seg_off, "segment offsets required when S > 1");
+    APRB_REQUIRE((d_x2 == nullptr) == (d_gstat_x2 == nullptr), "second tensor and its group statistics go together");
+    if (N == 0) return APRB_OK;
+    APRB_REQUIRE(d_x && d_gstat_x && d_stats, "null pointer");
+    const int nt = d_x2 ? 2 : 1, Cq = C / 4;
+    int Wg = 1;
+    while (Wg < Cq && Wg < 8) Wg <<= 1;
+    APRB_TIMED("norm_seg_groups_kernel", st, 1, (norm_seg_groups_kernel<<<dim3(cdiv(Cq, Wg), S * nt), 256, 0, st>>>(
+        d_x, d_x2, d_gstat_x, d_gstat_x2, d_seg_off, N, C, Wg, nt, 0, nt, eps, d_stats)));
+    APRB_LAUNCH_OK();
+    return APRB_OK;
 }
 
 extern "C" int aprb_instnorm_lrelu_seg(const float* d_x, int N, int C, const int32_t* d_seg_off, int S, float eps,

@@ -188,6 +188,24 @@ int aprb_instnorm_lrelu_seg_f16(const float* d_x, int N, int C, const int32_t* d
 /* max_pool on fp16 features (C a multiple of 128, <= 1024; int32 indices). */
 int aprb_max_pool_f16(const void* d_x16, const int32_t* d_idx, int ld_idx, int Nq, int Ns, int H, int C,
                       void* d_out16, void* stream);
+/* Recompute path for the Linears that end a ResnetBottleneckBlock (unary2 and the shortcut Linear, each followed by
+ * BatchNormBlock = InstanceNorm, models/blocks.py:496-510, :669-681): their fp32 output exists only to be standardised,
+ * so it is never materialised. Three calls replace Linear -> norm -> (+ shortcut) -> LeakyReLU:
+ *  1. aprb_linear_f16_stats_ragged: the product's group statistics (as aprb_linear_f16_stats); d_y receives only the
+ *     rows the statistics need from the tensor itself (the ragged last 32-row group and the groups that straddle a
+ *     segment boundary), everything else of d_y is left untouched;
+ *  2. aprb_instnorm_seg_stats: d_stats[seg][t][mean | rstd][C] for one (d_x2 == NULL) or two tensors;
+ *  3. aprb_linear_f16_norm_apply: repeats the contraction (bit-identical accumulators) and stores
+ *       y = LeakyReLU((x16 @ W16^T - mean) * rstd + shortcut), rounded to the 10-bit mantissa, fp16 or fp32,
+ *     where shortcut = d_res16 (plain fp16 rows), or (d_sc16 @ d_Wsc16^T - mean1) * rstd1 with tensor 1 of d_stats,
+ *     or nothing. Cin, Csc % 64 == 0, Cout % 16 == 0. Same values as the three-kernel sequence. */
+int aprb_linear_f16_stats_ragged(const void* d_x16, const void* d_W16, int N, int Cin, int Cout, float* d_y,
+                                 float* d_gstat, const int32_t* d_seg_off, int S, void* stream);
+int aprb_instnorm_seg_stats(const float* d_x, const float* d_x2, int N, int C, const int32_t* d_seg_off, int S, float eps,
+                            const float* d_gstat_x, const float* d_gstat_x2, float* d_stats, void* stream);
+int aprb_linear_f16_norm_apply(const void* d_x16, const void* d_W16, int N, int Cin, int Cout, const void* d_sc16,
+                               const void* d_Wsc16, int Csc, const void* d_res16, const int32_t* d_seg_off, int S,
+                               const float* d_stats, float slope, void* d_y, int out_is_f16, void* stream);
 /* y (fp32) = x16 @ W16^T with fp16 operands on tcgen05 (Cin % 64 == 0, Cout % 16 == 0) + group statistics of y. */
 int aprb_linear_f16_stats(const void* d_x16, const void* d_W16, int N, int Cin, int Cout, float* d_y,
                           float* d_gstat, int* stats_written, void* stream);

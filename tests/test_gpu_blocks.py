@@ -432,6 +432,122 @@ def test_native_pipeline_matches_module_path(cuda, oracle):
     assert e < 1e-2
 
 
+def test_linear_norm_apply_recompute_equals_three_kernel_sequence(cuda):
+    """Recompute path of the block-closing Linears (aprb_linear_f16_stats_ragged -> aprb_instnorm_seg_stats ->
+    aprb_linear_f16_norm_apply: the fp32 product is never materialised) == Linear -> segmented InstanceNorm (+ plain
+    fp16 residual | + standardised shortcut product) -> LeakyReLU through the stored fp32 tensor. Same accumulators; the
+    group statistics are summed in a different order and the shortcut is added unfused (as the reference does), so
+    the two agree up to fp32 round-off, which the 10-bit rounding of the stored activation turns into a rare one-ulp
+    (2^-10) difference. Segment bounds unaligned to the 32-row groups, shorter than a group, empty; fp16 and fp32
+    outputs. The product buffer is poisoned with NaN first: only the ragged rows may be read."""
+    from apr_b200 import _native
+    L = _native.lib()
+    P, sp = _native.ptr, _native.stream_ptr
+    gen = torch.Generator().manual_seed(5)
+    cases = ((5000, 64, 256, 128, [0, 1234, 1250, 1250, 3001, 5000]), (700, 128, 512, 256, [0, 700]),
+             (4097, 64, 128, 64, [0, 31, 64, 4097]), (40, 64, 64, 64, [0, 7, 40]), (20000, 256, 1024, 512, [0, 9000, 20000]))
+    for n, cin, cout, csc, bounds in cases:
+        S = len(bounds) - 1
+        x = torch.nn.functional.leaky_relu(torch.randn(n, cin, generator=gen), 0.1).half().to(cuda)
+        w = (torch.randn(cout, cin, generator=gen) / np.sqrt(cin)).half().to(cuda)
+        xs = torch.randn(n, csc, generator=gen).half().to(cuda)
+        ws = (torch.randn(cout, csc, generator=gen) / np.sqrt(csc)).half().to(cuda)
+        res = torch.randn(n, cout, generator=gen).half().to(cuda)
+        seg = torch.tensor(bounds, dtype=torch.int32, device=cuda)
+        gbytes = int(L.aprb_group_stats_bytes(n, cout))
+        ws_norm = torch.empty(int(L.aprb_instnorm_seg_ws_bytes(n, cout, S)), dtype=torch.uint8, device=cuda)
+
+        def old(variant, out16):
+            y = torch.empty(n, cout, device=cuda); g = torch.empty(gbytes // 4, device=cuda)
+            wr = _native.C.c_int(0)
+            _native.check(L.aprb_linear_f16_stats(P(x), P(w), n, cin, cout, P(y), P(g), _native.C.byref(wr), sp()), "linear")
+            assert wr.value == 1
+            y2 = g2 = None
+            if variant == "dual":
+                y2 = torch.empty(n, cout, device=cuda); g2 = torch.empty(gbytes // 4, device=cuda)
+                _native.check(L.aprb_linear_f16_stats(P(xs), P(ws), n, csc, cout, P(y2), P(g2), _native.C.byref(wr), sp()), "linear")
+            out = torch.empty(n, cout, dtype=torch.float16 if out16 else torch.float32, device=cuda)
+            r = {"dual": y2, "res": res, "none": None}[variant]
+            _native.check(L.aprb_instnorm_lrelu_seg_f16(P(y), n, cout, P(seg), S, 1e-5, 0.1, P(r), 1 if variant == "res" else 0,
+                                                        1 if variant == "dual" else 0, 1, P(out), out16, P(g), P(g2),
+                                                        P(ws_norm), ws_norm.numel(), sp()), "norm")
+            return out
+
+        def new(variant, out16):
+            y = torch.full((n, cout), float("nan"), device=cuda); g = torch.empty(gbytes // 4, device=cuda)
+            _native.check(L.aprb_linear_f16_stats_ragged(P(x), P(w), n, cin, cout, P(y), P(g), P(seg), S, sp()), "ragged")
+            y2 = g2 = None
+            if variant == "dual":
+                y2 = torch.full((n, cout), float("nan"), device=cuda); g2 = torch.empty(gbytes // 4, device=cuda)
+                _native.check(L.aprb_linear_f16_stats_ragged(P(xs), P(ws), n, csc, cout, P(y2), P(g2), P(seg), S, sp()), "ragged")
+            nt = 2 if variant == "dual" else 1
+            st = torch.empty(S * nt * 2 * cout, device=cuda)
+            _native.check(L.aprb_instnorm_seg_stats(P(y), P(y2), n, cout, P(seg), S, 1e-5, P(g), P(g2), P(st), sp()), "stats")
+            out = torch.empty(n, cout, dtype=torch.float16 if out16 else torch.float32, device=cuda)
+            _native.check(L.aprb_linear_f16_norm_apply(P(x), P(w), n, cin, cout, P(xs) if variant == "dual" else None,
+                                                       P(ws) if variant == "dual" else None, csc,
+                                                       P(res) if variant == "res" else None, P(seg), S, P(st), 0.1, P(out),
+                                                       out16, sp()), "apply")
+            frac_nan = torch.isnan(y).float().mean().item()
+            return out, frac_nan
+
+        for variant in ("none", "res", "dual"):
+            for out16 in (1, 0):
+                a = old(variant, out16)
+                b, frac_nan = new(variant, out16)
+                torch.cuda.synchronize()
+                assert torch.isfinite(b.float()).all(), (n, variant, out16)
+                af, bf = a.float(), b.float()
+                assert rel(bf, af) < 2e-5, (n, cin, cout, variant, out16, rel(bf, af))
+                assert ((af - bf).abs() <= 2.0 ** -10 * torch.maximum(af.abs(), bf.abs()) + 1e-6).all(), (n, variant, out16)
+                if n >= 4097:
+                    assert frac_nan > 0.9                            # the product really was not materialised
+        # and against torch for the plain-residual variant, segment by segment (fp16 operands, fp32 math)
+        b, _ = new("res", 0)
+        yf = x.float() @ w.float().t()
+        for s0, s1 in zip(bounds[:-1], bounds[1:]):
+            if s1 > s0:
+                ys = yf[s0:s1]
+                ref = (ys - ys.mean(0)) / torch.sqrt(ys.var(0, unbiased=False) + 1e-5) + res[s0:s1].float()
+                ref = torch.nn.functional.leaky_relu(ref, 0.1)
+                assert rel(b[s0:s1], ref) < 6e-4                     # 10-bit mantissa rounding of the stored activation
+
+
+def test_native_pipeline_recompute_path_equals_stored_path(cuda, oracle):
+    """aprb_kfe_forward with the recompute path (default) vs with the stored fp32 products (gemm_apply = 0), single pair
+    and super-batch of three pairs (segment bounds inside tiles): equal up to the re-rounding drift of 11 blocks."""
+    from apr_b200 import _native, synth
+    from apr_b200.pipeline import KFEPipeline
+    cfg = kitti_config()
+    limits = [30, 31, 32, 33]
+    torch.manual_seed(0); np.random.seed(0)
+    enc = KPFCNNEncoder(cfg).to(cuda).eval()
+    pairs = []
+    for sd, (na, nb) in enumerate([(3000, 2600), (1800, 3300), (2500, 2500)]):
+        a, b = synth.small_cloud(81 + 2 * sd, na), synth.small_cloud(82 + 2 * sd, nb)
+        pairs.append(oracle.subsample_batch(np.concatenate([a, b]), np.array([len(a), len(b)], np.int32), sampleDl=0.3))
+    setopt = lambda v: _native.check(_native.lib().aprb_set_option(b"gemm_apply", v), "aprb_set_option")
+    for cps, sel in ((0, pairs[:1]), (2, pairs)):
+        P0 = np.concatenate([p for p, _ in sel]); L0 = np.concatenate([l for _, l in sel])
+        pipe = KFEPipeline(enc, cfg, limits, clouds_per_segment=cps)
+        got = pipe.forward(_t(P0, cuda), _t(L0, cuda)).clone()
+        n1 = _native.launch_count()
+        pipe.forward(_t(P0, cuda), _t(L0, cuda))
+        n1 = _native.launch_count() - n1
+        try:
+            setopt(0)
+            want = pipe.forward(_t(P0, cuda), _t(L0, cuda)).clone()
+            n0 = _native.launch_count()
+            pipe.forward(_t(P0, cuda), _t(L0, cuda))
+            n0 = _native.launch_count() - n0
+        finally:
+            setopt(1)
+        torch.cuda.synchronize()
+        e = rel(got, want)
+        print(f"launches per forward: recompute {n1}, stored {n0}; recompute vs stored {e:.2e}")
+        assert e < 5e-3                                              # the TF32 re-rounding drift class (see above)
+
+
 def test_native_pipeline_arena_estimate_and_fallback(cuda):
     """The arena is sized for level sizes N * 0.6^l; a pyramid that shrinks less (here: estimate forced to 0.05) makes
     the native driver return APRB_ERR_WORKSPACE before writing past the arena, and the call is retried with the
