@@ -66,6 +66,7 @@ SIGNATURES = {
     "aprb_kfe_forward_host": (_i, [_p, _p, _p, _i, _i, _p, _sz, _p, _i, _p, _p, _p]),
     "aprb_kfe_forward_host_async": (_i, [_p, _p, _p, _i, _i, _p, _sz, _p, _i, _p, _p, _p, _p]),
     "aprb_kfe_wait_host": (_i, [_p, _i]),
+    "aprb_kfe_set_host_output_f16": (_i, [_p, _i]),
     "aprb_kfe_get": (_i, [_p, _i, _i, _p, _p, _p]),
 }
 

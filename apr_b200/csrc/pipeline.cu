@@ -48,6 +48,8 @@ struct aprb_kfe {
     int parity;
     float* y_last;            // where the final block must write (NULL: carve from the arena)
     int y_last_rows_cap;
+    int host_out_f16;         // aprb_kfe_set_host_output_f16: the asynchronous host output is fp16
+    int y_last_f16;           // set while such a call is being queued: the final block stores fp16 into y_last
 };
 
 using namespace aprb;
@@ -208,7 +210,7 @@ int run_block16(const aprb_kfe& h, size_t bi, const void* feat, bool feat16, boo
     const float* s = h.pts[l];
     const int* idx = b.strided ? h.pool[l] : h.conv[l];
     const int H = h.cfg.limits[l];
-    const int out16 = last ? 0 : 1;
+    const int out16 = (last && !h.y_last_f16) ? 0 : 1;
 #define KFE_GSTAT(var, rows, cols)                                                                       \
     GStat var;                                                                                               \
     if (aprb::g_fuse_stats) {                                                                                \
@@ -337,6 +339,7 @@ extern "C" int aprb_kfe_create(const aprb_kfe_config* cfg, const aprb_kfe_block*
     h->h_counts = nullptr; h->h_counts_cap = 0; h->B = 0; h->S = 1;
     h->out_dev[0] = h->out_dev[1] = nullptr; h->out_dev_floats = 0; h->copy_st = nullptr; h->ev_done = nullptr;
     h->ev_copied[0] = h->ev_copied[1] = nullptr; h->parity = 0; h->y_last = nullptr; h->y_last_rows_cap = 0;
+    h->host_out_f16 = 0; h->y_last_f16 = 0;
     for (int l = 0; l < KFE_MAX_LEVELS; ++l) {
         h->ev[l] = nullptr; h->n[l] = 0; h->pts[l] = nullptr; h->lens[l] = nullptr; h->conv[l] = h->pool[l] = h->up[l] = nullptr;
         if (cudaEventCreateWithFlags(&h->ev[l], cudaEventDisableTiming) != cudaSuccess) { set_error("cudaEventCreate failed"); delete h; return APRB_ERR_CUDA; }
@@ -613,10 +616,13 @@ extern "C" int aprb_kfe_forward_host_async(aprb_kfe* h, const float* h_pts, cons
     APRB_CUDA_OK(cudaMemcpyAsync(d_lens, h_lens, (size_t)B * 4, cudaMemcpyHostToDevice, st));
     APRB_CUDA_OK(cudaStreamWaitEvent(st, h->ev_copied[p], 0));     // the copy that last read out_dev[p] (two calls ago)
     const float* y = nullptr;
-    h->y_last = d_alias ? d_alias : h->out_dev[p]; h->y_last_rows_cap = h_out_rows_cap;
+    const bool act16 = aprb::g_act_f16 && aprb::g_kpconv_f16 && h->act16_ok;
+    if (h->host_out_f16 && !act16) { set_error("aprb_kfe_forward_host_async: fp16 host output needs the fp16 activation mode"); return APRB_ERR_UNSUPPORTED; }
+    h->y_last = d_alias ? d_alias : h->out_dev[p]; h->y_last_rows_cap = h_out_rows_cap; h->y_last_f16 = h->host_out_f16;
     int rc = aprb_kfe_forward(h, d_pts, d_lens, nullptr, N, B, (char*)d_arena + head, arena_bytes - head, &y, out_rows, out_cols, st);
-    h->y_last = nullptr; h->y_last_rows_cap = 0;
+    h->y_last = nullptr; h->y_last_rows_cap = 0; h->y_last_f16 = 0;
     if (rc) return rc;
+    const size_t elt = h->host_out_f16 ? 2 : sizeof(float);
     if (d_alias) {                                                   // the output is complete when the stream gets here
         APRB_CUDA_OK(cudaEventRecord(h->ev_copied[p], st));
         *ticket = p;
@@ -626,10 +632,19 @@ extern "C" int aprb_kfe_forward_host_async(aprb_kfe* h, const float* h_pts, cons
     APRB_CUDA_OK(cudaEventRecord(h->ev_done, st));
     APRB_CUDA_OK(cudaStreamWaitEvent(h->copy_st, h->ev_done, 0));
     if (!aprb::g_dbg_skip_d2h)   // diagnostic only (aprb_set_option("dbg_skip_d2h")): how much of e2e is the output copy
-        APRB_CUDA_OK(cudaMemcpyAsync(h_out, y, (size_t)(*out_rows) * (*out_cols) * sizeof(float), cudaMemcpyDeviceToHost, h->copy_st));
+        APRB_CUDA_OK(cudaMemcpyAsync(h_out, y, (size_t)(*out_rows) * (*out_cols) * elt, cudaMemcpyDeviceToHost, h->copy_st));
     APRB_CUDA_OK(cudaEventRecord(h->ev_copied[p], h->copy_st));
     *ticket = p;
     h->parity = p ^ 1;
+    return APRB_OK;
+}
+
+// The encoder output of aprb_kfe_forward_host_async as fp16: the final activation is already rounded to a 10-bit
+// mantissa, so for |v| >= 2^-14 the fp16 value converts back to the identical fp32 value (below that: fp16 subnormals,
+// absolute error <= 2^-25) and the device-to-host copy moves half the bytes. Needs the fp16 activation mode.
+extern "C" int aprb_kfe_set_host_output_f16(aprb_kfe* h, int on) {
+    APRB_REQUIRE(h, "null handle");
+    h->host_out_f16 = on ? 1 : 0;
     return APRB_OK;
 }
 

@@ -156,9 +156,14 @@ class KFEPipeline:
         """Like forward_host, but returns as soon as the call is queued: (view of `out`, ticket). The encoder output
         lands in `out` (pinned host tensor [>= N_last, C]) through a side stream while the next call — which must use a
         different `out` — already runs; `wait_host(ticket)` blocks until this call's output is complete. At most two
-        calls in flight per pipeline."""
+        calls in flight per pipeline. `out` may be float16: the final activation is rounded to a 10-bit mantissa, so the
+        fp16 copy converts back to the same fp32 values (|v| >= 2^-14) and moves half the bytes over PCIe."""
         pts, lens = points.float().contiguous(), lengths.int().contiguous()
         n, b = pts.shape[0], lens.shape[0]
+        if out.dtype not in (torch.float32, torch.float16):
+            raise TypeError("forward_host_async: out must be float32 or float16")
+        N.check(self.lib.aprb_kfe_set_host_output_f16(self.handle, 1 if out.dtype == torch.float16 else 0),
+                "aprb_kfe_set_host_output_f16")
         rows, cols, ticket = C.c_int(), C.c_int(), C.c_int()
         rc = self._call(lambda arena: self.lib.aprb_kfe_forward_host_async(
             self.handle, pts.data_ptr(), lens.data_ptr(), n, b, arena.data_ptr(), arena.numel(), out.data_ptr(), out.shape[0],

@@ -287,6 +287,10 @@ int aprb_kfe_forward_host(aprb_kfe* h, const float* h_pts, const int32_t* h_lens
 int aprb_kfe_forward_host_async(aprb_kfe* h, const float* h_pts, const int32_t* h_lens, int N, int B, void* d_arena,
                                 size_t arena_bytes, float* h_out, int h_out_rows_cap, int* out_rows, int* out_cols,
                                 int* ticket, void* stream);
+/* Host output of aprb_kfe_forward_host_async in fp16 (h_out then holds rows x cols halves): the final activation is
+ * rounded to a 10-bit mantissa anyway, so fp16 converts back to the identical fp32 value for |v| >= 2^-14 (absolute
+ * error <= 2^-25 below) at half the PCIe bytes. Only in the fp16 activation mode (the default). */
+int aprb_kfe_set_host_output_f16(aprb_kfe* h, int on);
 int aprb_kfe_wait_host(aprb_kfe* h, int ticket);
 /* After a forward: pyramid tensors in the arena. what: 0 = points [n,3] f32, 1 = neighbors, 2 = pools, 3 = upsamples
  * (int32 [n, limit]), 4 = stack lengths [B] i32. Pointers stay valid until the next forward on this handle. */

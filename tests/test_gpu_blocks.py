@@ -422,6 +422,17 @@ def test_native_pipeline_matches_module_path(cuda, oracle):
         pending = (y, ticket)
     pipe.wait_host(pending[1])
     assert torch.equal(pending[0], got.cpu())
+    # fp16 host output: the final activation is already rounded to a 10-bit mantissa -> same values, half the bytes
+    bufs16 = [torch.empty((got.shape[0] + 7, got.shape[1]), dtype=torch.float16).pin_memory() for _ in range(2)]
+    for c in range(3):
+        y16, ticket = pipe.forward_host_async(hp, hl, bufs16[c & 1])
+        pipe.wait_host(ticket)
+        assert torch.equal(y16, got.cpu().half())
+        big = got.cpu().abs() >= 2.0 ** -14
+        assert torch.equal(y16.float()[big], got.cpu()[big])
+    y32, ticket = pipe.forward_host_async(hp, hl, bufs[0])           # and back to fp32 on the same handle
+    pipe.wait_host(ticket)
+    assert torch.equal(y32, got.cpu())
     # vs the fp32 CPU oracle end to end (drift over 11 blocks, TF32 tensor path): reported, loose bound
     cpu = dict(points=[torch.from_numpy(p) for p in ref["points"]], neighbors=[torch.from_numpy(n).long() for n in ref["neighbors"]],
                pools=[torch.from_numpy(n).long() for n in ref["pools"]], features=torch.ones(len(p0), 1))
