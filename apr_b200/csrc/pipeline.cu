@@ -17,6 +17,11 @@ extern int g_act_f16;
 extern int g_dbg_skip_d2h;
 extern int g_host_zero_copy;
 extern int g_gemm_apply;
+// aprb_set_option("blocking_sync"): the events a host thread waits on (per-level counts, host-output copies) are created
+// with cudaEventBlockingSync, so a waiting thread sleeps instead of spinning. One process per GPU with several calls in
+// flight each puts more waiting threads on the box than it has cores (8 ranks x 5 streams on 32 cores); spinning
+// waiters then take the cores from the threads that launch kernels.
+int g_blocking_sync = 1;
 }
 
 struct aprb_kfe {
@@ -342,7 +347,7 @@ extern "C" int aprb_kfe_create(const aprb_kfe_config* cfg, const aprb_kfe_block*
     h->host_out_f16 = 0; h->y_last_f16 = 0;
     for (int l = 0; l < KFE_MAX_LEVELS; ++l) {
         h->ev[l] = nullptr; h->n[l] = 0; h->pts[l] = nullptr; h->lens[l] = nullptr; h->conv[l] = h->pool[l] = h->up[l] = nullptr;
-        if (cudaEventCreateWithFlags(&h->ev[l], cudaEventDisableTiming) != cudaSuccess) { set_error("cudaEventCreate failed"); delete h; return APRB_ERR_CUDA; }
+        if (cudaEventCreateWithFlags(&h->ev[l], cudaEventDisableTiming | (aprb::g_blocking_sync ? cudaEventBlockingSync : 0)) != cudaSuccess) { set_error("cudaEventCreate failed"); delete h; return APRB_ERR_CUDA; }
     }
     // fp16 activation mode: shape constraints of the fp16 kernels, and fp16 copies of the unary weights
     h->act16_ok = nblocks >= 2 && blocks[0].type == 0;
@@ -584,7 +589,8 @@ extern "C" int aprb_kfe_forward_host_async(aprb_kfe* h, const float* h_pts, cons
     if (!h->copy_st) {
         APRB_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_st, cudaStreamNonBlocking));
         APRB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
-        for (int i = 0; i < 2; ++i) APRB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i)
+            APRB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming | (aprb::g_blocking_sync ? cudaEventBlockingSync : 0)));
     }
     const int cols = h->blocks.back().type == 0 ? h->blocks.back().out_dim / 2 : h->blocks.back().out_dim;
     const size_t need = (size_t)h_out_rows_cap * cols;
