@@ -181,9 +181,10 @@ template <int BN, bool F16>
 __global__ void __launch_bounds__(192, 1)
 gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                             int K, int num_n, int total_tiles, const float* __restrict__ rowscale, float* __restrict__ C,
-                            float* __restrict__ gstat) {
+                            float* __restrict__ gstat, const int STAGES) {
+    // STAGES (<= Cfg::STAGES) = ring depth of this launch: a shallower ring leaves shared memory for the CTAs of other
+    // streams' kernels on the same SM (aprb_set_option("gemm_stages")).
     using Cfg = GemmPCfg<BN>;
-    constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -330,6 +331,7 @@ struct NrmArgs {
     int M, N;
     int nkb_main, nkb_sc;            // k-blocks (64 fp16) of the main product and of the shortcut product (0: none)
     int num_n, total_tiles;
+    int stages;                      // smem ring depth of this launch
     const int* seg_off;              // S + 1 row offsets of the normalisation segments, or NULL (one segment)
     int S;
     // STATS
@@ -366,7 +368,8 @@ __global__ void __launch_bounds__(GemmNCfg::THREADS, 1)
 gemm_nrm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const NrmArgs p) {
     using Cfg = GemmNCfg;
-    constexpr int BN = Cfg::BN, STAGES = Cfg::STAGES;
+    constexpr int BN = Cfg::BN;
+    const int STAGES = p.stages;                                     // ring depth of this launch (<= Cfg::STAGES)
     constexpr int ACC = DUAL ? 2 * BN : BN;                          // TMEM columns per tile (main | shortcut)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -717,6 +720,7 @@ static int launch_gemm(const float* A, const float* Bt, int M, int N, int K, int
     return APRB_OK;
 }
 
+int g_gemm_stages = 0;       // aprb_set_option("gemm_stages"): cap on the smem ring depth of the persistent kernels (0 = deepest)
 int g_gemm_bn = 0;           // aprb_set_option("gemm_bn"): force the persistent kernel's tile width (0 = by wave count)
 int g_gemm_persistent = 1;   // aprb_set_option("gemm_persistent"): persistent double-buffered kernel when no split-K is needed
 
@@ -735,9 +739,11 @@ static int launch_gemm_persistent(const void* A, const void* Bt, int M, int N, i
     }
     const int num_n = cdiv(N, BN), total = num_n * cdiv(M, GEMM_BM);
     const int grid = min(total, sm_count());
+    const int stages = g_gemm_stages >= 2 ? min(g_gemm_stages, GemmPCfg<BN>::STAGES) : GemmPCfg<BN>::STAGES;
+    const int smem = GemmPCfg<BN>::SMEM - (GemmPCfg<BN>::STAGES - stages) * (GemmPCfg<BN>::A_BYTES + GemmPCfg<BN>::B_BYTES);
     {
         ProfScope ps("gemm_tf32_kernel", st, 1);
-        gemm_tf32_persistent_kernel<BN, F16><<<grid, 192, GemmPCfg<BN>::SMEM, st>>>(tmA, tmB, M, N, K, num_n, total, rowscale, C, gstat);
+        gemm_tf32_persistent_kernel<BN, F16><<<grid, 192, smem, st>>>(tmA, tmB, M, N, K, num_n, total, rowscale, C, gstat, stages);
     }
     APRB_LAUNCH_OK();
     return APRB_OK;
@@ -864,10 +870,12 @@ static int launch_gemm_nrm(const void* A, const void* Bt, int K, const void* A2,
     }
     p.nkb_main = K / 64; p.nkb_sc = DUAL ? K2 / 64 : 0;
     p.num_n = cdiv(p.N, BN); p.total_tiles = p.num_n * cdiv(p.M, GEMM_BM);
+    p.stages = g_gemm_stages >= 2 ? min(g_gemm_stages, GemmNCfg::STAGES) : GemmNCfg::STAGES;
+    const int smem = GemmNCfg::SMEM - (GemmNCfg::STAGES - p.stages) * (GemmNCfg::A_BYTES + GemmNCfg::B_BYTES);
     const int grid = min(p.total_tiles, sm_count());
     {
         ProfScope ps(STATS ? "gemm_nrm_stats_kernel" : "gemm_nrm_apply_kernel", st, 1);
-        gemm_nrm_f16_kernel<DUAL, STATS><<<grid, GemmNCfg::THREADS, GemmNCfg::SMEM, st>>>(tmA, tmB, tmA2, tmB2, p);
+        gemm_nrm_f16_kernel<DUAL, STATS><<<grid, GemmNCfg::THREADS, smem, st>>>(tmA, tmB, tmA2, tmB2, p);
     }
     APRB_LAUNCH_OK();
     return APRB_OK;
@@ -913,6 +921,7 @@ extern "C" int aprb_set_option(const char* name, int value) {
     if (strcmp(name, "gemm_costages") == 0) { g_gemm_costages = value; return APRB_OK; }
     if (strcmp(name, "gemm_persistent") == 0) { g_gemm_persistent = value; return APRB_OK; }
     if (strcmp(name, "gemm_bn") == 0) { g_gemm_bn = value; return APRB_OK; }
+    if (strcmp(name, "gemm_stages") == 0) { g_gemm_stages = value; return APRB_OK; }
     if (strcmp(name, "kpconv_chunk_mb") == 0) { g_kpconv_chunk_mb = value; return APRB_OK; }
     if (strcmp(name, "kpw_version") == 0) { g_kpw_version = value; return APRB_OK; }
     if (strcmp(name, "fuse_stats") == 0) { g_fuse_stats = value; return APRB_OK; }
