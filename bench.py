@@ -212,11 +212,16 @@ def encoder_shapes(enc, n_levels):
         nq, ns = (n_levels[l + 1] if strided else n_levels[l]), n_levels[l]
         c = m.KPConv
         if isinstance(m, blocks.ResnetBottleneckBlock):
+            # 5th field: which kernel runs it on the native path — "gemm" = persistent tcgen05 GEMM (product stored),
+            # "nrm" = gemm_nrm_f16_kernel (statistics pass + recompute; pipeline.cu: K_main + K_shortcut <= 1024)
+            has_sc = isinstance(m.unary_shortcut, blocks.UnaryBlock)
+            k_total = m.out_dim // 4 + (m.in_dim if has_sc else 0)
+            closing = "nrm" if k_total <= 1024 else "gemm"
             if isinstance(m.unary1, blocks.UnaryBlock):
-                tr.append(("linear", ns, m.in_dim, m.out_dim // 4))
-            tr.append(("linear", nq, m.out_dim // 4, m.out_dim))
-            if isinstance(m.unary_shortcut, blocks.UnaryBlock):
-                tr.append(("linear", nq, m.in_dim, m.out_dim))
+                tr.append(("linear", ns, m.in_dim, m.out_dim // 4, "gemm"))
+            tr.append(("linear", nq, m.out_dim // 4, m.out_dim, closing))
+            if has_sc:
+                tr.append(("linear", nq, m.in_dim, m.out_dim, closing))
         tr.append(("kpconv", nq, ns, None, c.K, c.in_channels, c.out_channels))
     return tr
 
@@ -385,7 +390,17 @@ def run_ours(args):
     kp_flops = sum(2.0 * r[1] * r[4] * r[5] * r[6] for r in trace if r[0] == "kpconv")
     lin_flops = sum(2.0 * r[1] * r[2] * r[3] for r in trace if r[0] == "linear")
     # tensor-path flops: KPConv contractions that run on tcgen05 (K*Cin % 32 == 0) + the unary Linear layers
-    tc_flops = sum(2.0 * r[1] * r[4] * r[5] * r[6] for r in trace if r[0] == "kpconv" and (r[4] * r[5]) % 32 == 0) + lin_flops
+    recompute = int(dict(kv.split("=") for kv in args.opt).get("gemm_apply", 1)) != 0
+    nrm_flops = sum(2.0 * r[1] * r[2] * r[3] for r in trace if r[0] == "linear" and r[4] == "nrm") if recompute else 0.0
+    # flops of the launches timed under "gemm_tf32_kernel": KPConv contractions on tcgen05, unary1, stored-path closing Linears
+    tc_flops = sum(2.0 * r[1] * r[4] * r[5] * r[6] for r in trace if r[0] == "kpconv" and (r[4] * r[5]) % 32 == 0) \
+        + lin_flops - nrm_flops
+    # recompute kernels: operands twice (both passes) + fp16 output + fp16 residual rows where the shortcut is not a product
+    nrm_blocks = {}
+    for r in trace:
+        if r[0] == "linear" and r[4] == "nrm":
+            nrm_blocks.setdefault((r[1], r[3]), []).append(r[2])
+    nrm_bytes = sum(2 * 2.0 * n * sum(ks) + 2.0 * n * c + (2.0 * n * c if len(ks) == 1 else 0.0) for (n, c), ks in nrm_blocks.items())
     opts = dict(kv.split("=") for kv in args.opt)
     f16_mode = int(opts.get("act_f16", 1)) != 0 and int(opts.get("kpconv_f16", 1)) != 0
     # kp_weighted4 (every KPConv but the first, whose Cin = 1 runs kp_weighted_c1): gathers x [Ns, Cin] and writes the
@@ -430,17 +445,32 @@ def run_ours(args):
             roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "traffic": traffic_of(name), "launches_per_step": cnt / args.steps,
                     "note": f"algorithmic flops = 2*Nq*K*Cin*Cout over the KPConv contractions + 2*N*Cin*Cout over the unary "
-                            f"Linears = {tc_flops / 1e9:.1f} GFLOP/call ({P} pair(s)); peak = {pk['src']} bf16 sustained"
+                            f"Linears this kernel runs (unary1 and the stored-path blocks; the recomputed closing Linears, "
+                            f"{nrm_flops / 1e9:.1f} GFLOP/call, are gemm_nrm launches) = {tc_flops / 1e9:.1f} GFLOP/call ({P} pair(s)); peak = {pk['src']} bf16 sustained"
                             f"{'' if f16_mode else ' / 2 (TF32)'}; the HBM-bound launches of this kernel (levels 0-1) are read in "
                             f"profiles/; share of kernel time {share:.2f}"}
         else:
-            by = kpw_bytes if name == "kp_weighted_kernel" else 0.0
+            by = kpw_bytes if name == "kp_weighted_kernel" else (nrm_bytes if name.startswith("gemm_nrm") else 0.0)
             ach = by / per_step_s / 1e9 if per_step_s > 0 else 0.0
             roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                     "traffic": traffic_of(name), "launches_per_step": cnt / args.steps,
-                    "note": f"algorithmic bytes = {int(eb)}*(Ns*Cin + Nq*K*Cin) + 4*Nq*H + 12*(Nq+Ns) = {by / 1e6:.0f} MB/call "
+                    "note": (f"algorithmic bytes of the recompute kernels (fp16 operands of both passes + fp16 output + fp16 residual "
+                             f"rows) = {by / 1e6:.0f} MB/call over the stats + apply launches; peak = {pk['src']} HBM copy bandwidth; "
+                             f"share of kernel time {share:.2f}") if name.startswith("gemm_nrm") else
+                            f"algorithmic bytes = {int(eb)}*(Ns*Cin + Nq*K*Cin) + 4*Nq*H + 12*(Nq+Ns) = {by / 1e6:.0f} MB/call "
                             f"({P} pair(s)); peak = {pk['src']} HBM copy bandwidth; the kernel is instruction-issue bound "
                             f"(profiles/), so this fraction is its distance from the HBM floor; share of kernel time {share:.2f}"}
+    # the tensor path beside the dominant kernel (north_star: tensor-pipe evidence for the KPConv contraction)
+    roof_tensor = None
+    if "gemm_tf32_kernel" in prof and prof["gemm_tf32_kernel"][1] > 0:
+        cnt_g, ms_g = prof["gemm_tf32_kernel"]
+        peak = pk["bf16"] if f16_mode else pk["bf16"] / 2.0
+        ach = tc_flops / (ms_g / args.steps * 1e-3) / 1e12
+        roof_tensor = {"kernel": "gemm_tf32_kernel", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                       "frac": ach / peak, "traffic": traffic_of("gemm_tf32_kernel"), "launches_per_step": cnt_g / args.steps,
+                       "note": f"persistent tcgen05 GEMM: KPConv contractions + unary1 (+ stored-path closing Linears) = "
+                               f"{tc_flops / 1e9:.1f} GFLOP/call; blended over its HBM-bound level-0/1 and tensor-bound level-2/3 "
+                               f"launches (per launch: profiles/r01_ncu_traffic_v12_summary.txt)"}
     kernels = {k: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps} for k, v in
                sorted(prof.items(), key=lambda kv: -kv[1][1])[:14]}
 
@@ -467,7 +497,7 @@ def run_ours(args):
                            + ("host output in fp16: the final activation is rounded to a 10-bit mantissa, so it converts back to "
                               "the same fp32 values (|v| >= 2^-14), half the PCIe bytes; --e2e-out f32 copies fp32"
                               if args.e2e_out == "f16" else "host output in fp32")},
-            "roofline": roof, "kernels": kernels,
+            "roofline": roof, "roofline_tensor": roof_tensor, "kernels": kernels,
             "wall_ms_per_step": 1e3 * wall_dev / args.steps, "ms_steps": steps_dev}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
