@@ -484,22 +484,39 @@ def test_linear_norm_apply_recompute_equals_three_kernel_sequence(cuda):
                                                         P(ws_norm), ws_norm.numel(), sp()), "norm")
             return out
 
+        GUARD = 4096                                                 # canary elements on both sides of every written buffer
+
+        def guarded(numel, dtype, fill):
+            big = torch.full((numel + 2 * GUARD,), fill, dtype=dtype, device=cuda)
+            return big, big[GUARD:GUARD + numel]
+
+        def intact(big, numel, fill):
+            head, tail = big[:GUARD], big[GUARD + numel:]
+            same = (lambda t: torch.isnan(t).all()) if fill != fill else (lambda t: (t == fill).all())
+            return bool(same(head)) and bool(same(tail))
+
         def new(variant, out16):
-            y = torch.full((n, cout), float("nan"), device=cuda); g = torch.empty(gbytes // 4, device=cuda)
+            ybig, yflat = guarded(n * cout, torch.float32, float("nan")); y = yflat.view(n, cout)
+            gbig, g = guarded(gbytes // 4, torch.float32, 12345.0)
             _native.check(L.aprb_linear_f16_stats_ragged(P(x), P(w), n, cin, cout, P(y), P(g), P(seg), S, sp()), "ragged")
             y2 = g2 = None
             if variant == "dual":
                 y2 = torch.full((n, cout), float("nan"), device=cuda); g2 = torch.empty(gbytes // 4, device=cuda)
                 _native.check(L.aprb_linear_f16_stats_ragged(P(xs), P(ws), n, csc, cout, P(y2), P(g2), P(seg), S, sp()), "ragged")
             nt = 2 if variant == "dual" else 1
-            st = torch.empty(S * nt * 2 * cout, device=cuda)
+            stbig, st = guarded(S * nt * 2 * cout, torch.float32, 777.0)
             _native.check(L.aprb_instnorm_seg_stats(P(y), P(y2), n, cout, P(seg), S, 1e-5, P(g), P(g2), P(st), sp()), "stats")
-            out = torch.empty(n, cout, dtype=torch.float16 if out16 else torch.float32, device=cuda)
+            obig, oflat = guarded(n * cout, torch.float16 if out16 else torch.float32, 321.0)
+            out = oflat.view(n, cout)
             _native.check(L.aprb_linear_f16_norm_apply(P(x), P(w), n, cin, cout, P(xs) if variant == "dual" else None,
                                                        P(ws) if variant == "dual" else None, csc,
                                                        P(res) if variant == "res" else None, P(seg), S, P(st), 0.1, P(out),
                                                        out16, sp()), "apply")
             frac_nan = torch.isnan(y).float().mean().item()
+            torch.cuda.synchronize()
+            # no kernel of the sequence wrote outside its buffers (compute-sanitizer is closed on this pool)
+            assert intact(ybig, n * cout, float("nan")) and intact(gbig, gbytes // 4, 12345.0), (n, variant, "stats pass")
+            assert intact(stbig, S * nt * 2 * cout, 777.0) and intact(obig, n * cout, 321.0), (n, variant, "apply pass")
             return out, frac_nan
 
         for variant in ("none", "res", "dual"):
