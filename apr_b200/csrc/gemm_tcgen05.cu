@@ -332,6 +332,7 @@ struct NrmArgs {
     int nkb_main, nkb_sc;            // k-blocks (64 fp16) of the main product and of the shortcut product (0: none)
     int num_n, total_tiles;
     int stages;                      // smem ring depth of this launch
+    int park;                        // TMA / MMA lanes wait with the suspend hint instead of polling (aprb_set_option("nrm_park"))
     const int* seg_off;              // S + 1 row offsets of the normalisation segments, or NULL (one segment)
     int S;
     // STATS
@@ -355,6 +356,13 @@ struct GemmNCfg {
     static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + TBUF + 1024 + 256;
     static constexpr int THREADS = 64 + 32 * EPI_WARPS;
 };
+
+// The kernel lives in its epilogue, so the single TMA and MMA lanes mostly wait: polling, they take a third of the issued
+// instructions from the epilogue warps that share their schedulers; parked, the hardware wakes them on the phase flip.
+__device__ __forceinline__ void nrm_wait(uint32_t bar, uint32_t parity, int park) {
+    if (park) mbar_wait_parked(bar, parity);
+    else mbar_wait(bar, parity);
+}
 
 __device__ __forceinline__ float nrm_act_round(float v, float slope) {
     v = v >= 0.f ? v : v * slope;
@@ -409,14 +417,14 @@ gemm_nrm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int m0 = (t / p.num_n) * GEMM_BM, n0 = (t % p.num_n) * BN;
                 if (DUAL)
                     for (int kb = 0; kb < p.nkb_sc; ++kb) {
-                        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                        nrm_wait(bar_empty + 8 * s, ph ^ 1, p.park);
                         mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::A_BYTES + Cfg::B_BYTES);
                         tma_load_2d(sA + s * Cfg::A_BYTES, &tmA2, bar_full + 8 * s, kb * 64, m0);
                         tma_load_2d(sB + s * Cfg::B_BYTES, &tmB2, bar_full + 8 * s, kb * 64, n0);
                         if (++s == STAGES) { s = 0; ph ^= 1; }
                     }
                 for (int kb = 0; kb < p.nkb_main; ++kb) {
-                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    nrm_wait(bar_empty + 8 * s, ph ^ 1, p.park);
                     mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::A_BYTES + Cfg::B_BYTES);
                     tma_load_2d(sA + s * Cfg::A_BYTES, &tmA, bar_full + 8 * s, kb * 64, m0);
                     tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, bar_full + 8 * s, kb * 64, n0);
@@ -431,12 +439,12 @@ gemm_nrm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int i = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
                 const int ab = i & 1;
-                mbar_wait(bar_tempty + 8 * ab, ((uint32_t)(i >> 1) & 1u) ^ 1u);
+                nrm_wait(bar_tempty + 8 * ab, ((uint32_t)(i >> 1) & 1u) ^ 1u, p.park);
                 tc_fence_after();
                 const uint32_t acc_main = tmem_base + (uint32_t)(ab * ACC), acc_sc = acc_main + BN;
                 if (DUAL)
                     for (int kb = 0; kb < p.nkb_sc; ++kb) {
-                        mbar_wait(bar_full + 8 * s, ph);
+                        nrm_wait(bar_full + 8 * s, ph, p.park);
                         tc_fence_after();
                         const uint64_t da = make_smem_desc(sA + s * Cfg::A_BYTES), db = make_smem_desc(sB + s * Cfg::B_BYTES);
 #pragma unroll
@@ -445,7 +453,7 @@ gemm_nrm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         if (++s == STAGES) { s = 0; ph ^= 1; }
                     }
                 for (int kb = 0; kb < p.nkb_main; ++kb) {
-                    mbar_wait(bar_full + 8 * s, ph);
+                    nrm_wait(bar_full + 8 * s, ph, p.park);
                     tc_fence_after();
                     const uint64_t da = make_smem_desc(sA + s * Cfg::A_BYTES), db = make_smem_desc(sB + s * Cfg::B_BYTES);
 #pragma unroll
@@ -720,6 +728,7 @@ static int launch_gemm(const float* A, const float* Bt, int M, int N, int K, int
     return APRB_OK;
 }
 
+int g_nrm_park = 0;          // aprb_set_option("nrm_park"): parked mbarrier waits for the TMA / MMA lanes of gemm_nrm_f16_kernel (measured: no gain)
 int g_gemm_stages = 0;       // aprb_set_option("gemm_stages"): cap on the smem ring depth of the persistent kernels (0 = deepest)
 int g_gemm_bn = 0;           // aprb_set_option("gemm_bn"): force the persistent kernel's tile width (0 = by wave count)
 int g_gemm_persistent = 1;   // aprb_set_option("gemm_persistent"): persistent double-buffered kernel when no split-K is needed
@@ -871,6 +880,7 @@ static int launch_gemm_nrm(const void* A, const void* Bt, int K, const void* A2,
     p.nkb_main = K / 64; p.nkb_sc = DUAL ? K2 / 64 : 0;
     p.num_n = cdiv(p.N, BN); p.total_tiles = p.num_n * cdiv(p.M, GEMM_BM);
     p.stages = g_gemm_stages >= 2 ? min(g_gemm_stages, GemmNCfg::STAGES) : GemmNCfg::STAGES;
+    p.park = g_nrm_park;
     const int smem = GemmNCfg::SMEM - (GemmNCfg::STAGES - p.stages) * (GemmNCfg::A_BYTES + GemmNCfg::B_BYTES);
     const int grid = min(p.total_tiles, sm_count());
     {
@@ -922,6 +932,7 @@ extern "C" int aprb_set_option(const char* name, int value) {
     if (strcmp(name, "gemm_persistent") == 0) { g_gemm_persistent = value; return APRB_OK; }
     if (strcmp(name, "gemm_bn") == 0) { g_gemm_bn = value; return APRB_OK; }
     if (strcmp(name, "gemm_stages") == 0) { g_gemm_stages = value; return APRB_OK; }
+    if (strcmp(name, "nrm_park") == 0) { g_nrm_park = value; return APRB_OK; }
     if (strcmp(name, "kpconv_chunk_mb") == 0) { g_kpconv_chunk_mb = value; return APRB_OK; }
     if (strcmp(name, "kpw_version") == 0) { g_kpw_version = value; return APRB_OK; }
     if (strcmp(name, "fuse_stats") == 0) { g_fuse_stats = value; return APRB_OK; }

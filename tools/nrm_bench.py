@@ -19,7 +19,11 @@ SHAPES = [("b1  L0 dual", N[0], 64, 256, 128, 1), ("b2  L1 res ", N[1], 64, 256,
           ("b4  L1 res ", N[1], 128, 512, 0, 1), ("b5  L2 res ", N[2], 128, 512, 0, 1), ("b6  L2 dual", N[2], 256, 1024, 512, 1),
           ("b7  L2 res ", N[2], 256, 1024, 0, 1), ("b8  L3 res ", N[3], 256, 1024, 0, 1), ("b9  L3 dual", N[3], 512, 2048, 1024, 1),
           ("b10 L3 res ", N[3], 512, 2048, 0, 0)]
-L = _native.lib(); ptr = _native.ptr; sp = _native.stream_ptr; C = _native.C
+L = _native.lib()
+for kv in os.environ.get("NRM_OPTS", "").split(","):                 # e.g. NRM_OPTS=nrm_park=0
+    if "=" in kv:
+        _native.check(L.aprb_set_option(kv.split("=")[0].encode(), int(kv.split("=")[1])), "aprb_set_option")
+ptr = _native.ptr; sp = _native.stream_ptr; C = _native.C
 dev = torch.device("cuda", 0)
 g = torch.Generator().manual_seed(0)
 tot = [0.0, 0.0]
