@@ -47,7 +47,16 @@ long long aprb_launch_count(void);
  * device and writes "kernel_name launches total_ms" lines into buf and clears the records. */
 int aprb_prof_enable(int on);
 int aprb_prof_report(char* buf, size_t cap);
-/* Tuning switches (for A/B measurements): "gemm_cluster" = 1 | 2 (thread-block-cluster size of the tcgen05 GEMM). */
+/* Tuning switches (process-wide, for A/B measurements; defaults are the measured-best settings):
+ *   "kpconv_f16" 1, "act_f16" 1   fp16 operands / fp16 activation storage in aprb_kfe_forward (0: TF32 in fp32 storage)
+ *   "fuse_stats" 1                InstanceNorm statistics from the GEMM epilogue's group partials
+ *   "gemm_apply" 1                recompute path for the block-closing Linears (0: stored fp32 products; 2: every block)
+ *   "kpconv_fused" 0              one-kernel fused KPConv (parity-green, slower)
+ *   "blocking_sync" 1             host waits sleep (cudaEventBlockingSync) instead of spinning; read at aprb_kfe_create
+ *   "gemm_persistent" 1, "gemm_bn" 0, "gemm_costages" 1, "gemm_cluster" 1, "gemm_stages" 0, "nrm_park" 0,
+ *   "kpw_version" 4, "kpconv_chunk_mb" 0, "host_zero_copy" 0   kernel-selection experiments kept for reproducibility
+ *   "dbg_skip_d2h" 0              diagnostic: skip the host-output copy
+ * Unknown names return APRB_ERR_INVALID. */
 int aprb_set_option(const char* name, int value);
 /* Device properties the host side sizes grids with (SM count etc.). Returns status. */
 int aprb_device_info(int* sm_count, int* cc_major, int* cc_minor);
