@@ -50,6 +50,12 @@ ProfScope::~ProfScope() {
     }
 }
 
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return dev;
+}
+
 int sm_count() {
     static int n = 0;
     if (n == 0) {

@@ -49,6 +49,7 @@ static inline size_t align256(size_t b) { return (b + 255) & ~size_t(255); }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 int sm_count();
+int current_device();   // cudaGetDevice, 0 on error
 
 // ---- launch accounting + optional per-kernel CUDA-event timing (aprb_prof_*) --------------------------------------
 // Every kernel launch (or CUB call, with its kernel count) goes through APRB_TIMED: it bumps the launch counter and,

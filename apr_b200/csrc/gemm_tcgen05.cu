@@ -706,11 +706,12 @@ static int launch_gemm(const float* A, const float* Bt, int M, int N, int K, int
     if (rc) return rc;
     rc = make_tmap(&tmB, Bt, N, K, BN / CL);                        // each CTA loads a BN/CL-row slice of the B tile
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};                              // function attributes are per device
+    const int dev_i = current_device() & 63;
+    if (!attr_set[dev_i]) {
         APRB_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           GemmCfg<BN>::smem(GemmCfg<BN>::MAX_STAGES)));
-        attr_set = true;
+        attr_set[dev_i] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(cdiv(N, BN), cdiv(cdiv(M, GEMM_BM), CL) * CL, splits);   // grid.y padded to whole clusters
@@ -741,10 +742,11 @@ static int launch_gemm_persistent(const void* A, const void* Bt, int M, int N, i
     if (rc) return rc;
     rc = F16 ? make_tmap_f16(&tmB, Bt, N, K, BN) : make_tmap(&tmB, (const float*)Bt, N, K, BN);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};                              // function attributes are per device
+    const int dev_i = current_device() & 63;
+    if (!attr_set[dev_i]) {
         APRB_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_persistent_kernel<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmPCfg<BN>::SMEM));
-        attr_set = true;
+        attr_set[dev_i] = true;
     }
     const int num_n = cdiv(N, BN), total = num_n * cdiv(M, GEMM_BM);
     const int grid = min(total, sm_count());
@@ -872,10 +874,11 @@ static int launch_gemm_nrm(const void* A, const void* Bt, int K, const void* A2,
         rc = make_tmap_f16(&tmB2, Bt2, p.N, K2, BN);
         if (rc) return rc;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};                              // function attributes are per device
+    const int dev_i = current_device() & 63;
+    if (!attr_set[dev_i]) {
         APRB_CUDA_OK(cudaFuncSetAttribute(gemm_nrm_f16_kernel<DUAL, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmNCfg::SMEM));
-        attr_set = true;
+        attr_set[dev_i] = true;
     }
     p.nkb_main = K / 64; p.nkb_sc = DUAL ? K2 / 64 : 0;
     p.num_n = cdiv(p.N, BN); p.total_tiles = p.num_n * cdiv(p.M, GEMM_BM);

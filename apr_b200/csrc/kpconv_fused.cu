@@ -368,10 +368,11 @@ template <typename IdxT, int CIN, int COUT, int NH>
 static int launch_fused(const CUtensorMap& tmB, const float* d_q, const float4* s4, const void* d_idx, int ld,
                         const float* d_x, const float* d_kp, float extent, int Nq, int Ns, int H, int K, float* d_out,
                         float* d_gstat, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};                              // function attributes are per device
+    const int dev_i = current_device() & 63;
+    if (!attr_set[dev_i]) {
         APRB_CUDA_OK(cudaFuncSetAttribute(kpconv_fused_kernel<IdxT, CIN, COUT, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, KpfCfg<COUT>::SMEM));
-        attr_set = true;
+        attr_set[dev_i] = true;
     }
     {
         ProfScope ps("kpconv_fused_kernel", st, 1);
