@@ -68,6 +68,12 @@ SIGNATURES = {
     "aprb_kfe_wait_host": (_i, [_p, _i]),
     "aprb_kfe_set_host_output_f16": (_i, [_p, _i]),
     "aprb_kfe_get": (_i, [_p, _i, _i, _p, _p, _p]),
+    "aprb_kfe_set_tap": (_i, [_p, _p, _sz]),
+    "aprb_kfe_tap_count": (_i, [_p]),
+    "aprb_kfe_get_tap": (_i, [_p, _i, _p, _p, _p, _p, _p]),
+    "aprb_max_pool_seg": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p]),
+    "aprb_pool_seg_widths": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p, _p]),
+    "aprb_cell_grid_query_seg": (_i, [_p, _sz, _p, _p, _i, _i, _i, _f, _i, _p, _i, _i, _p, _p]),
 }
 
 _lib = None

@@ -35,9 +35,11 @@ def closest_pool(x, inds):
     return ops.closest_pool(x, inds)
 
 
-def max_pool(x, inds):
-    """blocks.py:86-102 — max over the neighbourhood, zero shadow row included."""
-    return ops.max_pool(x, inds)
+def max_pool(x, inds, width=None):
+    """blocks.py:86-102 — max over the neighbourhood, zero shadow row included. `width` (device int32 [1], optional) is
+    the reference's matrix width min(max_count, limit) when `inds` is a fixed-width device matrix (dataloader.
+    build_pyramid_device's batch['pool_widths']): columns beyond it are all-pad artefacts and do not take part."""
+    return ops.max_pool(x, inds, width_dev=width)
 
 
 def global_average(x, batch_lengths):
@@ -148,11 +150,6 @@ def block_decider(block_name, radius, in_dim, out_dim, layer_ind, config):
     raise ValueError('Unknown block name in the architecture definition : ' + block_name)
 
 
-# Super-batched pairs on the module path: {row count of a level: segment offsets [S+1] i32 (ops.segment_offsets)}.
-# Empty = the stacked clouds are one collate, statistics over all rows (the reference, blocks.py:459-468).
-NORM_SEGMENTS = {}
-
-
 class BatchNormBlock(nn.Module):
     """blocks.py:436-473 — despite the name, nn.InstanceNorm1d over ALL rows of the stacked pair (no affine, no
     running stats, eps 1e-5), or a learned bias when use_bn is False. `fused(x, slope, residual, norm_residual)` is
@@ -173,8 +170,8 @@ class BatchNormBlock(nn.Module):
 
     def fused(self, x, slope=1.0, residual=None, norm_residual=False):
         if self.use_bn:
-            if x.shape[1] % 4 == 0:      # two-launch segmented kernels (one segment unless NORM_SEGMENTS says otherwise)
-                return ops.instnorm_lrelu_seg(x, NORM_SEGMENTS.get(x.shape[0]), slope=slope, residual=residual,
+            if x.shape[1] % 4 == 0:      # two-launch kernels; the module path is one collate = one segment over all rows
+                return ops.instnorm_lrelu_seg(x, None, slope=slope, residual=residual,
                                               norm_residual=norm_residual, round_tf32=(LINEAR_MODE == 'tf32'))
             return ops.instnorm_lrelu(x, slope=slope, residual=residual, norm_residual=norm_residual,
                                       round_tf32=(LINEAR_MODE == 'tf32'))
@@ -307,7 +304,11 @@ class ResnetBottleneckBlock(nn.Module):
         x = self.unary1(features)
         x = self.KPConv(q_pts, s_pts, neighb_inds, x)
         x = self.batch_norm_conv.fused(x, slope=0.1)
-        shortcut = max_pool(features, neighb_inds) if 'strided' in self.block_name else features
+        if 'strided' in self.block_name:
+            widths = batch.get('pool_widths') if isinstance(batch, dict) else None
+            shortcut = max_pool(features, neighb_inds, widths[self.layer_ind] if widths else None)
+        else:
+            shortcut = features
         x2 = _linear(self.unary2.mlp, x)
         if isinstance(self.unary_shortcut, nn.Identity):
             # LeakyReLU(IN(x2) + shortcut) in one pass
@@ -352,4 +353,5 @@ class MaxPoolBlock(nn.Module):
         self.layer_ind = layer_ind
 
     def forward(self, x, batch):
-        return max_pool(x, batch['pools'][self.layer_ind + 1])
+        widths = batch.get('pool_widths') if isinstance(batch, dict) else None
+        return max_pool(x, batch['pools'][self.layer_ind + 1], widths[self.layer_ind + 1] if widths else None)

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(128)
 nb_query_kernel(const float* __restrict__ q, int Nq, const int* __restrict__ qoff, const int* __restrict__ soff, int B,
                 int Ns, const NbGrid* __restrict__ grids, const int* __restrict__ cell_start,
                 const float4* __restrict__ sorted, float radius, int W, int cap, int* __restrict__ out, int ld,
-                int* __restrict__ counts, int* __restrict__ max_count) {
+                int* __restrict__ counts, int* __restrict__ max_count, int cps, int* __restrict__ seg_width) {
     extern __shared__ uint64_t s_keys[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int qi = blockIdx.x * (blockDim.x >> 5) + wib;
@@ -262,6 +262,8 @@ nb_query_kernel(const float* __restrict__ q, int Nq, const int* __restrict__ qof
     if (lane == 0) {
         if (counts) counts[qi] = total;
         if (max_count) atomicMax(max_count, total);
+        // width of the reference's matrix for this query's segment (collated pair): min(max_count, limit)
+        if (seg_width && total > 0) atomicMax(seg_width + b / cps, min(total, W));
     }
 }
 
@@ -313,7 +315,9 @@ static int build_grid(const float* d_s, const int32_t* d_slens, int B, int Ns, f
 }
 
 static int query_grid(const float* d_q, const int32_t* d_qlens, int B, int Nq, int Ns, float radius, int width,
-                      int32_t* d_out_idx, int ld, int32_t* d_counts, int32_t* d_max_count, NbWs& w, cudaStream_t st) {
+                      int32_t* d_out_idx, int ld, int32_t* d_counts, int32_t* d_max_count, NbWs& w, cudaStream_t st,
+                      int cps = 1, int32_t* d_seg_width = nullptr) {
+    if (d_seg_width) APRB_CUDA_OK(cudaMemsetAsync(d_seg_width, 0, sizeof(int) * (size_t)cdiv(B, cps), st));
     // query offsets + reset of the max_count scalar in one tiny launch
     APRB_TIMED("setup_kernel", st, 1, (setup_kernel<<<1, 256, 0, st>>>(d_qlens, w.qoff, nullptr, nullptr, B, nullptr, d_max_count, d_max_count ? 1 : 0)));
     int cap = 64;
@@ -324,7 +328,7 @@ static int query_grid(const float* d_q, const int32_t* d_qlens, int B, int Nq, i
     if (smem > 48 * 1024)
         APRB_CUDA_OK(cudaFuncSetAttribute(nb_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     APRB_TIMED("nb_query_kernel", st, 1, (nb_query_kernel<<<cdiv(Nq, wpb), wpb * 32, smem, st>>>(d_q, Nq, w.qoff, w.soff, B, Ns, w.grids, w.cell_start, w.sorted,
-                                                        radius, width, cap, d_out_idx, ld, d_counts, d_max_count)));
+                                                        radius, width, cap, d_out_idx, ld, d_counts, d_max_count, cps, d_seg_width)));
     APRB_LAUNCH_OK();
     return APRB_OK;
 }
@@ -368,6 +372,25 @@ extern "C" int aprb_cell_grid_query(const void* d_grid, size_t grid_bytes, const
     carve_nb(c, 0, Ns > 0 ? Ns : 1, B, &w);
     if (!c.ok()) { set_error("aprb_cell_grid_query: grid buffer too small"); return APRB_ERR_WORKSPACE; }
     return query_grid(d_q, d_qlens, B, Nq, Ns, radius, width, d_out_idx, ld, d_counts, d_max_count, w, st);
+}
+
+// aprb_cell_grid_query that also records, per segment of `clouds_per_segment` clouds, the width the reference's matrix
+// would have for that collate: d_seg_width[s] = min(max over the segment's queries of the neighbour count, width).
+extern "C" int aprb_cell_grid_query_seg(const void* d_grid, size_t grid_bytes, const float* d_q, const int32_t* d_qlens, int B,
+                                        int Nq, int Ns, float radius, int width, int32_t* d_out_idx, int ld,
+                                        int clouds_per_segment, int32_t* d_seg_width, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    NB_COMMON_CHECKS();
+    APRB_REQUIRE(Nq >= 0 && d_qlens && d_grid && d_seg_width && clouds_per_segment >= 1, "bad query arguments");
+    APRB_REQUIRE(width >= 1 && width <= 16352, "width must be in [1, 16352]");
+    APRB_REQUIRE(ld >= width, "ld < width");
+    if (Nq == 0) { APRB_CUDA_OK(cudaMemsetAsync(d_seg_width, 0, sizeof(int) * (size_t)cdiv(B, clouds_per_segment), st)); return APRB_OK; }
+    APRB_REQUIRE(d_q && d_out_idx, "null point/output pointer");
+    Carver c(const_cast<void*>(d_grid), grid_bytes);
+    NbWs w;
+    carve_nb(c, 0, Ns > 0 ? Ns : 1, B, &w);
+    if (!c.ok()) { set_error("aprb_cell_grid_query_seg: grid buffer too small"); return APRB_ERR_WORKSPACE; }
+    return query_grid(d_q, d_qlens, B, Nq, Ns, radius, width, d_out_idx, ld, nullptr, nullptr, w, st, clouds_per_segment, d_seg_width);
 }
 
 extern "C" int aprb_radius_neighbors_batch(const float* d_q, const float* d_s, const int32_t* d_qlens,

@@ -39,7 +39,12 @@ struct aprb_kfe {
     const int* pool[aprb::KFE_MAX_LEVELS];
     const int* up[aprb::KFE_MAX_LEVELS];
     const int* seg[aprb::KFE_MAX_LEVELS];   // per level: row offsets of the S normalisation segments (S+1 ints), or NULL
+    const int* pool_w[aprb::KFE_MAX_LEVELS]; // per level: [S] width of the reference's pool matrix per segment, min(max_count, limit)
     int S;
+    // per-block taps (aprb_kfe_set_tap): device copies of every block's output, for per-block parity tests
+    char* tap_buf; size_t tap_cap, tap_off;
+    struct Tap { size_t off; int rows, cols, f16, tag; };   // tag = 4 * block + kind (0 block output, 1 KPConv output, 2 KPConv input)
+    std::vector<Tap> taps;
     // fp16 activation mode: fp16 copies of the unary weights, owned by the handle (cudaMalloc at create), per block
     // [unary1, unary2, shortcut]; act16_ok = every block fits the fp16 kernels' shape constraints
     std::vector<void*> w16;
@@ -95,6 +100,18 @@ struct GStat {
     int written = 0;
     const float* get() const { return written ? buf : nullptr; }
 };
+
+// Debug tap (aprb_kfe_set_tap): stream-ordered device copy of an intermediate tensor of the running forward.
+int tap_push(const aprb_kfe& hc, const void* p, int rows, int cols, int f16, int tag, cudaStream_t st) {
+    aprb_kfe& h = const_cast<aprb_kfe&>(hc);
+    if (!h.tap_buf) return APRB_OK;
+    const size_t bytes = (size_t)rows * cols * (f16 ? 2 : 4);
+    if (h.tap_off + bytes > h.tap_cap) { set_error("aprb_kfe_forward: tap buffer too small (tag %d needs %zu more bytes)", tag, bytes); return APRB_ERR_WORKSPACE; }
+    APRB_CUDA_OK(cudaMemcpyAsync(h.tap_buf + h.tap_off, p, bytes, cudaMemcpyDeviceToDevice, st));
+    h.taps.push_back({h.tap_off, rows, cols, f16, tag});
+    h.tap_off += align256(bytes);
+    return APRB_OK;
+}
 
 int kpconv_call(const aprb_kfe& h, const aprb_kfe_block& b, const float* q, const float* s, const int* idx, int ld,
                 const float* x, int nq, int ns, int H, int cin, int cout, float* out, GStat* gs, Arena& A, cudaStream_t st) {
@@ -177,7 +194,7 @@ int run_block(const aprb_kfe& h, const aprb_kfe_block& b, const float* feat, con
     const float* sc = feat;
     if (b.strided) {                                               // shortcut = max_pool(features, pools)
         KFE_ALLOC(mp, float, (size_t)nq * b.in_dim);
-        KFE_OK(aprb_max_pool(feat, idx, 0, H, nq, ns, H, b.in_dim, nullptr, mp, st));
+        KFE_OK(aprb_max_pool_seg(feat, 0, idx, 0, H, nq, ns, H, b.in_dim, h.seg[lq], h.S, h.pool_w[l], mp, st));
         sc = mp;
     }
     if (b.shortcut_W) {                                            // LeakyReLU(IN(x3) + IN(Linear(sc)))
@@ -266,13 +283,15 @@ int run_block16(const aprb_kfe& h, size_t bi, const void* feat, bool feat16, boo
                                          H, h.cfg.K, mid, mid, t2raw, 4, g2.buf, g2.buf ? &g2.written : nullptr, A.scratch(),
                                          A.scratch_bytes(), st));
     }
+    KFE_OK(tap_push(h, x1, ns, mid, 1, 4 * (int)bi + 2, st));
+    KFE_OK(tap_push(h, t2raw, nq, mid, 0, 4 * (int)bi + 1, st));
     KFE_OK(norm16_call(h, lq, t2raw, nq, mid, nullptr, 0, 0, t2, 1, &g2, nullptr, A, st));
     KFE_ALLOC(t3, float, (size_t)nq * cout);
     KFE_GSTAT(g3, nq, cout);
     const void* sc = feat;
     if (b.strided) {
         KFE_ALLOC(mp, float, (size_t)nq * b.in_dim / 2 + 8);
-        KFE_OK(aprb_max_pool_f16(feat, idx, H, nq, ns, H, b.in_dim, mp, st));
+        KFE_OK(aprb_max_pool_seg(feat, 1, idx, 0, H, nq, ns, H, b.in_dim, h.seg[lq], h.S, h.pool_w[l], mp, st));
         sc = mp;
     }
     // Measured per block shape (tools/nrm_bench.py, profiles/r01_nrm_recompute.txt): recomputing wins while the products
@@ -345,6 +364,8 @@ extern "C" int aprb_kfe_create(const aprb_kfe_config* cfg, const aprb_kfe_block*
     h->out_dev[0] = h->out_dev[1] = nullptr; h->out_dev_floats = 0; h->copy_st = nullptr; h->ev_done = nullptr;
     h->ev_copied[0] = h->ev_copied[1] = nullptr; h->parity = 0; h->y_last = nullptr; h->y_last_rows_cap = 0;
     h->host_out_f16 = 0; h->y_last_f16 = 0;
+    h->tap_buf = nullptr; h->tap_cap = 0; h->tap_off = 0;
+    for (int l = 0; l < KFE_MAX_LEVELS; ++l) h->pool_w[l] = nullptr;
     for (int l = 0; l < KFE_MAX_LEVELS; ++l) {
         h->ev[l] = nullptr; h->n[l] = 0; h->pts[l] = nullptr; h->lens[l] = nullptr; h->conv[l] = h->pool[l] = h->up[l] = nullptr;
         if (cudaEventCreateWithFlags(&h->ev[l], cudaEventDisableTiming | (aprb::g_blocking_sync ? cudaEventBlockingSync : 0)) != cudaSuccess) { set_error("cudaEventCreate failed"); delete h; return APRB_ERR_CUDA; }
@@ -453,7 +474,8 @@ extern "C" int aprb_kfe_forward(aprb_kfe* hp, const float* d_pts, const int32_t*
     h.n[0] = N; h.pts[0] = d_pts; h.lens[0] = d_lens;
     const int cps = cfg.clouds_per_segment > 0 ? cfg.clouds_per_segment : B;
     h.S = cdiv(B, cps);
-    for (int l = 0; l < KFE_MAX_LEVELS; ++l) h.seg[l] = nullptr;
+    for (int l = 0; l < KFE_MAX_LEVELS; ++l) { h.seg[l] = nullptr; h.pool_w[l] = nullptr; }
+    h.taps.clear(); h.tap_off = 0;
     if (h.S > 1) {
         KFE_ALLOC(seg0, int, (size_t)h.S + 1);
         KFE_OK(aprb_segment_offsets(d_lens, B, cps, seg0, st));
@@ -486,7 +508,14 @@ extern "C" int aprb_kfe_forward(aprb_kfe* hp, const float* d_pts, const int32_t*
             } else {
                 KFE_OK(run_block(h, h.blocks[bi], x, &y, &yc, A, st));
             }
-            x = y; xc = yc; ++bi;
+            x = y; xc = yc;
+            if (h.tap_buf) {                                        // debug tap: keep a copy of this block's output
+                const aprb_kfe_block& tb = h.blocks[bi];
+                const int rows = tb.strided ? h.n[tb.layer + 1] : h.n[tb.layer];
+                const int f16 = (act16 && (x_is16 || (bi + 1 == h.blocks.size() && h.y_last_f16))) ? 1 : 0;
+                KFE_OK(tap_push(h, y, rows, yc, f16, 4 * (int)bi + 0, st));
+            }
+            ++bi;
         }
         return APRB_OK;
     };
@@ -535,8 +564,9 @@ extern "C" int aprb_kfe_forward(aprb_kfe* hp, const float* d_pts, const int32_t*
                 h.seg[l + 1] = segn;
             }
             KFE_ALLOC(pool, int, (size_t)h.n[l + 1] * lim);
-            KFE_OK(aprb_cell_grid_query(grid[l], grid_bytes[l], npts, nlens, B, h.n[l + 1], h.n[l], r, lim, pool, lim, nullptr, nullptr, st));
-            h.pool[l] = pool;
+            KFE_ALLOC(poolw, int, (size_t)h.S);
+            KFE_OK(aprb_cell_grid_query_seg(grid[l], grid_bytes[l], npts, nlens, B, h.n[l + 1], h.n[l], r, lim, pool, lim, cps, poolw, st));
+            h.pool[l] = pool; h.pool_w[l] = poolw;
             grid_bytes[l + 1] = aprb_cell_grid_bytes(h.n[l + 1], B);
             grid[l + 1] = A.take<char>(grid_bytes[l + 1]);
             if (!grid[l + 1]) { set_error("aprb_kfe_forward: arena too small"); return APRB_ERR_WORKSPACE; }
@@ -658,6 +688,22 @@ extern "C" int aprb_kfe_wait_host(aprb_kfe* h, int ticket) {
     APRB_REQUIRE(h && (ticket == 0 || ticket == 1), "bad argument");
     if (!h->ev_copied[ticket]) return APRB_OK;
     APRB_CUDA_OK(cudaEventSynchronize(h->ev_copied[ticket]));
+    return APRB_OK;
+}
+
+extern "C" int aprb_kfe_set_tap(aprb_kfe* h, void* d_buf, size_t bytes) {
+    APRB_REQUIRE(h, "null handle");
+    h->tap_buf = (char*)d_buf; h->tap_cap = d_buf ? bytes : 0; h->tap_off = 0; h->taps.clear();
+    return APRB_OK;
+}
+
+extern "C" int aprb_kfe_tap_count(const aprb_kfe* h) { return h ? (int)h->taps.size() : 0; }
+
+extern "C" int aprb_kfe_get_tap(const aprb_kfe* h, int i, const void** d_ptr, int* rows, int* cols, int* is_f16, int* tag) {
+    APRB_REQUIRE(h && d_ptr && rows && cols && is_f16 && tag, "null argument");
+    APRB_REQUIRE(i >= 0 && (size_t)i < h->taps.size(), "tap index out of range");
+    const aprb_kfe::Tap& t = h->taps[(size_t)i];
+    *d_ptr = h->tap_buf + t.off; *rows = t.rows; *cols = t.cols; *is_f16 = t.f16; *tag = t.tag;
     return APRB_OK;
 }
 

@@ -25,15 +25,28 @@ __device__ __forceinline__ void store_half4(__half* p, const float4 v) {
     *reinterpret_cast<uint2*>(p) = u;
 }
 
+// Columns of the index row that take part in the max: all H, or the reference's pool-matrix width min(max_count, limit)
+// (neighbors.cpp:296-304 + dataloader.py:66-70) when the caller knows it — one scalar for a single collate, or one
+// value per segment (collated pair) of a super-batch, looked up through the segments' query-row offsets.
+__device__ __forceinline__ int pool_row_width(const int* __restrict__ d_width, const int* __restrict__ seg_off, int S, int n, int H) {
+    if (!d_width) return H;
+    int s = 0;
+    if (seg_off) {
+        while (s + 1 < S && n >= seg_off[s + 1]) ++s;
+    }
+    return min(H, max(d_width[s], 1));   // an all-pad segment keeps one (pad) column: the zero row
+}
+
 template <typename IdxT>
 __global__ void max_pool_kernel(const float* __restrict__ x, const IdxT* __restrict__ idx, int ld, int Nq, int Ns,
-                                int H, int C, const int* __restrict__ d_width, float* __restrict__ out) {
+                                int H, int C, const int* __restrict__ d_width, const int* __restrict__ seg_off, int S,
+                                float* __restrict__ out) {
     // one thread per (query, 4-channel group); C % 4 == 0 path uses float4
     const int groups = C >> 2;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)Nq * groups) return;
     int n = (int)(t / groups), gch = (int)(t % groups);
-    int Hn = d_width ? min(H, *d_width) : H;
+    int Hn = pool_row_width(d_width, seg_off, S, n, H);
     float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     const IdxT* row = idx + (size_t)n * ld;
     for (int h = 0; h < Hn; ++h) {
@@ -51,12 +64,12 @@ __global__ void max_pool_kernel(const float* __restrict__ x, const IdxT* __restr
 template <typename IdxT, int NV, bool H16>
 __global__ void __launch_bounds__(256)
 max_pool_warp_kernel(const float* __restrict__ x, const IdxT* __restrict__ idx, int ld, int Nq, int Ns, int H,
-                     const int* __restrict__ d_width, float* __restrict__ out) {
+                     const int* __restrict__ d_width, const int* __restrict__ seg_off, int S, float* __restrict__ out) {
     constexpr int C = 128 * NV;
     const int lane = threadIdx.x & 31;
     const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (n >= Nq) return;
-    const int Hn = d_width ? min(H, *d_width) : H;
+    const int Hn = pool_row_width(d_width, seg_off, S, n, H);
     float4 m[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j) m[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
@@ -97,11 +110,12 @@ max_pool_warp_kernel(const float* __restrict__ x, const IdxT* __restrict__ idx, 
 
 template <typename IdxT>
 __global__ void max_pool_scalar_kernel(const float* __restrict__ x, const IdxT* __restrict__ idx, int ld, int Nq,
-                                       int Ns, int H, int C, const int* __restrict__ d_width, float* __restrict__ out) {
+                                       int Ns, int H, int C, const int* __restrict__ d_width, const int* __restrict__ seg_off,
+                                       int S, float* __restrict__ out) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)Nq * C) return;
     int n = (int)(t / C), c = (int)(t % C);
-    int Hn = d_width ? min(H, *d_width) : H;
+    int Hn = pool_row_width(d_width, seg_off, S, n, H);
     float m = -INFINITY;
     const IdxT* row = idx + (size_t)n * ld;
     for (int h = 0; h < Hn; ++h) {
@@ -268,17 +282,64 @@ norm_apply_kernel(const float* __restrict__ x, int N, int C, int chunks, int row
 
 using namespace aprb;
 
-extern "C" int aprb_max_pool(const float* d_x, const void* d_idx, int idx_is_i64, int ld_idx, int Nq, int Ns, int H,
-                             int C, const int32_t* d_width, float* d_out, void* stream) {
+// last valid column + 1 of every index row, max-reduced per segment: the reference's pool-matrix width
+template <typename IdxT>
+__global__ void pool_seg_width_kernel(const IdxT* __restrict__ idx, int ld, int Nq, int Ns, int H, const int* __restrict__ seg_off,
+                                      int S, int* __restrict__ seg_width) {
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (n >= Nq) return;
+    int last = 0;
+    for (int h = lane; h < H; h += 32) {
+        const long long v = (long long)idx[(size_t)n * ld + h];
+        if (v >= 0 && v < Ns) last = h + 1;
+    }
+    last = __reduce_max_sync(0xffffffffu, last);
+    if (lane == 0 && last > 0) {
+        int s = 0;
+        if (seg_off) { while (s + 1 < S && n >= seg_off[s + 1]) ++s; }
+        atomicMax(seg_width + s, last);
+    }
+}
+
+extern "C" int aprb_pool_seg_widths(const void* d_idx, int idx_is_i64, int ld_idx, int Nq, int Ns, int H,
+                                    const int32_t* d_seg_off, int S, int32_t* d_seg_width, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    APRB_REQUIRE(Nq >= 0 && Ns >= 0 && H >= 1 && C >= 1 && ld_idx >= H, "bad shape");
+    APRB_REQUIRE(Nq >= 0 && Ns >= 0 && H >= 1 && ld_idx >= H && S >= 1 && d_seg_width, "bad argument");
+    APRB_REQUIRE(S == 1 || d_seg_off, "segment offsets missing");
+    APRB_CUDA_OK(cudaMemsetAsync(d_seg_width, 0, sizeof(int) * (size_t)S, st));
     if (Nq == 0) return APRB_OK;
-    APRB_REQUIRE(d_idx && d_out && (d_x || Ns == 0), "null pointer");
+    APRB_REQUIRE(d_idx, "null pointer");
+    if (idx_is_i64) APRB_TIMED("pool_seg_width_kernel", st, 1, (pool_seg_width_kernel<long long><<<cdiv(Nq, 8), 256, 0, st>>>((const long long*)d_idx, ld_idx, Nq, Ns, H, d_seg_off, S, d_seg_width)));
+    else APRB_TIMED("pool_seg_width_kernel", st, 1, (pool_seg_width_kernel<int><<<cdiv(Nq, 8), 256, 0, st>>>((const int*)d_idx, ld_idx, Nq, Ns, H, d_seg_off, S, d_seg_width)));
+    APRB_LAUNCH_OK();
+    return APRB_OK;
+}
+
+static int max_pool_impl(const void* d_xv, int x_is_f16, const void* d_idx, int idx_is_i64, int ld_idx, int Nq, int Ns, int H,
+                         int C, const int32_t* d_width, const int32_t* d_seg_off, int S, void* d_outv, cudaStream_t st) {
+    APRB_REQUIRE(Nq >= 0 && Ns >= 0 && H >= 1 && C >= 1 && ld_idx >= H, "bad shape");
+    APRB_REQUIRE(!d_seg_off || (d_width && S >= 1), "segment offsets need per-segment widths");
+    if (Nq == 0) return APRB_OK;
+    APRB_REQUIRE(d_idx && d_outv && (d_xv || Ns == 0), "null pointer");
+    const float* d_x = (const float*)d_xv;
+    float* d_out = (float*)d_outv;
     const int T = 256;
+    if (x_is_f16) {
+        APRB_REQUIRE(C >= 128 && C % 128 == 0 && C <= 1024 && !idx_is_i64, "fp16 max_pool needs C in {128, ..., 1024} and int32 indices");
+#define MPH(NV) APRB_TIMED("max_pool_kernel", st, 1, (max_pool_warp_kernel<int, NV, true><<<cdiv(Nq, 8), 256, 0, st>>>(d_x, (const int*)d_idx, ld_idx, Nq, Ns, H, d_width, d_seg_off, S, d_out)))
+        switch (C / 128) {
+            case 1: MPH(1); break; case 2: MPH(2); break; case 3: MPH(3); break; case 4: MPH(4); break;
+            case 5: MPH(5); break; case 6: MPH(6); break; case 7: MPH(7); break; default: MPH(8); break;
+        }
+#undef MPH
+        APRB_LAUNCH_OK();
+        return APRB_OK;
+    }
     if (C % 4 == 0 && ((uintptr_t)d_x % 16 == 0) && ((uintptr_t)d_out % 16 == 0)) {
         long long total = (long long)Nq * (C / 4);
         if (C % 128 == 0 && C <= 1024 && H >= 1) {
-#define MPW(IDX, NV) APRB_TIMED("max_pool_kernel", st, 1, (max_pool_warp_kernel<IDX, NV, false><<<cdiv(Nq, 8), 256, 0, st>>>(d_x, (const IDX*)d_idx, ld_idx, Nq, Ns, H, d_width, d_out)))
+#define MPW(IDX, NV) APRB_TIMED("max_pool_kernel", st, 1, (max_pool_warp_kernel<IDX, NV, false><<<cdiv(Nq, 8), 256, 0, st>>>(d_x, (const IDX*)d_idx, ld_idx, Nq, Ns, H, d_width, d_seg_off, S, d_out)))
 #define MPW_NV(IDX) do { if (C == 128) MPW(IDX, 1); else if (C == 256) MPW(IDX, 2); else if (C == 384) MPW(IDX, 3); else if (C == 512) MPW(IDX, 4); \
                          else if (C == 640) MPW(IDX, 5); else if (C == 768) MPW(IDX, 6); else if (C == 896) MPW(IDX, 7); else MPW(IDX, 8); } while (0)
             if (idx_is_i64) MPW_NV(long long); else MPW_NV(int);
@@ -287,31 +348,32 @@ extern "C" int aprb_max_pool(const float* d_x, const void* d_idx, int idx_is_i64
             APRB_LAUNCH_OK();
             return APRB_OK;
         }
-        if (idx_is_i64) APRB_TIMED("max_pool_kernel", st, 1, (max_pool_kernel<long long><<<cdiv(total, T), T, 0, st>>>(d_x, (const long long*)d_idx, ld_idx, Nq, Ns, H, C, d_width, d_out)));
-        else APRB_TIMED("max_pool_kernel", st, 1, (max_pool_kernel<int><<<cdiv(total, T), T, 0, st>>>(d_x, (const int*)d_idx, ld_idx, Nq, Ns, H, C, d_width, d_out)));
+        if (idx_is_i64) APRB_TIMED("max_pool_kernel", st, 1, (max_pool_kernel<long long><<<cdiv(total, T), T, 0, st>>>(d_x, (const long long*)d_idx, ld_idx, Nq, Ns, H, C, d_width, d_seg_off, S, d_out)));
+        else APRB_TIMED("max_pool_kernel", st, 1, (max_pool_kernel<int><<<cdiv(total, T), T, 0, st>>>(d_x, (const int*)d_idx, ld_idx, Nq, Ns, H, C, d_width, d_seg_off, S, d_out)));
     } else {
         long long total = (long long)Nq * C;
-        if (idx_is_i64) APRB_TIMED("max_pool_scalar_kernel", st, 1, (max_pool_scalar_kernel<long long><<<cdiv(total, T), T, 0, st>>>(d_x, (const long long*)d_idx, ld_idx, Nq, Ns, H, C, d_width, d_out)));
-        else APRB_TIMED("max_pool_scalar_kernel", st, 1, (max_pool_scalar_kernel<int><<<cdiv(total, T), T, 0, st>>>(d_x, (const int*)d_idx, ld_idx, Nq, Ns, H, C, d_width, d_out)));
+        if (idx_is_i64) APRB_TIMED("max_pool_scalar_kernel", st, 1, (max_pool_scalar_kernel<long long><<<cdiv(total, T), T, 0, st>>>(d_x, (const long long*)d_idx, ld_idx, Nq, Ns, H, C, d_width, d_seg_off, S, d_out)));
+        else APRB_TIMED("max_pool_scalar_kernel", st, 1, (max_pool_scalar_kernel<int><<<cdiv(total, T), T, 0, st>>>(d_x, (const int*)d_idx, ld_idx, Nq, Ns, H, C, d_width, d_seg_off, S, d_out)));
     }
     APRB_LAUNCH_OK();
     return APRB_OK;
 }
 
+extern "C" int aprb_max_pool(const float* d_x, const void* d_idx, int idx_is_i64, int ld_idx, int Nq, int Ns, int H,
+                             int C, const int32_t* d_width, float* d_out, void* stream) {
+    return max_pool_impl(d_x, 0, d_idx, idx_is_i64, ld_idx, Nq, Ns, H, C, d_width, nullptr, 1, d_out, (cudaStream_t)stream);
+}
+
 extern "C" int aprb_max_pool_f16(const void* d_x16, const int32_t* d_idx, int ld_idx, int Nq, int Ns, int H, int C,
                                  void* d_out16, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    APRB_REQUIRE(Nq >= 0 && Ns >= 0 && H >= 1 && C >= 128 && C % 128 == 0 && C <= 1024 && ld_idx >= H, "need C in {128, ..., 1024}, H >= 1");
-    if (Nq == 0) return APRB_OK;
-    APRB_REQUIRE(d_idx && d_out16 && (d_x16 || Ns == 0), "null pointer");
-#define MPH(NV) APRB_TIMED("max_pool_kernel", st, 1, (max_pool_warp_kernel<int, NV, true><<<cdiv(Nq, 8), 256, 0, st>>>((const float*)d_x16, d_idx, ld_idx, Nq, Ns, H, nullptr, (float*)d_out16)))
-    switch (C / 128) {
-        case 1: MPH(1); break; case 2: MPH(2); break; case 3: MPH(3); break; case 4: MPH(4); break;
-        case 5: MPH(5); break; case 6: MPH(6); break; case 7: MPH(7); break; default: MPH(8); break;
-    }
-#undef MPH
-    APRB_LAUNCH_OK();
-    return APRB_OK;
+    return max_pool_impl(d_x16, 1, d_idx, 0, ld_idx, Nq, Ns, H, C, nullptr, nullptr, 1, d_out16, (cudaStream_t)stream);
+}
+
+extern "C" int aprb_max_pool_seg(const void* d_x, int x_is_f16, const void* d_idx, int idx_is_i64, int ld_idx, int Nq, int Ns,
+                                 int H, int C, const int32_t* d_seg_off, int S, const int32_t* d_seg_width, void* d_out,
+                                 void* stream) {
+    return max_pool_impl(d_x, x_is_f16, d_idx, idx_is_i64, ld_idx, Nq, Ns, H, C, d_seg_width, S > 1 ? d_seg_off : nullptr, S,
+                         d_out, (cudaStream_t)stream);
 }
 
 __global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n) {

@@ -154,6 +154,18 @@ def kpconv_prepare_weights(weights):
 FUSE_STATS = True
 
 
+def _gstat_of(t):
+    rec = getattr(t, "_aprb_gstat", None)
+    if rec is None or rec[1] != t._version:
+        return None
+    return rec[0]
+
+
+def group_stats(t):
+    """The GEMM-epilogue group statistics attached to a produced tensor ([groups, 2, C] floats, flat), or None."""
+    return _gstat_of(t)
+
+
 def _group_stats_buffer(n, c, device):
     nbytes = N.lib().aprb_group_stats_bytes(int(n), int(c))
     return torch.empty(nbytes // 4, dtype=torch.float32, device=device)
@@ -175,9 +187,15 @@ def kpconv_f16_supported(k, cin, cout, h):
 
 
 def kpconv(q_pts, s_pts, neighb_inds, x, kernel_points, weights, extent, wprep=None, mode=0):
-    """K5. Returns [Nq,Cout] f32."""
+    """K5. Returns [Nq,Cout] f32. mode 4 takes x in fp16 (the native pipeline's activation storage)."""
     N.require_cuda()
-    q, s, xx = _dev_f32(q_pts, "q_pts"), _dev_f32(s_pts, "s_pts"), _dev_f32(x, "x")
+    q, s = _dev_f32(q_pts, "q_pts"), _dev_f32(s_pts, "s_pts")
+    if mode == 4:
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float16):
+            raise N.NativeError("kpconv mode 4: x must be a CUDA float16 tensor")
+        xx = x.contiguous()
+    else:
+        xx = _dev_f32(x, "x")
     kp, w = _dev_f32(kernel_points.detach(), "kernel_points"), _dev_f32(weights.detach(), "weights")
     idx, is64, ld = _idx(neighb_inds, "neighb_inds")
     nq, ns, h = q.shape[0], s.shape[0], idx.shape[1]
@@ -195,22 +213,48 @@ def kpconv(q_pts, s_pts, neighb_inds, x, kernel_points, weights, extent, wprep=N
                                            N.ptr(ws), ws.numel(), N.stream_ptr())
     N.check(rc, "aprb_kpconv_forward")
     if written.value:
-        out._aprb_gstat = gs
+        out._aprb_gstat = (gs, out._version)
     if TRACE is not None:
         TRACE.append(("kpconv", nq, ns, h, k, cin, cout))
     return out
 
 
-def max_pool(x, inds, width_dev=None):
-    """K4. x [Ns,C], inds [Nq,H] -> [Nq,C]; the shadow index Ns contributes an all-zero row."""
+def max_pool(x, inds, width_dev=None, seg_off=None):
+    """K4. x [Ns,C] f32 (or f16: C % 128 == 0, int32 inds), inds [Nq,H] -> [Nq,C]; the shadow index Ns contributes an
+    all-zero row. width_dev (device i32): columns that take part — one value, or one per segment with seg_off [S+1]
+    (query-row offsets of the collated pairs of a super-batch)."""
     N.require_cuda()
-    xx = _dev_f32(x, "x")
+    if isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float16:
+        xx, f16 = x.contiguous(), 1
+    else:
+        xx, f16 = _dev_f32(x, "x"), 0
     idx, is64, ld = _idx(inds, "inds")
     nq, h = idx.shape
     ns, c = xx.shape
-    out = torch.empty((nq, c), dtype=torch.float32, device=xx.device)
-    rc = N.lib().aprb_max_pool(N.ptr(xx), N.ptr(idx), is64, ld, nq, ns, h, c, N.ptr(width_dev), N.ptr(out), N.stream_ptr())
+    out = torch.empty((nq, c), dtype=xx.dtype, device=xx.device)
+    if f16 or seg_off is not None:
+        wd = _dev_i32(width_dev, "width_dev") if width_dev is not None else None
+        so = _dev_i32(seg_off, "seg_off") if seg_off is not None else None
+        nseg = so.shape[0] - 1 if so is not None else 1
+        rc = N.lib().aprb_max_pool_seg(N.ptr(xx), f16, N.ptr(idx), is64, ld, nq, ns, h, c, N.ptr(so), nseg, N.ptr(wd),
+                                       N.ptr(out), N.stream_ptr())
+    else:
+        rc = N.lib().aprb_max_pool(N.ptr(xx), N.ptr(idx), is64, ld, nq, ns, h, c, N.ptr(width_dev), N.ptr(out), N.stream_ptr())
     N.check(rc, "aprb_max_pool")
+    return out
+
+
+def pool_seg_widths(inds, ns, seg_off=None):
+    """Per-segment width of the reference's pool matrix recovered from a fixed-width index matrix: 1 + last valid column
+    over the segment's rows (device i32 [S])."""
+    N.require_cuda()
+    idx, is64, ld = _idx(inds, "inds")
+    nq, h = idx.shape
+    so = _dev_i32(seg_off, "seg_off") if seg_off is not None else None
+    nseg = so.shape[0] - 1 if so is not None else 1
+    out = torch.empty(nseg, dtype=torch.int32, device=idx.device)
+    N.check(N.lib().aprb_pool_seg_widths(N.ptr(idx), is64, ld, nq, int(ns), h, N.ptr(so), nseg, N.ptr(out), N.stream_ptr()),
+            "aprb_pool_seg_widths")
     return out
 
 
@@ -267,8 +311,9 @@ def instnorm_lrelu_seg(x, seg_off=None, slope=0.1, residual=None, norm_residual=
     y = out if out is not None else torch.empty_like(xx)
     ws = _workspace(N.lib().aprb_instnorm_seg_ws_bytes(n, c, nseg), xx.device)
     # group statistics left on the tensors by the GEMM that produced them (only valid for that very tensor object)
-    gx = getattr(x, "_aprb_gstat", None) if xx is x else None
-    gr = getattr(residual, "_aprb_gstat", None) if (res is not None and res is residual and norm_residual) else None
+    # (and only while it has not been modified in place since: the producer records the tensor's version counter)
+    gx = _gstat_of(x) if xx is x else None
+    gr = _gstat_of(residual) if (res is not None and res is residual and norm_residual) else None
     rc = N.lib().aprb_instnorm_lrelu_seg_pre(N.ptr(xx), n, c, N.ptr(so), nseg, float(eps), float(slope), N.ptr(res),
                                              1 if norm_residual else 0, 1 if round_tf32 else 0, N.ptr(y), N.ptr(gx), N.ptr(gr),
                                              N.ptr(ws), ws.numel(), N.stream_ptr())
@@ -294,7 +339,7 @@ def linear_tf32(x, weight):
                                            C.byref(written) if gs is not None else None, N.ptr(ws), ws.numel(), N.stream_ptr()),
             "aprb_linear_tf32")
     if written.value:
-        y._aprb_gstat = gs
+        y._aprb_gstat = (gs, y._version)
     if TRACE is not None:
         TRACE.append(("linear", n, cin, cout))
     return y

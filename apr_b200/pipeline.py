@@ -28,7 +28,10 @@ class _Config(C.Structure):
 
 
 class KFEPipeline:
-    """encoder: an `apr_b200.architectures.KPFCNNEncoder` on a CUDA device (its parameters are used in place).
+    """encoder: an `apr_b200.architectures.KPFCNNEncoder` on a CUDA device. The native handle works on SNAPSHOTS of its
+    parameters taken at construction (prepared TF32 / fp16 KPConv operands, rounded unary weights, fp16 copies); after
+    load_state_dict or an optimizer step call `refresh_weights()` — `forward*` does so by itself when a parameter's
+    (data_ptr, version) changed.
 
     clouds_per_segment=0: the stacked clouds of one call are ONE collate (the reference: one pair, dataloader.py:76).
     clouds_per_segment=2: the call carries P collated pairs stacked (B = 2P clouds); every kernel runs once over the
@@ -40,6 +43,37 @@ class KFEPipeline:
         self.config = config
         self.device = next(encoder.parameters()).device
         self.stream = stream if stream is not None else torch.cuda.current_stream(self.device)
+        self.encoder = encoder
+        self._limits = [int(v) for v in list(neighborhood_limits)[:8]]
+        self._build_upsamples = bool(build_upsamples)
+        self._cps = int(clouds_per_segment)
+        self.handle = None
+        self.arena = None
+        self._tap = None
+        self._host_out = None
+        self._build()
+
+    def _param_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.encoder.parameters())
+
+    def refresh_weights(self):
+        """Rebuild the native handle from the encoder's current parameters (waits for the calls in flight)."""
+        self.stream.synchronize()
+        if self.handle:
+            self.lib.aprb_kfe_destroy(self.handle)
+            self.handle = None
+        self._build()
+        if self._tap is not None:
+            N.check(self.lib.aprb_kfe_set_tap(self.handle, self._tap.data_ptr(), self._tap.numel()), "aprb_kfe_set_tap")
+
+    def _fresh(self):
+        if self._param_key() != self._weights_key:
+            self.refresh_weights()
+
+    def _build(self):
+        encoder, config = self.encoder, self.config
+        neighborhood_limits, build_upsamples, clouds_per_segment = self._limits, self._build_upsamples, self._cps
+        self._weights_key = self._param_key()
         self._keep = []                      # tensors whose device memory the native handle points into
         blks = []
         with torch.cuda.stream(self.stream):
@@ -82,9 +116,8 @@ class KFEPipeline:
         h = C.c_void_p()
         N.check(self.lib.aprb_kfe_create(C.byref(cfg), arr, len(blks), C.byref(h)), "aprb_kfe_create")
         self.handle = h
-        self.arena = None
         self._out_cols = blks[-1].out_dim if blks[-1].type == 1 else blks[-1].out_dim // 2
-        self._host_out = None
+        self._nblocks = len(blks)
         self.stream.synchronize()
 
     def __del__(self):
@@ -103,8 +136,16 @@ class KFEPipeline:
         else:
             need = self.lib.aprb_kfe_arena_bytes_est(self.handle, int(n), int(b), C.c_float(self.LEVEL_RATIO))
         if self.arena is None or self.arena.numel() < need:
-            self.arena = None                                       # release before growing
-            self.arena = torch.empty(int(need * 1.05) + 4096, dtype=torch.uint8, device=self.device)
+            # Kernels of earlier calls (this stream and the handle's copy stream) may still be reading the old arena, and
+            # the caching allocator would hand its block to the next allocation at once: drain them before the release,
+            # and allocate the new arena on the stream that uses it.
+            if self.arena is not None:
+                self.stream.synchronize()
+                for t in (0, 1):
+                    self.lib.aprb_kfe_wait_host(self.handle, t)
+            self.arena = None
+            with torch.cuda.stream(self.stream):
+                self.arena = torch.empty(int(need * 1.05) + 4096, dtype=torch.uint8, device=self.device)
         return self.arena
 
     def _call(self, fn, n, b):
@@ -124,6 +165,7 @@ class KFEPipeline:
     def forward(self, points, lengths):
         """points [N,3] f32 cuda, lengths [B] i32 cuda -> encoder output [N_last, C] (a view into the arena, valid until
         the next forward). Kernels are queued on self.stream; the call returns without waiting for them."""
+        self._fresh()
         pts, lens = points.float().contiguous(), lengths.int().contiguous()
         out, rows, cols = C.c_void_p(), C.c_int(), C.c_int()
         rc = self._call(lambda arena: self.lib.aprb_kfe_forward(
@@ -138,6 +180,7 @@ class KFEPipeline:
         tensor [N_last, C]; does H2D, the whole path and D2H, and synchronises the stream."""
         pts = points if isinstance(points, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(points, np.float32))
         lens = lengths if isinstance(lengths, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(lengths, np.int32))
+        self._fresh()
         pts, lens = pts.float().contiguous(), lens.int().contiguous()
         n, b = pts.shape[0], lens.shape[0]
         if out is None:
@@ -158,6 +201,7 @@ class KFEPipeline:
         different `out` — already runs; `wait_host(ticket)` blocks until this call's output is complete. At most two
         calls in flight per pipeline. `out` may be float16: the final activation is rounded to a 10-bit mantissa, so the
         fp16 copy converts back to the same fp32 values (|v| >= 2^-14) and moves half the bytes over PCIe."""
+        self._fresh()
         pts, lens = points.float().contiguous(), lengths.int().contiguous()
         n, b = pts.shape[0], lens.shape[0]
         if out.dtype not in (torch.float32, torch.float16):
@@ -174,6 +218,27 @@ class KFEPipeline:
 
     def wait_host(self, ticket):
         N.check(self.lib.aprb_kfe_wait_host(self.handle, int(ticket)), "aprb_kfe_wait_host")
+
+    def set_tap(self, nbytes):
+        """Test hook: keep a device copy of every encoder block's output of the following forwards (nbytes of device
+        memory; 0 switches it off). Read them with `taps()`."""
+        self.stream.synchronize()
+        self._tap = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device) if nbytes else None
+        N.check(self.lib.aprb_kfe_set_tap(self.handle, self._tap.data_ptr() if nbytes else None, int(nbytes)), "aprb_kfe_set_tap")
+
+    def taps(self):
+        """{(block, kind): tensor} of the last forward (views into the tap buffer, fp16 or fp32); kind 'out' = block
+        output, 'kp_out' = raw KPConv output, 'kp_in' = KPConv input."""
+        out = {}
+        for i in range(self.lib.aprb_kfe_tap_count(self.handle)):
+            p, r, c, f, tag = C.c_void_p(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+            N.check(self.lib.aprb_kfe_get_tap(self.handle, i, C.byref(p), C.byref(r), C.byref(c), C.byref(f), C.byref(tag)),
+                    "aprb_kfe_get_tap")
+            dt, es = (torch.float16, 2) if f.value else (torch.float32, 4)
+            off = p.value - self._tap.data_ptr()
+            t = self._tap[off:off + r.value * c.value * es].view(dt).view(r.value, c.value)
+            out[(tag.value // 4, ("out", "kp_out", "kp_in")[tag.value % 4])] = t
+        return out
 
     def pyramid(self):
         """The batch dict of the last forward (views into the arena): points, neighbors, pools, upsamples, stack_lengths."""

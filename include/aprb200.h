@@ -104,6 +104,12 @@ int aprb_cell_grid_query(const void* d_grid, size_t grid_bytes, const float* d_q
                          int Nq, int Ns, float radius, int width, int32_t* d_out_idx, int ld,
                          int32_t* d_counts, int32_t* d_max_count, void* stream);
 
+/* aprb_cell_grid_query that also records, per segment of clouds_per_segment consecutive clouds (one collated pair), the
+ * width of the reference's matrix for that collate: d_seg_width[s] = min(max neighbour count in the segment, width). */
+int aprb_cell_grid_query_seg(const void* d_grid, size_t grid_bytes, const float* d_q, const int32_t* d_qlens, int B,
+                             int Nq, int Ns, float radius, int width, int32_t* d_out_idx, int ld,
+                             int clouds_per_segment, int32_t* d_seg_width, void* stream);
+
 /* ---------------------------------------------------------------- K5: KPConv forward ------------------------- */
 /* Prepared weights: the [K,Cin,Cout] fp32 parameter re-laid as the K-major, TF32-rounded B operand
  * [Cout, K*Cin] used by the tcgen05 contraction. d_wprep has K*Cin*Cout floats. Run once per weight update. */
@@ -155,6 +161,17 @@ int aprb_kpconv_backward_data(const float* d_q, const float* d_s, const void* d_
 /* out[n,c] = max_h (x ++ 0)[idx[n,h], c] over h < min(H, *d_width if non-NULL). */
 int aprb_max_pool(const float* d_x, const void* d_idx, int idx_is_i64, int ld_idx, int Nq, int Ns, int H, int C,
                   const int32_t* d_width, float* d_out, void* stream);
+/* Super-batched form: rows [d_seg_off[s], d_seg_off[s+1]) of the query set belong to segment s (one collated pair) and use
+ * the width d_seg_width[s] — the width of the reference's pool matrix for that pair, min(max_count, limit)
+ * (neighbors.cpp:296-304, dataloader.py:66-70): a fixed-width device matrix has extra all-pad columns when
+ * max_count < limit, and those must not inject the zero shadow row into a row the reference sees full. S == 1 may pass
+ * d_seg_off == NULL. d_x / d_out are fp32, or fp16 when x_is_f16 (C a multiple of 128, <= 1024; int32 indices). */
+int aprb_max_pool_seg(const void* d_x, int x_is_f16, const void* d_idx, int idx_is_i64, int ld_idx, int Nq, int Ns, int H,
+                      int C, const int32_t* d_seg_off, int S, const int32_t* d_seg_width, void* d_out, void* stream);
+/* d_seg_width[s] = 1 + last valid column over the rows of segment s of an index matrix (0 for an all-pad segment): the
+ * reference width recovered from a fixed-width matrix whose rows hold their valid entries first (radius search output). */
+int aprb_pool_seg_widths(const void* d_idx, int idx_is_i64, int ld_idx, int Nq, int Ns, int H, const int32_t* d_seg_off,
+                         int S, int32_t* d_seg_width, void* stream);
 /* Gradient of aprb_max_pool: d_dx [Ns,C] (zeroed by the call) += d_dy[n,c] at the first neighbour attaining the max. */
 int aprb_max_pool_backward(const float* d_x, const void* d_idx, int idx_is_i64, int ld_idx, int Nq, int Ns, int H, int C,
                            const float* d_dy, float* d_dx, void* stream);
@@ -304,6 +321,13 @@ int aprb_kfe_wait_host(aprb_kfe* h, int ticket);
 /* After a forward: pyramid tensors in the arena. what: 0 = points [n,3] f32, 1 = neighbors, 2 = pools, 3 = upsamples
  * (int32 [n, limit]), 4 = stack lengths [B] i32. Pointers stay valid until the next forward on this handle. */
 int aprb_kfe_get(const aprb_kfe* h, int what, int level, const void** d_ptr, int* rows, int* cols);
+/* Test hook: with a tap buffer set, every forward also copies intermediate tensors (device to device, stream ordered)
+ * into d_buf: tag 4*b + 0 = output of encoder block b, 4*b + 1 = raw output of its KPConv (fp32), 4*b + 2 = the input of
+ * its KPConv (fp16 activation mode only). aprb_kfe_get_tap(h, i) returns the i-th recorded tensor [rows, cols], fp16
+ * when *is_f16. The per-block parity tests feed block b's oracle with block b-1's tap. d_buf == NULL: taps off. */
+int aprb_kfe_set_tap(aprb_kfe* h, void* d_buf, size_t bytes);
+int aprb_kfe_tap_count(const aprb_kfe* h);
+int aprb_kfe_get_tap(const aprb_kfe* h, int i, const void** d_ptr, int* rows, int* cols, int* is_f16, int* tag);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,354 @@
+"""Parity of the path bench.py times — aprb_kfe_forward in its default mode (fp16 activation storage, KPConv mode 4,
+recompute path for the block-closing Linears, super-batched pairs with per-pair InstanceNorm) — on the shapes BASELINE
+names: a full KITTI-shaped pair, a nuScenes-shaped pair and a LoKITTI-shaped distant pair, with calibrated limits.
+
+Every block is checked on its own with IDENTICAL inputs on both sides: the device copies (taps) of block b-1's output and
+of KPConv b's input feed the fp32 CPU oracle (oracle/blocks_ref.py <- models/blocks.py:229-374, :653-681), whose result
+is compared with the tap of block b's output / KPConv b's raw output. Bars: KPConv <= 1e-3 (north_star), block <= TOL_BLOCK.
+The kernels that exist only on this path get direct tests: KPConv mode 4, fp16 max_pool, fp16 segmented InstanceNorm,
+and the `dual` / `none` variants of the recompute-apply GEMM against torch."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from apr_b200 import _native, blocks, dataloader, ops, synth
+from apr_b200.architectures import KPFCNNEncoder
+from apr_b200.config import kitti_config, nuscenes_config
+from apr_b200.pipeline import KFEPipeline
+from oracle import blocks_ref
+from oracle.ref import calibrate_ref, collate_ref
+
+pytestmark = pytest.mark.gpu
+
+TOL_KPCONV = 1e-3     # north_star: KPConv features within 1e-3 relative of the fp32 reference
+TOL_BLOCK = 1.5e-3    # a whole ResnetBottleneckBlock: three fp16-operand contractions + two 10-bit re-roundings of stored
+                      # activations (measured 5-9e-4 on B200, printed below)
+TOL_ENCODER = 8e-3    # 11 blocks end to end (drift compounds through InstanceNorm; measured 4-6e-3)
+
+
+def rel(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _t(a, cuda):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+
+
+def _voxel_pair(oracle, seed, kind, distant):
+    a, b = synth.pair_raw(seed, kind, distant)
+    raw = np.concatenate([a, b]); lens = np.array([len(a), len(b)], np.int32)
+    return oracle.subsample_batch(raw, lens, sampleDl=0.3)               # first-level voxelisation (stand-in)
+
+
+def _pair_batch(pyr, j, nlev):
+    """CPU batch dict (reference layout: local indices, pad = the pair's own support count) of pair j of a super-batched
+    device pyramid, plus the pair's row range per level."""
+    rows, out = [], dict(points=[], neighbors=[], pools=[])
+    for l in range(nlev):
+        lens = pyr["stack_lengths"][l].cpu().numpy().astype(np.int64)
+        off = int(lens[:2 * j].sum()); n = int(lens[2 * j] + lens[2 * j + 1])
+        rows.append((off, n))
+    for l in range(nlev):
+        off, n = rows[l]
+        out["points"].append(pyr["points"][l][off:off + n].cpu())
+        ns_tot = pyr["points"][l].shape[0]
+        t = pyr["neighbors"][l][off:off + n].cpu().long()
+        out["neighbors"].append(torch.where(t >= ns_tot, torch.full_like(t, n), t - off))
+        if l + 1 < nlev and pyr["pools"][l].shape[0]:
+            qo, qn = rows[l + 1]
+            t = pyr["pools"][l][qo:qo + qn].cpu().long()
+            out["pools"].append(torch.where(t >= ns_tot, torch.full_like(t, n), t - off))
+        else:
+            out["pools"].append(torch.zeros((0, 1), dtype=torch.long))
+    return out, rows
+
+
+def _cut_to_reference_width(m, pad):
+    """The reference's matrix has min(max_count, limit) columns: drop the trailing columns that are pad in every row."""
+    valid = (m != pad).any(0)
+    w = int(valid.nonzero().max()) + 1 if bool(valid.any()) else 1
+    return m[:, :w]
+
+
+@pytest.mark.parametrize("kind,distant", [("kitti", False), ("nuscenes", False), ("kitti", True)],
+                         ids=["kitti_pair", "nuscenes_pair", "lokitti_distant_pair"])
+def test_benchmarked_path_per_block_vs_oracle(cuda, oracle, kind, distant):
+    cfg = kitti_config() if kind == "kitti" else nuscenes_config()
+    nlev = cfg.num_layers
+    pairs = [_voxel_pair(oracle, seed, kind, distant) for seed in (3, 4, 5)]
+    dev = [(_t(p, cuda), _t(l, cuda)) for p, l in pairs]
+    limits = [int(v) for v in dataloader.calibrate_neighbors_device(dev, cfg)]
+    torch.manual_seed(0); np.random.seed(0)
+    enc = KPFCNNEncoder(cfg).to(cuda).eval()
+    sd = {k: v.detach().cpu() for k, v in enc.state_dict().items()}
+    pipe = KFEPipeline(enc, cfg, limits, clouds_per_segment=2)            # the bench's configuration: super-batched pairs
+    pipe.set_tap(3 << 30)
+    P0 = torch.cat([p for p, _ in dev]); L0 = torch.cat([l for _, l in dev])
+    out = pipe.forward(P0, L0).clone()
+    torch.cuda.synchronize()
+    pyr, taps = pipe.pyramid(), pipe.taps()
+    j = 1                                                                 # the middle pair: segment bounds inside tiles
+    cpu, rows = _pair_batch(pyr, j, nlev)
+    # the oracle sees what the reference would: matrices cut to min(max_count, limit) columns
+    cpu_ref = dict(points=cpu["points"],
+                   neighbors=[_cut_to_reference_width(m, len(cpu["points"][l])) for l, m in enumerate(cpu["neighbors"])],
+                   pools=[_cut_to_reference_width(m, len(cpu["points"][l])) if m.shape[0] else m for l, m in enumerate(cpu["pools"])])
+    print(f"\n{kind}{' distant' if distant else ''}: stacked pair rows per level {[n for _, n in rows]}, limits {limits}, "
+          f"reference widths conv {[m.shape[1] for m in cpu_ref['neighbors']]} pool {[m.shape[1] for m in cpu_ref['pools'][:-1]]}")
+    r = cfg.first_subsampling_dl * cfg.conv_radius
+    layer, worst_kp, worst_blk = 0, 0.0, 0.0
+    feats = torch.ones(rows[0][1], 1)
+    arch = [b for b in cfg.architecture if "upsample" not in b and "unary" not in b]
+    for bi, name in enumerate(arch):
+        prefix = f"encoder_blocks.{bi}."
+        extent = r * cfg.KP_extent / cfg.conv_radius
+        strided = "strided" in name
+        off_o, n_o = rows[layer + 1] if strided else rows[layer]
+        off_i, n_i = rows[layer]
+        got = taps[(bi, "out")][off_o:off_o + n_o].float().cpu()
+        if "simple" in name:
+            want = blocks_ref.simple_ref(feats, cpu_ref, sd, prefix, name, layer, extent)
+            e_kp = float("nan")
+        else:
+            want = blocks_ref.resnetb_ref(feats, cpu_ref, sd, prefix, name, layer, extent)
+            x1 = taps[(bi, "kp_in")][off_i:off_i + n_i].float().cpu()   # fp16 storage of a 10-bit value: exact widening
+            q, s, inds = blocks_ref._select(name, layer, cpu_ref)
+            want_kp = blocks_ref.kpconv_ref(q, s, inds, x1, sd[prefix + "KPConv.kernel_points"], sd[prefix + "KPConv.weights"], extent)
+            e_kp = rel(taps[(bi, "kp_out")][off_o:off_o + n_o], want_kp)
+            worst_kp = max(worst_kp, e_kp)
+        e = rel(got, want)
+        worst_blk = max(worst_blk, e)
+        print(f"  block {bi:2d} {name:16s} L{layer} rows {n_o:6d}  KPConv rel err {e_kp:.2e}   block rel err {e:.2e}")
+        feats = got                                                        # next block: identical input on both sides
+        if strided:
+            layer += 1; r *= 2
+    # end of encoder: free-running oracle (no re-synchronisation of inputs)
+    cpu_ref["features"] = torch.ones(rows[0][1], 1)
+    y = blocks_ref.encoder_ref(cpu_ref, sd, cfg)
+    off, n = rows[nlev - 1]
+    drift = rel(out[off:off + n], y)
+    print(f"  worst KPConv {worst_kp:.2e}, worst block {worst_blk:.2e}, end-of-encoder drift {drift:.2e}")
+    assert worst_kp < TOL_KPCONV
+    assert worst_blk < TOL_BLOCK
+    assert drift < TOL_ENCODER
+    pipe.set_tap(0)
+
+
+@pytest.mark.parametrize("cin,cout,h", [(64, 64, 57), (128, 128, 33), (256, 256, 40), (512, 512, 20), (64, 128, 56)])
+def test_kpconv_mode4_fp16_features_vs_oracle(cuda, cin, cout, h):
+    """KPConv with fp16 feature rows in (mode 4, what aprb_kfe_forward runs): the oracle is fed the same fp16 values."""
+    gen = torch.Generator().manual_seed(cin + h)
+    ns, nq = 2000, 1500
+    s = torch.rand(ns, 3, generator=gen) * 2
+    q = torch.rand(nq, 3, generator=gen) * 2
+    inds = torch.randint(0, ns + 1, (nq, h), generator=gen)
+    inds[:3] = ns
+    inds[5, h // 2:] = ns
+    x16 = F.leaky_relu(torch.randn(ns, cin, generator=gen), 0.1).half()
+    x16[::7] = -x16[::7].abs()                                            # rows with negative sums: not counted in neighbor_num
+    kp = torch.randn(15, 3, generator=gen) * 0.4
+    w = torch.randn(15, cin, cout, generator=gen) / np.sqrt(15 * cin)
+    want = blocks_ref.kpconv_ref(q, s, inds, x16.float(), kp, w, 0.7)
+    wd = w.to(cuda)
+    got = ops.kpconv(q.to(cuda), s.to(cuda), inds.to(cuda).int(), x16.to(cuda), kp.to(cuda), wd, 0.7,
+                     wprep=ops.kpconv_prepare_weights_f16(wd), mode=4)
+    e = rel(got, want)
+    print(f"kpconv mode 4 Cin={cin} Cout={cout} H={h}: rel err {e:.2e}")
+    assert e < TOL_KPCONV
+    assert torch.all(got[:3] == 0)
+
+
+def test_max_pool_f16_vs_oracle(cuda):
+    """fp16 max_pool (product path): the max of fp16 values is exact, so the result is bit-identical to the oracle's on
+    the same values — pads anywhere, all-pad rows, H > 32, and per-segment reference widths."""
+    gen = torch.Generator().manual_seed(8)
+    for c, h in ((128, 9), (256, 56), (512, 33), (1024, 70)):
+        x = torch.randn(300, c, generator=gen).half()
+        inds = torch.randint(0, 301, (77, h), generator=gen)
+        inds[3] = 300
+        inds[4, : h // 2] = 300
+        for xx in (x, -x.abs()):
+            want = blocks_ref.max_pool_ref(xx.float(), inds).half()
+            got = ops.max_pool(xx.to(cuda), inds.to(cuda).int())
+            assert got.dtype == torch.float16 and torch.equal(got.cpu(), want)
+    # per-segment widths: trailing all-pad columns of a segment do not inject the zero row (negative features stay negative)
+    ns, c, h = 200, 128, 12
+    x = (-torch.rand(ns, c, generator=gen) - 0.5).half()
+    inds = torch.full((60, h), ns, dtype=torch.int64)
+    for n in range(60):
+        k = 5 if n < 30 else 9                                            # segment 0 rows hold <= 5, segment 1 rows <= 9 valid entries
+        cnt = int(torch.randint(1, k + 1, (1,), generator=gen))
+        if n in (0, 30):
+            cnt = k                                                       # one row per segment attains the segment's width
+        inds[n, :cnt] = torch.randint(0, ns, (cnt,), generator=gen)
+    seg = torch.tensor([0, 30, 60], dtype=torch.int32, device=cuda)
+    widths = ops.pool_seg_widths(inds.to(cuda).int(), ns, seg)
+    assert widths.cpu().tolist() == [5, 9]
+    want = torch.cat([blocks_ref.max_pool_ref(x.float(), inds[:30, :5]), blocks_ref.max_pool_ref(x.float(), inds[30:, :9])])
+    for xd, cast in ((x.to(cuda), lambda t: t.half()), (x.float().to(cuda), lambda t: t)):
+        got = ops.max_pool(xd, inds.to(cuda).int(), width_dev=widths, seg_off=seg)
+        assert torch.equal(got.cpu(), cast(want))
+        assert bool((got[0] < 0).all()) and bool((got[30] < 0).all())    # full rows: no phantom zero
+        full = ops.max_pool(xd, inds.to(cuda).int())                      # without the widths every row sees a pad
+        assert bool((full == 0).all())
+
+
+def test_instnorm_seg_f16_vs_torch(cuda):
+    """aprb_instnorm_lrelu_seg_f16 (fp32 GEMM output in, fp16 activation out, optional fp16 residual) vs torch per segment;
+    the stored value is the 10-bit rounding of the fp32 result."""
+    L, P, sp = _native.lib(), _native.ptr, _native.stream_ptr
+    gen = torch.Generator().manual_seed(21)
+    for bounds, c in (([0, 700, 1350, 2150, 2180, 2181, 3081], 64), ([0, 5000, 9000], 128), ([0, 300], 2048)):
+        n, S = bounds[-1], len(bounds) - 1
+        x = (torch.randn(n, c, generator=gen) * 2 + torch.linspace(-20, 20, n).unsqueeze(1)).to(cuda)
+        res = torch.randn(n, c, generator=gen).half().to(cuda)
+        seg = torch.tensor(bounds, dtype=torch.int32, device=cuda)
+        ws = torch.empty(int(L.aprb_instnorm_seg_ws_bytes(n, c, S)), dtype=torch.uint8, device=cuda)
+        for use_res in (False, True):
+            for out16 in (1, 0):
+                y = torch.empty(n, c, dtype=torch.float16 if out16 else torch.float32, device=cuda)
+                _native.check(L.aprb_instnorm_lrelu_seg_f16(P(x), n, c, P(seg), S, 1e-5, 0.1, P(res) if use_res else None, 1, 0, 1,
+                                                            P(y), out16, None, None, P(ws), ws.numel(), sp()), "norm16")
+                for s0, s1 in zip(bounds[:-1], bounds[1:]):
+                    if s1 - s0 > 1:
+                        xs = x[s0:s1].double()
+                        ref = (xs - xs.mean(0)) / torch.sqrt(xs.var(0, unbiased=False) + 1e-5)
+                        if use_res:
+                            ref = ref + res[s0:s1].double()
+                        ref = F.leaky_relu(ref, 0.1).float()
+                        got = y[s0:s1].float()
+                        assert ((got - ref).abs() <= 2.0 ** -10 * ref.abs() + 2e-4).all(), (bounds, c, use_res, out16)
+                        assert rel(got, ref) < 6e-4
+
+
+def test_linear_norm_apply_all_variants_vs_torch(cuda):
+    """The recompute-apply GEMM (gemm_nrm_f16_kernel) in its three forms — no shortcut, fp16 residual rows, and `dual`
+    (the shortcut product accumulated and standardised in the same CTA) — against plain torch on the same fp16 operands."""
+    L, P, sp = _native.lib(), _native.ptr, _native.stream_ptr
+    gen = torch.Generator().manual_seed(15)
+    for n, cin, cout, csc, bounds in ((5000, 64, 256, 128, [0, 1234, 1250, 3001, 5000]), (20000, 256, 1024, 512, [0, 9000, 20000]),
+                                      (700, 128, 512, 256, [0, 700])):
+        S = len(bounds) - 1
+        x = F.leaky_relu(torch.randn(n, cin, generator=gen), 0.1).half().to(cuda)
+        w = (torch.randn(cout, cin, generator=gen) / np.sqrt(cin)).half().to(cuda)
+        xs = torch.randn(n, csc, generator=gen).half().to(cuda)
+        wsc = (torch.randn(cout, csc, generator=gen) / np.sqrt(csc)).half().to(cuda)
+        res = torch.randn(n, cout, generator=gen).half().to(cuda)
+        seg = torch.tensor(bounds, dtype=torch.int32, device=cuda)
+        gbytes = int(L.aprb_group_stats_bytes(n, cout))
+        yf, y2f = x.float() @ w.float().t(), xs.float() @ wsc.float().t()
+        for variant in ("none", "res", "dual"):
+            y = torch.full((n, cout), float("nan"), device=cuda); g = torch.empty(gbytes // 4, device=cuda)
+            _native.check(L.aprb_linear_f16_stats_ragged(P(x), P(w), n, cin, cout, P(y), P(g), P(seg), S, sp()), "ragged")
+            y2 = g2 = None
+            if variant == "dual":
+                y2 = torch.full((n, cout), float("nan"), device=cuda); g2 = torch.empty(gbytes // 4, device=cuda)
+                _native.check(L.aprb_linear_f16_stats_ragged(P(xs), P(wsc), n, csc, cout, P(y2), P(g2), P(seg), S, sp()), "ragged")
+            st = torch.empty(S * (2 if variant == "dual" else 1) * 2 * cout, device=cuda)
+            _native.check(L.aprb_instnorm_seg_stats(P(y), P(y2), n, cout, P(seg), S, 1e-5, P(g), P(g2), P(st), sp()), "stats")
+            out = torch.empty(n, cout, device=cuda)
+            _native.check(L.aprb_linear_f16_norm_apply(P(x), P(w), n, cin, cout, P(xs) if variant == "dual" else None,
+                                                       P(wsc) if variant == "dual" else None, csc, P(res) if variant == "res" else None,
+                                                       P(seg), S, P(st), 0.1, P(out), 0, sp()), "apply")
+            for s0, s1 in zip(bounds[:-1], bounds[1:]):
+                ys = yf[s0:s1]
+                ref = (ys - ys.mean(0)) / torch.sqrt(ys.var(0, unbiased=False) + 1e-5)
+                if variant == "res":
+                    ref = ref + res[s0:s1].float()
+                elif variant == "dual":
+                    y2s = y2f[s0:s1]
+                    ref = ref + (y2s - y2s.mean(0)) / torch.sqrt(y2s.var(0, unbiased=False) + 1e-5)
+                ref = F.leaky_relu(ref, 0.1)
+                e = rel(out[s0:s1], ref)
+                assert e < 6e-4, (n, cin, cout, variant, e)              # 10-bit mantissa rounding of the stored activation
+
+
+def test_pool_width_guard_sparse_cloud(cuda, oracle):
+    """a pool search whose max_count is below the limit leaves all-pad columns in the fixed-width device matrix;
+    the max_pool of a strided shortcut must cut at the reference's width min(max_count, limit) per collated pair, or rows
+    the reference sees full gain a phantom zero. Sparse clouds + wide limits, single pair and super-batch, native and
+    module path, against the oracle on the reference-width matrices (collate_ref)."""
+    cfg = kitti_config()
+    limits = [45, 45, 45, 45]
+    torch.manual_seed(0); np.random.seed(0)
+    enc = KPFCNNEncoder(cfg).to(cuda).eval()
+    sd = {k: v.detach().cpu() for k, v in enc.state_dict().items()}
+    pairs = []
+    for sdn, (na, nb) in enumerate([(700, 600), (1500, 400)]):
+        a, b = synth.small_cloud(91 + sdn, na, extent=(25.0, 15.0, 3.0)), synth.small_cloud(95 + sdn, nb, extent=(25.0, 15.0, 3.0))
+        pairs.append(oracle.subsample_batch(np.concatenate([a, b]), np.array([len(a), len(b)], np.int32), sampleDl=0.3))
+    refs, narrow = [], 0
+    for p0, l0 in pairs:
+        ref = collate_ref(p0, l0, cfg, limits, oracle.subsample_batch, oracle.batch_query)
+        narrow += sum(int(m.shape[0] > 0 and m.shape[1] < lim) for m, lim in zip(ref["pools"], limits))
+        cpu = dict(points=[torch.from_numpy(p) for p in ref["points"]], neighbors=[torch.from_numpy(n).long() for n in ref["neighbors"]],
+                   pools=[torch.from_numpy(n).long() for n in ref["pools"]], features=torch.ones(len(p0), 1))
+        refs.append(blocks_ref.encoder_ref(cpu, sd, cfg, return_all=True))
+    assert narrow >= 2, "test clouds are not sparse enough to exercise the width cut"
+    # native, super-batch of both pairs: per-pair widths
+    pipe = KFEPipeline(enc, cfg, limits, clouds_per_segment=2)
+    pipe.set_tap(1 << 30)
+    P0 = np.concatenate([p for p, _ in pairs]); L0 = np.concatenate([l for _, l in pairs])
+    for act16 in (1, 0):
+        _native.check(_native.lib().aprb_set_option(b"act_f16", act16), "aprb_set_option")
+        try:
+            pipe.forward(_t(P0, cuda), _t(L0, cuda))
+            torch.cuda.synchronize()
+            pyr, taps = pipe.pyramid(), pipe.taps()
+        finally:
+            _native.check(_native.lib().aprb_set_option(b"act_f16", 1), "aprb_set_option")
+        for j in range(2):
+            _, rows = _pair_batch(pyr, j, cfg.num_layers)
+            layer = 0
+            for bi, name in enumerate(b for b in cfg.architecture if "upsample" not in b and "unary" not in b):
+                if "strided" in name:
+                    layer += 1
+                off, n = rows[layer]
+                e = rel(taps[(bi, "out")][off:off + n], refs[j][bi])
+                assert e < 1e-2, (act16, j, bi, name, e)                   # a phantom zero row costs > 5e-2 at the strided blocks
+    pipe.set_tap(0)
+    # module path, one pair, widths from build_pyramid_device
+    p0, l0 = pairs[0]
+    pyr = dataloader.build_pyramid_device(_t(p0, cuda), _t(l0, cuda), cfg, limits)
+    blocks.LINEAR_MODE = 'tf32'
+    try:
+        got = enc(pyr)
+    finally:
+        blocks.LINEAR_MODE = 'fp32'
+    assert rel(got, refs[0][-1]) < 1e-2
+
+
+def test_calibrate_neighbors_device_vs_oracle(cuda, oracle):
+    """calibrate_neighbors_device (what bench.py uses) == the reference's calibrate_neighbors (dataloader.py:200-232)
+    restated on the oracle, on two small pairs."""
+    cfg = kitti_config()
+    pairs = []
+    for sdn in (0, 1):
+        a, b = synth.small_cloud(31 + sdn, 2500), synth.small_cloud(41 + sdn, 2300)
+        pairs.append(oracle.subsample_batch(np.concatenate([a, b]), np.array([len(a), len(b)], np.int32), sampleDl=0.3))
+    want = calibrate_ref(pairs, cfg, oracle.subsample_batch, oracle.batch_query, samples_threshold=10 ** 9)
+    got = dataloader.calibrate_neighbors_device([(_t(p, cuda), _t(l, cuda)) for p, l in pairs], cfg, samples_threshold=10 ** 9)
+    assert np.array_equal(np.asarray(got), np.asarray(want)), (got, want)
+
+
+def test_pipeline_refreshes_stale_weights(cuda, oracle):
+    """the native handle snapshots the encoder's weights; a later load_state_dict / in-place update must not
+    leave the tensor path on stale operands."""
+    cfg = kitti_config()
+    a, b = synth.small_cloud(11, 1500), synth.small_cloud(12, 1300)
+    p0, l0 = oracle.subsample_batch(np.concatenate([a, b]), np.array([len(a), len(b)], np.int32), sampleDl=0.3)
+    limits = [30, 30, 30, 30]
+    torch.manual_seed(0); np.random.seed(0)
+    enc = KPFCNNEncoder(cfg).to(cuda).eval()
+    torch.manual_seed(1); np.random.seed(1)
+    other = KPFCNNEncoder(cfg).to(cuda).eval()
+    pipe = KFEPipeline(enc, cfg, limits)
+    y0 = pipe.forward(_t(p0, cuda), _t(l0, cuda)).clone()
+    want = KFEPipeline(other, cfg, limits).forward(_t(p0, cuda), _t(l0, cuda)).clone()
+    enc.load_state_dict(other.state_dict())
+    y1 = pipe.forward(_t(p0, cuda), _t(l0, cuda)).clone()
+    torch.cuda.synchronize()
+    assert not torch.equal(y0, y1)
+    assert torch.equal(y1, want)

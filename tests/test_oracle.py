@@ -152,3 +152,20 @@ def test_pyramid_schedule_and_calibration(oracle):
         assert pyr["neighbors"][l].shape[1] <= 20
     lims = calibrate_ref([(p0, l0)], cfg, oracle.subsample_batch, oracle.batch_query)
     assert lims.shape == (4,) and np.all(lims > 0)
+
+
+def test_load_kernels_matches_reference_golden():
+    """apr_b200.kernel_points.load_kernels == the reference's load_kernels (kernels/kernel_points.py:388-470) bit for bit
+    under the same numpy global seed and call order (fixture: oracle/make_golden_kernel_points.py, run on the reference)."""
+    import os
+    from apr_b200.kernel_points import load_kernels
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kernel_points.npz"))
+    for seed in (0, 1, 12345):
+        np.random.seed(seed)
+        for i, radius in enumerate((1.275, 2.55, 5.1, 10.2)):
+            kp = load_kernels(radius, 15, dimension=3, fixed='center')
+            want = g[f"s{seed}_{i}"]
+            assert kp.dtype == np.float32 and kp.shape == (15, 3)
+            assert np.array_equal(kp, want), (seed, i)
+    with pytest.raises(NotImplementedError):
+        load_kernels(1.0, 13, dimension=3, fixed='center')
