@@ -30,7 +30,14 @@ for _mod in ("torch.backends.mkldnn", "torch.backends.mkldnn.matmul", "torch.bac
         pass
 
 
-def kpconv_ref(q_pts, s_pts, inds, x, kernel_points, weights, extent):
+def _id(t):
+    return t
+
+
+def kpconv_ref(q_pts, s_pts, inds, x, kernel_points, weights, extent, quant=_id):
+    """quant (default: identity = the fp32 reference) emulates a reduced-precision OPERAND format: it is applied to the
+    weights and to the weighted tile, i.e. to the two operands of the contraction, nothing else. Tests use it to tell
+    the drift that a 10-bit-mantissa operand format causes by itself from kernel error."""
     inds = inds.long()
     s = torch.cat((s_pts, torch.zeros_like(s_pts[:1, :]) + 1e6), 0)           # :269 shadow point
     nb = s[inds, :] - q_pts.unsqueeze(1)                                      # :272-275
@@ -39,8 +46,8 @@ def kpconv_ref(q_pts, s_pts, inds, x, kernel_points, weights, extent):
     w = torch.clamp(1 - torch.sqrt(sq) / extent, min=0.0).transpose(1, 2)     # :328-329 [N,K,H]
     xz = torch.cat((x, torch.zeros_like(x[:1, :])), 0)                        # :348 zero feature row
     nx = xz[inds]                                                             # :351 [N,H,Cin]
-    wf = torch.matmul(w, nx)                                                  # :354 [N,K,Cin]
-    out = torch.matmul(wf.permute(1, 0, 2), weights).sum(dim=0)               # :361-366
+    wf = quant(torch.matmul(w, nx))                                           # :354 [N,K,Cin]
+    out = torch.matmul(wf.permute(1, 0, 2), quant(weights)).sum(dim=0)        # :361-366
     nn_ = torch.sum(torch.gt(torch.sum(nx, dim=-1), 0.0), dim=-1)             # :369-370
     nn_ = torch.max(nn_, torch.ones_like(nn_))                                # :371
     return out / nn_.unsqueeze(1)                                             # :372
@@ -62,8 +69,8 @@ def instnorm_ref(x, eps=1e-5):
     return (x - mean) / torch.sqrt(var + eps)
 
 
-def unary_ref(x, weight, relu=True):
-    y = instnorm_ref(F.linear(x, weight))
+def unary_ref(x, weight, relu=True, quant=_id):
+    y = instnorm_ref(F.linear(quant(x), quant(weight)))
     return F.leaky_relu(y, 0.1) if relu else y
 
 
@@ -73,27 +80,31 @@ def _select(name, layer, batch):
     return batch['points'][layer], batch['points'][layer], batch['neighbors'][layer]
 
 
-def simple_ref(x, batch, sd, prefix, name, layer, extent):
+def simple_ref(x, batch, sd, prefix, name, layer, extent, quant=_id, quant_in=True):
     q, s, inds = _select(name, layer, batch)
-    y = kpconv_ref(q, s, inds, x, sd[prefix + 'KPConv.kernel_points'], sd[prefix + 'KPConv.weights'], extent)
-    return F.leaky_relu(instnorm_ref(y), 0.1)
+    # (the first block's KPConv runs in fp32 on the product path too: Cin = 1, CUDA cores)
+    y = kpconv_ref(q, s, inds, x, sd[prefix + 'KPConv.kernel_points'], sd[prefix + 'KPConv.weights'], extent,
+                   quant if quant_in else _id)
+    return quant(F.leaky_relu(instnorm_ref(y), 0.1))
 
 
-def resnetb_ref(feats, batch, sd, prefix, name, layer, extent):
+def resnetb_ref(feats, batch, sd, prefix, name, layer, extent, quant=_id):
+    """quant != identity: every stored activation (= every InstanceNorm + LeakyReLU output) and every contraction operand
+    is passed through it — the product path's storage/operand format; statistics and accumulation stay fp32."""
     q, s, inds = _select(name, layer, batch)
     x = feats
     if prefix + 'unary1.mlp.weight' in sd:                                    # :665 (Identity if in == out/4)
-        x = unary_ref(x, sd[prefix + 'unary1.mlp.weight'])
-    x = kpconv_ref(q, s, inds, x, sd[prefix + 'KPConv.kernel_points'], sd[prefix + 'KPConv.weights'], extent)
-    x = F.leaky_relu(instnorm_ref(x), 0.1)                                    # :669
-    x = unary_ref(x, sd[prefix + 'unary2.mlp.weight'], relu=False)            # :672
+        x = quant(unary_ref(x, sd[prefix + 'unary1.mlp.weight'], quant=quant))
+    x = kpconv_ref(q, s, inds, x, sd[prefix + 'KPConv.kernel_points'], sd[prefix + 'KPConv.weights'], extent, quant)
+    x = quant(F.leaky_relu(instnorm_ref(x), 0.1))                             # :669
+    x = unary_ref(x, sd[prefix + 'unary2.mlp.weight'], relu=False, quant=quant)   # :672
     sc = max_pool_ref(feats, inds) if 'strided' in name else feats            # :675-678
     if prefix + 'unary_shortcut.mlp.weight' in sd:
-        sc = unary_ref(sc, sd[prefix + 'unary_shortcut.mlp.weight'], relu=False)
-    return F.leaky_relu(x + sc, 0.1)                                          # :681
+        sc = unary_ref(sc, sd[prefix + 'unary_shortcut.mlp.weight'], relu=False, quant=quant)
+    return quant(F.leaky_relu(x + sc, 0.1))                                   # :681
 
 
-def encoder_ref(batch, sd, config, return_all=False):
+def encoder_ref(batch, sd, config, return_all=False, quant=_id):
     """Runs the encoder blocks (architectures.py:37-71 bookkeeping, :149-153 loop). batch holds CPU tensors."""
     x = batch['features'].clone()
     r = config.first_subsampling_dl * config.conv_radius
@@ -104,9 +115,9 @@ def encoder_ref(batch, sd, config, return_all=False):
         extent = r * config.KP_extent / config.conv_radius                   # blocks.py:552 / :609
         prefix = f'encoder_blocks.{bi}.'
         if 'simple' in block:
-            x = simple_ref(x, batch, sd, prefix, block, layer, extent)
+            x = simple_ref(x, batch, sd, prefix, block, layer, extent, quant, quant_in=False)
         else:
-            x = resnetb_ref(x, batch, sd, prefix, block, layer, extent)
+            x = resnetb_ref(x, batch, sd, prefix, block, layer, extent, quant)
         outs.append(x)
         bi += 1
         if 'pool' in block or 'strided' in block:
