@@ -36,6 +36,9 @@ SIGNATURES = {
     "aprb_kpconv_forward": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _i, _p, _i, _p, _sz, _p]),
     "aprb_kpconv_weighted_ws_bytes": (_sz, [_i]),
     "aprb_kpconv_weighted": (_i, [_p, _p, _p, _i, _i, _p, _p, _f, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
+    "aprb_kpconv_weighted_f16": (_i, [_p, _p, _p, _i, _p, _p, _f, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
+    "aprb_kpconv_tc_supported": (_i, [_i, _i, _i, _i, _i]),
+    "aprb_kpconv_prepare_weights_f16_ck": (_i, [_p, _i, _i, _i, _p, _p]),
     "aprb_kpconv_backward_data": (_i, [_p, _p, _p, _i, _i, _p, _f, _i, _i, _i, _i, _i, _p, _p, _p]),
     "aprb_max_pool_backward": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "aprb_max_pool": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),

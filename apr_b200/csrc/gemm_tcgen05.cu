@@ -768,6 +768,8 @@ extern int g_act_f16;
 extern int g_dbg_skip_d2h;
 extern int g_host_zero_copy;
 extern int g_kpconv_fused;
+extern int g_kpconv_tc;
+extern int g_ktc_dbg;
 extern int g_gemm_apply;
 extern int g_blocking_sync;
 int g_gemm_cluster = 1;   // 1 disables the cluster/multicast path (aprb_set_option)
@@ -944,6 +946,8 @@ extern "C" int aprb_set_option(const char* name, int value) {
     if (strcmp(name, "dbg_skip_d2h") == 0) { g_dbg_skip_d2h = value; return APRB_OK; }
     if (strcmp(name, "host_zero_copy") == 0) { g_host_zero_copy = value; return APRB_OK; }
     if (strcmp(name, "kpconv_fused") == 0) { g_kpconv_fused = value; return APRB_OK; }
+    if (strcmp(name, "kpconv_tc") == 0) { g_kpconv_tc = value; return APRB_OK; }
+    if (strcmp(name, "ktc_dbg") == 0) { g_ktc_dbg = value; return APRB_OK; }
     if (strcmp(name, "gemm_apply") == 0) { g_gemm_apply = value; return APRB_OK; }
     if (strcmp(name, "blocking_sync") == 0) { g_blocking_sync = value; return APRB_OK; }
     set_error("aprb_set_option: unknown option %s", name);

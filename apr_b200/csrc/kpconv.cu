@@ -26,6 +26,9 @@ int kpconv_fused_run(const float* d_q, const float4* s4, const void* d_idx, int 
                      const float* d_kp, const float* d_wprep, float extent, int Nq, int Ns, int H, int K, int Cin, int Cout,
                      float* d_out, float* d_gstat, cudaStream_t st);
 bool gemm_tf32_supported(int M, int N, int K);
+bool kpconv_tc_supported(int H, int K, int Cin, long long Ns);                 // kpconv_tc.cu
+int kpconv_tc_run(const float* d_q, const float4* s4, const int* d_idx, int ld, const void* d_x16, const float* d_kp,
+                  float extent, int Nq, int Ns, int H, int K, int Cin, void* d_wf16, float* d_inv_nn, cudaStream_t st);
 
 int g_kpw_version = 4;       // aprb_set_option("kpw_version"): 3 = per-kernel-point tables, 4 = CSR lists + lane groups
 int g_kpconv_chunk_mb = 0;   // aprb_set_option("kpconv_chunk_mb"): L2-sized row chunks of the tensor path (0 = off)
@@ -613,6 +616,28 @@ __global__ void prep_weights_f16_kernel(const float* __restrict__ W, int KC, int
     Wt[t] = __float2half_rn(W[(size_t)kc * Cout + o]);
 }
 
+// W [K,Cin,Cout] -> Wt [Cout, Cin*16] fp16 with column c*16 + k (zero for k >= K): B operand for the weighted tile of the
+// tcgen05 weighting kernel (kpconv_tc.cu), which is channel-major / kernel-point-minor
+__global__ void prep_weights_f16_ck_kernel(const float* __restrict__ W, int K, int Cin, int Cout, __half* __restrict__ Wt) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)Cin * KP_MAX_K * Cout) return;
+    const int o = (int)(t / (Cin * KP_MAX_K)), ck = (int)(t % (Cin * KP_MAX_K));
+    const int c = ck / KP_MAX_K, k = ck % KP_MAX_K;
+    Wt[t] = k < K ? __float2half_rn(W[((size_t)k * Cin + c) * Cout + o]) : __float2half_rn(0.f);
+}
+
+extern "C" int aprb_kpconv_prepare_weights_f16_ck(const float* d_W, int K, int Cin, int Cout, void* d_wprep16ck, void* stream) {
+    APRB_REQUIRE(d_W && d_wprep16ck && K >= 1 && K <= KP_MAX_K && Cin >= 1 && Cout >= 1, "bad argument");
+    long long total = (long long)Cin * KP_MAX_K * Cout;
+    APRB_TIMED("prep_weights_kernel", (cudaStream_t)stream, 1, (prep_weights_f16_ck_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(d_W, K, Cin, Cout, (__half*)d_wprep16ck)));
+    APRB_LAUNCH_OK();
+    return APRB_OK;
+}
+
+extern "C" int aprb_kpconv_tc_supported(int H, int K, int Cin, int Cout, int Ns) {
+    return kpconv_tc_supported(H, K, Cin, Ns) && gemm_f16_supported(1, Cout, KP_MAX_K * Cin) ? 1 : 0;
+}
+
 extern "C" int aprb_kpconv_prepare_weights_f16(const float* d_W, int K, int Cin, int Cout, void* d_wprep16, void* stream) {
     APRB_REQUIRE(d_W && d_wprep16 && K >= 1 && Cin >= 1 && Cout >= 1, "bad argument");
     long long total = (long long)K * Cin * Cout;
@@ -764,9 +789,29 @@ extern "C" int aprb_kpconv_forward_stats(const float* d_q, const float* d_s, con
     APRB_REQUIRE((long long)Ns * Cin < 0x7FFFFFFFLL, "feature table too large for 32-bit row offsets");
     if (Nq == 0) return APRB_OK;
     APRB_REQUIRE(d_q && d_idx && d_kp && d_out && d_ws && (Ns == 0 || (d_s && d_x)), "null pointer");
-    APRB_REQUIRE(mode >= 0 && mode <= 4, "mode must be 0 .. 4");
+    APRB_REQUIRE(mode >= 0 && mode <= 5, "mode must be 0 .. 5");
     if (ws_bytes < aprb_kpconv_ws_bytes(Nq, Ns, H, K, Cin, Cout)) { set_error("aprb_kpconv_forward: workspace too small"); return APRB_ERR_WORKSPACE; }
     const int KC = K * Cin;
+    if (mode == 5) {
+        // fp16 features, weighting stage on tcgen05 (kpconv_tc.cu), weighted tile [Nq, Cin*16] channel-major, contraction
+        // against the ck-ordered fp16 operand (aprb_kpconv_prepare_weights_f16_ck)
+        APRB_REQUIRE(d_wprep && !idx_is_i64, "mode 5 needs the ck-ordered fp16 prepared weights and int32 indices");
+        if (Ns == 0 || !kpconv_tc_supported(H, K, Cin, Ns) || !gemm_f16_supported(Nq, Cout, KP_MAX_K * Cin)) {
+            set_error("aprb_kpconv_forward: mode 5 unsupported for H=%d Cin=%d Cout=%d", H, Cin, Cout);
+            return APRB_ERR_UNSUPPORTED;
+        }
+        Carver c5(d_ws, ws_bytes);
+        size_t rows5 = ((size_t)Nq + 127) & ~size_t(127);
+        float* wf5 = c5.take<float>(rows5 * KC);                      // same carving as the other modes; holds Nq*Cin*16 halves
+        float* inv5 = c5.take<float>(rows5);
+        unsigned char* flag5 = c5.take<unsigned char>((size_t)Ns + 1);
+        float4* s45 = c5.take<float4>((size_t)Ns + 1);
+        APRB_REQUIRE((((uintptr_t)d_x | (uintptr_t)wf5) & 15) == 0, "mode 5 needs 16-byte aligned features");
+        APRB_TIMED("rowsum_pos_kernel", st, 1, (rowsum_pos_kernel<<<cdiv(Ns, 8), 256, 0, st>>>(d_x, d_s, Ns, Cin, flag5, s45, 1)));
+        int rc = kpconv_tc_run(d_q, s45, (const int*)d_idx, ld_idx, d_x, d_kp, extent, Nq, Ns, H, K, Cin, wf5, inv5, st);
+        if (rc) return rc;
+        return gemm_f16_rowscale(wf5, d_wprep, Nq, Cout, KP_MAX_K * Cin, inv5, d_out, st, d_gstat, stats_written);
+    }
     if (mode == 3 || mode == 4) {
         const int x16 = mode == 4;                                    // mode 4: d_x itself is fp16 [Ns, Cin]
         // tcgen05 with fp16 operands: d_wprep is the fp16 prepared operand (aprb_kpconv_prepare_weights_f16); the weighted
@@ -870,6 +915,33 @@ extern "C" int aprb_kpconv_weighted(const float* d_q, const float* d_s, const vo
     }
     return launch_kp_weighted(d_q, d_s, d_idx, idx_is_i64, ld_idx, d_x, d_kp, flag, s4, extent, 0, Nq, Ns, H, K, Cin, round_tf32 != 0,
                               d_wf, d_inv_nn, st);
+}
+
+// Stage A+B alone in the native pipeline's format: fp16 features in, fp16 weighted tile out. layout_ck = 0: [Nq, K*Cin]
+// kernel-point-major by the CUDA-core list kernel (mode 4 of aprb_kpconv_forward); 1: [Nq, Cin*16] channel-major by the
+// tcgen05 weighting kernel (mode 5).
+extern "C" int aprb_kpconv_weighted_f16(const float* d_q, const float* d_s, const int32_t* d_idx, int ld_idx, const void* d_x16,
+                                        const float* d_kp, float extent, int Nq, int Ns, int H, int K, int Cin, int layout_ck,
+                                        void* d_wf16, float* d_inv_nn, void* d_ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    APRB_REQUIRE(Nq >= 0 && Ns >= 0 && H >= 1 && H <= 128, "need Nq,Ns >= 0 and 1 <= H <= 128");
+    APRB_REQUIRE(K >= 1 && K <= KP_MAX_K && Cin >= 4 && Cin % 4 == 0 && ld_idx >= H && extent > 0.f, "need 1 <= K <= 16, Cin % 4 == 0, ld >= H, extent > 0");
+    APRB_REQUIRE((long long)Ns * Cin < (1LL << 30), "feature table too large for 32-bit row offsets");
+    if (Nq == 0) return APRB_OK;
+    APRB_REQUIRE(d_q && d_idx && d_kp && d_wf16 && d_inv_nn && d_ws && (Ns == 0 || (d_s && d_x16)), "null pointer");
+    if (ws_bytes < aprb_kpconv_weighted_ws_bytes(Ns)) { set_error("aprb_kpconv_weighted_f16: workspace too small"); return APRB_ERR_WORKSPACE; }
+    unsigned char* flag = (unsigned char*)d_ws;
+    float4* s4 = (float4*)((char*)d_ws + align256((size_t)Ns + 1));
+    if (Ns > 0) APRB_TIMED("rowsum_pos_kernel", st, 1, (rowsum_pos_kernel<<<cdiv(Ns, 8), 256, 0, st>>>((const float*)d_x16, d_s, Ns, Cin, flag, s4, 1)));
+    if (layout_ck) {
+        if (!(Ns > 0 && kpconv_tc_supported(H, K, Cin, Ns) && (((uintptr_t)d_x16 | (uintptr_t)d_wf16) & 15) == 0)) {
+            set_error("aprb_kpconv_weighted_f16: the tcgen05 weighting kernel does not support H=%d Cin=%d", H, Cin);
+            return APRB_ERR_UNSUPPORTED;
+        }
+        return kpconv_tc_run(d_q, s4, d_idx, ld_idx, d_x16, d_kp, extent, Nq, Ns, H, K, Cin, d_wf16, d_inv_nn, st);
+    }
+    return launch_kp_weighted(d_q, d_s, d_idx, 0, ld_idx, (const float*)d_x16, d_kp, flag, s4, extent, 0, Nq, Ns, H, K, Cin, false,
+                              (float*)d_wf16, d_inv_nn, st, 1, 1);
 }
 
 extern "C" int aprb_kpconv_backward_data(const float* d_q, const float* d_s, const void* d_idx, int idx_is_i64, int ld_idx,

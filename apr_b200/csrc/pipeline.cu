@@ -279,8 +279,11 @@ int run_block16(const aprb_kfe& h, size_t bi, const void* feat, bool feat16, boo
     {
         size_t need = aprb_kpconv_ws_bytes(nq, ns, H, h.cfg.K, mid, mid);
         if (A.scratch_bytes() < need) { set_error("aprb_kfe_forward: arena too small for the KPConv workspace"); return APRB_ERR_WORKSPACE; }
-        KFE_OK(aprb_kpconv_forward_stats(q, s, idx, 0, H, (const float*)x1, b.kp, b.kp_W, (const float*)b.kp_Wprep16, b.extent, nq, ns,
-                                         H, h.cfg.K, mid, mid, t2raw, 4, g2.buf, g2.buf ? &g2.written : nullptr, A.scratch(),
+        // weighting stage on tcgen05 (mode 5) when the block carries the ck-ordered operand and the shape allows
+        const bool tc = b.kp_Wprep16ck && aprb_kpconv_tc_supported(H, h.cfg.K, mid, mid, ns);
+        KFE_OK(aprb_kpconv_forward_stats(q, s, idx, 0, H, (const float*)x1, b.kp, b.kp_W,
+                                         (const float*)(tc ? b.kp_Wprep16ck : b.kp_Wprep16), b.extent, nq, ns,
+                                         H, h.cfg.K, mid, mid, t2raw, tc ? 5 : 4, g2.buf, g2.buf ? &g2.written : nullptr, A.scratch(),
                                          A.scratch_bytes(), st));
     }
     KFE_OK(tap_push(h, x1, ns, mid, 1, 4 * (int)bi + 2, st));

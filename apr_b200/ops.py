@@ -182,6 +182,21 @@ def kpconv_prepare_weights_f16(weights):
     return out
 
 
+def kpconv_prepare_weights_f16_ck(weights):
+    """[K,Cin,Cout] f32 -> fp16 operand [Cout, Cin*16], column c*16 + k (kpconv mode 5: tcgen05 weighting kernel)."""
+    N.require_cuda()
+    w = _dev_f32(weights.detach(), "weights")
+    k, cin, cout = w.shape
+    out = torch.empty((cout, cin * 16), dtype=torch.float16, device=w.device)
+    N.check(N.lib().aprb_kpconv_prepare_weights_f16_ck(N.ptr(w), k, cin, cout, N.ptr(out), N.stream_ptr()),
+            "aprb_kpconv_prepare_weights_f16_ck")
+    return out
+
+
+def kpconv_tc_supported(h, k, cin, cout, ns=1):
+    return bool(N.lib().aprb_kpconv_tc_supported(int(h), int(k), int(cin), int(cout), int(ns)))
+
+
 def kpconv_f16_supported(k, cin, cout, h):
     return (k * cin) % 64 == 0 and cout % 16 == 0 and cin % 4 == 0 and h <= 128
 
@@ -190,9 +205,9 @@ def kpconv(q_pts, s_pts, neighb_inds, x, kernel_points, weights, extent, wprep=N
     """K5. Returns [Nq,Cout] f32. mode 4 takes x in fp16 (the native pipeline's activation storage)."""
     N.require_cuda()
     q, s = _dev_f32(q_pts, "q_pts"), _dev_f32(s_pts, "s_pts")
-    if mode == 4:
+    if mode in (4, 5):
         if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float16):
-            raise N.NativeError("kpconv mode 4: x must be a CUDA float16 tensor")
+            raise N.NativeError("kpconv mode 4/5: x must be a CUDA float16 tensor")
         xx = x.contiguous()
     else:
         xx = _dev_f32(x, "x")
@@ -369,6 +384,27 @@ def kpconv_weighted(q_pts, s_pts, neighb_inds, x, kernel_points, extent, round_t
                                       k, cin, 1 if round_tf32 else 0, N.ptr(wf), N.ptr(inv_nn), N.ptr(ws), ws.numel(),
                                       N.stream_ptr())
     N.check(rc, "aprb_kpconv_weighted")
+    return wf, inv_nn
+
+
+def kpconv_weighted_f16(q_pts, s_pts, neighb_inds, x16, kernel_points, extent, layout_ck=False):
+    """Stage A+B in the native pipeline's format: fp16 features -> (wf fp16, inv_nn [Nq] f32). wf is [Nq, K*Cin]
+    (kernel-point-major, CUDA-core list kernel) or, with layout_ck, [Nq, Cin*16] (tcgen05 weighting kernel)."""
+    N.require_cuda()
+    q, s = _dev_f32(q_pts, "q_pts"), _dev_f32(s_pts, "s_pts")
+    kp = _dev_f32(kernel_points.detach(), "kernel_points")
+    idx = _dev_i32(neighb_inds, "neighb_inds")
+    if not (x16.is_cuda and x16.dtype == torch.float16):
+        raise N.NativeError("kpconv_weighted_f16: x must be a CUDA float16 tensor")
+    xx = x16.contiguous()
+    nq, ns, h, k, cin = q.shape[0], s.shape[0], idx.shape[1], kp.shape[0], xx.shape[1]
+    wf = torch.empty((nq, (16 if layout_ck else k) * cin), dtype=torch.float16, device=q.device)
+    inv_nn = torch.empty(nq, dtype=torch.float32, device=q.device)
+    ws = _workspace(N.lib().aprb_kpconv_weighted_ws_bytes(ns), q.device)
+    rc = N.lib().aprb_kpconv_weighted_f16(N.ptr(q), N.ptr(s), N.ptr(idx), idx.shape[1], N.ptr(xx), N.ptr(kp), float(extent), nq, ns,
+                                          h, k, cin, 1 if layout_ck else 0, N.ptr(wf), N.ptr(inv_nn), N.ptr(ws), ws.numel(),
+                                          N.stream_ptr())
+    N.check(rc, "aprb_kpconv_weighted_f16")
     return wf, inv_nn
 
 

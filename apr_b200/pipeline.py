@@ -18,7 +18,7 @@ class _Block(C.Structure):
     _fields_ = [("type", C.c_int), ("strided", C.c_int), ("layer", C.c_int), ("in_dim", C.c_int), ("out_dim", C.c_int),
                 ("radius", C.c_float), ("extent", C.c_float), ("kp", C.c_void_p), ("kp_W", C.c_void_p),
                 ("kp_Wprep", C.c_void_p), ("unary1_W", C.c_void_p), ("unary2_W", C.c_void_p), ("shortcut_W", C.c_void_p),
-                ("kp_Wprep16", C.c_void_p)]
+                ("kp_Wprep16", C.c_void_p), ("kp_Wprep16ck", C.c_void_p)]
 
 
 class _Config(C.Structure):
@@ -96,6 +96,10 @@ class KFEPipeline:
                     wp16 = ops.kpconv_prepare_weights_f16(w)          # KPConv on fp16 operands (its input is a norm output)
                     self._keep.append(wp16)
                     b.kp_Wprep16 = wp16.data_ptr()
+                    if ops.kpconv_tc_supported(1, conv.K, conv.in_channels, conv.out_channels):
+                        wck = ops.kpconv_prepare_weights_f16_ck(w)   # tcgen05 weighting kernel: channel-major weighted tile
+                        self._keep.append(wck)
+                        b.kp_Wprep16ck = wck.data_ptr()
                 for name in ("unary1", "unary2", "unary_shortcut"):
                     sub = getattr(m, name, None)
                     if isinstance(sub, blocks.UnaryBlock):

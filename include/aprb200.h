@@ -127,7 +127,9 @@ size_t aprb_kpconv_ws_bytes(int Nq, int Ns, int H, int K, int Cin, int Cout);
  * 2 = tcgen05 TF32 (error if unsupported shape), 3 = tcgen05 with fp16 operands: d_wprep is then the fp16 operand of
  * aprb_kpconv_prepare_weights_f16 and the weighted tile is produced in fp16 — the 10-bit mantissa of TF32 at half the
  * bytes, for features of O(1) magnitude such as InstanceNorm outputs (K*Cin % 64 == 0, Cin % 4 == 0, H <= 128).
- * 4 = as 3, and d_x itself is fp16 [Ns, Cin] (int32 indices, Cin a multiple of the producer's 32/64/128/256/512 slab). */
+ * 4 = as 3, and d_x itself is fp16 [Ns, Cin] (int32 indices, Cin a multiple of the producer's 32/64/128/256/512 slab).
+ * 5 = fp16 features like 4, with the weighting stage itself on tcgen05 (kpconv_tc.cu) and d_wprep the ck-ordered operand
+ *     of aprb_kpconv_prepare_weights_f16_ck; shapes per aprb_kpconv_tc_supported. */
 int aprb_kpconv_forward(const float* d_q, const float* d_s, const void* d_idx, int idx_is_i64, int ld_idx,
                         const float* d_x, const float* d_kp, const float* d_W, const float* d_wprep,
                         float extent, int Nq, int Ns, int H, int K, int Cin, int Cout,
@@ -151,6 +153,17 @@ size_t aprb_kpconv_weighted_ws_bytes(int Ns);
 int aprb_kpconv_weighted(const float* d_q, const float* d_s, const void* d_idx, int idx_is_i64, int ld_idx,
                          const float* d_x, const float* d_kp, float extent, int Nq, int Ns, int H, int K, int Cin,
                          int round_tf32, float* d_wf, float* d_inv_nn, void* d_ws, size_t ws_bytes, void* stream);
+/* Stage A+B in the native pipeline's storage format: d_x16 [Ns, Cin] fp16 -> fp16 weighted tile (+ d_inv_nn), int32
+ * indices. layout_ck = 0: d_wf16 [Nq, K*Cin] (kernel-point-major) by the CUDA-core list kernel; layout_ck = 1: d_wf16
+ * [Nq, Cin*16] (channel-major, kernel point minor, zero beyond K) by the tcgen05 weighting kernel (kpconv_tc.cu: per
+ * query, D[c, k] = sum_h X[c, h] w[h, k] with the gathered feature rows as an MN-major operand; Cin in {64, 128, 256},
+ * H <= 64 — aprb_kpconv_tc_supported). */
+int aprb_kpconv_weighted_f16(const float* d_q, const float* d_s, const int32_t* d_idx, int ld_idx, const void* d_x16,
+                             const float* d_kp, float extent, int Nq, int Ns, int H, int K, int Cin, int layout_ck,
+                             void* d_wf16, float* d_inv_nn, void* d_ws, size_t ws_bytes, void* stream);
+int aprb_kpconv_tc_supported(int H, int K, int Cin, int Cout, int Ns);
+/* Prepared operand for mode 5: [Cout, Cin*16] fp16, column c*16 + k = W[k, c, :] (zero for k >= K). */
+int aprb_kpconv_prepare_weights_f16_ck(const float* d_W, int K, int Cin, int Cout, void* d_wprep16ck, void* stream);
 /* Data gradient of stage A+B: d_dx [Ns,Cin] = scatter-add over the neighbour lists of w[n,k,h] * d_dwf[n,k,:]
  * (d_dx is zeroed by the call; fp32 red.add, so the summation order is not fixed). */
 int aprb_kpconv_backward_data(const float* d_q, const float* d_s, const void* d_idx, int idx_is_i64, int ld_idx,
@@ -272,6 +285,8 @@ typedef struct {
     const float* shortcut_W;  /* [out, in]    TF32-rounded, NULL when in_dim == out_dim                                   */
     const void* kp_Wprep16;   /* fp16 prepared [Cout, K*Cin] (aprb_kpconv_prepare_weights_f16) or NULL: when set, KPConv  */
                               /* runs with fp16 operands (mode 3) — its input here is always an InstanceNorm output       */
+    const void* kp_Wprep16ck; /* fp16 prepared [Cout, Cin*16] (aprb_kpconv_prepare_weights_f16_ck) or NULL: when set and   */
+                              /* the shape allows, the weighting stage runs on tcgen05 (mode 5)                           */
 } aprb_kfe_block;
 
 typedef struct {

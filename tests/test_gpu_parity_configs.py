@@ -200,6 +200,16 @@ def test_kpconv_mode4_fp16_features_vs_oracle(cuda, cin, cout, h):
     print(f"kpconv mode 4 Cin={cin} Cout={cout} H={h}: rel err {e:.2e}")
     assert e < TOL_KPCONV
     assert torch.all(got[:3] == 0)
+    # mode 5: the weighting stage itself on tcgen05 (kpconv_tc.cu), weighted tile channel-major
+    if ops.kpconv_tc_supported(h, 15, cin, cout, ns):
+        got5 = ops.kpconv(q.to(cuda), s.to(cuda), inds.to(cuda).int(), x16.to(cuda), kp.to(cuda), wd, 0.7,
+                          wprep=ops.kpconv_prepare_weights_f16_ck(wd), mode=5)
+        e5 = rel(got5, want)
+        print(f"kpconv mode 5 Cin={cin} Cout={cout} H={h}: rel err {e5:.2e}")
+        assert e5 < TOL_KPCONV
+        assert torch.all(got5[:3] == 0)
+    else:
+        assert cin == 512
 
 
 def test_max_pool_f16_vs_oracle(cuda):
