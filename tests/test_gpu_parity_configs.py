@@ -200,16 +200,35 @@ def test_kpconv_mode4_fp16_features_vs_oracle(cuda, cin, cout, h):
     print(f"kpconv mode 4 Cin={cin} Cout={cout} H={h}: rel err {e:.2e}")
     assert e < TOL_KPCONV
     assert torch.all(got[:3] == 0)
-    # mode 5: the weighting stage itself on tcgen05 (kpconv_tc.cu), weighted tile channel-major
-    if ops.kpconv_tc_supported(h, 15, cin, cout, ns):
-        got5 = ops.kpconv(q.to(cuda), s.to(cuda), inds.to(cuda).int(), x16.to(cuda), kp.to(cuda), wd, 0.7,
-                          wprep=ops.kpconv_prepare_weights_f16_ck(wd), mode=5)
-        e5 = rel(got5, want)
-        print(f"kpconv mode 5 Cin={cin} Cout={cout} H={h}: rel err {e5:.2e}")
-        assert e5 < TOL_KPCONV
-        assert torch.all(got5[:3] == 0)
-    else:
-        assert cin == 512
+    # mode 5: the weighting stage itself on tcgen05 (kpconv_tc.cu, optional: slower than the list kernel, see
+    # profiles/r02_kpconv_tc.txt), weighted tile channel-major
+    setopt = lambda v: _native.check(_native.lib().aprb_set_option(b"kpconv_tc", v), "aprb_set_option")
+    try:
+        setopt(1)
+        if ops.kpconv_tc_supported(h, 15, cin, cout, ns):
+            got5 = ops.kpconv(q.to(cuda), s.to(cuda), inds.to(cuda).int(), x16.to(cuda), kp.to(cuda), wd, 0.7,
+                              wprep=ops.kpconv_prepare_weights_f16_ck(wd), mode=5)
+            e5 = rel(got5, want)
+            print(f"kpconv mode 5 Cin={cin} Cout={cout} H={h}: rel err {e5:.2e}")
+            assert e5 < TOL_KPCONV
+            assert torch.all(got5[:3] == 0)
+            # the weighted tile itself, against its fp32 definition (blocks.py:269-354), query ranges that end inside a tile
+            for nq_part in (nq, 1, 37):
+                wf, inv = ops.kpconv_weighted_f16(q[:nq_part].to(cuda), s.to(cuda), inds[:nq_part].to(cuda).int(), x16.to(cuda), kp.to(cuda), 0.7,
+                                                  layout_ck=True)
+                sp = torch.cat((s, torch.zeros(1, 3) + 1e6)); nb = sp[inds[:nq_part]] - q[:nq_part].unsqueeze(1)
+                w = torch.clamp(1 - torch.sqrt(((nb.unsqueeze(2) - kp) ** 2).sum(3)) / 0.7, min=0).transpose(1, 2)
+                xz = torch.cat((x16.float(), torch.zeros(1, cin)))
+                want_wf = torch.matmul(w, xz[inds[:nq_part]])                       # [nq, 15, cin]
+                got_wf = wf.float().cpu().view(nq_part, cin, 16)
+                assert rel(got_wf[:, :, :15].permute(0, 2, 1), want_wf) < 6e-4
+                assert bool((got_wf[:, :, 15] == 0).all())
+                nn_ = (xz[inds[:nq_part]].sum(-1) > 0).sum(-1).clamp_min(1).float()
+                assert torch.equal(inv.cpu(), 1.0 / nn_)
+        else:
+            assert cin == 512
+    finally:
+        setopt(0)
 
 
 def test_max_pool_f16_vs_oracle(cuda):

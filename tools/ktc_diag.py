@@ -35,16 +35,16 @@ if len(sys.argv) > 1 and sys.argv[1] == "time":
     pyr = dataloader.build_pyramid_device(p0, l0, cfg, [56, 55, 56, 58])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     setopt("kpconv_tc", 1)
-    for l, cin in ((1, 128),):
+    for l, cin in ((0, 64), (1, 128), (2, 256)):
         q = s = pyr['points'][l]; inds = pyr['neighbors'][l]
         x = torch.randn(len(s), cin, generator=gen).half().to(dev)
         r = 0.3 * 4.25 * 2 ** l
         kp = (torch.randn(15, 3, generator=gen)); kp = (kp / kp.norm(dim=1, keepdim=True) * 0.66 * r).to(dev); kp[0] = 0
-        for dbg in (16,):
+        for dbg in (0, 1, 2, 4, 32):
             setopt("ktc_dbg", dbg)
             ops.kpconv_weighted_f16(q, s, inds, x, kp, r * 2.0 / 4.25, layout_ck=True)
             _native.prof_enable(True); _native.prof_report()
-            for _ in range(1):
+            for _ in range(3):
                 flush.zero_(); ops.kpconv_weighted_f16(q, s, inds, x, kp, r * 2.0 / 4.25, layout_ck=True)
             prof = _native.prof_report(); _native.prof_enable(False)
             print(f"L{l} C{cin} Nq {len(q)} dbg={dbg:2d}: " + " ".join(f"{k} {ms / 3 * 1e3:7.1f} us" for k, (c, ms) in prof.items()))
