@@ -134,12 +134,57 @@ def reference_run(ref, cfg, sd, limits, pairs, n_steps, budget_s):
     return done, dt
 
 
-def reference_setup(cfg, n_pairs, seed0):
+CALIB_PAIRS = 10     # both arms calibrate the neighbourhood limits on the same first pairs of the synthetic set
+
+
+def reference_limits(ref, cfg, pairs):
+    """calibrate_neighbors (datasets/dataloader.py:200-232) restated on the reference's own search: the limits the
+    reference would use on this data — the same pairs our arm calibrates on, so both arms run the same widths."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle.ref import calibrate_ref
+    return [int(v) for v in calibrate_ref(pairs, cfg, ref.subsample_batch, ref.batch_query, samples_threshold=10 ** 9)]
+
+
+def reference_gpu_eager_run(ref, cfg, sd, limits, pairs, dev, budget_s):
+    """The reference's actual deployment shape (lib/tester.py:49-57, datasets/dataloader.py:252-260): pyramids on the HOST by
+    the cpp_wrappers object code (pair-parallel, like DataLoader workers), then the KFE encoder as eager PyTorch ops on the
+    GPU (oracle/blocks_ref.py, the fp32 restatement of models/blocks.py, fed CUDA tensors: int64 indices shipped H2D like
+    lib/trainer.py:299-305 does). Returns (pairs, seconds)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import blocks_ref
+    sd_dev = {k: v.to(dev) for k, v in sd.items()}
+    def to_dev(b):
+        return {k: ([t.to(dev, non_blocking=True) for t in v] if isinstance(v, list) else v.to(dev)) for k, v in b.items()}
+    with torch.no_grad():
+        blocks_ref.encoder_ref(to_dev(reference_pyramid(ref, cfg, limits, *pairs[0])), sd_dev, cfg)   # warm-up (cuBLAS, allocator)
+        torch.cuda.synchronize(dev)
+        cores = torch.get_num_threads()
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=max(1, min(cores, len(pairs)))) as ex:
+            batches = list(ex.map(lambda pr: reference_pyramid(ref, cfg, limits, *pr), pairs))
+        t_pyr = time.perf_counter() - t0
+        done = 0
+        for b in batches:
+            y = blocks_ref.encoder_ref(to_dev(b), sd_dev, cfg).cpu()
+            done += 1
+            if time.perf_counter() - t0 > budget_s:
+                break
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+    if done < len(pairs):
+        dt -= t_pyr * (1.0 - done / len(pairs))
+    return done, dt, t_pyr * done / len(pairs)
+
+
+def reference_setup(cfg, n_pairs, seed0, kind_name="kitti", distant=False):
     from oracle.ref import Oracle, RefL1
     ref = RefL1() if RefL1.available() else Oracle()
-    kind = "reference" if RefL1.available() else "port"
+    # the pyramid half is the reference's own object code when oracle/_ref is built; the encoder half is ALWAYS the
+    # builder's fp32 torch restatement (oracle/blocks_ref.py): models/blocks.py cannot travel to the GPU box
+    kind = "reference+port" if RefL1.available() else "port"
     pairs = []
-    for a, b in raw_pairs(n_pairs, seed0):
+    for i in range(n_pairs):
+        a, b = synth.pair_raw(seed0 + i, kind_name, distant)
         raw = np.concatenate([a, b]); lens = np.array([len(a), len(b)], np.int32)
         pairs.append(ref.subsample_batch(raw, lens, sampleDl=cfg.first_subsampling_dl))   # first-level voxelisation
     from apr_b200.architectures import KPFCNNEncoder
@@ -158,24 +203,24 @@ def run_reference(args):
         torch.set_num_threads(len(os.sched_getaffinity(0)))
     except Exception:
         torch.set_num_threads(os.cpu_count() or 1)
-    ref, kind, pairs, sd = reference_setup(cfg, 2, 0)
+    ref, kind, pairs, sd = reference_setup(cfg, CALIB_PAIRS, 0)
     cores = torch.get_num_threads()
-    limits = LIMITS_FALLBACK
+    limits = reference_limits(ref, cfg, pairs) if not args.no_calibrate else LIMITS_FALLBACK   # same pairs as our arm
     warm = min(args.warmup, 1)
     for i in range(warm):
         reference_step(ref, None, cfg, sd, limits, *pairs[i % len(pairs)])
     done, dt = reference_run(ref, cfg, sd, limits, pairs, args.steps, 420.0)   # keep the whole run within a few minutes
     value = 2.0 * done / dt
     sample = (f"{done} step(s) x 1 KITTI-shaped pair; pyramids = "
-              f"{'reference object code oracle/_ref (nanoflann)' if kind == 'reference' else 'oracle C port'}, built "
-              f"pair-parallel on up to {cores} threads; encoder = fp32 torch-CPU restatement oracle/blocks_ref.py on {cores} threads")
+              f"{'reference object code oracle/_ref (nanoflann)' if kind != 'port' else 'oracle C port'}, built "
+              f"pair-parallel on up to {cores} threads; encoder = fp32 torch-CPU restatement oracle/blocks_ref.py on {cores} threads; "
+              f"limits calibrated (calibrate_neighbors on the reference search) over the same {CALIB_PAIRS} pairs as the GPU arm")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
             "warmup": warm, "ms_per_step": 1e3 * dt / done, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "kitti_pair_kfe_encoder", "pairs_per_step": 1, "points_stacked": int(len(pairs[0][0])),
                        "limits": limits},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port" if kind == "port" else "reference",
-                             "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
@@ -253,11 +298,19 @@ def run_ours(args):
     n_distinct = max(args.pairs, S, P + 2 if P > 1 else 0)
     seeds = shard_indices(n_distinct * world, rank, world)              # round-robin over the global pair list
     kind, distant, wl_name = WORKLOADS[args.workload]
-    for a, b in [synth.pair_raw(sd, kind, distant) for sd in seeds]:
-        raw = torch.from_numpy(np.concatenate([a, b])).to(dev)
-        lens = torch.tensor([len(a), len(b)], dtype=torch.int32, device=dev)
-        p0, l0 = ops.grid_subsample(raw, lens, cfg.first_subsampling_dl)
-        single_dev.append((p0.contiguous().clone(), l0.clone()))
+    by_seed = {}
+
+    def voxelised(sd):
+        if sd not in by_seed:
+            a, b = synth.pair_raw(sd, kind, distant)
+            raw = torch.from_numpy(np.concatenate([a, b])).to(dev)
+            lens = torch.tensor([len(a), len(b)], dtype=torch.int32, device=dev)
+            p0, l0 = ops.grid_subsample(raw, lens, cfg.first_subsampling_dl)
+            by_seed[sd] = (p0.contiguous().clone(), l0.clone(), (a, b))
+        return by_seed[sd]
+
+    for sd in seeds:
+        single_dev.append(voxelised(sd)[:2])
     for j in range(max(args.pairs, S)):                                 # call j carries P distinct pairs, stacked
         sel = [single_dev[(j + t) % n_distinct] for t in range(P)]
         p0 = torch.cat([x[0] for x in sel]).contiguous(); l0 = torch.cat([x[1] for x in sel]).contiguous()
@@ -265,7 +318,10 @@ def run_ours(args):
         pairs_host.append((p0.cpu().pin_memory(), l0.cpu().pin_memory()))
     torch.manual_seed(0); np.random.seed(0)
     enc = KPFCNNEncoder(cfg).to(dev).eval()
-    limits = dataloader.calibrate_neighbors_device(single_dev, cfg) if not args.no_calibrate else LIMITS_FALLBACK
+    # neighbourhood limits: calibrate_neighbors (dataloader.py:200-232) over the first CALIB_PAIRS pairs of the synthetic
+    # set — the same pairs, on every rank and in the reference arm, so that all arms run the same widths
+    calib = [voxelised(sd)[:2] for sd in range(CALIB_PAIRS)] if kind == "kitti" and not distant else single_dev
+    limits = dataloader.calibrate_neighbors_device(calib, cfg, samples_threshold=10 ** 9) if not args.no_calibrate else LIMITS_FALLBACK
     limits = [int(x) for x in limits]
     torch.cuda.synchronize(dev)
 
@@ -333,8 +389,9 @@ def run_ours(args):
 
     out_rows_cap = max(4096, int(pairs_host[0][0].shape[0]) // 4)     # the last level keeps ~6 % of the level-0 rows
     out_cols = pipes[0]._out_cols
-    out_dt = torch.float16 if args.e2e_out == "f16" else torch.float32
-    host_out = [[torch.empty((out_rows_cap, out_cols), dtype=out_dt).pin_memory() for _ in range(2)] for _ in range(S)]
+    host_out_by_dt = {dt: [[torch.empty((out_rows_cap, out_cols), dtype=dt).pin_memory() for _ in range(2)] for _ in range(S)]
+                      for dt in (torch.float16, torch.float32)}
+    host_out = host_out_by_dt[torch.float16 if args.e2e_out == "f16" else torch.float32]
     checks = [0.0] * S
 
     def timed_e2e(steps, warmup):
@@ -376,6 +433,39 @@ def run_ours(args):
         return e0.elapsed_time(e1), time.perf_counter() - t0, (hb // steps, db // steps)
 
     ms_e2e, wall_e2e, io = timed_e2e(args.steps, max(args.warmup, 3))
+    # the other output dtype beside it (the reference hands back fp32; fp16 is the lossless-above-2^-14 compact form)
+    other_dt = torch.float32 if args.e2e_out == "f16" else torch.float16
+    host_out = host_out_by_dt[other_dt]
+    ms_e2e_other, _, io_other = timed_e2e(max(3, args.steps // 2), 3)
+    steps_other = max(3, args.steps // 2)
+
+    # ---- strict drop-in leg: ONE pair per step exactly as the reference's collate + model run it —
+    # numpy in / numpy out through the cpp_wrappers-compatible modules (every subsample_batch / batch_query call pays its
+    # own H2D + D2H), the collated batch moved to the device, the module-path encoder, the output copied back.
+    def dropin_leg(n_steps):
+        from apr_b200 import dataloader as dl
+        items = [voxelised(sd) for sd in seeds[:min(len(seeds), 3)]]
+        np_pairs = []
+        for p0, l0, _ in items:
+            h = p0.cpu().numpy(); n0 = int(l0[0])
+            np_pairs.append((h[:n0].copy(), h[n0:].copy()))
+        def one(i):
+            src, tgt = np_pairs[i % len(np_pairs)]
+            batch = dl.collate_fn_descriptor(dl.make_list_data(src, tgt), cfg, limits)
+            gpu = {k: ([t.to(dev, non_blocking=True) for t in v] if isinstance(v, list) else v)
+                   for k, v in batch.items() if k in ("points", "neighbors", "pools", "upsamples", "stack_lengths")}
+            gpu["features"] = batch["features"].to(dev)
+            with torch.no_grad():
+                return enc(gpu).cpu()
+        one(0)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for i in range(n_steps):
+            y = one(i)
+        torch.cuda.synchronize(dev)
+        return 2.0 * n_steps / (time.perf_counter() - t0), int(y.shape[0])
+
+    dropin_value, _ = dropin_leg(3) if rank == 0 else (None, 0)
 
     # ---- per-kernel pass (one stream, CUDA events around every launch on the launching stream) for the roofline
     _native.prof_enable(True); _native.prof_report()
@@ -411,9 +501,9 @@ def run_ours(args):
 
     if world > 1:
         import torch.distributed as dist
-        t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms_dev, ms_e2e, ms_e2e_other], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev, ms_e2e = t.tolist()
+        ms_dev, ms_e2e, ms_e2e_other = t.tolist()
     clouds = 2.0 * S * P * args.steps * world
     value = clouds / (ms_dev * 1e-3)
     e2e = clouds / (ms_e2e * 1e-3)
@@ -474,6 +564,35 @@ def run_ours(args):
     kernels = {k: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps} for k, v in
                sorted(prof.items(), key=lambda kv: -kv[1][1])[:14]}
 
+    # ---- the memory-bound stages north_star names, each against the HBM peak with SURVEY.md 8d's algorithmic bytes
+    Bc = int(pairs_dev[0][1].shape[0])
+    L = len(n_levels)
+    nb_bytes = 0.0
+    for l in range(L):
+        W = limits[l]
+        nb_bytes += 24.0 * n_levels[l] + 8.0 * Bc + 4.0 * n_levels[l] * W                                    # conv(l)
+        if l + 1 < L:
+            nb_bytes += 12.0 * (n_levels[l + 1] + n_levels[l]) + 8.0 * Bc + 4.0 * n_levels[l + 1] * W          # pool(l)
+            nb_bytes += 12.0 * (n_levels[l] + n_levels[l + 1]) + 8.0 * Bc + 4.0 * n_levels[l] * W              # upsample(l)
+    sub_bytes = sum(12.0 * (n_levels[l] + n_levels[l + 1]) + 8.0 * Bc for l in range(L - 1))
+    def stage(names, nbytes, what):
+        ms = sum(prof[n][1] for n in names if n in prof) / args.steps
+        cnt = sum(prof[n][0] for n in names if n in prof) / args.steps
+        ach = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        return {"kernels": [n for n in names if n in prof], "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                "frac": ach / pk["hbm"], "traffic": None, "ms_per_call": ms, "launches_per_call": cnt,
+                "algorithmic_bytes_per_call": nbytes, "note": what}
+    roof_stages = {
+        "radius_search": stage(["nb_query_kernel", "nb_count_kernel", "nb_scatter_kernel", "nb_grid_params_kernel"], nb_bytes,
+                               "10 searches on 4 cell lists; bytes = 12*Nq + 12*Ns + 8*B + 4*Nq*W per search (SURVEY 8d). The query "
+                               "kernel is instruction-issue bound (candidate scan + (d2, index) sort), not HBM bound: this fraction is "
+                               "its distance from the HBM floor"),
+        "grid_subsample": stage(["sub_params_kernel", "sub_keys_kernel", "cub_radix_sort_pairs32", "cub_radix_sort_pairs64",
+                                 "sub_flags_kernel", "sub_lens_kernel", "sub_emit_kernel"], sub_bytes,
+                                "3 subsamplings; bytes = 12*N_in + 12*M_out + 8*B each (SURVEY 8d); 6.7 MB per call spread over "
+                                "~20 dependent launches: launch-latency bound at this size"),
+    }
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16" if f16_mode else "tf32", "data": "synthetic",
@@ -497,7 +616,15 @@ def run_ours(args):
                            + ("host output in fp16: the final activation is rounded to a 10-bit mantissa, so it converts back to "
                               "the same fp32 values (|v| >= 2^-14), half the PCIe bytes; --e2e-out f32 copies fp32"
                               if args.e2e_out == "f16" else "host output in fp32")},
-            "roofline": roof, "roofline_tensor": roof_tensor, "kernels": kernels,
+            "e2e_other_dtype": {"value": 2.0 * S * P * steps_other * world / (ms_e2e_other * 1e-3), "unit": UNIT,
+                                "out_dtype": "f32" if args.e2e_out == "f16" else "f16", "steps": steps_other,
+                                "d2h_bytes_per_step": int(io_other[1])},
+            "dropin_e2e": ({"value": dropin_value, "unit": UNIT, "sample": "3 steps x 1 pair on rank 0",
+                            "how": "strict drop-in, one pair per step like the reference: numpy in / numpy out through "
+                                   "apr_b200.dataloader.collate_fn_descriptor (13 cpp_wrappers-compatible calls, each with its own "
+                                   "H2D + D2H, int64 indices), H2D of the collated batch, the module-path encoder "
+                                   "(apr_b200.blocks), D2H of the fp32 output; wall clock"} if dropin_value else None),
+            "roofline": roof, "roofline_tensor": roof_tensor, "roofline_stages": roof_stages, "kernels": kernels,
             "wall_ms_per_step": 1e3 * wall_dev / args.steps, "ms_steps": steps_dev}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -509,11 +636,20 @@ def run_ours(args):
         ref, kind, pairs, sd = reference_setup(cfg_r, 2, 0)
         reference_step(ref, None, cfg_r, sd, limits, *pairs[1])          # untimed warm-up (thread pools, allocator)
         done, dt = reference_run(ref, cfg_r, sd, limits, pairs, 8, 15.0)   # bounded sample: ~10-20 s of CPU work
-        line["cpu_baseline"] = {"value": 2.0 * done / dt, "unit": UNIT, "cores": torch.get_num_threads(),
-                                "kind": "reference" if kind == "reference" else "port",
-                                "sample": f"{done} KITTI-shaped pairs in {dt:.1f} s: pyramids by oracle/_ref (reference object "
-                                          "code, pair-parallel over the host threads as DataLoader workers would) + KFE "
-                                          "encoder by oracle/blocks_ref.py (fp32 torch CPU, all threads)"}
+        line["cpu_baseline"] = {"value": 2.0 * done / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                                "sample": f"{done} KITTI-shaped pairs in {dt:.1f} s, same limits as the GPU arm: pyramids by "
+                                          "oracle/_ref (reference object code, pair-parallel over the host threads as DataLoader "
+                                          "workers would) + KFE encoder by oracle/blocks_ref.py (the builder's fp32 torch-CPU "
+                                          "restatement of models/blocks.py, all threads)"}
+        # the reference's deployment shape beside it: host pyramids (reference object code) + eager PyTorch blocks on THIS GPU
+        pairs8 = [pairs[i % len(pairs)] for i in range(8)]
+        gdone, gdt, gpyr = reference_gpu_eager_run(ref, cfg_r, sd, limits, pairs8, dev, 20.0)
+        line["ref_gpu_eager"] = {"value": 2.0 * gdone / gdt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                                 "host_pyramid_share": gpyr / gdt,
+                                 "sample": f"{gdone} KITTI-shaped pairs in {gdt:.1f} s: pyramids on the host by oracle/_ref "
+                                           "(pair-parallel), int64 batch shipped to the device, encoder = oracle/blocks_ref.py run "
+                                           "as eager PyTorch CUDA ops (fp32, cuBLAS): the reference's own GPU path "
+                                           "(lib/tester.py:49-57), restated"}
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:

@@ -20,7 +20,7 @@ def test_reference_arm_line_contract():
     assert d["metric"].startswith("KITTI-shaped clouds/sec") and d["config"]["workload"] == "kitti_pair_kfe_encoder"
     assert d["steps"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None
     cb = d["cpu_baseline"]
-    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert cb["kind"] in ("reference+port", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
