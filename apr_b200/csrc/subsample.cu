@@ -148,6 +148,106 @@ __global__ void sub_emit_kernel(const float* __restrict__ pts, const float* __re
     }
 }
 
+// ---- first-level voxelisation of raw scans, open3d semantics ------------------------------------------------------------
+// The step before the path: raw KITTI scans are float32 [n, 4] (x, y, z, reflectance; datasets/kitti.py:191-194) and are
+// voxelised with open3d's PointCloud.voxel_down_sample(voxel_size) (kitti.py:468-471, :588-589; open3d==0.10.0.0,
+// requirements.txt:5 — third party, absent here: parity UNPINNED, the algorithm below restates its published source,
+// open3d/geometry/PointCloud.cpp VoxelDownSample): points widened to double, voxel_min_bound = min_bound - 0.5 * voxel_size,
+// voxel index = floor((p - voxel_min_bound) / voxel_size) per axis, per-voxel double sum in point order, output =
+// sum / count. The reference then narrows to fp32 (dataloader.py:125/:163). Same arithmetic here (double index and sum,
+// input-order summation, one final narrowing); the row order is ascending (cloud, iz, iy, ix) instead of open3d's
+// unordered_map iteration order.
+struct O3dGrid {
+    double ox, oy, oz;
+    int nx, ny, nz;
+};
+
+__global__ void raw_bbox_kernel(const float* __restrict__ pts, int stride, int N, const int* __restrict__ off, int B,
+                                int* __restrict__ bbox) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int b = find_cloud(off, B, i);
+    const float* p = pts + (size_t)i * stride;
+    int* bb = bbox + 6 * b;
+    // warp-level pre-reduction when the whole warp lies in one cloud
+    int v[6] = {f2ord(p[0]), f2ord(p[1]), f2ord(p[2]), f2ord(p[0]), f2ord(p[1]), f2ord(p[2])};
+    const unsigned act = __activemask();
+    const int b0 = __shfl_sync(act, b, __ffs(act) - 1);
+    if (__all_sync(act, b == b0)) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { v[k] = __reduce_min_sync(act, v[k]); v[3 + k] = __reduce_max_sync(act, v[3 + k]); }
+        if ((threadIdx.x & 31) == __ffs(act) - 1) {
+            for (int k = 0; k < 3; ++k) { atomicMin(bb + k, v[k]); atomicMax(bb + 3 + k, v[3 + k]); }
+        }
+    } else {
+        for (int k = 0; k < 3; ++k) { atomicMin(bb + k, v[k]); atomicMax(bb + 3 + k, v[3 + k]); }
+    }
+}
+
+__global__ void o3d_params_kernel(const int* __restrict__ bbox, const int* __restrict__ off, int B, double vs,
+                                  O3dGrid* __restrict__ grids, int* __restrict__ gdims) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    O3dGrid g = {0.0, 0.0, 0.0, 0, 0, 0};
+    if (off[b + 1] > off[b]) {
+        const int* bb = bbox + 6 * b;
+        g.ox = (double)ord2f(bb[0]) - vs * 0.5; g.oy = (double)ord2f(bb[1]) - vs * 0.5; g.oz = (double)ord2f(bb[2]) - vs * 0.5;
+        const double lim = 2147483632.0;
+        g.nx = (int)fmin(fmax(floor(((double)ord2f(bb[3]) - g.ox) / vs) + 1.0, 1.0), lim);
+        g.ny = (int)fmin(fmax(floor(((double)ord2f(bb[4]) - g.oy) / vs) + 1.0, 1.0), lim);
+        g.nz = (int)fmin(fmax(floor(((double)ord2f(bb[5]) - g.oz) / vs) + 1.0, 1.0), lim);
+        atomicMax(gdims + 0, g.nx); atomicMax(gdims + 1, g.ny); atomicMax(gdims + 2, g.nz);
+    }
+    grids[b] = g;
+}
+
+template <typename KeyT>
+__global__ void o3d_keys_kernel(const float* __restrict__ pts, int stride, int N, const int* __restrict__ off, int B, double vs,
+                                const O3dGrid* __restrict__ grids, const int* __restrict__ gdims, KeyT* __restrict__ keys,
+                                int* __restrict__ vals, int* __restrict__ status) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int bx = bitlen((unsigned)max(gdims[0] - 1, 0)), by = bitlen((unsigned)max(gdims[1] - 1, 0)),
+        bz = bitlen((unsigned)max(gdims[2] - 1, 0)), bc = bitlen((unsigned)max(B - 1, 0));
+    if (i == 0 && status) *status = (bx + by + bz + bc > 64) ? 1 : ((bx + by + bz + bc > (int)sizeof(KeyT) * 8) ? 2 : 0);
+    int b = find_cloud(off, B, i);
+    O3dGrid g = grids[b];
+    const float* p = pts + (size_t)i * stride;
+    long long ix = (long long)floor(((double)p[0] - g.ox) / vs), iy = (long long)floor(((double)p[1] - g.oy) / vs),
+              iz = (long long)floor(((double)p[2] - g.oz) / vs);
+    ix = min(max(ix, 0LL), (long long)g.nx - 1); iy = min(max(iy, 0LL), (long long)g.ny - 1);
+    iz = min(max(iz, 0LL), (long long)g.nz - 1);
+    uint64_t key = (uint64_t)b;
+    key = (key << bz) | (uint64_t)iz;
+    key = (key << by) | (uint64_t)iy;
+    key = (key << bx) | (uint64_t)ix;
+    keys[i] = (KeyT)key;
+    vals[i] = i;
+}
+
+template <typename KeyT>
+__global__ void o3d_emit_kernel(const float* __restrict__ pts, int stride, int N, const KeyT* __restrict__ skeys,
+                                const int* __restrict__ svals, const int* __restrict__ pos, const int* __restrict__ off, int B,
+                                const int* __restrict__ out_start, float* __restrict__ out_pts) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    KeyT key = skeys[i];
+    if (i > 0 && skeys[i - 1] == key) return;  // not a voxel head
+    int b = find_cloud(off, B, i);
+    int row = out_start[b] + pos[i] - pos[off[b]];
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    int cnt = 0;
+    int end = off[b + 1];
+    for (int j = i; j < end && skeys[j] == key; ++j) {   // stable sort => ascending point index = open3d's accumulation order
+        const float* p = pts + (size_t)svals[j] * stride;
+        sx += (double)p[0]; sy += (double)p[1]; sz += (double)p[2];
+        ++cnt;
+    }
+    const double c = (double)cnt;
+    out_pts[3 * (size_t)row] = (float)(sx / c); out_pts[3 * (size_t)row + 1] = (float)(sy / c);
+    out_pts[3 * (size_t)row + 2] = (float)(sz / c);
+}
+
 struct SubWs {
     int *off, *bbox, *gdims, *vals_in, *vals_out, *flags, *pos, *out_start;
     CloudGrid* grids;
@@ -209,6 +309,57 @@ static int run_subsample(const float* d_pts, const int32_t* d_lens, int B, int N
                                                     w.out_start, d_out_pts, d_out_feats)));
     APRB_LAUNCH_OK();
     return APRB_OK;
+}
+
+template <typename KeyT>
+static int run_voxel_raw(const float* d_raw, int stride, const int32_t* d_lens, int B, int N, double vs, float* d_out_pts,
+                         int32_t* d_out_lens, int32_t* d_out_M, int32_t* d_status, SubWs& w, O3dGrid* grids, cudaStream_t st) {
+    const int T = 256;
+    KeyT* keys_in = reinterpret_cast<KeyT*>(w.keys_in);
+    KeyT* keys_out = reinterpret_cast<KeyT*>(w.keys_out);
+    APRB_TIMED("setup_kernel", st, 1, (setup_kernel<<<1, 256, 0, st>>>(d_lens, w.off, nullptr, nullptr, B, w.bbox, w.gdims, 4)));
+    APRB_TIMED("raw_bbox_kernel", st, 1, (raw_bbox_kernel<<<cdiv(N, T), T, 0, st>>>(d_raw, stride, N, w.off, B, w.bbox)));
+    APRB_TIMED("o3d_params_kernel", st, 1, (o3d_params_kernel<<<cdiv(B, T), T, 0, st>>>(w.bbox, w.off, B, vs, grids, w.gdims)));
+    APRB_TIMED("o3d_keys_kernel", st, 1, (o3d_keys_kernel<KeyT><<<cdiv(N, T), T, 0, st>>>(d_raw, stride, N, w.off, B, vs, grids, w.gdims, keys_in, w.vals_in, d_status)));
+    APRB_LAUNCH_OK();
+    int rc = sort_pairs_i32(keys_in, keys_out, w.vals_in, w.vals_out, N, w.temp, w.temp_bytes, st);
+    if (rc) return rc;
+    APRB_TIMED("sub_flags_kernel", st, 1, (sub_flags_kernel<KeyT><<<cdiv(N + 1, T), T, 0, st>>>(keys_out, N, w.flags)));
+    rc = exclusive_scan_i32(w.flags, w.pos, N + 1, w.temp, w.temp_bytes, st);
+    if (rc) return rc;
+    APRB_TIMED("sub_lens_kernel", st, 1, (sub_lens_kernel<<<1, 256, 0, st>>>(w.pos, w.off, B, 0, d_out_lens, w.out_start, d_out_M)));
+    APRB_TIMED("o3d_emit_kernel", st, 1, (o3d_emit_kernel<KeyT><<<cdiv(N, T), T, 0, st>>>(d_raw, stride, N, keys_out, w.vals_out, w.pos, w.off, B, w.out_start, d_out_pts)));
+    APRB_LAUNCH_OK();
+    return APRB_OK;
+}
+
+extern "C" size_t aprb_voxel_downsample_ws_bytes(int N, int B) {
+    if (N < 0 || B < 0) return 0;
+    return aprb_grid_subsample_ws_bytes(N, B, 0) + align256(sizeof(O3dGrid) * (size_t)(B > 0 ? B : 1)) + 256;
+}
+
+extern "C" int aprb_voxel_downsample_raw(const float* d_raw, int stride, const int32_t* d_lens, int B, int N, double voxel_size,
+                                         float* d_out_pts, int32_t* d_out_lens, int32_t* d_out_M, int32_t* d_status,
+                                         int key_bits, void* d_ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    APRB_REQUIRE(B >= 1 && N >= 0 && stride >= 3, "need B >= 1, N >= 0 and a row stride of at least 3 floats");
+    APRB_REQUIRE(d_lens && d_out_lens && d_out_M, "null length/output pointer");
+    APRB_REQUIRE(voxel_size > 0.0, "voxel_size must be positive");
+    APRB_REQUIRE(key_bits == 32 || key_bits == 64, "key_bits must be 32 or 64");
+    if (N == 0) {
+        if (d_status) APRB_CUDA_OK(cudaMemsetAsync(d_status, 0, sizeof(int), st));
+        APRB_CUDA_OK(cudaMemsetAsync(d_out_lens, 0, sizeof(int) * B, st));
+        APRB_CUDA_OK(cudaMemsetAsync(d_out_M, 0, sizeof(int), st));
+        return APRB_OK;
+    }
+    APRB_REQUIRE(d_raw && d_out_pts && d_ws, "null point/workspace pointer");
+    Carver c(d_ws, ws_bytes);
+    SubWs w;
+    carve_sub(c, N, B, &w);
+    O3dGrid* grids = c.take<O3dGrid>(B);
+    if (!c.ok()) { set_error("aprb_voxel_downsample_raw: workspace too small (%zu < %zu)", ws_bytes, c.off); return APRB_ERR_WORKSPACE; }
+    if (key_bits == 32) return run_voxel_raw<uint32_t>(d_raw, stride, d_lens, B, N, voxel_size, d_out_pts, d_out_lens, d_out_M, d_status, w, grids, st);
+    return run_voxel_raw<uint64_t>(d_raw, stride, d_lens, B, N, voxel_size, d_out_pts, d_out_lens, d_out_M, d_status, w, grids, st);
 }
 
 extern "C" int aprb_grid_subsample_batch(const float* d_pts, const int32_t* d_lens, int B, int N, float dl, int max_p,

@@ -82,6 +82,32 @@ def grid_subsample(points, lens, dl, max_p=0, features=None, sync=True, key_bits
     return out[:m], out_lens, out_f[:m]
 
 
+def voxel_downsample_raw(raw, lens, voxel_size, sync=True, key_bits=32):
+    """First-level voxelisation of raw scans with open3d's voxel_down_sample semantics (kitti.py:468-471). raw [N, >=3]
+    f32 cuda rows starting with x, y, z (KITTI: [N,4] xyzr), lens [B] i32 cuda -> (points [M,3] f32, lens [B] i32);
+    with sync=False the full-capacity buffers and the device scalars [M, status]."""
+    N.require_cuda()
+    if not (isinstance(raw, torch.Tensor) and raw.is_cuda and raw.dtype == torch.float32 and raw.dim() == 2 and raw.shape[1] >= 3):
+        raise N.NativeError("voxel_downsample_raw: expected a CUDA float32 tensor [N, >= 3]")
+    rr, ll = raw.contiguous(), _dev_i32(lens, "lens")
+    n, stride, b = rr.shape[0], rr.shape[1], ll.shape[0]
+    out = torch.empty((max(n, 1), 3), dtype=torch.float32, device=rr.device)
+    out_lens = torch.empty(b, dtype=torch.int32, device=rr.device)
+    m_dev = torch.zeros(2, dtype=torch.int32, device=rr.device)
+    ws = _workspace(N.lib().aprb_voxel_downsample_ws_bytes(n, b), rr.device)
+    rc = N.lib().aprb_voxel_downsample_raw(N.ptr(rr), stride, N.ptr(ll), b, n, float(voxel_size), N.ptr(out), N.ptr(out_lens),
+                                           N.ptr(m_dev[0:1]), N.ptr(m_dev[1:2]), int(key_bits), N.ptr(ws), ws.numel(), N.stream_ptr())
+    N.check(rc, "aprb_voxel_downsample_raw")
+    if not sync:
+        return out, out_lens, m_dev
+    m, status = m_dev.tolist()
+    if status == 2 and key_bits == 32:
+        return voxel_downsample_raw(raw, lens, voxel_size, sync, key_bits=64)
+    if status != 0:
+        raise N.NativeError("voxel_downsample_raw: voxel grid does not fit the 64-bit sort key")
+    return out[:m], out_lens
+
+
 def radius_neighbors(queries, supports, q_lens, s_lens, radius, width, want_counts=False):
     """K2+K3. Returns idx [Nq,width] i32 (pad = Ns), and optionally (counts [Nq] i32, max_count [1] i32) on device."""
     N.require_cuda()

@@ -220,6 +220,22 @@ class KFEPipeline:
         self._last_host_inputs = (pts, lens)                         # keep the host buffers alive until the copy ran
         return out[:rows.value], ticket.value
 
+    def forward_from_raw(self, raw_host, lens_host, out_host):
+        """The path from RAW scans: raw_host [N, 4] f32 pinned (x, y, z, reflectance rows of the stacked
+        scans, datasets/kitti.py:191-194), lens_host [B] i32 -> H2D, first-level voxelisation at first_subsampling_dl with
+        open3d's voxel_down_sample semantics (ops.voxel_downsample_raw), pyramid + encoder, D2H of the fp32 output into
+        out_host (pinned [>= rows, C]). Synchronises the stream; returns the filled view of out_host."""
+        self._fresh()
+        with torch.cuda.stream(self.stream):
+            raw = raw_host.to(self.device, non_blocking=True)
+            lens = lens_host.to(self.device, non_blocking=True)
+            p0, l0 = ops.voxel_downsample_raw(raw, lens, self.config.first_subsampling_dl)   # reads M back: one sync
+            y = self.forward(p0, l0)
+            view = out_host[:y.shape[0]]
+            view.copy_(y, non_blocking=True)
+        self.stream.synchronize()
+        return view
+
     def wait_host(self, ticket):
         N.check(self.lib.aprb_kfe_wait_host(self.handle, int(ticket)), "aprb_kfe_wait_host")
 

@@ -78,6 +78,19 @@ int aprb_grid_subsample_batch(const float* d_pts, const int32_t* d_lens, int B, 
                               float* d_out_pts, int32_t* d_out_lens, int32_t* d_out_M, float* d_out_feats,
                               int32_t* d_status, int key_bits, void* d_ws, size_t ws_bytes, void* stream);
 
+/* First-level voxelisation of RAW scans (the step before the path): d_raw [N, stride] fp32 rows whose first
+ * three floats are x, y, z (KITTI .bin: stride 4 = x, y, z, reflectance, datasets/kitti.py:191-194), stacked clouds of
+ * d_lens [B] points, with open3d's PointCloud.voxel_down_sample(voxel_size) semantics (kitti.py:468-471, :588-589;
+ * open3d==0.10.0.0 is a third-party dependency absent from this tree: parity UNPINNED, the published algorithm is restated):
+ * points widened to double, grid origin = min_bound - 0.5 * voxel_size, voxel = floor((p - origin) / voxel_size), per-voxel
+ * double sum in point order, output = float(sum / count) — the narrowing datasets/dataloader.py:125/:163 applies anyway.
+ * Rows come out in ascending (cloud, iz, iy, ix) order (open3d: unordered_map order). Outputs / status / key_bits as in
+ * aprb_grid_subsample_batch. */
+size_t aprb_voxel_downsample_ws_bytes(int N, int B);
+int aprb_voxel_downsample_raw(const float* d_raw, int stride, const int32_t* d_lens, int B, int N, double voxel_size,
+                              float* d_out_pts, int32_t* d_out_lens, int32_t* d_out_M, int32_t* d_status, int key_bits,
+                              void* d_ws, size_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------- K2+K3: batched radius neighbour search ----- */
 size_t aprb_radius_neighbors_ws_bytes(int Nq, int Ns, int B);
 

@@ -223,3 +223,26 @@ def test_collate_host_and_device_pyramids_agree_with_oracle(cuda, oracle):
     lim = dl.calibrate_neighbors([dl.make_list_data(p0[:l0[0]], p0[l0[0]:])[0]], cfg, dl.collate_fn_descriptor)
     from oracle.ref import calibrate_ref
     assert np.array_equal(lim, calibrate_ref([(p0, l0)], cfg, oracle.subsample_batch, oracle.batch_query))
+
+
+def test_voxel_downsample_raw_open3d_semantics(cuda):
+    """First-level voxelisation of raw [n,4] scans: the CUDA path vs the numpy restatement of open3d 0.10's
+    VoxelDownSample (oracle/o3d_voxel_ref.py — parity unpinned: open3d itself is absent) — bit-exact, raw KITTI-shaped
+    scan pair with a reflectance column, plus an empty cloud in the batch; and the voxel grid differs from
+    grid_subsampling's (origin at min - 0.5 voxel instead of floor(min/dl)*dl)."""
+    import torch
+    from apr_b200 import ops, synth
+    from oracle.o3d_voxel_ref import voxel_down_sample_batch_ref
+    a, b = synth.pair_raw(2, "kitti")
+    a, b = a[:30000], b[:25000]
+    rng = np.random.default_rng(0)
+    raw = np.concatenate([a, np.zeros((0, 3), np.float32), b])
+    raw4 = np.concatenate([raw, rng.random((len(raw), 1), dtype=np.float32)], 1)          # x, y, z, reflectance
+    lens = np.array([len(a), 0, len(b)], np.int32)
+    want_p, want_l = voxel_down_sample_batch_ref(raw4, lens, 0.3)
+    got_p, got_l = ops.voxel_downsample_raw(torch.from_numpy(raw4).to(cuda), torch.from_numpy(lens).to(cuda), 0.3)
+    assert np.array_equal(got_l.cpu().numpy(), want_l)
+    assert np.array_equal(got_p.cpu().numpy(), want_p)
+    ref_p, ref_l = ops.grid_subsample(torch.from_numpy(raw).to(cuda), torch.from_numpy(lens).to(cuda), 0.3)
+    assert abs(int(ref_l.sum()) - int(want_l.sum())) < 0.05 * int(want_l.sum())              # same density, different grid
+    assert ref_p.shape != got_p.shape or not torch.equal(ref_p, got_p)
