@@ -73,6 +73,7 @@ SIGNATURES = {
     "aprb_kfe_wait_host": (_i, [_p, _i]),
     "aprb_kfe_set_host_output_f16": (_i, [_p, _i]),
     "aprb_kfe_get": (_i, [_p, _i, _i, _p, _p, _p]),
+    "aprb_kfe_get_block_output": (_i, [_p, _i, _p, _p, _p, _p]),
     "aprb_kfe_set_tap": (_i, [_p, _p, _sz]),
     "aprb_kfe_tap_count": (_i, [_p]),
     "aprb_kfe_get_tap": (_i, [_p, _i, _p, _p, _p, _p, _p]),

@@ -45,6 +45,8 @@ struct aprb_kfe {
     char* tap_buf; size_t tap_cap, tap_off;
     struct Tap { size_t off; int rows, cols, f16, tag; };   // tag = 4 * block + kind (0 block output, 1 KPConv output, 2 KPConv input)
     std::vector<Tap> taps;
+    struct BlockOut { const void* p; int rows, cols, f16; };
+    std::vector<BlockOut> block_out;        // every encoder block's output of the last forward (lives in the arena)
     // fp16 activation mode: fp16 copies of the unary weights, owned by the handle (cudaMalloc at create), per block
     // [unary1, unary2, shortcut]; act16_ok = every block fits the fp16 kernels' shape constraints
     std::vector<void*> w16;
@@ -479,6 +481,7 @@ extern "C" int aprb_kfe_forward(aprb_kfe* hp, const float* d_pts, const int32_t*
     h.S = cdiv(B, cps);
     for (int l = 0; l < KFE_MAX_LEVELS; ++l) { h.seg[l] = nullptr; h.pool_w[l] = nullptr; }
     h.taps.clear(); h.tap_off = 0;
+    h.block_out.clear();
     if (h.S > 1) {
         KFE_ALLOC(seg0, int, (size_t)h.S + 1);
         KFE_OK(aprb_segment_offsets(d_lens, B, cps, seg0, st));
@@ -512,6 +515,11 @@ extern "C" int aprb_kfe_forward(aprb_kfe* hp, const float* d_pts, const int32_t*
                 KFE_OK(run_block(h, h.blocks[bi], x, &y, &yc, A, st));
             }
             x = y; xc = yc;
+            {
+                const aprb_kfe_block& ob = h.blocks[bi];
+                h.block_out.push_back({y, ob.strided ? h.n[ob.layer + 1] : h.n[ob.layer], yc,
+                                       (act16 && (x_is16 || (bi + 1 == h.blocks.size() && h.y_last_f16))) ? 1 : 0});
+            }
             if (h.tap_buf) {                                        // debug tap: keep a copy of this block's output
                 const aprb_kfe_block& tb = h.blocks[bi];
                 const int rows = tb.strided ? h.n[tb.layer + 1] : h.n[tb.layer];
@@ -697,6 +705,14 @@ extern "C" int aprb_kfe_wait_host(aprb_kfe* h, int ticket) {
 extern "C" int aprb_kfe_set_tap(aprb_kfe* h, void* d_buf, size_t bytes) {
     APRB_REQUIRE(h, "null handle");
     h->tap_buf = (char*)d_buf; h->tap_cap = d_buf ? bytes : 0; h->tap_off = 0; h->taps.clear();
+    return APRB_OK;
+}
+
+extern "C" int aprb_kfe_get_block_output(const aprb_kfe* h, int block, const void** d_ptr, int* rows, int* cols, int* is_f16) {
+    APRB_REQUIRE(h && d_ptr && rows && cols && is_f16, "null argument");
+    APRB_REQUIRE(block >= 0 && (size_t)block < h->block_out.size(), "block index out of range (run a forward first)");
+    const aprb_kfe::BlockOut& o = h->block_out[(size_t)block];
+    *d_ptr = o.p; *rows = o.rows; *cols = o.cols; *is_f16 = o.f16;
     return APRB_OK;
 }
 

@@ -239,6 +239,15 @@ class KFEPipeline:
     def wait_host(self, ticket):
         N.check(self.lib.aprb_kfe_wait_host(self.handle, int(ticket)), "aprb_kfe_wait_host")
 
+    def block_output(self, i):
+        """Output of encoder block i of the last forward (fp16 or fp32 view into the arena, valid until the next one)."""
+        p, r, c, f = C.c_void_p(), C.c_int(), C.c_int(), C.c_int()
+        N.check(self.lib.aprb_kfe_get_block_output(self.handle, int(i), C.byref(p), C.byref(r), C.byref(c), C.byref(f)),
+                "aprb_kfe_get_block_output")
+        dt, es = (torch.float16, 2) if f.value else (torch.float32, 4)
+        off = p.value - self.arena.data_ptr()
+        return self.arena[off:off + r.value * c.value * es].view(dt).view(r.value, c.value)
+
     def set_tap(self, nbytes):
         """Test hook: keep a device copy of every encoder block's output of the following forwards (nbytes of device
         memory; 0 switches it off). Read them with `taps()`."""
@@ -277,3 +286,79 @@ class KFEPipeline:
                     t = self._view(p.value, r.value, c.value, dt)
                 out[key].append(t.view(-1) if what == 4 else t)
         return out
+
+
+class KPFCNNPipeline:
+    """BASELINE config 3: the full KPFCNN forward (models/architectures.py:137-212) for P collated pairs stacked in one
+    call, stream-ordered on one CUDA stream: the KFE encoder natively (`aprb_kfe_forward`), then the bottleneck Conv1d, the
+    GCN (per pair: self / cross attention on the coarsest level, N_3 ~ 2k points — library ops, models/gcn.py), the
+    cross-saliency softmax and the nearest-upsample + unary decoder, super-batched with per-pair InstanceNorm segments
+    (`ops.closest_pool`, `ops.instnorm_lrelu_seg`, Linear through cuBLAS or the tcgen05 GEMM by shape).
+    net: apr_b200.architectures.KPFCNN on the device. Returns (feats_f [N0, D], scores_overlap [N0], scores_saliency [N0])."""
+
+    def __init__(self, net, config, neighborhood_limits, stream=None, clouds_per_segment=2):
+        self.net, self.config = net, config
+        self.enc = KFEPipeline(net, config, neighborhood_limits, build_upsamples=True, stream=stream,
+                               clouds_per_segment=clouds_per_segment)
+        self.stream, self.device = self.enc.stream, self.enc.device
+        self.cps = max(int(clouds_per_segment), 0)
+
+    @torch.no_grad()
+    def forward(self, points, lengths):
+        import torch.nn.functional as F
+        from .gcn import _conv1d
+        net, cfg = self.net, self.config
+        y = self.enc.forward(points, lengths)                         # encoder output [N_last, C] fp32 (arena view)
+        with torch.cuda.stream(self.stream):
+            pyr = self.enc.pyramid()
+            nlev = cfg.num_layers
+            cps = self.cps if self.cps > 0 else int(lengths.shape[0])
+            segs = [ops.segment_offsets(pyr['stack_lengths'][l], cps) for l in range(nlev)]
+            # skip features = the INPUT of every strided block (architectures.py:149-152) = the previous block's output
+            skips = [self.enc.block_output(bi - 1).float() for bi in net.encoder_skips if 0 < bi < len(net.encoder_blocks)]
+            # one tiny read-back: rows per cloud and level (the GCN runs per pair; so does InstanceNorm on odd widths)
+            lens_h = torch.stack([pyr['stack_lengths'][l] for l in range(nlev)]).cpu()
+            lens_c = lens_h[nlev - 1].view(-1, 2) if cps == 2 else lens_h[nlev - 1].view(1, -1)
+            pair_rows = [lens_h[l].view(-1, cps).sum(1).tolist() for l in range(nlev)]
+            pts_c = pyr['points'][nlev - 1]
+            feats_all = _conv1d(net.bottle, y)                          # bottleneck, all pairs at once
+            rows, a = [], 0
+            for pr in range(lens_c.shape[0]):                           # GCN + cross saliency: per collated pair
+                n_src, n_tgt = int(lens_c[pr, 0]), int(lens_c[pr, 1])
+                f = feats_all[a:a + n_src + n_tgt]
+                p = pts_c[a:a + n_src + n_tgt]
+                f0, f1 = net.gnn(p[:n_src], p[n_src:], f[:n_src], f[n_src:])
+                g = _conv1d(net.proj_gnn, torch.cat([f0, f1], dim=0))
+                scores = _conv1d(net.proj_score, g)
+                fn = F.normalize(g, p=2, dim=1)
+                inner = fn[:n_src] @ fn[n_src:].t()
+                temperature = torch.exp(net.epsilon) + 0.03
+                s1 = torch.softmax(inner / temperature, dim=1) @ scores[n_src:]
+                s2 = torch.softmax(inner.t() / temperature, dim=1) @ scores[:n_src]
+                body = g if net.condition else f
+                rows.append(torch.cat([scores, torch.cat((s1, s2), dim=0), body] if net.add_cross_overlap else [scores, body], dim=1))
+                a += n_src + n_tgt
+            x = torch.cat(rows, dim=0)
+            layer = nlev - 1
+            for i, blk in enumerate(net.decoder_blocks):                # decoder, super-batched
+                if i in net.decoder_concats:
+                    x = torch.cat([x, skips.pop()], dim=1)
+                if isinstance(blk, blocks.NearestUpsampleBlock):
+                    x = ops.closest_pool(x, pyr['upsamples'][blk.layer_ind - 1])
+                    layer -= 1
+                elif isinstance(blk, blocks.LastUnaryBlock):
+                    x = blocks._linear(blk.mlp, x)
+                else:                                                    # UnaryBlock: Linear -> per-pair InstanceNorm -> LeakyReLU
+                    t = blocks._linear(blk.mlp, x)
+                    slope = 1.0 if blk.no_relu else 0.1
+                    if t.shape[1] % 4 == 0:
+                        x = ops.instnorm_lrelu_seg(t, segs[layer], slope=slope)
+                    else:                                                # odd widths (g + 2 = 258): the generic kernel, pair by pair
+                        x, r0 = torch.empty_like(t), 0
+                        for nr in pair_rows[layer]:
+                            ops.instnorm_lrelu(t[r0:r0 + nr], slope=slope, out=x[r0:r0 + nr])
+                            r0 += nr
+            d = net.final_feats_dim
+            overlap = net.regular_score(torch.sigmoid(x[:, d]).clamp(0, 1))
+            sal = net.regular_score(torch.sigmoid(x[:, d + 1]).clamp(0, 1))
+            return F.normalize(x[:, :d], p=2, dim=1), overlap, sal

@@ -704,6 +704,127 @@ def run_ours(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------------ config 3: full KPFCNN
+def run_kpfcnn(args):
+    """BASELINE configs[2]: full KPFCNN encoder-decoder forward (models/architectures.py:137-212) on LoKITTI-shaped distant
+    pairs, sharded by pair over the ranks (no collective). Per call: P stacked pairs through KPFCNNPipeline (native KFE
+    encoder, then bottleneck / GCN / cross-saliency / decoder stream-ordered in the same call). `value` device-resident,
+    `e2e` from pinned host points to pinned host (feats_f, scores) with one stream sync per call."""
+    from concurrent.futures import ThreadPoolExecutor
+    from apr_b200 import _native, blocks, dataloader, ops
+    from apr_b200.architectures import KPFCNN
+    from apr_b200.pipeline import KPFCNNPipeline
+    from apr_b200.shard import shard_indices
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    _native.require_cuda()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = kitti_config() if args.workload != "nuscenes" else nuscenes_config()
+    blocks.LINEAR_MODE = "tf32"
+    S, P = max(1, args.streams), max(1, args.batch)
+    kind, distant, wl_name = WORKLOADS[args.workload]
+    n_distinct = max(args.pairs, S, P + 2)
+    single = []
+    for sd in shard_indices(n_distinct * world, rank, world):
+        a, b = synth.pair_raw(sd, kind, distant)
+        raw = torch.from_numpy(np.concatenate([a, b])).to(dev)
+        lens = torch.tensor([len(a), len(b)], dtype=torch.int32, device=dev)
+        p0, l0 = ops.grid_subsample(raw, lens, cfg.first_subsampling_dl)
+        single.append((p0.contiguous().clone(), l0.clone()))
+    calls = []
+    for j in range(max(args.pairs, S)):
+        sel = [single[(j + t) % n_distinct] for t in range(P)]
+        p0 = torch.cat([x[0] for x in sel]).contiguous(); l0 = torch.cat([x[1] for x in sel]).contiguous()
+        calls.append((p0, l0, p0.cpu().pin_memory(), l0.cpu().pin_memory()))
+    limits = [int(x) for x in dataloader.calibrate_neighbors_device(single, cfg, samples_threshold=10 ** 9)]
+    torch.manual_seed(0); np.random.seed(0)
+    net = KPFCNN(cfg).to(dev).eval()
+    streams = [torch.cuda.Stream(dev) for _ in range(S)]
+    pipes = [KPFCNNPipeline(net, cfg, limits, stream=streams[k], clouds_per_segment=2) for k in range(S)]
+    pool = ThreadPoolExecutor(max_workers=S) if S > 1 else None
+    main_stream = torch.cuda.current_stream(dev)
+    done_ev = [torch.cuda.Event() for _ in range(S)]
+    n0max = max(c[0].shape[0] for c in calls)
+    host_out = [torch.empty((n0max, cfg.final_feats_dim + 2), dtype=torch.float32).pin_memory() for _ in range(S)]
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def run(n_calls, first, from_host):
+        start = torch.cuda.Event(); start.record(main_stream)
+        def work(k):
+            streams[k].wait_event(start)
+            hb = db = 0
+            for c in range(n_calls):
+                p0, l0, hp, hl = calls[((first + c) * S + k) % len(calls)]
+                if from_host:
+                    with torch.cuda.stream(streams[k]):
+                        p0 = hp.to(dev, non_blocking=True); l0 = hl.to(dev, non_blocking=True)
+                ff, so, ss = pipes[k].forward(p0, l0)
+                if from_host:
+                    with torch.cuda.stream(streams[k]):
+                        out = host_out[k][:ff.shape[0]]
+                        out.copy_(torch.cat([ff, so[:, None], ss[:, None]], dim=1), non_blocking=True)
+                    streams[k].synchronize()
+                    hb += hp.numel() * 4 + hl.numel() * 4; db += out.numel() * 4
+            done_ev[k].record(streams[k])
+            return hb, db
+        res = list(pool.map(work, range(S))) if pool else [work(0)]
+        for k in range(S):
+            main_stream.wait_event(done_ev[k])
+        return sum(r[0] for r in res), sum(r[1] for r in res)
+
+    def timed(steps, warmup, from_host):
+        run(warmup, 0, from_host)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0c = _native.launch_count()
+        e0.record(main_stream)
+        io = run(steps, warmup, from_host)
+        e1.record(main_stream)
+        barrier()
+        return e0.elapsed_time(e1), io, _native.launch_count() - l0c
+
+    clk = ClockSampler(local); clk.start()
+    ms_dev, _, launches = timed(args.steps, args.warmup, False)
+    clocks = clk.stop()
+    ms_e2e, io, _ = timed(args.steps, 3, True)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = t.tolist()
+    clouds = 2.0 * S * P * args.steps * world
+    if rank == 0:
+        print(json.dumps({"metric": METRIC.replace("KFE)", "full KPFCNN encoder-decoder)"), "value": clouds / (ms_dev * 1e-3), "unit": UNIT,
+                          "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+                          "config": {"workload": wl_name.replace("kfe_encoder", "kpfcnn_forward"), "pairs_per_step": S * P,
+                                     "pairs_per_call": P, "concurrent_streams": S, "points_stacked": int(calls[0][0].shape[0]),
+                                     "limits": limits, "parallelism": f"pairs x{world}",
+                                     "path": "KPFCNNPipeline: native aprb_kfe_forward + bottleneck / GCN / decoder stream-ordered",
+                                     "l2": "working set per call >> L2, streams free-running"},
+                          "clocks": clocks, "gpu_launches": int(launches),
+                          "e2e": {"value": clouds / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(io[0] // args.steps),
+                                  "d2h_bytes_per_step": int(io[1] // args.steps),
+                                  "how": "pinned host points -> H2D -> KPFCNNPipeline.forward -> D2H of [N0, final_feats_dim + 2] fp32 "
+                                         "(feats_f, scores_overlap, scores_saliency), one stream sync per call"}}))
+    if pool:
+        pool.shutdown()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
 # ------------------------------------------------------------------------------------------------ training step
 def run_train(args):
     """BASELINE configs[4]: one APR training step per rank and step — differentiable KPFCNN forward (our KPConv kernels),
@@ -812,6 +933,8 @@ def main():
     ap.add_argument("--e2e-out", default="f16", choices=["f16", "f32"],
                     help="dtype of the encoder output copied to the host in the e2e leg (f16 is lossless for |v| >= 2^-14)")
     ap.add_argument("--opt", action="append", default=[], help="native tuning switch name=value (aprb_set_option)")
+    ap.add_argument("--net", default="kfe", choices=["kfe", "kpfcnn"],
+                    help="kfe = the KFE encoder (the headline metric); kpfcnn = full encoder-decoder forward (BASELINE configs[2])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -819,6 +942,8 @@ def main():
     args.warmup = max(args.warmup, 3)
     if args.mode == "train":
         return run_train(args)
+    if args.net == "kpfcnn":
+        return run_kpfcnn(args)
     return run_ours(args)
 
 

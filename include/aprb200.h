@@ -349,6 +349,10 @@ int aprb_kfe_wait_host(aprb_kfe* h, int ticket);
 /* After a forward: pyramid tensors in the arena. what: 0 = points [n,3] f32, 1 = neighbors, 2 = pools, 3 = upsamples
  * (int32 [n, limit]), 4 = stack lengths [B] i32. Pointers stay valid until the next forward on this handle. */
 int aprb_kfe_get(const aprb_kfe* h, int what, int level, const void** d_ptr, int* rows, int* cols);
+/* Output of encoder block `block` of the last forward ([rows, cols], fp16 when *is_f16; a pointer into the arena, valid
+ * until the next forward): the decoder half of KPFCNN concatenates the inputs of the strided blocks as skip features
+ * (models/architectures.py:149-152, :195-197). */
+int aprb_kfe_get_block_output(const aprb_kfe* h, int block, const void** d_ptr, int* rows, int* cols, int* is_f16);
 /* Test hook: with a tap buffer set, every forward also copies intermediate tensors (device to device, stream ordered)
  * into d_buf: tag 4*b + 0 = output of encoder block b, 4*b + 1 = raw output of its KPConv (fp32), 4*b + 2 = the input of
  * its KPConv (fp16 activation mode only). aprb_kfe_get_tap(h, i) returns the i-th recorded tensor [rows, cols], fp16

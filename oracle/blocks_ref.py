@@ -175,9 +175,11 @@ def cross_attention_ref(x, src, sd, prefix, heads):
     return conv('mlp.3', F.relu(h))
 
 
-def kpfcnn_ref(batch, sd, config):
-    """Full KPFCNN.forward (architectures.py:137-212) on CPU tensors -> (feats_f, scores_overlap, scores_saliency)."""
-    outs = encoder_ref(batch, sd, config, return_all=True)
+def kpfcnn_ref(batch, sd, config, enc_outs=None):
+    """Full KPFCNN.forward (architectures.py:137-212) on CPU tensors -> (feats_f, scores_overlap, scores_saliency).
+    enc_outs (optional): the outputs of the encoder blocks to use instead of running the encoder — tests feed the bottleneck
+    / GNN / decoder half with the product's own encoder activations to check that half on identical inputs."""
+    outs = enc_outs if enc_outs is not None else encoder_ref(batch, sd, config, return_all=True)
     arch = list(config.architecture)
     start = next(i for i, b in enumerate(arch) if 'upsample' in b)
     skips, x_in = [], batch['features']

@@ -423,3 +423,59 @@ def test_pipeline_refreshes_stale_weights(cuda, oracle):
     torch.cuda.synchronize()
     assert not torch.equal(y0, y1)
     assert torch.equal(y1, want)
+
+
+def test_kpfcnn_pipeline_config3_vs_oracle(cuda, oracle):
+    """BASELINE config 3's network through KPFCNNPipeline (native encoder + bottleneck / GCN / decoder stream-ordered in the
+    same call, two LoKITTI-like pairs super-batched) at the KITTI widths:
+      (a) the bottleneck / GNN / decoder half on IDENTICAL inputs — the oracle (blocks_ref.kpfcnn_ref <- architectures.py:
+          155-212, models/gcn.py) is fed the product's own encoder activations — <= 5e-3 (the bar VERDICT r1 set);
+      (b) end to end against the free-running fp32 oracle: reported, bounded by the operand-format drift (see above)."""
+    from apr_b200.architectures import KPFCNN
+    from apr_b200.pipeline import KPFCNNPipeline
+    cfg = kitti_config()
+    limits = [32, 32, 32, 32]
+    torch.manual_seed(0); np.random.seed(0)
+    net = KPFCNN(cfg).eval()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.to(cuda)
+    pairs = []
+    for sdn in (0, 1):
+        a = synth.small_cloud(71 + sdn, 3200)
+        b = synth.small_cloud(71 + sdn, 3000) + np.array([6.0, 0.5, 0.0], np.float32)      # same scene, shifted sensor
+        pairs.append(oracle.subsample_batch(np.concatenate([a, b]), np.array([len(a), len(b)], np.int32), sampleDl=0.3))
+    P0 = np.concatenate([p for p, _ in pairs]); L0 = np.concatenate([l for _, l in pairs])
+    blocks.LINEAR_MODE = 'tf32'
+    try:
+        pipe = KPFCNNPipeline(net, cfg, limits, clouds_per_segment=2)
+        ff, so, ss = pipe.forward(_t(P0, cuda), _t(L0, cuda))
+        torch.cuda.synchronize()
+        pyr = pipe.enc.pyramid()
+        enc_outs = [pipe.enc.block_output(i).float().cpu() for i in range(len(net.encoder_blocks))]
+    finally:
+        blocks.LINEAR_MODE = 'fp32'
+    n_enc = len(net.encoder_blocks)
+    arch = [b for b in cfg.architecture if "upsample" not in b and "unary" not in b]
+    for j, (p0, l0) in enumerate(pairs):
+        ref = collate_ref(p0, l0, cfg, limits, oracle.subsample_batch, oracle.batch_query)
+        cpu = dict(points=[torch.from_numpy(p) for p in ref["points"]], neighbors=[torch.from_numpy(n).long() for n in ref["neighbors"]],
+                   pools=[torch.from_numpy(n).long() for n in ref["pools"]], upsamples=[torch.from_numpy(n).long() for n in ref["upsamples"]],
+                   stack_lengths=[torch.from_numpy(l) for l in ref["stack_lengths"]], features=torch.ones(len(p0), 1))
+        _, rows = _pair_batch(pyr, j, cfg.num_layers)
+        # this pair's rows of every encoder block output
+        outs_j, layer = [], 0
+        for bi, name in enumerate(arch):
+            if "strided" in name:
+                layer += 1
+            off, n = rows[layer]
+            outs_j.append(enc_outs[bi][off:off + n])
+        off0, n0 = rows[0]
+        got = (ff[off0:off0 + n0], so[off0:off0 + n0], ss[off0:off0 + n0])
+        half = blocks_ref.kpfcnn_ref(cpu, sd, cfg, enc_outs=outs_j)           # decoder half on identical inputs
+        full = blocks_ref.kpfcnn_ref(cpu, sd, cfg)                            # free-running fp32 oracle
+        for gt, wh, wf_, name in zip(got, half, full, ("feats_f", "scores_overlap", "scores_saliency")):
+            e_half, e_full = rel(gt, wh), rel(gt, wf_)
+            print(f"pair {j} KPFCNN {name}: decoder half on identical inputs {e_half:.2e}; end to end vs fp32 oracle {e_full:.2e}")
+            assert gt.shape == wh.shape
+            assert e_half < 1e-4, (j, name, e_half)                          # measured 6e-8 .. 2.5e-7 (fp32 library ops)
+            assert e_full < 5e-3, (j, name, e_full)                          # measured 2e-4 .. 1.1e-3 on these clouds
