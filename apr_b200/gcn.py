@@ -132,3 +132,75 @@ class GCN(nn.Module):
                 desc0 = layer(coords0, desc0)
                 desc1 = layer(coords1, desc1)
         return desc0, desc1
+
+
+# ---- padded-batch form (BASELINE config 3 with P collated pairs per call) ------------------------------------------------
+# The same layers over B = 2P clouds at once: clouds are padded to the longest one ([B, Nmax, C] + validity mask), every
+# reduction that the per-cloud form takes over "all points of the cloud" (k-NN candidates, InstanceNorm statistics,
+# attention keys) is masked. One pass of ~150 library ops per call instead of one per pair: with several calls in flight
+# from several host threads the per-pair Python loop was the bottleneck of the whole KPFCNN forward (GIL-bound dispatch).
+def _masked_stats(t, mask, dims):
+    """mean / biased variance of t over `dims`, counting only the positions where mask (broadcastable to t) is set"""
+    m = mask.to(t.dtype)
+    cnt = m.expand_as(t).sum(dim=dims, keepdim=True).clamp_min(1.0)
+    mean = (t * m).sum(dim=dims, keepdim=True) / cnt
+    var = (((t - mean) * m) ** 2).sum(dim=dims, keepdim=True) / cnt
+    return mean, var
+
+
+def _edge_conv_padded(x, idx, weight, mask, slope=0.2, eps=1e-5):
+    """_edge_conv on padded clouds: x [B,N,C], idx [B,N,k] (local indices), mask [B,N] -> [B,N,Cout]"""
+    w = weight.reshape(weight.shape[0], -1)
+    c = x.shape[2]
+    wa, wb = w[:, :c], w[:, c:]
+    centre = x @ (wa - wb).t()
+    neigh = x @ wb.t()
+    b, n, k = idx.shape
+    gathered = torch.gather(neigh, 1, idx.reshape(b, n * k, 1).expand(-1, -1, neigh.shape[2])).view(b, n, k, -1)
+    e = centre.unsqueeze(2) + gathered                                   # [B,N,k,Cout]
+    mean, var = _masked_stats(e, mask[:, :, None, None], (1, 2))
+    e = F.leaky_relu((e - mean) * torch.rsqrt(var + eps), slope)
+    return e.max(dim=2)[0]
+
+
+def self_attention_padded(layer, coords, feats, mask):
+    """SelfAttention.forward on padded clouds: coords [B,N,3], feats [B,N,C], mask [B,N]"""
+    sq = (coords * coords).sum(dim=2)
+    dist = (-2.0 * coords @ coords.transpose(1, 2) + sq[:, :, None] + sq[:, None, :]).clamp_min(1e-12)
+    dist = dist.masked_fill(~mask[:, None, :], float("inf"))             # padded points are nobody's neighbour
+    idx = dist.topk(layer.k + 1, dim=2, largest=False, sorted=True)[1][:, :, 1:]
+    x1 = _edge_conv_padded(feats, idx, layer.conv1.weight, mask)
+    x2 = _edge_conv_padded(x1, idx, layer.conv2.weight, mask)
+    x3 = torch.cat((feats, x1, x2), dim=2) @ layer.conv3.weight.reshape(layer.conv3.weight.shape[0], -1).t()
+    mean, var = _masked_stats(x3, mask[:, :, None], (1,))
+    return F.leaky_relu((x3 - mean) * torch.rsqrt(var + 1e-5), 0.2)
+
+
+def cross_attention_padded(layer, x, source, mask_x, mask_s):
+    """AttentionalPropagation.forward on padded clouds: x [P,N,C] attends to source [P,M,C]"""
+    att = layer.attn
+    def proj(l, t):
+        return _conv1d(l, t).view(t.shape[0], t.shape[1], att.dim, att.num_heads).permute(0, 3, 1, 2)   # [P,heads,N,dim]
+    q, k, v = proj(att.proj[0], x), proj(att.proj[1], source), proj(att.proj[2], source)
+    logits = q @ k.transpose(2, 3) / att.dim ** .5
+    prob = torch.softmax(logits.masked_fill(~mask_s[:, None, None, :], float("-inf")), dim=-1)
+    msg = (prob @ v).permute(0, 2, 3, 1).reshape(x.shape[0], x.shape[1], att.dim * att.num_heads)
+    msg = _conv1d(att.merge, msg)
+    h = _conv1d(layer.mlp[0], torch.cat([x, msg], dim=2))
+    mean, var = _masked_stats(h, mask_x[:, :, None], (1,))
+    return _conv1d(layer.mlp[3], F.relu((h - mean) * torch.rsqrt(var + 1e-5)))
+
+
+def gcn_padded(gcn, coords, feats, mask):
+    """GCN.forward for P pairs at once: coords [2P,N,3], feats [2P,N,C], mask [2P,N]; clouds 2p / 2p+1 are pair p's
+    source / target. Returns the updated [2P,N,C] (padding rows hold garbage)."""
+    for layer, name in zip(gcn.layers, gcn.names):
+        if name == 'cross':
+            d0, d1 = feats[0::2], feats[1::2]
+            m0, m1 = mask[0::2], mask[1::2]
+            d0 = d0 + cross_attention_padded(layer, d0, d1, m0, m1)
+            d1 = d1 + cross_attention_padded(layer, d1, d0, m1, m0)           # sees the already-updated d0 (gcn.py:199-200)
+            feats = torch.stack([d0, d1], dim=1).reshape(feats.shape)
+        else:
+            feats = self_attention_padded(layer, coords, feats, mask)
+    return feats

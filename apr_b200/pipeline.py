@@ -322,23 +322,47 @@ class KPFCNNPipeline:
             pair_rows = [lens_h[l].view(-1, cps).sum(1).tolist() for l in range(nlev)]
             pts_c = pyr['points'][nlev - 1]
             feats_all = _conv1d(net.bottle, y)                          # bottleneck, all pairs at once
-            rows, a = [], 0
-            for pr in range(lens_c.shape[0]):                           # GCN + cross saliency: per collated pair
-                n_src, n_tgt = int(lens_c[pr, 0]), int(lens_c[pr, 1])
-                f = feats_all[a:a + n_src + n_tgt]
-                p = pts_c[a:a + n_src + n_tgt]
-                f0, f1 = net.gnn(p[:n_src], p[n_src:], f[:n_src], f[n_src:])
-                g = _conv1d(net.proj_gnn, torch.cat([f0, f1], dim=0))
-                scores = _conv1d(net.proj_score, g)
-                fn = F.normalize(g, p=2, dim=1)
-                inner = fn[:n_src] @ fn[n_src:].t()
+            if cps == 2:
+                # GCN + cross saliency for all pairs at once on clouds padded to the longest one (gcn.gcn_padded)
+                from .gcn import gcn_padded
+                lc = lens_h[nlev - 1]                                    # rows per cloud on the coarsest level (host)
+                nb, nmax = int(lc.shape[0]), int(lc.max())
+                lens_d = pyr['stack_lengths'][nlev - 1].long()
+                offs = torch.cumsum(lens_d, 0) - lens_d
+                jj = torch.arange(nmax, device=self.device)
+                mask = jj[None, :] < lens_d[:, None]                     # [2P, Nmax]
+                pad = offs[:, None] + torch.minimum(jj[None, :], (lens_d - 1).clamp_min(0)[:, None])
+                fp = gcn_padded(net.gnn, pts_c[pad], feats_all[pad], mask)
+                g = _conv1d(net.proj_gnn, fp)                            # [2P, Nmax, G]
+                scores = _conv1d(net.proj_score, g)                      # [2P, Nmax, 1]
+                fn = F.normalize(g, p=2, dim=2)
+                inner = fn[0::2] @ fn[1::2].transpose(1, 2)              # [P, Nmax_src, Nmax_tgt]
                 temperature = torch.exp(net.epsilon) + 0.03
-                s1 = torch.softmax(inner / temperature, dim=1) @ scores[n_src:]
-                s2 = torch.softmax(inner.t() / temperature, dim=1) @ scores[:n_src]
-                body = g if net.condition else f
-                rows.append(torch.cat([scores, torch.cat((s1, s2), dim=0), body] if net.add_cross_overlap else [scores, body], dim=1))
-                a += n_src + n_tgt
-            x = torch.cat(rows, dim=0)
+                m0, m1 = mask[0::2], mask[1::2]
+                s1 = torch.softmax((inner / temperature).masked_fill(~m1[:, None, :], float("-inf")), dim=2) @ scores[1::2]
+                s2 = torch.softmax((inner.transpose(1, 2) / temperature).masked_fill(~m0[:, None, :], float("-inf")), dim=2) @ scores[0::2]
+                sal = torch.stack([s1, s2], dim=1).reshape(nb, nmax, 1)
+                body = g if net.condition else feats_all[pad]
+                xp = torch.cat([scores, sal, body] if net.add_cross_overlap else [scores, body], dim=2)
+                x = xp[mask]                                              # back to the stacked rows (cloud-major order)
+            else:
+                rows, a = [], 0
+                for pr in range(lens_c.shape[0]):                       # one collate: GCN + cross saliency on its two clouds
+                    n_src, n_tgt = int(lens_c[pr, 0]), int(lens_c[pr, 1])
+                    f = feats_all[a:a + n_src + n_tgt]
+                    p = pts_c[a:a + n_src + n_tgt]
+                    f0, f1 = net.gnn(p[:n_src], p[n_src:], f[:n_src], f[n_src:])
+                    g = _conv1d(net.proj_gnn, torch.cat([f0, f1], dim=0))
+                    scores = _conv1d(net.proj_score, g)
+                    fn = F.normalize(g, p=2, dim=1)
+                    inner = fn[:n_src] @ fn[n_src:].t()
+                    temperature = torch.exp(net.epsilon) + 0.03
+                    s1 = torch.softmax(inner / temperature, dim=1) @ scores[n_src:]
+                    s2 = torch.softmax(inner.t() / temperature, dim=1) @ scores[:n_src]
+                    body = g if net.condition else f
+                    rows.append(torch.cat([scores, torch.cat((s1, s2), dim=0), body] if net.add_cross_overlap else [scores, body], dim=1))
+                    a += n_src + n_tgt
+                x = torch.cat(rows, dim=0)
             layer = nlev - 1
             for i, blk in enumerate(net.decoder_blocks):                # decoder, super-batched
                 if i in net.decoder_concats:
