@@ -47,6 +47,8 @@ SIGNATURES = {
     "aprb_closest_pool": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "aprb_instnorm_ws_bytes": (_sz, [_i, _i]),
     "aprb_instnorm_lrelu": (_i, [_p, _i, _i, _f, _f, _p, _i, _i, _p, _p, _sz, _p]),
+    "aprb_instnorm_backward_ws_bytes": (_sz, [_i]),
+    "aprb_instnorm_lrelu_backward": (_i, [_p, _p, _p, _i, _i, _f, _p, _p, _sz, _p]),
     "aprb_instnorm_seg_ws_bytes": (_sz, [_i, _i, _i]),
     "aprb_instnorm_lrelu_seg": (_i, [_p, _i, _i, _p, _i, _f, _f, _p, _i, _i, _p, _p, _sz, _p]),
     "aprb_segment_offsets": (_i, [_p, _i, _i, _p, _p]),

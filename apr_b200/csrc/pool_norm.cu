@@ -791,6 +791,48 @@ norm_seg_groups_kernel(const float* __restrict__ x, const float* __restrict__ x2
     }
 }
 
+// ---- training path: backward of y = LeakyReLU_slope(InstanceNorm(x)) (blocks.py:459-468 + :496-510) -----------------------
+// With xhat = (x - mean) * rstd (recovered from y: LeakyReLU is invertible) and dz = dy * act'(xhat):
+//   dx = rstd * (dz - mean_rows(dz) - xhat * mean_rows(dz * xhat)).
+// Pass 1: per (row chunk, column) partial sums of dz and dz * xhat, fixed order; pass 2: every thread combines the
+// partials of its column in chunk order and applies the formula. Deterministic, two launches.
+constexpr int NORM_BWD_CHUNKS = 64;
+
+__global__ void __launch_bounds__(256)
+norm_bwd_partial_kernel(const float* __restrict__ y, const float* __restrict__ dy, int N, int C, float slope, int rows_per_chunk,
+                        float* __restrict__ partial) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const int r0 = blockIdx.y * rows_per_chunk, r1 = min(N, r0 + rows_per_chunk);
+    const float inv_slope = 1.0f / slope;
+    float s1 = 0.f, s2 = 0.f;
+    for (int r = r0; r < r1; ++r) {
+        const float yv = y[(size_t)r * C + c], g = dy[(size_t)r * C + c];
+        const float xh = yv > 0.f ? yv : yv * inv_slope;
+        const float dz = yv > 0.f ? g : g * slope;
+        s1 += dz; s2 = fmaf(dz, xh, s2);
+    }
+    partial[((size_t)blockIdx.y * 2 + 0) * C + c] = s1;
+    partial[((size_t)blockIdx.y * 2 + 1) * C + c] = s2;
+}
+
+__global__ void __launch_bounds__(256)
+norm_bwd_apply_kernel(const float* __restrict__ y, const float* __restrict__ dy, const float* __restrict__ rstd, int N, int C,
+                      float slope, int chunks, int rows_per_block, const float* __restrict__ partial, float* __restrict__ dx) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = 0; k < chunks; ++k) { s1 += partial[((size_t)k * 2 + 0) * C + c]; s2 += partial[((size_t)k * 2 + 1) * C + c]; }
+    const float invn = 1.0f / (float)N, m1 = s1 * invn, m2 = s2 * invn, rs = rstd[c], inv_slope = 1.0f / slope;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(N, r0 + rows_per_block);
+    for (int r = r0; r < r1; ++r) {
+        const float yv = y[(size_t)r * C + c], g = dy[(size_t)r * C + c];
+        const float xh = yv > 0.f ? yv : yv * inv_slope;
+        const float dz = yv > 0.f ? g : g * slope;
+        dx[(size_t)r * C + c] = rs * (dz - m1 - xh * m2);
+    }
+}
+
 // seg_off[s] = first row of segment s = sum of the lengths of the clouds before cloud s*cps (S+1 entries)
 __global__ void seg_offsets_kernel(const int* __restrict__ lens, int B, int cps, int S, int* __restrict__ seg_off) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -811,6 +853,28 @@ int g_fuse_stats = 1;   // aprb_set_option("fuse_stats"): aprb_kfe_forward hands
 int g_gemm_apply = 1;   // aprb_set_option("gemm_apply"): unary2 / shortcut Linears are recomputed with the normalisation in the epilogue
 
 }  // namespace aprb
+
+extern "C" size_t aprb_instnorm_backward_ws_bytes(int C) {
+    return C < 0 ? 0 : align256((size_t)NORM_BWD_CHUNKS * 2 * (size_t)C * sizeof(float)) + 256;
+}
+
+extern "C" int aprb_instnorm_lrelu_backward(const float* d_y, const float* d_dy, const float* d_rstd, int N, int C, float slope,
+                                            float* d_dx, void* d_ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    APRB_REQUIRE(N >= 0 && C >= 1 && slope > 0.f, "need N >= 0, C >= 1 and a positive slope (1 = no activation)");
+    if (N == 0) return APRB_OK;
+    APRB_REQUIRE(d_y && d_dy && d_rstd && d_dx && d_ws, "null pointer");
+    if (ws_bytes < aprb_instnorm_backward_ws_bytes(C)) { set_error("aprb_instnorm_lrelu_backward: workspace too small"); return APRB_ERR_WORKSPACE; }
+    const int chunks = min(NORM_BWD_CHUNKS, max(1, cdiv(N, 64)));
+    const int rpc = cdiv(N, chunks);
+    float* partial = (float*)d_ws;
+    APRB_TIMED("norm_bwd_partial_kernel", st, 1, (norm_bwd_partial_kernel<<<dim3(cdiv(C, 256), chunks), 256, 0, st>>>(d_y, d_dy, N, C, slope, rpc, partial)));
+    const int ablocks = max(1, min(cdiv(N, 32), 4 * sm_count() / max(1, cdiv(C, 256))));
+    const int rpb = cdiv(N, ablocks);
+    APRB_TIMED("norm_bwd_apply_kernel", st, 1, (norm_bwd_apply_kernel<<<dim3(cdiv(C, 256), cdiv(N, rpb)), 256, 0, st>>>(d_y, d_dy, d_rstd, N, C, slope, cdiv(N, rpc), rpb, partial, d_dx)));
+    APRB_LAUNCH_OK();
+    return APRB_OK;
+}
 
 extern "C" int aprb_segment_offsets(const int32_t* d_lens, int B, int clouds_per_segment, int32_t* d_seg_off, void* stream) {
     APRB_REQUIRE(d_lens && d_seg_off && B >= 1 && clouds_per_segment >= 1, "bad argument");

@@ -448,6 +448,19 @@ def kpconv_backward_data(q_pts, s_pts, neighb_inds, kernel_points, extent, dwf, 
     return dx
 
 
+def instnorm_lrelu_backward(y, dy, rstd, slope):
+    """Gradient of y = LeakyReLU_slope(InstanceNorm(x)) w.r.t. x — see aprb_instnorm_lrelu_backward."""
+    N.require_cuda()
+    yy, gg, rr = _dev_f32(y, "y"), _dev_f32(dy, "dy"), _dev_f32(rstd.reshape(-1), "rstd")
+    n, c = yy.shape
+    dx = torch.empty_like(yy)
+    ws = _workspace(N.lib().aprb_instnorm_backward_ws_bytes(c), yy.device)
+    rc = N.lib().aprb_instnorm_lrelu_backward(N.ptr(yy), N.ptr(gg), N.ptr(rr), n, c, float(slope), N.ptr(dx), N.ptr(ws), ws.numel(),
+                                              N.stream_ptr())
+    N.check(rc, "aprb_instnorm_lrelu_backward")
+    return dx
+
+
 def max_pool_backward(x, inds, dy):
     """Gradient of max_pool w.r.t. x."""
     N.require_cuda()

@@ -3,8 +3,8 @@ reference's NPR generative head and loss terms, and a bucketed gradient all-redu
 
 What runs where:
   * KPConv forward/backward  -> our kernels for the gather/weighting (aprb_kpconv_weighted) and its transpose
-    (aprb_kpconv_backward_data, scatter-add over the neighbour lists), cuBLAS (torch.matmul) for the two dense
-    contractions out = wf @ W and dW = wf^T @ dOut (plain library GEMMs);
+    (aprb_kpconv_backward_data, scatter-add over the neighbour lists); the dense contractions out = wf @ W,
+    dwf = g @ W^T and dW = wf^T @ g on the hand-written tcgen05 TF32 GEMM (aprb_linear_tf32) where the shape allows;
   * strided shortcut          -> aprb_max_pool / aprb_max_pool_backward;
   * InstanceNorm, LeakyReLU, Linear, nearest upsample, the bottleneck GCN, the NPR MLP -> stock torch (autograd-native).
 The reference trains on ONE GPU (lib/trainer.py:316-322 accumulates `iter_size` pairs); averaging per-rank gradients
@@ -18,6 +18,32 @@ from . import blocks, ops
 from .gcn import _conv1d
 
 
+# The three dense contractions of a KPConv training step — out = wf @ W, dwf = g @ W^T, dW = wf^T @ g — on the hand-written
+# tcgen05 GEMM (TF32 operands rounded to nearest, fp32 accumulation in TMEM; aprb_linear_tf32, split-K when the output grid
+# cannot fill the SMs) where the shapes allow (K % 32 == 0, N % 16 == 0), else torch.matmul (fp32). False = fp32 everywhere.
+TENSOR_GEMM = True
+
+
+def _mm_nt(a, bt):
+    """a [M,K] @ bt [N,K]^T -> [M,N]"""
+    if TENSOR_GEMM and a.is_cuda and a.shape[0] > 0 and ops.linear_tf32_supported(a.shape[0], a.shape[1], bt.shape[0]):
+        return ops.linear_tf32(ops.round_tf32(a), ops.round_tf32(bt))
+    return a @ bt.t()
+
+
+def _mm_tn(a, b):
+    """a [R,M]^T @ b [R,N] -> [M,N] (reduction over the rows): both operands transposed into K-major form, the reduction
+    dimension zero-padded to a multiple of 32"""
+    r = a.shape[0]
+    if TENSOR_GEMM and a.is_cuda and r > 0 and b.shape[1] % 16 == 0:
+        rp = (r + 31) // 32 * 32
+        at = torch.zeros((a.shape[1], rp), dtype=torch.float32, device=a.device)
+        bt = torch.zeros((b.shape[1], rp), dtype=torch.float32, device=a.device)
+        at[:, :r] = a.t(); bt[:, :r] = b.t()
+        return ops.linear_tf32(ops.round_tf32(at), ops.round_tf32(bt))
+    return a.t() @ b
+
+
 class _KPConvFn(torch.autograd.Function):
     """KPConv.forward (models/blocks.py:229-374) with its gradients w.r.t. the features and the weights."""
 
@@ -28,16 +54,16 @@ class _KPConvFn(torch.autograd.Function):
         w2d = weights.reshape(k * cin, cout)
         ctx.save_for_backward(wf, inv_nn, w2d, q, s, idx, kp)
         ctx.extent, ctx.cin, ctx.wshape = extent, cin, weights.shape
-        return (wf @ w2d) * inv_nn.unsqueeze(1)
+        return _mm_nt(wf, w2d.t().contiguous()) * inv_nn.unsqueeze(1)
 
     @staticmethod
     def backward(ctx, dout):
         wf, inv_nn, w2d, q, s, idx, kp = ctx.saved_tensors
         g = dout.contiguous() * inv_nn.unsqueeze(1)
-        dw = (wf.t() @ g).reshape(ctx.wshape) if ctx.needs_input_grad[1] else None
+        dw = _mm_tn(wf, g).reshape(ctx.wshape) if ctx.needs_input_grad[1] else None
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = ops.kpconv_backward_data(q, s, idx, kp, ctx.extent, g @ w2d.t(), ctx.cin)
+            dx = ops.kpconv_backward_data(q, s, idx, kp, ctx.extent, _mm_nt(g, w2d.contiguous()), ctx.cin)
         return dx, dw, None, None, None, None, None
 
 
@@ -57,17 +83,45 @@ def kpconv(x, conv, q, s, idx):
     return _KPConvFn.apply(x, conv.weights, q, s, idx, conv.kernel_points, float(conv.KP_extent))
 
 
-def _norm(x, eps=1e-5):
-    """BatchNormBlock = InstanceNorm over all rows of the pair (blocks.py:459-468), autograd-native."""
+class _NormActFn(torch.autograd.Function):
+    """y = LeakyReLU_slope(InstanceNorm(x)) over all rows of the pair (BatchNormBlock, blocks.py:459-468, and the
+    activation that follows it): forward by the fused inference kernel (aprb_instnorm_lrelu), backward by
+    aprb_instnorm_lrelu_backward from y and the per-column rstd — x itself is not kept."""
+
+    @staticmethod
+    def forward(ctx, x, slope):
+        x = x.contiguous()
+        var = torch.var(x, dim=0, unbiased=False)
+        y = ops.instnorm_lrelu(x, slope=slope)
+        ctx.save_for_backward(y, torch.rsqrt(var + 1e-5))
+        ctx.slope = slope
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, rstd = ctx.saved_tensors
+        return ops.instnorm_lrelu_backward(y, dy.contiguous(), rstd, ctx.slope), None
+
+
+NATIVE_NORM = True     # InstanceNorm (+ LeakyReLU) forward/backward through the native kernels (False: stock torch autograd)
+
+
+def _norm(x, slope=1.0, eps=1e-5):
+    """LeakyReLU_slope(BatchNormBlock(x)); BatchNormBlock = InstanceNorm over all rows of the pair (blocks.py:459-468)."""
+    if NATIVE_NORM and x.is_cuda and x.shape[0] > 1:
+        return _NormActFn.apply(x, float(slope))
     var, mean = torch.var_mean(x, dim=0, unbiased=False, keepdim=True)
-    return (x - mean) * torch.rsqrt(var + eps)
+    y = (x - mean) * torch.rsqrt(var + eps)
+    return y if slope == 1.0 else F.leaky_relu(y, slope)
 
 
 def _unary(blk, x):
     y = F.linear(x, blk.mlp.weight)
     if isinstance(blk, blocks.LastUnaryBlock):
         return y
-    y = _norm(y) if blk.use_bn else y + blk.batch_norm.bias
+    if blk.use_bn:
+        return _norm(y, 1.0 if blk.no_relu else 0.1)
+    y = y + blk.batch_norm.bias
     return y if blk.no_relu else F.leaky_relu(y, 0.1)
 
 
@@ -79,11 +133,11 @@ def block_forward(blk, x, batch):
     """Differentiable forward of one block module of apr_b200.blocks (same parameters, same semantics)."""
     if isinstance(blk, blocks.SimpleBlock):
         q, s, idx = blocks._select(blk.block_name, blk.layer_ind, batch)
-        return F.leaky_relu(_norm(kpconv(x, blk.KPConv, q, s, idx)), 0.1)
+        return _norm(kpconv(x, blk.KPConv, q, s, idx), 0.1)
     if isinstance(blk, blocks.ResnetBottleneckBlock):
         q, s, idx = blocks._select(blk.block_name, blk.layer_ind, batch)
         y = _unary(blk.unary1, x) if isinstance(blk.unary1, blocks.UnaryBlock) else x
-        y = F.leaky_relu(_norm(kpconv(y, blk.KPConv, q, s, idx)), 0.1)
+        y = _norm(kpconv(y, blk.KPConv, q, s, idx), 0.1)
         y = _unary(blk.unary2, y)
         sc = _MaxPoolFn.apply(x, idx) if 'strided' in blk.block_name else x
         if isinstance(blk.unary_shortcut, blocks.UnaryBlock):
@@ -200,13 +254,33 @@ class GradBucketReducer:
                       for p, off in zip(b, [sum(q.numel() for q in b[:j]) for j in range(len(b))])}
         self.pending = [len(b) for b in self.buckets]
         self.work = [None] * len(self.buckets)
+        self.fired = set()
         self.launched = 0
+        self.sync = True            # False inside no_sync(): gradients accumulate locally, nothing is reduced
+        self.fired = set()
         for p in self.params:
             p.register_post_accumulate_grad_hook(self._hook)
 
+    def no_sync(self):
+        """Context manager for gradient accumulation (the reference's iter_size > 1, lib/trainer.py:316-322): backward
+        passes inside it only accumulate into p.grad; the LAST micro-batch runs outside it and reduces the sums."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            prev, self.sync = self.sync, False
+            try:
+                yield
+            finally:
+                self.sync = prev
+        return ctx()
+
     def _hook(self, p):
+        if not self.sync or p in self.fired:
+            return
         bi, off = self.where[p]
-        self.flat[bi][off:off + p.numel()].copy_(p.grad.reshape(-1))
+        self.fired.add(p)
+        self.flat[bi][off:off + p.numel()].copy_(p.grad.reshape(-1))   # post-accumulate: p.grad holds the accumulated sum
         self.pending[bi] -= 1
         if self.pending[bi] == 0:
             self._launch(bi)
@@ -218,12 +292,15 @@ class GradBucketReducer:
 
     def finish(self):
         """Call after backward(): reduces buckets whose parameters got no gradient this step too, waits, averages."""
-        for bi, b in enumerate(self.buckets):
+        for bi, b in enumerate(self.buckets):       # fixed bucket order on every rank
             if self.pending[bi] > 0:
-                for p in b:                      # parameters without a gradient contribute zeros
-                    if p.grad is None:
+                for p in b:                      # parameters whose hook did not fire this step: their current gradient, or zeros
+                    if p not in self.fired:
                         o = self.where[p][1]
-                        self.flat[bi][o:o + p.numel()].zero_()
+                        if p.grad is None:
+                            self.flat[bi][o:o + p.numel()].zero_()
+                        else:
+                            self.flat[bi][o:o + p.numel()].copy_(p.grad.reshape(-1))
                 self._launch(bi)
         for bi, b in enumerate(self.buckets):
             if self.work[bi] is not None:
@@ -236,3 +313,4 @@ class GradBucketReducer:
                 p.grad.copy_(self.flat[bi][o:o + p.numel()].view_as(p))
         self.pending = [len(b) for b in self.buckets]
         self.work = [None] * len(self.buckets)
+        self.fired = set()

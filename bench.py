@@ -910,7 +910,11 @@ def run_train(args):
                                      "allreduce_bytes_per_step": 4 * nparam if world > 1 else 0, "buckets": len(red.buckets),
                                      "limits": limits, "points_stacked": int(items[0][0].shape[0])},
                           "gpu_launches": int(_native.launch_count() - l0c),
-                          "loss_first_last": [float(losses[0]), float(losses[-1])]}))
+                          "loss_first_last": [float(sum(losses[:3]) / 3), float(sum(losses[-3:]) / 3)],
+                          "loss_note": "mean of the first 3 / last 3 timed steps (the warm-up steps already trained)",
+                          "contractions": "tcgen05 TF32 GEMM (aprb_linear_tf32) for out = wf W, dwf = g W^T, dW = wf^T g where the "
+                                          "shape allows; InstanceNorm+LeakyReLU forward/backward native; allreduce = bucketed NCCL, "
+                                          "launched from gradient hooks during backward"}))
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -216,6 +216,13 @@ int aprb_instnorm_lrelu(const float* d_x, int N, int C, float eps, float slope,
                         const float* d_residual, int norm_residual, int round_tf32, float* d_y,
                         void* d_ws, size_t ws_bytes, void* stream);
 
+/* Training path: gradient of y = LeakyReLU_slope(InstanceNorm(x)) w.r.t. x from y itself (LeakyReLU is invertible, slope > 0;
+ * slope == 1: no activation), the incoming gradient d_dy and the forward's per-column rstd [C]:
+ * dx = rstd * (dz - mean(dz) - xhat * mean(dz * xhat)), dz = dy * act'. Two launches, fixed summation order. */
+size_t aprb_instnorm_backward_ws_bytes(int C);
+int aprb_instnorm_lrelu_backward(const float* d_y, const float* d_dy, const float* d_rstd, int N, int C, float slope,
+                                 float* d_dx, void* d_ws, size_t ws_bytes, void* stream);
+
 /* Segmented form for super-batched pairs: rows [d_seg_off[s], d_seg_off[s+1]) (device int32 [S+1]) are normalised with
  * their own column statistics, i.e. S independent BatchNormBlock calls in two launches. S == 1 with d_seg_off == NULL
  * is the plain form. Needs C % 4 == 0 and 16-byte aligned tensors. */

@@ -35,12 +35,19 @@ def test_kpconv_gradients_vs_oracle_autograd(cuda, cin, cout, h):
     yr = blocks_ref.kpconv_ref(q, s, inds, xr, kp, wr, 0.7)
     yr.backward(gout)
     xg, wg = x.to(cuda).requires_grad_(), w.to(cuda).requires_grad_()
-    for idx in (inds.to(cuda), inds.to(cuda).int()):
-        xg.grad = wg.grad = None
-        y = train._KPConvFn.apply(xg, wg, q.to(cuda), s.to(cuda), idx, kp.to(cuda), 0.7)
-        y.backward(gout.to(cuda))
-        assert rel(y, yr) < 2e-5
-        assert rel(xg.grad, xr.grad) < 1e-4 and rel(wg.grad, wr.grad) < 1e-4
+    try:
+        # fp32 contractions (torch.matmul), then the tcgen05 TF32 GEMMs (10-bit operand mantissa: the KPConv feature bar 1e-3)
+        for tensor_gemm, tol_y, tol_g in ((False, 2e-5, 1e-4), (True, 1e-3, 1.5e-3)):
+            train.TENSOR_GEMM = tensor_gemm
+            for idx in (inds.to(cuda), inds.to(cuda).int()):
+                xg.grad = wg.grad = None
+                y = train._KPConvFn.apply(xg, wg, q.to(cuda), s.to(cuda), idx, kp.to(cuda), 0.7)
+                y.backward(gout.to(cuda))
+                print(f"Cin {cin} Cout {cout} tensor_gemm {tensor_gemm}: y {rel(y, yr):.1e} dx {rel(xg.grad, xr.grad):.1e} dW {rel(wg.grad, wr.grad):.1e}")
+                assert rel(y, yr) < tol_y
+                assert rel(xg.grad, xr.grad) < tol_g and rel(wg.grad, wr.grad) < tol_g
+    finally:
+        train.TENSOR_GEMM = True
 
 
 def test_max_pool_backward_vs_oracle_autograd(cuda):
@@ -70,6 +77,14 @@ def test_kpfcnn_train_step_gradients_vs_oracle(cuda, oracle, gold_kpfcnn):
     net = KPFCNN(cfg)
     net.load_state_dict(sd, strict=True)
     net = net.to(cuda)
+    train.TENSOR_GEMM = False          # the whole-network gradient check runs the fp32 contractions (first_feats_dim = 16: most
+    try:                               # KPConvs of this small golden network do not fit the tensor path's shape rules anyway)
+        _check_kpfcnn_gradients(net, gpu, cpu, sd, cfg, g, cuda)
+    finally:
+        train.TENSOR_GEMM = True
+
+
+def _check_kpfcnn_gradients(net, gpu, cpu, sd, cfg, g, cuda):
     ff, so, ss = train.kpfcnn_forward_train(net, gpu)
     for got, key in ((ff, "feats_f"), (so, "scores_overlap"), (ss, "scores_saliency")):
         assert rel(got, torch.from_numpy(g[key])) < 2e-4, key
@@ -133,3 +148,20 @@ def test_train_step_runs_and_learns(cuda, oracle):
         losses.append(loss.item())
     print("losses", [round(v, 4) for v in losses])
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+def test_instnorm_lrelu_backward_vs_autograd(cuda):
+    """aprb_instnorm_lrelu_backward (gradient of LeakyReLU(InstanceNorm(x)) from y and rstd) vs torch autograd in float64."""
+    gen = torch.Generator().manual_seed(21)
+    for n, c, slope in ((5000, 64, 0.1), (1567, 512, 0.1), (300, 7, 1.0), (40000, 128, 1.0), (2, 5, 0.1)):
+        x = torch.randn(n, c, generator=gen) * 2 + 3
+        g = torch.randn(n, c, generator=gen)
+        xr = x.double().requires_grad_()
+        yr = blocks_ref.instnorm_ref(xr)
+        yr = yr if slope == 1.0 else torch.nn.functional.leaky_relu(yr, slope)
+        yr.backward(g.double())
+        xg = x.to(cuda).requires_grad_()
+        y = train._NormActFn.apply(xg, slope)
+        y.backward(g.to(cuda))
+        assert rel(y, yr) < 1e-5
+        assert rel(xg.grad, xr.grad) < 2e-4, (n, c, slope, rel(xg.grad, xr.grad))

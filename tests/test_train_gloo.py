@@ -42,6 +42,50 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _worker_accum(rank, world, port, q):
+    """iter_size = 2 (lib/trainer.py:316-322): two micro-batches per step, the first inside no_sync()."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    net = _toy()
+    red = GradBucketReducer(net.parameters(), bucket_mb=0.01)
+    opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9)
+    micro = [_data(10 * rank), _data(10 * rank + 1)]
+    for _ in range(2):
+        opt.zero_grad(set_to_none=True)
+        with red.no_sync():
+            (((net[:5](micro[0][0]) - micro[0][1]) ** 2).mean() / 2).backward()
+        (((net[:5](micro[1][0]) - micro[1][1]) ** 2).mean() / 2).backward()
+        red.finish()
+        opt.step()
+    q.put((rank, [p.detach().numpy().copy() for p in net.parameters()]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_accumulation_no_sync():
+    import numpy as np
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker_accum, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    out = sorted((q.get(timeout=180) for _ in range(world)), key=lambda t: t[0])
+    [p.join(timeout=60) for p in ps]
+    assert all(p.exitcode == 0 for p in ps)
+    for a, b in zip(out[0][1], out[1][1]):
+        assert np.array_equal(a, b)
+    net = _toy()                                                       # single process: mean over the four micro-batches
+    opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9)
+    for _ in range(2):
+        opt.zero_grad(set_to_none=True)
+        loss = sum(((net[:5](x) - y) ** 2).mean() for x, y in (_data(0), _data(1), _data(10), _data(11))) / 4
+        loss.backward()
+        for p in net[5].parameters():
+            p.grad = torch.zeros_like(p)
+        opt.step()
+    for a, b in zip(out[0][1], net.parameters()):
+        assert np.allclose(a, b.detach().numpy(), atol=1e-6, rtol=1e-5)
+
+
 def test_two_rank_bucketed_allreduce_matches_single_process_mean():
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
