@@ -71,6 +71,10 @@ class KFEPipeline:
             self.refresh_weights()
 
     def _build(self):
+        with torch.cuda.device(self.device):
+            self._build_on_device()
+
+    def _build_on_device(self):
         encoder, config = self.encoder, self.config
         neighborhood_limits, build_upsamples, clouds_per_segment = self._limits, self._build_upsamples, self._cps
         self._weights_key = self._param_key()
@@ -155,10 +159,13 @@ class KFEPipeline:
     def _call(self, fn, n, b):
         """fn(arena) -> status; retried once with the unconditional arena bound when a level outgrew the estimate
         (the native driver checks every carve and returns APRB_ERR_WORKSPACE before writing past the arena)."""
-        rc = fn(self._ensure_arena(n, b))
-        if rc == -2:
-            torch.cuda.current_stream(self.device).synchronize(); self.stream.synchronize()
-            rc = fn(self._ensure_arena(n, b, full=True))
+        # the C-ABI launches on self.stream: the calling host thread must have that stream's device current (a worker
+        # thread of a multi-GPU process starts on device 0)
+        with torch.cuda.device(self.device):
+            rc = fn(self._ensure_arena(n, b))
+            if rc == -2:
+                torch.cuda.current_stream(self.device).synchronize(); self.stream.synchronize()
+                rc = fn(self._ensure_arena(n, b, full=True))
         return rc
 
     def _view(self, ptr, rows, cols, dtype):
@@ -226,7 +233,7 @@ class KFEPipeline:
         open3d's voxel_down_sample semantics (ops.voxel_downsample_raw), pyramid + encoder, D2H of the fp32 output into
         out_host (pinned [>= rows, C]). Synchronises the stream; returns the filled view of out_host."""
         self._fresh()
-        with torch.cuda.stream(self.stream):
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             raw = raw_host.to(self.device, non_blocking=True)
             lens = lens_host.to(self.device, non_blocking=True)
             p0, l0 = ops.voxel_downsample_raw(raw, lens, self.config.first_subsampling_dl)   # reads M back: one sync
@@ -237,7 +244,8 @@ class KFEPipeline:
         return view
 
     def wait_host(self, ticket):
-        N.check(self.lib.aprb_kfe_wait_host(self.handle, int(ticket)), "aprb_kfe_wait_host")
+        with torch.cuda.device(self.device):
+            N.check(self.lib.aprb_kfe_wait_host(self.handle, int(ticket)), "aprb_kfe_wait_host")
 
     def block_output(self, i):
         """Output of encoder block i of the last forward (fp16 or fp32 view into the arena, valid until the next one)."""
@@ -309,7 +317,7 @@ class KPFCNNPipeline:
         from .gcn import _conv1d
         net, cfg = self.net, self.config
         y = self.enc.forward(points, lengths)                         # encoder output [N_last, C] fp32 (arena view)
-        with torch.cuda.stream(self.stream):
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             pyr = self.enc.pyramid()
             nlev = cfg.num_layers
             cps = self.cps if self.cps > 0 else int(lengths.shape[0])

@@ -338,6 +338,7 @@ def run_ours(args):
         start = torch.cuda.Event()
         start.record(main_stream)
         def work(k):
+            torch.cuda.set_device(dev)                       # worker threads start on device 0
             streams[k].wait_event(start)
             r = fn(k, (i * S + k))
             done_ev[k].record(streams[k])
@@ -404,6 +405,7 @@ def run_ours(args):
             def work(k):
                 # two calls in flight per stream: call c is queued (H2D -> path -> D2H on the pipeline's copy stream into
                 # one of two pinned buffers), then the result of call c-1 is awaited and read
+                torch.cuda.set_device(dev)
                 streams[k].wait_event(start)
                 hb = db = 0
                 pending = None
@@ -484,6 +486,7 @@ def run_ours(args):
         def run(n_calls):
             start = torch.cuda.Event(); start.record(main_stream)
             def work(k):
+                torch.cuda.set_device(dev)
                 streams[k].wait_event(start)
                 for c in range(n_calls):
                     pipes[k].forward_from_raw(raw_host[k][0], raw_host[k][1], outs[k][c & 1])
@@ -761,6 +764,7 @@ def run_kpfcnn(args):
     def run(n_calls, first, from_host):
         start = torch.cuda.Event(); start.record(main_stream)
         def work(k):
+            torch.cuda.set_device(dev)
             streams[k].wait_event(start)
             hb = db = 0
             for c in range(n_calls):
