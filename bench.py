@@ -551,9 +551,9 @@ def run_ours(args):
 
     def traffic_of(kernel):
         """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this
-        workload (profiles/r01_traffic.json), or None when no capture covers the kernel / the options differ."""
+        workload (profiles/r02_traffic.json), or None when no capture covers the kernel / the options differ."""
         try:
-            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as f:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_traffic.json")) as f:
                 t = json.load(f)
             ok = t.get("workload") == wl_name and t.get("pairs_per_call") == P and not args.opt
             return float(t["kernels"][kernel]["dram_bytes_per_launch"]) if ok and kernel in t.get("kernels", {}) else None
@@ -599,7 +599,7 @@ def run_ours(args):
                        "frac": ach / peak, "traffic": traffic_of("gemm_tf32_kernel"), "launches_per_step": cnt_g / args.steps,
                        "note": f"persistent tcgen05 GEMM: KPConv contractions + unary1 (+ stored-path closing Linears) = "
                                f"{tc_flops / 1e9:.1f} GFLOP/call; blended over its HBM-bound level-0/1 and tensor-bound level-2/3 "
-                               f"launches (per launch: profiles/r01_ncu_traffic_v12_summary.txt)"}
+                               f"launches (per launch: profiles/r02_ncu_traffic_summary.txt)"}
     kernels = {k: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps} for k, v in
                sorted(prof.items(), key=lambda kv: -kv[1][1])[:14]}
 

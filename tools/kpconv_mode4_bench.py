@@ -20,7 +20,7 @@ for sd in range(P):
     p0, l0 = ops.grid_subsample(raw, lens, 0.3)
     ps.append(p0); ls.append(l0)
 p0, l0 = torch.cat(ps).contiguous(), torch.cat(ls).contiguous()
-pyr = dataloader.build_pyramid_device(p0, l0, cfg, [56, 55, 56, 58])
+pyr = dataloader.build_pyramid_device(p0, l0, cfg, [57, 53, 54, 55])
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 gen = torch.Generator(device="cpu").manual_seed(0)
 shapes = []

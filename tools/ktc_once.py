@@ -13,7 +13,7 @@ for sd in range(P):
     raw = torch.from_numpy(np.concatenate([a, b])).to(dev); lens = torch.tensor([len(a), len(b)], dtype=torch.int32, device=dev)
     p0, l0 = ops.grid_subsample(raw, lens, 0.3); ps.append(p0); ls.append(l0)
 p0, l0 = torch.cat(ps).contiguous(), torch.cat(ls).contiguous()
-pyr = dataloader.build_pyramid_device(p0, l0, cfg, [56, 55, 56, 58])
+pyr = dataloader.build_pyramid_device(p0, l0, cfg, [57, 53, 54, 55])
 for l, cin in ((0, 64), (1, 128)):
     q = s = pyr['points'][l]; inds = pyr['neighbors'][l]
     x = torch.randn(len(s), cin, generator=gen).half().to(dev)

@@ -20,7 +20,7 @@ for sd in range(P):
 p0, l0 = torch.cat(pts).contiguous(), torch.cat(lens).contiguous()
 torch.manual_seed(0); np.random.seed(0)
 enc = KPFCNNEncoder(cfg).to(dev).eval()
-pipe = KFEPipeline(enc, cfg, [56, 55, 56, 58], clouds_per_segment=2 if P > 1 else 0)
+pipe = KFEPipeline(enc, cfg, [57, 53, 54, 55], clouds_per_segment=2 if P > 1 else 0)
 torch.cuda.synchronize()
 print("setup done, launches so far", __import__("apr_b200._native", fromlist=["x"]).launch_count(), flush=True)
 for _ in range(iters):
