@@ -25,6 +25,7 @@ SIGNATURES = {
     "aprb_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "aprb_grid_subsample_ws_bytes": (_sz, [_i, _i, _i]),
     "aprb_grid_subsample_batch": (_i, [_p, _p, _i, _i, _f, _i, _p, _i, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
+    "aprb_grid_subsample_batch_labels": (_i, [_p, _p, _i, _i, _f, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
     "aprb_voxel_downsample_ws_bytes": (_sz, [_i, _i]),
     "aprb_voxel_downsample_raw": (_i, [_p, _i, _p, _i, _i, C.c_double, _p, _p, _p, _p, _i, _p, _sz, _p]),
     "aprb_radius_neighbors_ws_bytes": (_sz, [_i, _i, _i]),

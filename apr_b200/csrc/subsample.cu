@@ -148,6 +148,40 @@ __global__ void sub_emit_kernel(const float* __restrict__ pts, const float* __re
     }
 }
 
+// Per-voxel label vote (grid_subsampling.cpp:63-68 update_classes, :96-101 max_element over the per-dimension
+// label -> count map): out label = the most frequent label of the voxel's points, per label dimension. The reference
+// breaks ties by unordered_map iteration order (unspecified); here the smallest label value wins. One thread per
+// voxel head, O(n^2) over the voxel's points (a voxel holds a handful of points; off the hot path).
+template <typename KeyT>
+__global__ void sub_vote_kernel(const int* __restrict__ classes, int ldim, int N, const KeyT* __restrict__ skeys,
+                                const int* __restrict__ svals, const int* __restrict__ pos, const int* __restrict__ off,
+                                int B, int max_p, const int* __restrict__ out_start, int* __restrict__ out_classes) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    KeyT key = skeys[i];
+    if (i > 0 && skeys[i - 1] == key) return;
+    int b = find_cloud(off, B, i);
+    int rank = pos[i] - pos[off[b]];
+    if (max_p > 0 && rank >= max_p) return;
+    int row = out_start[b] + rank;
+    int end = off[b + 1], cnt = 0;
+    for (int j = i; j < end && skeys[j] == key; ++j) ++cnt;
+    for (int d = 0; d < ldim; ++d) {
+        int best = 0, bestc = 0;
+        for (int j = i; j < i + cnt; ++j) {
+            const int lj = classes[(size_t)svals[j] * ldim + d];
+            bool first = true;
+            for (int jj = i; jj < j; ++jj)
+                if (classes[(size_t)svals[jj] * ldim + d] == lj) { first = false; break; }
+            if (!first) continue;
+            int c = 1;
+            for (int jj = j + 1; jj < i + cnt; ++jj) c += classes[(size_t)svals[jj] * ldim + d] == lj ? 1 : 0;
+            if (c > bestc || (c == bestc && lj < best)) { best = lj; bestc = c; }
+        }
+        out_classes[(size_t)row * ldim + d] = best;
+    }
+}
+
 // ---- first-level voxelisation of raw scans, open3d semantics ------------------------------------------------------------
 // The step before the path: raw KITTI scans are float32 [n, 4] (x, y, z, reflectance; datasets/kitti.py:191-194) and are
 // voxelised with open3d's PointCloud.voxel_down_sample(voxel_size) (kitti.py:468-471, :588-589; open3d==0.10.0.0,
@@ -290,7 +324,8 @@ extern "C" size_t aprb_grid_subsample_ws_bytes(int N, int B, int fdim) {
 template <typename KeyT>
 static int run_subsample(const float* d_pts, const int32_t* d_lens, int B, int N, float dl, int max_p, const float* d_feats,
                          int fdim, float* d_out_pts, int32_t* d_out_lens, int32_t* d_out_M, float* d_out_feats,
-                         int32_t* d_status, SubWs& w, cudaStream_t st) {
+                         int32_t* d_status, SubWs& w, cudaStream_t st, const int32_t* d_classes = nullptr, int ldim = 0,
+                         int32_t* d_out_classes = nullptr) {
     const int T = 256;
     KeyT* keys_in = reinterpret_cast<KeyT*>(w.keys_in);
     KeyT* keys_out = reinterpret_cast<KeyT*>(w.keys_out);
@@ -307,6 +342,9 @@ static int run_subsample(const float* d_pts, const int32_t* d_lens, int B, int N
     APRB_TIMED("sub_lens_kernel", st, 1, (sub_lens_kernel<<<1, 256, 0, st>>>(w.pos, w.off, B, max_p, d_out_lens, w.out_start, d_out_M)));
     APRB_TIMED("sub_emit_kernel", st, 1, (sub_emit_kernel<KeyT><<<cdiv(N, T), T, 0, st>>>(d_pts, d_feats, fdim, N, keys_out, w.vals_out, w.pos, w.off, B, max_p,
                                                     w.out_start, d_out_pts, d_out_feats)));
+    if (d_classes)
+        APRB_TIMED("sub_vote_kernel", st, 1, (sub_vote_kernel<KeyT><<<cdiv(N, T), T, 0, st>>>(d_classes, ldim, N, keys_out, w.vals_out, w.pos, w.off, B, max_p,
+                                                        w.out_start, d_out_classes)));
     APRB_LAUNCH_OK();
     return APRB_OK;
 }
@@ -362,11 +400,12 @@ extern "C" int aprb_voxel_downsample_raw(const float* d_raw, int stride, const i
     return run_voxel_raw<uint64_t>(d_raw, stride, d_lens, B, N, voxel_size, d_out_pts, d_out_lens, d_out_M, d_status, w, grids, st);
 }
 
-extern "C" int aprb_grid_subsample_batch(const float* d_pts, const int32_t* d_lens, int B, int N, float dl, int max_p,
-                                         const float* d_feats, int fdim, float* d_out_pts, int32_t* d_out_lens,
-                                         int32_t* d_out_M, float* d_out_feats, int32_t* d_status, int key_bits,
-                                         void* d_ws, size_t ws_bytes, void* stream) {
+static int subsample_impl(const float* d_pts, const int32_t* d_lens, int B, int N, float dl, int max_p,
+                          const float* d_feats, int fdim, const int32_t* d_classes, int ldim, float* d_out_pts, int32_t* d_out_lens,
+                          int32_t* d_out_M, float* d_out_feats, int32_t* d_out_classes, int32_t* d_status, int key_bits,
+                          void* d_ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    APRB_REQUIRE(!(d_classes && (ldim <= 0 || !d_out_classes)), "classes given without ldim/out buffer");
     APRB_REQUIRE(B >= 1 && N >= 0, "need B >= 1 and N >= 0");
     APRB_REQUIRE(d_lens && d_out_lens && d_out_M, "null length/output pointer");
     APRB_REQUIRE(dl > 0.f, "sampleDl must be positive");
@@ -384,6 +423,23 @@ extern "C" int aprb_grid_subsample_batch(const float* d_pts, const int32_t* d_le
     carve_sub(c, N, B, &w);
     if (!c.ok()) { set_error("aprb_grid_subsample_batch: workspace too small (%zu < %zu)", ws_bytes, c.off); return APRB_ERR_WORKSPACE; }
     if (key_bits == 32)
-        return run_subsample<uint32_t>(d_pts, d_lens, B, N, dl, max_p, d_feats, fdim, d_out_pts, d_out_lens, d_out_M, d_out_feats, d_status, w, st);
-    return run_subsample<uint64_t>(d_pts, d_lens, B, N, dl, max_p, d_feats, fdim, d_out_pts, d_out_lens, d_out_M, d_out_feats, d_status, w, st);
+        return run_subsample<uint32_t>(d_pts, d_lens, B, N, dl, max_p, d_feats, fdim, d_out_pts, d_out_lens, d_out_M, d_out_feats, d_status, w, st, d_classes, ldim, d_out_classes);
+    return run_subsample<uint64_t>(d_pts, d_lens, B, N, dl, max_p, d_feats, fdim, d_out_pts, d_out_lens, d_out_M, d_out_feats, d_status, w, st, d_classes, ldim, d_out_classes);
+}
+
+extern "C" int aprb_grid_subsample_batch(const float* d_pts, const int32_t* d_lens, int B, int N, float dl, int max_p,
+                                         const float* d_feats, int fdim, float* d_out_pts, int32_t* d_out_lens,
+                                         int32_t* d_out_M, float* d_out_feats, int32_t* d_status, int key_bits,
+                                         void* d_ws, size_t ws_bytes, void* stream) {
+    return subsample_impl(d_pts, d_lens, B, N, dl, max_p, d_feats, fdim, nullptr, 0, d_out_pts, d_out_lens, d_out_M, d_out_feats,
+                          nullptr, d_status, key_bits, d_ws, ws_bytes, stream);
+}
+
+extern "C" int aprb_grid_subsample_batch_labels(const float* d_pts, const int32_t* d_lens, int B, int N, float dl, int max_p,
+                                                const float* d_feats, int fdim, const int32_t* d_classes, int ldim,
+                                                float* d_out_pts, int32_t* d_out_lens, int32_t* d_out_M, float* d_out_feats,
+                                                int32_t* d_out_classes, int32_t* d_status, int key_bits,
+                                                void* d_ws, size_t ws_bytes, void* stream) {
+    return subsample_impl(d_pts, d_lens, B, N, dl, max_p, d_feats, fdim, d_classes, ldim, d_out_pts, d_out_lens, d_out_M, d_out_feats,
+                          d_out_classes, d_status, key_bits, d_ws, ws_bytes, stream);
 }

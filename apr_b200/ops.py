@@ -46,8 +46,9 @@ def _idx(t, name):
 
 
 # --------------------------------------------------------------------------------------------------------------
-def grid_subsample(points, lens, dl, max_p=0, features=None, sync=True, key_bits=32):
-    """K1. points [N,3] f32 cuda, lens [B] i32 cuda. Returns (sub_points [M,3], sub_lens [B] i32[, sub_feats]).
+def grid_subsample(points, lens, dl, max_p=0, features=None, sync=True, key_bits=32, classes=None):
+    """K1. points [N,3] f32 cuda, lens [B] i32 cuda. Returns (sub_points [M,3], sub_lens [B] i32[, sub_feats][, sub_classes]).
+    classes [N] or [N,ldim] i32: per-voxel label vote (grid_subsampling.cpp:96-101; ties -> smallest label).
     With sync=False returns the full-capacity buffers plus the device scalars [M, status] (no host round trip).
     The 32-bit sort key is tried first; a grid that needs more bits is re-run with the 64-bit key."""
     N.require_cuda()
@@ -62,24 +63,31 @@ def grid_subsample(points, lens, dl, max_p=0, features=None, sync=True, key_bits
         feats = _dev_f32(features, "features")
         fdim = feats.shape[1]
         out_f = torch.empty((max(n, 1), fdim), dtype=torch.float32, device=dev)
+    ldim, cls, out_c = 0, None, None
+    if classes is not None:
+        cls = _dev_i32(classes.reshape(classes.shape[0], -1), "classes")
+        if cls.shape[0] != n:
+            raise ValueError("classes must have one row per point")
+        ldim = cls.shape[1]
+        out_c = torch.empty((max(n, 1), ldim), dtype=torch.int32, device=dev)
     nbytes = N.lib().aprb_grid_subsample_ws_bytes(n, b, fdim)
     ws = _workspace(nbytes, dev)
-    rc = N.lib().aprb_grid_subsample_batch(N.ptr(points), N.ptr(lens), b, n, float(dl), int(max_p), N.ptr(feats), fdim,
-                                           N.ptr(out), N.ptr(out_lens), N.ptr(m_dev[0:1]), N.ptr(out_f),
-                                           N.ptr(m_dev[1:2]), int(key_bits), N.ptr(ws), ws.numel(), N.stream_ptr())
-    N.check(rc, "aprb_grid_subsample_batch")
+    rc = N.lib().aprb_grid_subsample_batch_labels(N.ptr(points), N.ptr(lens), b, n, float(dl), int(max_p), N.ptr(feats), fdim,
+                                                  N.ptr(cls), ldim, N.ptr(out), N.ptr(out_lens), N.ptr(m_dev[0:1]),
+                                                  N.ptr(out_f), N.ptr(out_c), N.ptr(m_dev[1:2]), int(key_bits), N.ptr(ws),
+                                                  ws.numel(), N.stream_ptr())
+    N.check(rc, "aprb_grid_subsample_batch_labels")
+    extra = tuple(t for t in (out_f, out_c) if t is not None)
     if not sync:
-        return (out, out_lens, m_dev) if features is None else (out, out_lens, m_dev, out_f)
+        return (out, out_lens, m_dev) + extra
     m, status = m_dev.tolist()
     if status == 2 and key_bits == 32:
-        return grid_subsample(points, lens, dl, max_p, features, sync, key_bits=64)
+        return grid_subsample(points, lens, dl, max_p, features, sync, key_bits=64, classes=classes)
     if TRACE is not None:
         TRACE.append(("sub", n, m))
     if status != 0:
         raise N.NativeError("grid_subsample: voxel grid does not fit the 64-bit sort key (cloud extent / sampleDl too large)")
-    if features is None:
-        return out[:m], out_lens
-    return out[:m], out_lens, out_f[:m]
+    return (out[:m], out_lens) + tuple(t[:m] for t in extra)
 
 
 def voxel_downsample_raw(raw, lens, voxel_size, sync=True, key_bits=32):

@@ -78,6 +78,16 @@ int aprb_grid_subsample_batch(const float* d_pts, const int32_t* d_lens, int B, 
                               float* d_out_pts, int32_t* d_out_lens, int32_t* d_out_M, float* d_out_feats,
                               int32_t* d_status, int key_bits, void* d_ws, size_t ws_bytes, void* stream);
 
+/* The same with the per-voxel label vote of the reference (grid_subsampling.h:62-75 update_classes,
+ * grid_subsampling.cpp:96-101): d_classes [N,ldim] int32 -> d_out_classes [<=N,ldim], the most frequent label of the
+ * voxel's points per label dimension. Ties: the smallest label value (the reference: unordered_map iteration order,
+ * unspecified). Pass d_classes = NULL / ldim = 0 to skip; same workspace as aprb_grid_subsample_batch. */
+int aprb_grid_subsample_batch_labels(const float* d_pts, const int32_t* d_lens, int B, int N, float dl, int max_p,
+                                     const float* d_feats, int fdim, const int32_t* d_classes, int ldim,
+                                     float* d_out_pts, int32_t* d_out_lens, int32_t* d_out_M, float* d_out_feats,
+                                     int32_t* d_out_classes, int32_t* d_status, int key_bits, void* d_ws, size_t ws_bytes,
+                                     void* stream);
+
 /* First-level voxelisation of RAW scans (the step before the path): d_raw [N, stride] fp32 rows whose first
  * three floats are x, y, z (KITTI .bin: stride 4 = x, y, z, reflectance, datasets/kitti.py:191-194), stacked clouds of
  * d_lens [B] points, with open3d's PointCloud.voxel_down_sample(voxel_size) semantics (kitti.py:468-471, :588-589;

@@ -89,6 +89,11 @@ class RefL1:
         self.lib.ref_batch_grid_subsampling.restype = C.c_int
         self.lib.ref_batch_grid_subsampling.argtypes = [_f32p, C.c_int, _i32p, C.c_int, C.c_float, C.c_int,
                                                         C.POINTER(_f32p), _i32p]
+        if hasattr(self.lib, "ref_batch_grid_subsampling_full"):
+            self.lib.ref_batch_grid_subsampling_full.restype = C.c_int
+            self.lib.ref_batch_grid_subsampling_full.argtypes = [_f32p, C.c_int, _f32p, C.c_int, _i32p, C.c_int, _i32p, C.c_int,
+                                                                 C.c_float, C.c_int, C.POINTER(_f32p), C.POINTER(_f32p),
+                                                                 C.POINTER(_i32p), _i32p]
         self.lib.ref_batch_neighbors.restype = C.c_int
         self.lib.ref_batch_neighbors.argtypes = [_f32p, C.c_int, _f32p, C.c_int, _i32p, _i32p, C.c_int, C.c_float,
                                                  C.c_int, C.POINTER(_i32p)]
@@ -107,6 +112,27 @@ class RefL1:
         out = np.ctypeslib.as_array(ptr, shape=(max(m, 1) * 3,))[:m * 3].reshape(m, 3).copy()
         self.lib.ref_free(ptr)
         return out, ol
+
+    def subsample_batch_full(self, points, batches, features=None, classes=None, sampleDl=0.1, max_p=0):
+        """batch_grid_subsampling with features / labels: (points, lens, feats or None, classes [M,ldim] or None), rows in
+        the reference's own order. Labels: ldim == 1 or a single cloud only (see ref_shim.cpp)."""
+        p, l = _f32(points), _i32(batches)
+        f = _f32(features) if features is not None else None
+        c = _i32(classes).reshape(len(p), -1) if classes is not None else None
+        fdim, ldim = (f.shape[1] if f is not None else 0), (c.shape[1] if c is not None else 0)
+        assert ldim <= 1 or len(l) == 1
+        pp, pf, pc = _f32p(), _f32p(), _i32p()
+        ol = np.empty(len(l), np.int32)
+        m = self.lib.ref_batch_grid_subsampling_full(
+            p.ctypes.data_as(_f32p), len(p), f.ctypes.data_as(_f32p) if f is not None else None, fdim,
+            c.ctypes.data_as(_i32p) if c is not None else None, ldim, l.ctypes.data_as(_i32p), len(l),
+            np.float32(sampleDl), int(max_p), C.byref(pp), C.byref(pf), C.byref(pc), ol.ctypes.data_as(_i32p))
+        out = np.ctypeslib.as_array(pp, shape=(max(m, 1) * 3,))[:m * 3].reshape(m, 3).copy()
+        of = np.ctypeslib.as_array(pf, shape=(max(m * fdim, 1),))[:m * fdim].reshape(m, fdim).copy() if fdim else None
+        oc = np.ctypeslib.as_array(pc, shape=(max(m * ldim, 1),))[:m * ldim].reshape(m, ldim).copy() if ldim else None
+        for q in (pp, pf, pc):
+            self.lib.ref_free(q)
+        return out, ol, of, oc
 
     def batch_query(self, queries, supports, q_batches, s_batches, radius=0.1, variant="nanoflann"):
         q, s, ql, sl = _f32(queries), _f32(supports), _i32(q_batches), _i32(s_batches)

@@ -29,6 +29,29 @@ int ref_batch_grid_subsampling(const float* pts, int N, const int* lens, int B, 
     return M;
 }
 
+// The same with features [N,fdim] and labels [N,ldim] (either may be NULL / 0): outputs malloc'ed, rows in the reference's
+// own (unordered_map) order. The reference slices the labels of cloud b as [sum_b*ldim, sum_b + len*ldim)
+// (grid_subsampling.cpp:167-168), which is only right for ldim == 1 or B == 1: callers keep to those.
+int ref_batch_grid_subsampling_full(const float* pts, int N, const float* feats, int fdim, const int* classes, int ldim,
+                                    const int* lens, int B, float dl, int max_p, float** out_pts, float** out_feats,
+                                    int** out_classes, int* out_lens) {
+    std::vector<PointXYZ> op((const PointXYZ*)pts, (const PointXYZ*)pts + N), sp;
+    std::vector<float> of, sf;
+    if (feats && fdim > 0) of.assign(feats, feats + (size_t)N * fdim);
+    std::vector<int> oc, sc, ob(lens, lens + B), sb;
+    if (classes && ldim > 0) oc.assign(classes, classes + (size_t)N * ldim);
+    batch_grid_subsampling(op, sp, of, sf, oc, sc, ob, sb, dl, max_p);
+    int M = (int)sp.size();
+    *out_pts = (float*)malloc(sizeof(float) * 3 * (M > 0 ? M : 1));
+    if (M) memcpy(*out_pts, sp.data(), sizeof(float) * 3 * M);
+    *out_feats = (float*)malloc(sizeof(float) * (sf.size() ? sf.size() : 1));
+    if (sf.size()) memcpy(*out_feats, sf.data(), sizeof(float) * sf.size());
+    *out_classes = (int*)malloc(sizeof(int) * (sc.size() ? sc.size() : 1));
+    if (sc.size()) memcpy(*out_classes, sc.data(), sizeof(int) * sc.size());
+    for (int b = 0; b < B; ++b) out_lens[b] = sb[b];
+    return M;
+}
+
 // variant: 0 = batch_nanoflann_neighbors (the live one), 1 = batch_ordered_neighbors.
 // Returns width (max_count); *out_idx is malloc'ed [Nq,width].
 int ref_batch_neighbors(const float* q, int Nq, const float* s, int Ns, const int* ql, const int* sl, int B,

@@ -53,8 +53,10 @@ def test_subsample_argument_errors_match_reference_strings():
         cpp_subsampling.subsample_batch([["x", "y", "z"]], l, sampleDl=0.3)
     with pytest.raises(RuntimeError, match="^Error$"):                  # empty result (wrapper.cpp:267-271)
         cpp_subsampling.subsample_batch(np.zeros((0, 3), np.float32), np.array([0], np.int32), sampleDl=0.3)
-    with pytest.raises(RuntimeError, match="classes are not supported"):
-        cpp_subsampling.subsample_batch(p, l, classes=np.zeros((10, 1), np.int32), sampleDl=0.3)
+    with pytest.raises(RuntimeError, match=r"Wrong dimensions : classes.shape is not \(N,\) or \(N, d\)"):
+        cpp_subsampling.subsample_batch(p, l, classes=np.zeros((10, 1, 1), np.int32), sampleDl=0.3)
+    with pytest.raises(RuntimeError, match="Error converting input classes to numpy arrays of type int32"):
+        cpp_subsampling.subsample_batch(p, l, classes=[["a"]] * 10, sampleDl=0.3)
     with pytest.raises(TypeError):                                      # keyword-only options
         cpp_subsampling.subsample_batch(p, l, 0.3)
     with pytest.raises(RuntimeError, match=r"Wrong dimensions : points.shape is not \(N, 3\)"):

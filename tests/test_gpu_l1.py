@@ -246,3 +246,36 @@ def test_voxel_downsample_raw_open3d_semantics(cuda):
     ref_p, ref_l = ops.grid_subsample(torch.from_numpy(raw).to(cuda), torch.from_numpy(lens).to(cuda), 0.3)
     assert abs(int(ref_l.sum()) - int(want_l.sum())) < 0.05 * int(want_l.sum())              # same density, different grid
     assert ref_p.shape != got_p.shape or not torch.equal(ref_p, got_p)
+
+
+def test_subsample_label_vote_vs_reference(cuda, ref_l1):
+    """subsample_batch(classes=...) (grid_subsampling.cpp:63-68, :96-101): the drop-in's labels against the reference's
+    object code, rows matched through their barycentres; where the vote is tied the smallest label must win here."""
+    from apr_b200.cpp_wrappers.cpp_subsampling import grid_subsampling as gs
+    from tests.test_oracle import _vote_case, check_votes, voxel_votes
+    if not hasattr(ref_l1.lib, "ref_batch_grid_subsampling_full"):
+        pytest.skip("oracle/_ref predates the label shim")
+    for seed, n, lens, ldim, nl in ((0, 6000, [2500, 3500], 1, 3), (1, 5000, [5000], 2, 4), (2, 64, [64], 1, 2)):
+        pts, lens, feats, cls = _vote_case(seed, n, lens, ldim, nl)
+        rp, rl, rf, rc = ref_l1.subsample_batch_full(pts, lens, feats, cls, sampleDl=1.5)
+        p, l, f, c = gs.subsample_batch(pts, lens, features=feats, classes=cls if ldim > 1 else cls[:, 0], sampleDl=1.5)
+        assert c.dtype == np.int32 and c.shape == (len(p), ldim) and l.tolist() == rl.tolist()
+        check_votes(pts, lens, cls, 1.5, p, l, c)
+        votes = voxel_votes(pts, lens, cls, 1.5)
+        # order-free comparison with the reference: sort both by barycentre
+        off, n_differ = 0, 0
+        for m in l:
+            a = np.lexsort((p[off:off + m, 2], p[off:off + m, 1], p[off:off + m, 0])) + off
+            b = np.lexsort((rp[off:off + m, 2], rp[off:off + m, 1], rp[off:off + m, 0])) + off
+            assert np.array_equal(p[a], rp[b])
+            assert np.array_equal(f[a].view(np.int32), rf[b].view(np.int32))
+            differ = (c[a] != rc[b])
+            assert (c[a][differ] < rc[b][differ]).all()          # only on ties, and then the smaller label
+            n_differ += int(differ.sum())
+            off += m
+        tied = sum(1 for _, _, cnts in votes.values() for cn in cnts if sorted(cn.values())[-1:] == sorted(cn.values())[-2:-1])
+        assert n_differ <= tied
+    # single-cloud entry point: (points, classes)
+    pts, lens, feats, cls = _vote_case(5, 300, [300], 1, 3)
+    sp, sc = gs.subsample(pts, classes=cls, sampleDl=1.0)
+    assert sc.shape == (len(sp), 1)

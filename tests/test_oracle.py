@@ -169,3 +169,64 @@ def test_load_kernels_matches_reference_golden():
             assert np.array_equal(kp, want), (seed, i)
     with pytest.raises(NotImplementedError):
         load_kernels(1.0, 13, dimension=3, fixed='center')
+
+
+def _vote_case(seed, n, lens, ldim, n_labels):
+    rng = np.random.default_rng(seed)
+    pts = rng.uniform(-4, 4, (n, 3)).astype(np.float32)
+    feats = rng.normal(0, 1, (n, 3)).astype(np.float32)
+    cls = rng.integers(0, n_labels, (n, ldim)).astype(np.int32)
+    return pts, np.asarray(lens, np.int32), feats, cls
+
+
+def voxel_votes(pts, lens, cls, dl):
+    """numpy restatement of the label vote (grid_subsampling.cpp:27, :49-53 voxel of a point; grid_subsampling.h:62-75
+    counts; grid_subsampling.cpp:96-101 max count): {(cloud, voxel) -> (barycentre fp64, [Counter per label dim])}."""
+    from collections import Counter
+    out, off = {}, 0
+    for b, n in enumerate(lens):
+        p = pts[off:off + n]
+        if n:
+            dlf = np.float32(dl)
+            origin = np.floor(p.min(0) * (np.float32(1) / dlf)) * dlf
+            vox = np.floor((p - origin) / dlf).astype(np.int64)
+            for i in range(n):
+                key = (b,) + tuple(vox[i])
+                ent = out.setdefault(key, [np.zeros(3), 0, [Counter() for _ in range(cls.shape[1])]])
+                ent[0] += p[i]; ent[1] += 1
+                for d in range(cls.shape[1]):
+                    ent[2][d][int(cls[off + i, d])] += 1
+        off += n
+    return out
+
+
+def check_votes(pts, lens, cls, dl, out_pts, out_lens, out_cls):
+    """Every output row's label is one of the most frequent labels of the voxel its barycentre lies in."""
+    votes = voxel_votes(pts, lens, cls, dl)
+    by_cloud = {}
+    for key, (s, c, cnts) in votes.items():
+        by_cloud.setdefault(key[0], []).append((s / c, cnts))
+    assert int(np.sum(out_lens)) == len(out_pts) == len(out_cls) == len(votes)
+    off = 0
+    for b, m in enumerate(out_lens):
+        cand = by_cloud.get(b, [])
+        cen = np.stack([c[0] for c in cand]) if cand else np.zeros((0, 3))
+        for r in range(off, off + m):
+            j = int(np.argmin(np.abs(cen - out_pts[r]).sum(1)))
+            assert np.abs(cen[j] - out_pts[r]).max() < 1e-4
+            for d in range(out_cls.shape[1]):
+                cnt = cand[j][1][d]
+                assert cnt[int(out_cls[r, d])] == max(cnt.values())
+        off += m
+
+
+def test_reference_label_vote_and_feature_mean_semantics(ref_l1):
+    """Pins the restated semantics of update_all / the max_element vote on the reference's own object code."""
+    if not hasattr(ref_l1.lib, "ref_batch_grid_subsampling_full"):
+        pytest.skip("oracle/_ref predates the label shim")
+    for seed, n, lens, ldim, nl in ((0, 600, [250, 350], 1, 3), (1, 500, [500], 2, 4), (2, 64, [64], 1, 2)):
+        pts, lens, feats, cls = _vote_case(seed, n, lens, ldim, nl)
+        op, ol, of, oc = ref_l1.subsample_batch_full(pts, lens, feats, cls, sampleDl=1.5)
+        check_votes(pts, lens, cls, 1.5, op, ol, oc)
+        op2, ol2 = ref_l1.subsample_batch(pts, lens, sampleDl=1.5)
+        assert np.array_equal(op, op2) and np.array_equal(ol, ol2) and of.shape == (len(op), 3)
