@@ -67,6 +67,15 @@ struct ProfScope {
     } while (0)
 
 // ---- order-preserving float <-> int encoding for atomicMin/atomicMax on floats ---------------------------------
+// Two fp32 values -> packed fp16x2 (lo in the low half), round to nearest even, SATURATING to +-65504 (one
+// F2FP.SATFINITE.F16.F32.PACK_AB): every fp16 operand / activation store of the tensor path goes through this, so a
+// feature outside the fp16 range clamps instead of turning into inf and poisoning the accumulators.
+__device__ __forceinline__ unsigned pack_half2_sat(float lo, float hi) {
+    unsigned r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
 __device__ __forceinline__ int f2ord(float f) {
     int i = __float_as_int(f);
     return i >= 0 ? i : i ^ 0x7FFFFFFF;

@@ -596,9 +596,8 @@ gemm_nrm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             o.x = nrm_act_round(o.x, p.slope); o.y = nrm_act_round(o.y, p.slope);
                             o.z = nrm_act_round(o.z, p.slope); o.w = nrm_act_round(o.w, p.slope);
                             if (p.out16) {
-                                const __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
                                 uint2 u;
-                                u.x = *reinterpret_cast<const uint32_t*>(&h0); u.y = *reinterpret_cast<const uint32_t*>(&h1);
+                                u.x = pack_half2_sat(o.x, o.y); u.y = pack_half2_sat(o.z, o.w);
                                 *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + e) = u;
                             } else {
                                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + e) = o;
@@ -762,6 +761,7 @@ static int launch_gemm_persistent(const void* A, const void* Bt, int M, int N, i
 
 extern int g_kpconv_chunk_mb;
 extern int g_kpw_version;
+extern int g_kpw_fh;
 extern int g_fuse_stats;
 extern int g_kpconv_f16;
 extern int g_act_f16;
@@ -940,6 +940,7 @@ extern "C" int aprb_set_option(const char* name, int value) {
     if (strcmp(name, "nrm_park") == 0) { g_nrm_park = value; return APRB_OK; }
     if (strcmp(name, "kpconv_chunk_mb") == 0) { g_kpconv_chunk_mb = value; return APRB_OK; }
     if (strcmp(name, "kpw_version") == 0) { g_kpw_version = value; return APRB_OK; }
+    if (strcmp(name, "kpw_fh") == 0) { g_kpw_fh = value; return APRB_OK; }
     if (strcmp(name, "fuse_stats") == 0) { g_fuse_stats = value; return APRB_OK; }
     if (strcmp(name, "kpconv_f16") == 0) { g_kpconv_f16 = value; return APRB_OK; }
     if (strcmp(name, "act_f16") == 0) { g_act_f16 = value; return APRB_OK; }

@@ -31,6 +31,7 @@ int kpconv_tc_run(const float* d_q, const float4* s4, const int* d_idx, int ld, 
                   float extent, int Nq, int Ns, int H, int K, int Cin, void* d_wf16, float* d_inv_nn, cudaStream_t st);
 
 int g_kpw_version = 4;       // aprb_set_option("kpw_version"): 3 = per-kernel-point tables, 4 = CSR lists + lane groups
+int g_kpw_fh = 1;            // aprb_set_option("kpw_fh"): fp16 rows through the FHFMA kernel (v5); 0 = v4, 2 = Cin 64 with 2 rows per warp
 int g_kpconv_chunk_mb = 0;   // aprb_set_option("kpconv_chunk_mb"): L2-sized row chunks of the tensor path (0 = off)
 
 // flag[s] = 1 iff sum_c x[s,c] > 0 (one warp per support row; fixed reduction order), and the packed support record
@@ -251,9 +252,8 @@ constexpr int KPW_SLOT_BYTES = KPW_ECAP * 8 + 80;   // int2 ent[ECAP]; int off[K
 
 // fp16 form of the weighted tile (tensor path with fp16 operands: same 10-bit mantissa as TF32, half the bytes)
 __device__ __forceinline__ void store_half4(__half* dst, const float4 v) {
-    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
     uint2 u;
-    u.x = *reinterpret_cast<const unsigned*>(&a); u.y = *reinterpret_cast<const unsigned*>(&b);
+    u.x = pack_half2_sat(v.x, v.y); u.y = pack_half2_sat(v.z, v.w);
     *reinterpret_cast<uint2*>(dst) = u;
 }
 
@@ -443,6 +443,185 @@ kp_weighted4_kernel(const float* __restrict__ q, const float4* __restrict__ s4, 
                 kp_direct_row<IdxT, NH, ROUND_TF32, X16>(q, s4, idx, ld, x, s_kp, ext2, inv_ext, row0 + r, Ns, H, K, Cin,
                                                     out16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(wf) + (size_t)(row0 + r) * K * Cin)
                                                           : wf + (size_t)(row0 + r) * K * Cin, out16, lane);
+        }
+    }
+}
+
+// ---- v5 (fp16 features in, fp16 weighted tile out): the v4 structure with FHFMA ------------------------------------------
+// sm_100a has a mixed-precision FMA, fma.rn.f32.f16 (SASS FHFMA: fp16 x fp16 product, exact, added to an fp32 accumulator
+// with one rounding; it reads either half of a packed register). With the influence weight kept as fp16 bits in the list
+// entry the inner loop needs no widening of the feature row at all: per list entry LDS.64 + address + ONE 128-bit load
+// + 8 FHFMA for 8 channels, against LDS.64 + address + 2 LDG.64 + 8 conversions + 8 FFMA in v4 (phase 2 was 47 % of the
+// kernel's issued instructions). What it costs: the weight is rounded to an 11-bit significand (as the tcgen05 weighting
+// kernel does, kpconv_tc.cu); the accumulation stays fp32.
+__device__ __forceinline__ float fhfma(unsigned short a, unsigned short b, float c) {
+    asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(c) : "h"(a), "h"(b));
+    return c;
+}
+template <int NW> struct HWords { uint32_t r[NW]; };
+template <int NW> __device__ __forceinline__ HWords<NW> ld_hwords(const char* p);
+template <> __device__ __forceinline__ HWords<2> ld_hwords<2>(const char* p) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p)); HWords<2> h; h.r[0] = u.x; h.r[1] = u.y; return h;
+}
+template <> __device__ __forceinline__ HWords<4> ld_hwords<4>(const char* p) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p)); HWords<4> h; h.r[0] = u.x; h.r[1] = u.y; h.r[2] = u.z; h.r[3] = u.w; return h;
+}
+
+// Overflow path of v5: as kp_direct_row, fp16 rows, weight rounded to fp16 like the list entries.
+template <int NH>
+__device__ __noinline__ void kp_direct_row_h(const float* __restrict__ q, const float4* __restrict__ s4, const int* __restrict__ idx,
+                                             int ld, const __half* __restrict__ x, const float4* s_kp, float ext2, float inv_ext,
+                                             int n, int Ns, int H, int K, int Cin, __half* __restrict__ wrow, int lane) {
+    RowGeom<NH> g;
+    load_row_geom<int, NH>(q, s4, idx, ld, n, Ns, H, Cin * 2, lane, g);
+    for (int c0 = 0; c0 < Cin; c0 += 128) {
+        const int c = c0 + lane * 4;
+        const bool cok = c < Cin;
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) {
+            const float4 kpk = s_kp[k];
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < NH; ++j) {
+                if (!g.any[j]) continue;
+                bool in;
+                const float w = influence<NH>(g, j, kpk, ext2, inv_ext, in);
+                unsigned m = __ballot_sync(0xffffffffu, in);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const unsigned short wb = (unsigned short)__shfl_sync(0xffffffffu, (int)__half_as_ushort(__float2half_rn(w)), src);
+                    const int sib = __shfl_sync(0xffffffffu, g.sio[j], src);
+                    if (cok) {
+                        const HWords<2> xr = ld_hwords<2>(reinterpret_cast<const char*>(x) + (unsigned)sib + (unsigned)c * 2u);
+                        acc.x = fhfma(wb, (unsigned short)(xr.r[0] & 0xffffu), acc.x); acc.y = fhfma(wb, (unsigned short)(xr.r[0] >> 16), acc.y);
+                        acc.z = fhfma(wb, (unsigned short)(xr.r[1] & 0xffffu), acc.z); acc.w = fhfma(wb, (unsigned short)(xr.r[1] >> 16), acc.w);
+                    }
+                }
+            }
+            if (cok) store_half4(wrow + (size_t)k * Cin + c, acc);
+        }
+    }
+}
+
+// LG lanes per row, CPL (4 or 8) consecutive channels per lane and load, NV loads per lane: one pass covers LG*CPL*NV channels.
+template <int LG, int CPL, int NV, int NH>
+__global__ void __launch_bounds__(128)
+kp_weighted_h_kernel(const float* __restrict__ q, const float4* __restrict__ s4, const int* __restrict__ idx, int ld,
+                     const __half* __restrict__ x, const float* __restrict__ kp, float extent, int Nq, int Ns, int H, int K,
+                     int Cin, __half* __restrict__ wf, float* __restrict__ inv_nn) {
+    constexpr int RP = 32 / LG;
+    constexpr int NW = CPL / 2;
+    constexpr int CH = LG * CPL * NV;
+    constexpr int NU = 2;
+    extern __shared__ __align__(16) unsigned char s_rows[];
+    __shared__ float4 s_kp[KP_MAX_K];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    if (threadIdx.x < K) s_kp[threadIdx.x] = make_float4(kp[3 * threadIdx.x], kp[3 * threadIdx.x + 1], kp[3 * threadIdx.x + 2], 0.f);
+    __syncthreads();
+    const int row0 = (blockIdx.x * wpb + wib) * RP;
+    if (row0 >= Nq) return;
+    const float ext2 = extent * extent, inv_ext = 1.0f / extent;
+    unsigned char* wslots = s_rows + (size_t)wib * RP * KPW_SLOT_BYTES;
+
+    // ---- phase 1: CSR influence lists of the warp's RP rows (whole warp per row, lanes = neighbours) ----
+#pragma unroll 1
+    for (int r = 0; r < RP; ++r) {
+        int2* ent = reinterpret_cast<int2*>(wslots + (size_t)r * KPW_SLOT_BYTES);
+        int* off = reinterpret_cast<int*>(ent + KPW_ECAP);
+        const int n = row0 + r;
+        if (n >= Nq) {
+            if (lane <= KP_MAX_K) off[lane] = 0;
+            continue;
+        }
+        RowGeom<NH> g;
+        const int nn = load_row_geom<int, NH>(q, s4, idx, ld, n, Ns, H, Cin * 2, lane, g);
+        if (lane == 0) inv_nn[n] = 1.0f / (float)max(nn, 1);
+        build_row_list<NH, KPW_ECAP, true>(g, s_kp, K, ext2, inv_ext, ent, off, lane);
+    }
+    __syncwarp();
+
+    // ---- phase 2: lane group grp streams row row0 + grp (own trip counts per group, no warp primitive inside) ----
+    const int grp = lane / LG, lg = lane % LG;
+    const int n = row0 + grp;
+    const int2* ent = reinterpret_cast<const int2*>(wslots + (size_t)grp * KPW_SLOT_BYTES);
+    const int* off = reinterpret_cast<const int*>(ent + KPW_ECAP);
+    const bool ovf = off[KP_MAX_K] > KPW_ECAP;
+    const bool active = n < Nq && !ovf;
+    const char* xb = reinterpret_cast<const char*>(x);
+    for (int c0 = 0; c0 < Cin; c0 += CH) {
+        const int c = c0 + lg * CPL;
+        const char* xbc = xb + (size_t)c * 2;
+        size_t wo = (size_t)n * K * Cin + c;
+        int end = active ? off[0] : 0;
+#pragma unroll 1
+        for (int k = 0; k < K; ++k, wo += Cin) {
+            const int beg = end;
+            end = active ? off[k + 1] : 0;
+            float acc[NV][CPL];
+#pragma unroll
+            for (int j = 0; j < NV; ++j)
+#pragma unroll
+                for (int i = 0; i < CPL; ++i) acc[j][i] = 0.f;
+            int e = beg;
+#pragma unroll 1
+            for (; e + NU <= end; e += NU) {
+                int2 en[NU];
+                HWords<NW> xr[NU][NV];
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
+                    en[u] = ent[e + u];
+                    const char* xe = xbc + (unsigned)en[u].x;
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) xr[u][j] = ld_hwords<NW>(xe + j * LG * CPL * 2);
+                }
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
+                    const unsigned short w = (unsigned short)en[u].y;
+#pragma unroll
+                    for (int j = 0; j < NV; ++j)
+#pragma unroll
+                        for (int i = 0; i < NW; ++i) {
+                            acc[j][2 * i] = fhfma(w, (unsigned short)(xr[u][j].r[i] & 0xffffu), acc[j][2 * i]);
+                            acc[j][2 * i + 1] = fhfma(w, (unsigned short)(xr[u][j].r[i] >> 16), acc[j][2 * i + 1]);
+                        }
+                }
+            }
+#pragma unroll 1
+            for (; e < end; ++e) {
+                const int2 en = ent[e];
+                const char* xe = xbc + (unsigned)en.x;
+                const unsigned short w = (unsigned short)en.y;
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    const HWords<NW> xr = ld_hwords<NW>(xe + j * LG * CPL * 2);
+#pragma unroll
+                    for (int i = 0; i < NW; ++i) {
+                        acc[j][2 * i] = fhfma(w, (unsigned short)(xr.r[i] & 0xffffu), acc[j][2 * i]);
+                        acc[j][2 * i + 1] = fhfma(w, (unsigned short)(xr.r[i] >> 16), acc[j][2 * i + 1]);
+                    }
+                }
+            }
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    uint32_t o[NW];
+#pragma unroll
+                    for (int i = 0; i < NW; ++i) o[i] = pack_half2_sat(acc[j][2 * i], acc[j][2 * i + 1]);
+                    __half* dst = wf + wo + j * LG * CPL;
+                    if (NW == 2) *reinterpret_cast<uint2*>(dst) = make_uint2(o[0], o[1]);
+                    else *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[NW - 2], o[NW - 1]);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (__any_sync(0xffffffffu, ovf && n < Nq)) {
+#pragma unroll 1
+        for (int r = 0; r < RP; ++r) {
+            const int ovr = __shfl_sync(0xffffffffu, (int)ovf, r * LG);
+            if (ovr && row0 + r < Nq)
+                kp_direct_row_h<NH>(q, s4, idx, ld, x, s_kp, ext2, inv_ext, row0 + r, Ns, H, K, Cin, wf + (size_t)(row0 + r) * K * Cin, lane);
         }
     }
 }
@@ -742,6 +921,31 @@ static int launch_kp_weighted(const float* d_q, const float* d_s, const void* d_
         if (x16) {
             // fp16 features in, fp16 weighted tile out (the native pipeline's activation format): int32 indices, whole slabs
             if (idx_is_i64 || !full || !out16) { set_error("aprb_kpconv_forward: fp16 features need int32 indices and Cin %% %d == 0", chs[cfg]); return APRB_ERR_UNSUPPORTED; }
+            if (g_kpw_fh && Cin % 64 == 0) {
+                // v5 (FHFMA): 8 channels per lane and load; Cin = 64 runs 4 rows per warp (g_kpw_fh == 2: 2 rows, 4 channels per lane)
+#define KPWH_LAUNCH(LG, CPL, NV, NH)                                                                                  \
+                do {                                                                                                  \
+                    constexpr int wpbh = 4;                                                                           \
+                    constexpr int rph = 32 / LG;                                                                      \
+                    const size_t smemh = (size_t)wpbh * rph * KPW_SLOT_BYTES;                                         \
+                    APRB_TIMED("kp_weighted_kernel", st, 1, (kp_weighted_h_kernel<LG, CPL, NV, NH><<<cdiv(nr, wpbh * rph), wpbh * 32, smemh, st>>>( \
+                        d_q + 3 * (size_t)r0, s4, (const int*)d_idx + (size_t)r0 * ld_idx, ld_idx, (const __half*)d_x, d_kp, extent, nr, Ns, H, K, Cin, \
+                        (__half*)wf, inv_nn + r0)));                                                                  \
+                } while (0)
+#define KPWH_CFG(NH)                                                                                                  \
+                do {                                                                                                  \
+                    if (Cin == 64) { if (g_kpw_fh == 2) KPWH_LAUNCH(16, 4, 1, NH); else KPWH_LAUNCH(8, 8, 1, NH); }   \
+                    else if (Cin == 128) KPWH_LAUNCH(16, 8, 1, NH);                                                   \
+                    else if (Cin % 512 == 0) KPWH_LAUNCH(32, 8, 2, NH);                                               \
+                    else if (Cin % 256 == 0) KPWH_LAUNCH(32, 8, 1, NH);                                               \
+                    else KPWH_LAUNCH(8, 8, 1, NH);                                                                    \
+                } while (0)
+                if (nh == 2) KPWH_CFG(2); else KPWH_CFG(4);
+#undef KPWH_CFG
+#undef KPWH_LAUNCH
+                APRB_LAUNCH_OK();
+                return APRB_OK;
+            }
 #define KPW4_X16(NH)                                                                                                  \
             do {                                                                                                      \
                 if (cfg == 0) KPW4_LAUNCH(int, 8, 1, NH, true, false, true);                                          \
@@ -852,7 +1056,7 @@ extern "C" int aprb_kpconv_forward_stats(const float* d_q, const float* d_s, con
         const int x16 = mode == 4;                                    // mode 4: d_x itself is fp16 [Ns, Cin]
         // tcgen05 with fp16 operands: d_wprep is the fp16 prepared operand (aprb_kpconv_prepare_weights_f16); the weighted
         // tile is produced in fp16 (same 10-bit mantissa as TF32, half the bytes of the largest tensor of the path).
-        // For features of O(1) magnitude (after InstanceNorm); |sum_h w x| must stay below 65504.
+        // fp16 range: the weighted tile saturates at +-65504 (pack_half2_sat) instead of overflowing to inf.
         APRB_REQUIRE(d_wprep, "mode 3 needs the fp16 prepared weights");
         if (!gemm_f16_supported(Nq, Cout, KC)) { set_error("aprb_kpconv_forward: fp16 path unsupported for K*Cin=%d Cout=%d", KC, Cout); return APRB_ERR_UNSUPPORTED; }
         Carver c3(d_ws, ws_bytes);

@@ -2,6 +2,7 @@
 // the fused gather -> influence -> tcgen05 contraction kernel): per-row neighbour geometry and the linear influence
 // max(0, 1 - d / KP_extent) of /root/reference/Predator_APR/models/blocks.py:269-289, :328-329.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace aprb {
@@ -71,7 +72,8 @@ __device__ __forceinline__ float influence(const RowGeom<NH>& g, int j, const fl
 // CSR influence list of ONE query row, built by a whole warp (lanes = neighbours), kernel-point-major so that the
 // (byte offset of the feature row, weight) pairs of kernel point k follow those of k-1: ent[0..min(total, ECAP)) and
 // off[0..KP_MAX_K] (off[K..] = total). Entries beyond ECAP are dropped; the caller checks off[KP_MAX_K] > ECAP.
-template <int NH, int ECAP>
+// W16: the weight is stored as fp16 bits (round to nearest even) in the low half of .y — the form FHFMA consumes.
+template <int NH, int ECAP, bool W16 = false>
 __device__ __forceinline__ void build_row_list(const RowGeom<NH>& g, const float4* s_kp, int K, float ext2, float inv_ext,
                                                int2* ent, int* off, int lane) {
     const unsigned ltmask = (1u << lane) - 1u;
@@ -88,7 +90,7 @@ __device__ __forceinline__ void build_row_list(const RowGeom<NH>& g, const float
                     const float w = influence<NH>(g, j, kpk, ext2, inv_ext, in);
                     const unsigned m = __ballot_sync(0xffffffffu, in);
                     const int pos = run + __popc(m & ltmask);
-                    if (in && pos < ECAP) ent[pos] = make_int2(g.sio[j], __float_as_int(w));
+                    if (in && pos < ECAP) ent[pos] = make_int2(g.sio[j], W16 ? (int)__half_as_ushort(__float2half_rn(w)) : __float_as_int(w));
                     run += __popc(m);
                 }
             }

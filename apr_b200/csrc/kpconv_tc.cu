@@ -343,8 +343,7 @@ kpconv_tc_kernel(const float* __restrict__ q, const float4* __restrict__ s4, con
                             uint32_t h[8];
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
-                                const __half2 t = __floats2half2_rn(__uint_as_float(v[ii][mb][2 * k]), __uint_as_float(v[ii][mb][2 * k + 1]));
-                                h[k] = *reinterpret_cast<const uint32_t*>(&t);
+                                h[k] = pack_half2_sat(__uint_as_float(v[ii][mb][2 * k]), __uint_as_float(v[ii][mb][2 * k + 1]));
                             }
                             row[mb * 128 * 2] = make_uint4(h[0], h[1], h[2], h[3]);
                             row[mb * 128 * 2 + 1] = make_uint4(h[4], h[5], h[6], h[7]);

@@ -252,7 +252,7 @@ def test_subsample_label_vote_vs_reference(cuda, ref_l1):
     """subsample_batch(classes=...) (grid_subsampling.cpp:63-68, :96-101): the drop-in's labels against the reference's
     object code, rows matched through their barycentres; where the vote is tied the smallest label must win here."""
     from apr_b200.cpp_wrappers.cpp_subsampling import grid_subsampling as gs
-    from tests.test_oracle import _vote_case, check_votes, voxel_votes
+    from test_oracle import _vote_case, check_votes, voxel_votes
     if not hasattr(ref_l1.lib, "ref_batch_grid_subsampling_full"):
         pytest.skip("oracle/_ref predates the label shim")
     for seed, n, lens, ldim, nl in ((0, 6000, [2500, 3500], 1, 3), (1, 5000, [5000], 2, 4), (2, 64, [64], 1, 2)):

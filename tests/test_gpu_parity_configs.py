@@ -231,6 +231,28 @@ def test_kpconv_mode4_fp16_features_vs_oracle(cuda, cin, cout, h):
         setopt(0)
 
 
+def test_fp16_operand_path_saturates_instead_of_overflowing(cuda):
+    """Mode 3 takes arbitrary fp32 features: a weighted sum outside the fp16 range clamps to +-65504 in the weighted tile
+    (pack_half2_sat) — the output stays finite, and rows with in-range features are unaffected."""
+    gen = torch.Generator().manual_seed(3)
+    ns, nq, h, cin, cout = 600, 400, 20, 64, 64
+    s = torch.rand(ns, 3, generator=gen); q = torch.rand(nq, 3, generator=gen)
+    inds = torch.randint(0, ns, (nq, h), generator=gen)
+    inds[: nq // 2] = inds[: nq // 2] % (ns // 2)                           # first half of the queries: supports < ns/2 only
+    x = torch.randn(ns, cin, generator=gen)
+    kp = torch.randn(15, 3, generator=gen) * 0.3
+    w = torch.randn(15, cin, cout, generator=gen) / np.sqrt(15 * cin)
+    wd = w.to(cuda); prep = ops.kpconv_prepare_weights_f16(wd)
+    base = ops.kpconv(q.to(cuda), s.to(cuda), inds.to(cuda).int(), x.to(cuda), kp.to(cuda), wd, 0.5, wprep=prep, mode=3)
+    xb = x.clone(); xb[ns // 2:] *= 1e6                                     # second half of the supports: far outside fp16
+    got = ops.kpconv(q.to(cuda), s.to(cuda), inds.to(cuda).int(), xb.to(cuda), kp.to(cuda), wd, 0.5, wprep=prep, mode=3)
+    assert bool(torch.isfinite(got).all())
+    assert torch.equal(got[: nq // 2], base[: nq // 2])
+    h16 = ops.f32_to_f16(torch.tensor([1e9, -1e9, 65504.0, 1.0, float("inf")], device=cuda)) if hasattr(ops, "f32_to_f16") else None
+    if h16 is not None:
+        assert h16.cpu().tolist() == [65504.0, -65504.0, 65504.0, 1.0, 65504.0]
+
+
 def test_max_pool_f16_vs_oracle(cuda):
     """fp16 max_pool (product path): the max of fp16 values is exact, so the result is bit-identical to the oracle's on
     the same values — pads anywhere, all-pad rows, H > 32, and per-segment reference widths."""
