@@ -626,6 +626,10 @@ kp_weighted_h_kernel(const float* __restrict__ q, const float4* __restrict__ s4,
     }
 }
 
+// (Round 2 also measured v5 with the list consumed as ONE stream — entries tagged with "last of kernel point k", 4 entries
+// and their rows in flight across kernel-point boundaries: bit-identical output, same time within 3 % on all seven encoder
+// shapes (gpurun log r02c), so phase 2 is not latency-bound either; the per-kernel-point form stays.)
+
 // (Round 1 also measured this stage on mma.sync — dense per-query 16 x H x Cin products, three variants. On B200 every
 // legacy HMMA.1688 is charged ~4 LSU data-pipe wavefronts, so that path is LSU-bound at the speed of this kernel or
 // worse: profiles/r01_kp_weighted_variants.txt; the code is in the history at commit "KPConv weighting on mma.sync".)
@@ -921,7 +925,7 @@ static int launch_kp_weighted(const float* d_q, const float* d_s, const void* d_
         if (x16) {
             // fp16 features in, fp16 weighted tile out (the native pipeline's activation format): int32 indices, whole slabs
             if (idx_is_i64 || !full || !out16) { set_error("aprb_kpconv_forward: fp16 features need int32 indices and Cin %% %d == 0", chs[cfg]); return APRB_ERR_UNSUPPORTED; }
-            if (g_kpw_fh && Cin % 64 == 0) {
+            if (g_kpw_fh && Cin % 64 == 0 && Ns > 0) {
                 // v5 (FHFMA): 8 channels per lane and load; Cin = 64 runs 4 rows per warp (g_kpw_fh == 2: 2 rows, 4 channels per lane)
 #define KPWH_LAUNCH(LG, CPL, NV, NH)                                                                                  \
                 do {                                                                                                  \
