@@ -628,7 +628,12 @@ kp_weighted_h_kernel(const float* __restrict__ q, const float4* __restrict__ s4,
 
 // (Round 2 also measured v5 with the list consumed as ONE stream — entries tagged with "last of kernel point k", 4 entries
 // and their rows in flight across kernel-point boundaries: bit-identical output, same time within 3 % on all seven encoder
-// shapes (gpurun log r02c), so phase 2 is not latency-bound either; the per-kernel-point form stays.)
+// shapes (gpurun log r02c), so phase 2 is not latency-bound either; the per-kernel-point form stays.
+// And v6, list building with lane = (kernel point, neighbour parity) walking the row's compacted neighbours and appending
+// to its own fixed slot — no ballots, no prefix sums, ~500 instead of ~830 instructions per row on paper: 1.4-2x SLOWER
+// (583 vs 425 us at L0). Real kernel points with KP_extent 2.0 put up to 27 neighbours in one extent, so slots of 24
+// entries per kernel point are needed (1.9 KB per row: occupancy), and the walk is a serial, branchy latency chain where
+// v4/v5's 30 evaluations per row are independent and fully unrolled. Removed; numbers in DESIGN.md 4.4d.)
 
 // (Round 1 also measured this stage on mma.sync — dense per-query 16 x H x Cin products, three variants. On B200 every
 // legacy HMMA.1688 is charged ~4 LSU data-pipe wavefronts, so that path is LSU-bound at the speed of this kernel or
