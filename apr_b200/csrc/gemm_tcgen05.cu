@@ -688,6 +688,12 @@ bool gemm_tf32_supported(int M, int N, int K) {
 
 int g_gemm_costages = 1;  // aprb_set_option("gemm_costages"): shallow rings / several CTAs per SM when the grid allows
 
+// Timer label of the next GEMM launches of this thread: the KPConv contraction tags itself ("kpconv_gemm_kernel") so that the
+// bench line can report the whole KPConv operator (weighting + contraction) apart from the Linear layers.
+static thread_local const char* t_gemm_label = nullptr;
+void set_gemm_label(const char* label) { t_gemm_label = label; }
+static inline const char* gemm_label() { return t_gemm_label ? t_gemm_label : "gemm_tf32_kernel"; }
+
 template <int BN, int CL>
 static int launch_gemm(const float* A, const float* Bt, int M, int N, int K, int splits, int kb_per_split,
                        const float* rowscale, float* C, float* gstat, cudaStream_t st) {
@@ -722,7 +728,7 @@ static int launch_gemm(const float* A, const float* Bt, int M, int N, int K, int
     attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = CL; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     {
-        ProfScope ps("gemm_tf32_kernel", st, 1);
+        ProfScope ps(gemm_label(), st, 1);
         APRB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, CL>, tmA, tmB, M, N, K, kb_per_split, stages, rowscale, C, gstat));
     }
     return APRB_OK;
@@ -752,7 +758,7 @@ static int launch_gemm_persistent(const void* A, const void* Bt, int M, int N, i
     const int stages = g_gemm_stages >= 2 ? min(g_gemm_stages, GemmPCfg<BN>::STAGES) : GemmPCfg<BN>::STAGES;
     const int smem = GemmPCfg<BN>::SMEM - (GemmPCfg<BN>::STAGES - stages) * (GemmPCfg<BN>::A_BYTES + GemmPCfg<BN>::B_BYTES);
     {
-        ProfScope ps("gemm_tf32_kernel", st, 1);
+        ProfScope ps(gemm_label(), st, 1);
         gemm_tf32_persistent_kernel<BN, F16><<<grid, 192, smem, st>>>(tmA, tmB, M, N, K, num_n, total, rowscale, C, gstat, stages);
     }
     APRB_LAUNCH_OK();

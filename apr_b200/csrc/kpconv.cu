@@ -26,6 +26,7 @@ int kpconv_fused_run(const float* d_q, const float4* s4, const void* d_idx, int 
                      const float* d_kp, const float* d_wprep, float extent, int Nq, int Ns, int H, int K, int Cin, int Cout,
                      float* d_out, float* d_gstat, cudaStream_t st);
 bool gemm_tf32_supported(int M, int N, int K);
+void set_gemm_label(const char* label);                                           // gemm_tcgen05.cu: timer label of this thread's next GEMMs
 bool kpconv_tc_supported(int H, int K, int Cin, long long Ns);                 // kpconv_tc.cu
 int kpconv_tc_run(const float* d_q, const float4* s4, const int* d_idx, int ld, const void* d_x16, const float* d_kp,
                   float extent, int Nq, int Ns, int H, int K, int Cin, void* d_wf16, float* d_inv_nn, cudaStream_t st);
@@ -1059,7 +1060,10 @@ extern "C" int aprb_kpconv_forward_stats(const float* d_q, const float* d_s, con
         launch_rowsum_pos(d_x, d_s, Ns, Cin, flag5, s45, 1, st);
         int rc = kpconv_tc_run(d_q, s45, (const int*)d_idx, ld_idx, d_x, d_kp, extent, Nq, Ns, H, K, Cin, wf5, inv5, st);
         if (rc) return rc;
-        return gemm_f16_rowscale(wf5, d_wprep, Nq, Cout, KP_MAX_K * Cin, inv5, d_out, st, d_gstat, stats_written);
+        set_gemm_label("kpconv_gemm_kernel");
+        rc = gemm_f16_rowscale(wf5, d_wprep, Nq, Cout, KP_MAX_K * Cin, inv5, d_out, st, d_gstat, stats_written);
+        set_gemm_label(nullptr);
+        return rc;
     }
     if (mode == 3 || mode == 4) {
         const int x16 = mode == 4;                                    // mode 4: d_x itself is fp16 [Ns, Cin]
@@ -1077,7 +1081,10 @@ extern "C" int aprb_kpconv_forward_stats(const float* d_q, const float* d_s, con
         if (Ns > 0) launch_rowsum_pos(d_x, d_s, Ns, Cin, flag3, s43, x16, st);
         int rc = launch_kp_weighted(d_q, d_s, d_idx, idx_is_i64, ld_idx, d_x, d_kp, flag3, s43, extent, 0, Nq, Ns, H, K, Cin, false, wf3, inv3, st, 1, x16);
         if (rc) return rc;
-        return gemm_f16_rowscale(wf3, d_wprep, Nq, Cout, KC, inv3, d_out, st, d_gstat, stats_written);
+        set_gemm_label("kpconv_gemm_kernel");
+        rc = gemm_f16_rowscale(wf3, d_wprep, Nq, Cout, KC, inv3, d_out, st, d_gstat, stats_written);
+        set_gemm_label(nullptr);
+        return rc;
     }
     bool tensor_ok = d_wprep && gemm_tf32_supported(Nq, Cout, KC);
     if (mode == 2 && !tensor_ok) { set_error("aprb_kpconv_forward: tcgen05 path unsupported for K*Cin=%d Cout=%d", KC, Cout); return APRB_ERR_UNSUPPORTED; }
@@ -1116,8 +1123,10 @@ extern "C" int aprb_kpconv_forward_stats(const float* d_q, const float* d_s, con
             int rc = launch_kp_weighted(d_q, d_s, d_idx, idx_is_i64, ld_idx, d_x, d_kp, flag, s4, extent, r0, nr, Ns, H, K, Cin, true, wf, inv_nn, st);
             if (rc) return rc;
             // group statistics only when the operator is one GEMM over all rows (row chunks would misalign the groups)
+            set_gemm_label("kpconv_gemm_kernel");
             rc = gemm_tf32_rowscale(wf, d_wprep, nr, Cout, KC, inv_nn + r0, d_out + (size_t)r0 * Cout, gws, gws_bytes, st,
                                     chunk_rows == Nq ? d_gstat : nullptr, chunk_rows == Nq ? stats_written : nullptr);
+            set_gemm_label(nullptr);
             if (rc) return rc;
         }
         return APRB_OK;
