@@ -149,8 +149,11 @@ size_t aprb_kpconv_ws_bytes(int Nq, int Ns, int H, int K, int Cin, int Cout);
  * may be NULL to force the fp32 CUDA-core path). mode: 0 = auto (tensor path when supported), 1 = fp32 CUDA cores,
  * 2 = tcgen05 TF32 (error if unsupported shape), 3 = tcgen05 with fp16 operands: d_wprep is then the fp16 operand of
  * aprb_kpconv_prepare_weights_f16 and the weighted tile is produced in fp16 — the 10-bit mantissa of TF32 at half the
- * bytes, for features of O(1) magnitude such as InstanceNorm outputs (K*Cin % 64 == 0, Cin % 4 == 0, H <= 128).
- * 4 = as 3, and d_x itself is fp16 [Ns, Cin] (int32 indices, Cin a multiple of the producer's 32/64/128/256/512 slab).
+ * bytes (K*Cin % 64 == 0, Cin % 4 == 0, H <= 128). Every fp16 store of this path saturates: a weighted sum outside the
+ * fp16 range clamps to +-65504 instead of becoming inf (features are expected to be O(1), e.g. InstanceNorm outputs).
+ * 4 = as 3, and d_x itself is fp16 [Ns, Cin] (int32 indices, Cin a multiple of the producer's 32/64/128/256/512 slab);
+ *     for Cin % 64 == 0 the weighting kernel multiplies with fma.rn.f32.f16: the influence weight is rounded to fp16 as well
+ *     (fp32 accumulation; aprb_set_option("kpw_fh", 0) keeps fp32 weights).
  * 5 = fp16 features like 4, with the weighting stage itself on tcgen05 (kpconv_tc.cu) and d_wprep the ck-ordered operand
  *     of aprb_kpconv_prepare_weights_f16_ck; shapes per aprb_kpconv_tc_supported. */
 int aprb_kpconv_forward(const float* d_q, const float* d_s, const void* d_idx, int idx_is_i64, int ld_idx,
