@@ -82,6 +82,7 @@ SIGNATURES = {
     "aprb_kfe_get_tap": (_i, [_p, _i, _p, _p, _p, _p, _p]),
     "aprb_max_pool_seg": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p]),
     "aprb_pool_seg_widths": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p, _p]),
+    "aprb_cell_grid_query_nearest": (_i, [_p, _sz, _p, _p, _i, _i, _i, _f, _p, _i, _p]),
     "aprb_cell_grid_query_seg": (_i, [_p, _sz, _p, _p, _i, _i, _i, _f, _i, _p, _i, _i, _p, _p]),
 }
 

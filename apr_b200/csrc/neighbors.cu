@@ -267,6 +267,45 @@ nb_query_kernel(const float* __restrict__ q, int Nq, const int* __restrict__ qof
     }
 }
 
+// Nearest support only — column 0 of the matrix nb_query_kernel would produce (same fp32 non-FMA d2, strict d2 < r2, ties by
+// ascending support index), pad = Ns when the ball is empty. This is all the reference ever reads of an upsample matrix
+// (closest_pool: inds[:, 0], models/blocks.py:71-83). One thread per query: no candidate buffer, no sort.
+__global__ void __launch_bounds__(128)
+nb_nearest_kernel(const float* __restrict__ q, int Nq, const int* __restrict__ qoff, int B, int Ns,
+                  const NbGrid* __restrict__ grids, const int* __restrict__ cell_start, const float4* __restrict__ sorted,
+                  float radius, int* __restrict__ out, int ld) {
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= Nq) return;
+    const float r2 = __fmul_rn(radius, radius);
+    const int b = find_cloud(qoff, B, qi);
+    const NbGrid g = grids[b];
+    const float qx = q[3 * (size_t)qi], qy = q[3 * (size_t)qi + 1], qz = q[3 * (size_t)qi + 2];
+    uint64_t best = ~0ull;
+    if (g.dx > 0) {
+        const int cx = cell_coord(qx, g.ox, g.inv_cell), cy = cell_coord(qy, g.oy, g.inv_cell),
+                  cz = cell_coord(qz, g.oz, g.inv_cell);
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
+        if (x0 <= x1) {
+            for (int zz = max(cz - 1, 0); zz <= min(cz + 1, g.dz - 1); ++zz) {
+                for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g.dy - 1); ++yy) {
+                    const int row = g.base + (zz * g.dy + yy) * g.dx;
+                    const int s0 = cell_start[row + x0], e0 = cell_start[row + x1 + 1];
+                    for (int j = s0; j < e0; ++j) {
+                        const float4 sp = sorted[j];
+                        const float ddx = __fsub_rn(qx, sp.x), ddy = __fsub_rn(qy, sp.y), ddz = __fsub_rn(qz, sp.z);
+                        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
+                        if (d2 < r2) {
+                            const uint64_t key = ((uint64_t)__float_as_uint(d2) << 32) | (uint32_t)__float_as_int(sp.w);
+                            best = key < best ? key : best;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    out[(size_t)qi * ld] = best == ~0ull ? Ns : (int)(uint32_t)best;
+}
+
 struct NbWs {
     int *qoff, *soff, *bbox, *total_cells, *cell_of, *cell_count, *cell_start;
     NbGrid* grids;
@@ -391,6 +430,25 @@ extern "C" int aprb_cell_grid_query_seg(const void* d_grid, size_t grid_bytes, c
     carve_nb(c, 0, Ns > 0 ? Ns : 1, B, &w);
     if (!c.ok()) { set_error("aprb_cell_grid_query_seg: grid buffer too small"); return APRB_ERR_WORKSPACE; }
     return query_grid(d_q, d_qlens, B, Nq, Ns, radius, width, d_out_idx, ld, nullptr, nullptr, w, st, clouds_per_segment, d_seg_width);
+}
+
+// Nearest support within `radius` per query: out[n * ld] = column 0 of aprb_cell_grid_query's matrix (pad Ns).
+extern "C" int aprb_cell_grid_query_nearest(const void* d_grid, size_t grid_bytes, const float* d_q, const int32_t* d_qlens, int B,
+                                            int Nq, int Ns, float radius, int32_t* d_out_idx, int ld, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    NB_COMMON_CHECKS();
+    APRB_REQUIRE(Nq >= 0 && d_qlens && d_grid && ld >= 1, "bad query arguments");
+    if (Nq == 0) return APRB_OK;
+    APRB_REQUIRE(d_q && d_out_idx, "null point/output pointer");
+    Carver c(const_cast<void*>(d_grid), grid_bytes);
+    NbWs w;
+    carve_nb(c, 0, Ns > 0 ? Ns : 1, B, &w);
+    if (!c.ok()) { set_error("aprb_cell_grid_query_nearest: grid buffer too small"); return APRB_ERR_WORKSPACE; }
+    APRB_TIMED("setup_kernel", st, 1, (setup_kernel<<<1, 256, 0, st>>>(d_qlens, w.qoff, nullptr, nullptr, B, nullptr, nullptr, 0)));
+    APRB_TIMED("nb_nearest_kernel", st, 1, (nb_nearest_kernel<<<cdiv(Nq, 128), 128, 0, st>>>(d_q, Nq, w.qoff, B, Ns, w.grids, w.cell_start, w.sorted,
+                                                                                             radius, d_out_idx, ld)));
+    APRB_LAUNCH_OK();
+    return APRB_OK;
 }
 
 extern "C" int aprb_radius_neighbors_batch(const float* d_q, const float* d_s, const int32_t* d_qlens,

@@ -582,7 +582,11 @@ extern "C" int aprb_kfe_forward(aprb_kfe* hp, const float* d_pts, const int32_t*
             grid[l + 1] = A.take<char>(grid_bytes[l + 1]);
             if (!grid[l + 1]) { set_error("aprb_kfe_forward: arena too small"); return APRB_ERR_WORKSPACE; }
             KFE_OK(aprb_cell_grid_build(npts, nlens, B, h.n[l + 1], 2 * r, grid[l + 1], grid_bytes[l + 1], st));
-            if (cfg.build_upsamples) {
+            if (cfg.build_upsamples == 2) {                        // nearest support only: the column closest_pool reads
+                KFE_ALLOC(up, int, (size_t)h.n[l]);
+                KFE_OK(aprb_cell_grid_query_nearest(grid[l + 1], grid_bytes[l + 1], h.pts[l], h.lens[l], B, h.n[l], h.n[l + 1], 2 * r, up, 1, st));
+                h.up[l] = up;
+            } else if (cfg.build_upsamples) {
                 KFE_ALLOC(up, int, (size_t)h.n[l] * lim);
                 KFE_OK(aprb_cell_grid_query(grid[l + 1], grid_bytes[l + 1], h.pts[l], h.lens[l], B, h.n[l], h.n[l + 1], 2 * r, lim, up, lim, nullptr, nullptr, st));
                 h.up[l] = up;
@@ -734,7 +738,7 @@ extern "C" int aprb_kfe_get(const aprb_kfe* h, int what, int level, const void**
         case 0: *d_ptr = h->pts[level]; *rows = h->n[level]; *cols = 3; break;
         case 1: *d_ptr = h->conv[level]; *rows = h->conv[level] ? h->n[level] : 0; *cols = lim; break;
         case 2: *d_ptr = h->pool[level]; *rows = h->pool[level] ? h->n[level + 1] : 0; *cols = lim; break;
-        case 3: *d_ptr = h->up[level]; *rows = h->up[level] ? h->n[level] : 0; *cols = lim; break;
+        case 3: *d_ptr = h->up[level]; *rows = h->up[level] ? h->n[level] : 0; *cols = h->cfg.build_upsamples == 2 ? 1 : lim; break;
         case 4: *d_ptr = h->lens[level]; *rows = h->B; *cols = 1; break;
         default: set_error("aprb_kfe_get: unknown selector %d", what); return APRB_ERR_INVALID;
     }

@@ -170,6 +170,19 @@ class CellGrid:
             TRACE.append(("nb", nq, self.ns, width))
         return (out, counts[:nq], maxc) if want_counts else out
 
+    def query_nearest(self, queries, q_lens, radius):
+        """[Nq, 1] int32: column 0 of query(...)'s matrix — the nearest support inside the ball (pad = Ns when it is empty),
+        all the reference reads of an upsample matrix (closest_pool, blocks.py:71-83)."""
+        if float(radius) > self.radius * (1 + 1e-6):
+            raise N.NativeError("CellGrid.query_nearest: radius larger than the radius the grid was built for")
+        q, ql = _dev_f32(queries, "queries"), _dev_i32(q_lens, "q_lens")
+        nq = q.shape[0]
+        out = torch.empty((nq, 1), dtype=torch.int32, device=q.device)
+        rc = N.lib().aprb_cell_grid_query_nearest(N.ptr(self.buf), self.buf.numel(), N.ptr(q), N.ptr(ql), self.b, nq, self.ns,
+                                                  float(radius), N.ptr(out), 1, N.stream_ptr())
+        N.check(rc, "aprb_cell_grid_query_nearest")
+        return out
+
 
 def kpconv_prepare_weights(weights):
     """[K,Cin,Cout] f32 -> prepared TF32 K-major operand [Cout, K*Cin]."""

@@ -45,7 +45,9 @@ class KFEPipeline:
         self.stream = stream if stream is not None else torch.cuda.current_stream(self.device)
         self.encoder = encoder
         self._limits = [int(v) for v in list(neighborhood_limits)[:8]]
-        self._build_upsamples = bool(build_upsamples)
+        # True: full [N_l, limit] upsample matrices like the reference's collate; "nearest": only their column 0 ([N_l, 1]) —
+        # all the reference reads of them (closest_pool: inds[:, 0], blocks.py:71-83); False: none
+        self._build_upsamples = 2 if build_upsamples in ("nearest", 2) else (1 if build_upsamples else 0)
         self._cps = int(clouds_per_segment)
         self.handle = None
         self.arena = None
@@ -117,7 +119,7 @@ class KFEPipeline:
         cfg.first_subsampling_dl, cfg.conv_radius = config.first_subsampling_dl, config.conv_radius
         for i, v in enumerate(list(neighborhood_limits)[:8]):
             cfg.limits[i] = int(v)
-        cfg.build_upsamples = 1 if build_upsamples else 0
+        cfg.build_upsamples = int(build_upsamples)
         cfg.in_feats_dim = config.in_feats_dim
         cfg.clouds_per_segment = int(clouds_per_segment)   # 2 = a super-batch of collated pairs (per-pair InstanceNorm)
         arr = (_Block * len(blks))(*blks)
@@ -306,7 +308,7 @@ class KPFCNNPipeline:
 
     def __init__(self, net, config, neighborhood_limits, stream=None, clouds_per_segment=2):
         self.net, self.config = net, config
-        self.enc = KFEPipeline(net, config, neighborhood_limits, build_upsamples=True, stream=stream,
+        self.enc = KFEPipeline(net, config, neighborhood_limits, build_upsamples="nearest", stream=stream,
                                clouds_per_segment=clouds_per_segment)
         self.stream, self.device = self.enc.stream, self.enc.device
         self.cps = max(int(clouds_per_segment), 0)

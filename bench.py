@@ -327,7 +327,8 @@ def run_ours(args):
 
     # ---- S native pipelines, one CUDA stream and one host thread each (aprb_kfe_forward releases the GIL)
     streams = [torch.cuda.Stream(dev) for _ in range(S)]
-    pipes = [KFEPipeline(enc, cfg, limits, build_upsamples=True, stream=streams[k], clouds_per_segment=2 if P > 1 else 0)
+    ups = "nearest" if args.upsamples == "nearest" else True
+    pipes = [KFEPipeline(enc, cfg, limits, build_upsamples=ups, stream=streams[k], clouds_per_segment=2 if P > 1 else 0)
              for k in range(S)]
     pool = ThreadPoolExecutor(max_workers=S) if S > 1 else None
     main_stream = torch.cuda.current_stream(dev)
@@ -387,6 +388,23 @@ def run_ours(args):
     ms_dev, wall_dev, launches, _ = timed(step_dev, args.steps, args.warmup, sampler=clk)
     steps_dev = timed.last_steps
     clocks = clk.stop()
+
+    # the same region with the FULL [N_l, limit] upsample matrices of the reference's collate (the default builds only their
+    # column 0): recorded beside the headline so that the cost of the columns nothing reads is in the line, not hidden
+    full_ups = None
+    if args.upsamples == "nearest":
+        pipes_full = [KFEPipeline(enc, cfg, limits, build_upsamples=True, stream=streams[k], clouds_per_segment=2 if P > 1 else 0)
+                      for k in range(S)]
+        n_full = max(3, args.steps // 3)
+        ms_f, _, _, _ = timed(lambda i: fan_out(lambda k, j: pipes_full[k].forward(*pairs_dev[j % len(pairs_dev)]), i), n_full, 3)
+        tf_ = torch.tensor([ms_f], dtype=torch.float64, device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(tf_, op=dist.ReduceOp.MAX)
+        full_ups = {"value": 2.0 * S * P * n_full * world / (float(tf_.item()) * 1e-3), "unit": UNIT, "steps": n_full,
+                    "how": "same timed region with build_upsamples = full [N_l, limit] matrices (--upsamples full makes it the headline)"}
+        del pipes_full
+        torch.cuda.empty_cache()
 
     out_rows_cap = max(4096, int(pairs_host[0][0].shape[0]) // 4)     # the last level keeps ~6 % of the level-0 rows
     out_cols = pipes[0]._out_cols
@@ -635,7 +653,7 @@ def run_ours(args):
         nb_bytes += 24.0 * n_levels[l] + 8.0 * Bc + 4.0 * n_levels[l] * W                                    # conv(l)
         if l + 1 < L:
             nb_bytes += 12.0 * (n_levels[l + 1] + n_levels[l]) + 8.0 * Bc + 4.0 * n_levels[l + 1] * W          # pool(l)
-            nb_bytes += 12.0 * (n_levels[l] + n_levels[l + 1]) + 8.0 * Bc + 4.0 * n_levels[l] * W              # upsample(l)
+            nb_bytes += 12.0 * (n_levels[l] + n_levels[l + 1]) + 8.0 * Bc + 4.0 * n_levels[l] * (1 if args.upsamples == "nearest" else W)   # upsample(l)
     sub_bytes = sum(12.0 * (n_levels[l] + n_levels[l + 1]) + 8.0 * Bc for l in range(L - 1))
     def stage(names, nbytes, what):
         ms = sum(prof[n][1] for n in names if n in prof) / args.steps
@@ -645,8 +663,9 @@ def run_ours(args):
                 "frac": ach / pk["hbm"], "traffic": None, "ms_per_call": ms, "launches_per_call": cnt,
                 "algorithmic_bytes_per_call": nbytes, "note": what}
     roof_stages = {
-        "radius_search": stage(["nb_query_kernel", "nb_count_kernel", "nb_scatter_kernel", "nb_grid_params_kernel"], nb_bytes,
-                               "10 searches on 4 cell lists; bytes = 12*Nq + 12*Ns + 8*B + 4*Nq*W per search (SURVEY 8d). The query "
+        "radius_search": stage(["nb_query_kernel", "nb_nearest_kernel", "nb_count_kernel", "nb_scatter_kernel", "nb_grid_params_kernel"], nb_bytes,
+                               "10 searches on 4 cell lists; bytes = 12*Nq + 12*Ns + 8*B + 4*Nq*W per search (SURVEY 8d; W = 1 for the "
+                               "upsample searches when only their nearest column is built). The query "
                                "kernel is instruction-issue bound (candidate scan + (d2, index) sort), not HBM bound: this fraction is "
                                "its distance from the HBM floor"),
         "grid_subsample": stage(["sub_params_kernel", "sub_keys_kernel", "cub_radix_sort_pairs32", "cub_radix_sort_pairs64",
@@ -661,6 +680,10 @@ def run_ours(args):
             "config": {"workload": wl_name, "pairs_per_step": S * P, "pairs_per_call": P,
                        "concurrent_streams": S, "points_stacked": int(pairs_dev[0][0].shape[0]), "level_points": n_levels,
                        "limits": limits,
+                       "upsample_matrices": ("column 0 only ([N_l, 1]: the nearest support, all the reference reads of an upsample "
+                                             "matrix — closest_pool inds[:, 0], blocks.py:71-83; SURVEY 8f-3; bit-identical to "
+                                             "column 0 of the full search); --upsamples full builds [N_l, limit]"
+                                             if args.upsamples == "nearest" else "full [N_l, limit] matrices like the reference's collate"),
                        "parallelism": f"pairs x{world}", "path": "native (aprb_kfe_forward)",
                        "l2": "flushed between steps (256 MiB memset outside the event pair)",
                        "precision": ("fp16 operands (10-bit mantissa, as TF32) with fp32 accumulation in TMEM for every contraction; "
@@ -692,6 +715,7 @@ def run_ours(args):
                                    "apr_b200.dataloader.collate_fn_descriptor (13 cpp_wrappers-compatible calls, each with its own "
                                    "H2D + D2H, int64 indices), H2D of the collated batch, the module-path encoder "
                                    "(apr_b200.blocks), D2H of the fp32 output; wall clock"} if dropin_value else None),
+            "value_full_upsample_matrices": full_ups,
             "roofline": roof, "roofline_tensor": roof_tensor, "roofline_kpconv_operator": roof_kpconv,
             "roofline_stages": roof_stages, "kernels": kernels,
             "wall_ms_per_step": 1e3 * wall_dev / args.steps, "ms_steps": steps_dev}
@@ -965,6 +989,9 @@ def main():
     ap.add_argument("--e2e-out", default="f16", choices=["f16", "f32"],
                     help="dtype of the encoder output copied to the host in the e2e leg (f16 is lossless for |v| >= 2^-14)")
     ap.add_argument("--opt", action="append", default=[], help="native tuning switch name=value (aprb_set_option)")
+    ap.add_argument("--upsamples", default="nearest", choices=["nearest", "full"],
+                    help="upsample searches of the device-resident pyramid: 'nearest' = only column 0 of each matrix (all the "
+                         "reference reads of them: closest_pool, blocks.py:71-83; SURVEY 8f-3), 'full' = [N_l, limit] matrices")
     ap.add_argument("--net", default="kfe", choices=["kfe", "kpfcnn"],
                     help="kfe = the KFE encoder (the headline metric); kpfcnn = full encoder-decoder forward (BASELINE configs[2])")
     args = ap.parse_args()

@@ -127,6 +127,11 @@ int aprb_cell_grid_query(const void* d_grid, size_t grid_bytes, const float* d_q
                          int Nq, int Ns, float radius, int width, int32_t* d_out_idx, int ld,
                          int32_t* d_counts, int32_t* d_max_count, void* stream);
 
+/* Nearest support within `radius` only: d_out_idx[n * ld] = column 0 of the matrix aprb_cell_grid_query would write (same
+ * d2 arithmetic, ties by ascending index, pad Ns). All the reference reads of an upsample matrix (closest_pool: inds[:, 0],
+ * models/blocks.py:71-83). */
+int aprb_cell_grid_query_nearest(const void* d_grid, size_t grid_bytes, const float* d_q, const int32_t* d_qlens, int B,
+                                 int Nq, int Ns, float radius, int32_t* d_out_idx, int ld, void* stream);
 /* aprb_cell_grid_query that also records, per segment of clouds_per_segment consecutive clouds (one collated pair), the
  * width of the reference's matrix for that collate: d_seg_width[s] = min(max neighbour count in the segment, width). */
 int aprb_cell_grid_query_seg(const void* d_grid, size_t grid_bytes, const float* d_q, const int32_t* d_qlens, int B,
@@ -327,7 +332,8 @@ typedef struct {
     int K;                    /* kernel points (15)                                                                       */
     float first_subsampling_dl, conv_radius;
     int limits[8];            /* neighbourhood limit per level (calibrate_neighbors, dataloader.py:200-232)               */
-    int build_upsamples;      /* also run the 3 upsample searches (needed by the decoder; part of the collate)            */
+    int build_upsamples;      /* 1 = also run the 3 upsample searches, full [N_l, limit] matrices like the collate; 2 = only   */
+                              /* their column 0 ([N_l, 1], the nearest support: all closest_pool reads); 0 = none */
     int in_feats_dim;         /* 1                                                                                         */
     int clouds_per_segment;   /* super-batching: P collated pairs stacked in one call = B = 2P clouds with 2 here, so that  */
                               /* BatchNormBlock keeps its per-pair statistics (blocks.py:459-468); 0 = all B clouds are ONE */

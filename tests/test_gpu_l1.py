@@ -279,3 +279,27 @@ def test_subsample_label_vote_vs_reference(cuda, ref_l1):
     pts, lens, feats, cls = _vote_case(5, 300, [300], 1, 3)
     sp, sc = gs.subsample(pts, classes=cls, sampleDl=1.0)
     assert sc.shape == (len(sp), 1)
+
+
+def test_nearest_only_search_is_column0_of_the_full_search(cuda, oracle):
+    """aprb_cell_grid_query_nearest (the upsample search of the device-resident pyramid): bit-identical to
+    column 0 of the full sorted matrix — upsample shapes (queries = finer level, supports = coarser level, radius 2r), empty
+    balls (pad), queries far outside the support bounding box, an empty cloud, exact d2 ties (duplicated supports)."""
+    rng = np.random.default_rng(3)
+    a, b = synth.pair_raw(1)
+    p0, l0 = oracle.subsample_batch(np.concatenate([a, b]), np.array([len(a), len(b)], np.int32), 0.3)
+    p1, l1 = oracle.subsample_batch(p0, l0, 0.6)
+    cases = [(p0, l0, p1, l1, 2.55), (p1, l1, p0, l0, 1.275), (p0, l0, p1, l1, 0.4)]
+    far = np.concatenate([p0[:50] + 500.0, p0[50:100]]).astype(np.float32)
+    cases.append((far, np.array([60, 40], np.int32), p1, l1, 2.55))
+    dup = np.concatenate([p1[:200], p1[:200]]).astype(np.float32)                  # every support twice: d2 ties, lower index wins
+    cases.append((p0[:300], np.array([300], np.int32), dup, np.array([400], np.int32), 2.55))
+    cases.append((p0[:100], np.array([60, 40], np.int32), p1[:80], np.array([0, 80], np.int32), 2.55))   # first cloud has no supports
+    for q, ql, s, sl, r in cases:
+        grid = ops.CellGrid(_dev(s, cuda), _dev(sl, cuda), r)
+        full = grid.query(_dev(q, cuda), _dev(ql, cuda), r, 40)
+        near = grid.query_nearest(_dev(q, cuda), _dev(ql, cuda), r)
+        assert near.shape == (len(q), 1) and torch.equal(near[:, 0], full[:, 0])
+        want = oracle.batch_query(q, s, ql, sl, radius=r)
+        col0 = want[:, 0] if want.shape[1] else np.full(len(q), len(s), np.int32)
+        assert np.array_equal(near[:, 0].cpu().numpy(), col0)

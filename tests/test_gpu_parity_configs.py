@@ -447,6 +447,32 @@ def test_pipeline_refreshes_stale_weights(cuda, oracle):
     assert torch.equal(y1, want)
 
 
+def test_pipeline_nearest_upsamples_equal_column0_of_the_full_matrices(cuda, oracle):
+    """build_upsamples="nearest" (the upsample search only needs column 0): [N_l, 1] matrices bit-identical to
+    column 0 of the full ones and of the oracle's collate; everything else of the pyramid and the encoder output unchanged."""
+    cfg = kitti_config()
+    clouds = [synth.small_cloud(21 + i, 1400 + 150 * i) for i in range(4)]          # two collated pairs in one call
+    p0, l0 = oracle.subsample_batch(np.concatenate(clouds), np.array([len(c) for c in clouds], np.int32), sampleDl=0.3)
+    limits = [30, 30, 30, 30]
+    torch.manual_seed(0); np.random.seed(0)
+    enc = KPFCNNEncoder(cfg).to(cuda).eval()
+    full = KFEPipeline(enc, cfg, limits, build_upsamples=True, clouds_per_segment=2)
+    near = KFEPipeline(enc, cfg, limits, build_upsamples="nearest", clouds_per_segment=2)
+    yf = full.forward(_t(p0, cuda), _t(l0, cuda)).clone()
+    yn = near.forward(_t(p0, cuda), _t(l0, cuda)).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(yf, yn)
+    pf, pn = full.pyramid(), near.pyramid()
+    for l in range(cfg.num_layers - 1):
+        assert pn["upsamples"][l].shape == (pf["points"][l].shape[0], 1)
+        assert torch.equal(pn["upsamples"][l][:, 0], pf["upsamples"][l][:, 0])
+        want = oracle.batch_query(pf["points"][l].cpu().numpy(), pf["points"][l + 1].cpu().numpy(), pf["stack_lengths"][l].cpu().numpy(),
+                                  pf["stack_lengths"][l + 1].cpu().numpy(), radius=2 * 1.275 * 2 ** l)
+        assert np.array_equal(pn["upsamples"][l][:, 0].cpu().numpy(), want[:, 0])
+        for key in ("neighbors", "pools"):
+            assert torch.equal(pn[key][l], pf[key][l])
+
+
 def test_kpfcnn_pipeline_config3_vs_oracle(cuda, oracle):
     """BASELINE config 3's network through KPFCNNPipeline (native encoder + bottleneck / GCN / decoder stream-ordered in the
     same call, two LoKITTI-like pairs super-batched) at the KITTI widths:
