@@ -734,6 +734,7 @@ static int launch_gemm(const float* A, const float* Bt, int M, int N, int K, int
     return APRB_OK;
 }
 
+X
 int g_nrm_park = 0;          // aprb_set_option("nrm_park"): parked mbarrier waits for the TMA / MMA lanes of gemm_nrm_f16_kernel (measured: no gain)
 int g_gemm_stages = 0;       // aprb_set_option("gemm_stages"): cap on the smem ring depth of the persistent kernels (0 = deepest)
 int g_gemm_bn = 0;           // aprb_set_option("gemm_bn"): force the persistent kernel's tile width (0 = by wave count)
@@ -891,9 +892,13 @@ static int launch_gemm_nrm(const void* A, const void* Bt, int K, const void* A2,
     p.nkb_main = K / 64; p.nkb_sc = DUAL ? K2 / 64 : 0;
     p.num_n = cdiv(p.N, BN); p.total_tiles = p.num_n * cdiv(p.M, GEMM_BM);
     p.stages = g_gemm_stages >= 2 ? min(g_gemm_stages, GemmNCfg::STAGES) : GemmNCfg::STAGES;
+    // aprb_set_option("nrm_ctas", 2): two CTAs per SM for the single-product forms (256 of the 512 TMEM columns each, a 2-stage
+    // ring each): the kernel is bound by its per-tile epilogue latency chain, a second CTA overlaps it with another tile's
+    const bool two = g_nrm_ctas == 2 && !DUAL && STATS;              // the apply forms need 156 registers x 320 threads: one CTA per SM
+    if (two) p.stages = 2;
     p.park = g_nrm_park;
     const int smem = GemmNCfg::SMEM - (GemmNCfg::STAGES - p.stages) * (GemmNCfg::A_BYTES + GemmNCfg::B_BYTES);
-    const int grid = min(p.total_tiles, sm_count());
+    const int grid = min(p.total_tiles, (two ? 2 : 1) * sm_count());
     {
         ProfScope ps(STATS ? "gemm_nrm_stats_kernel" : "gemm_nrm_apply_kernel", st, 1);
         gemm_nrm_f16_kernel<DUAL, STATS><<<grid, GemmNCfg::THREADS, smem, st>>>(tmA, tmB, tmA2, tmB2, p);
@@ -944,6 +949,7 @@ extern "C" int aprb_set_option(const char* name, int value) {
     if (strcmp(name, "gemm_bn") == 0) { g_gemm_bn = value; return APRB_OK; }
     if (strcmp(name, "gemm_stages") == 0) { g_gemm_stages = value; return APRB_OK; }
     if (strcmp(name, "nrm_park") == 0) { g_nrm_park = value; return APRB_OK; }
+    if (strcmp(name, "nrm_ctas") == 0) { g_nrm_ctas = value; return APRB_OK; }
     if (strcmp(name, "kpconv_chunk_mb") == 0) { g_kpconv_chunk_mb = value; return APRB_OK; }
     if (strcmp(name, "kpw_version") == 0) { g_kpw_version = value; return APRB_OK; }
     if (strcmp(name, "kpw_fh") == 0) { g_kpw_fh = value; return APRB_OK; }
