@@ -734,7 +734,7 @@ static int launch_gemm(const float* A, const float* Bt, int M, int N, int K, int
     return APRB_OK;
 }
 
-X
+int g_nrm_ctas = 1;          // aprb_set_option("nrm_ctas"): 2 = two CTAs per SM for the statistics pass (measured: 0.46 -> 0.41 ms per call alone, clouds/s unchanged)
 int g_nrm_park = 0;          // aprb_set_option("nrm_park"): parked mbarrier waits for the TMA / MMA lanes of gemm_nrm_f16_kernel (measured: no gain)
 int g_gemm_stages = 0;       // aprb_set_option("gemm_stages"): cap on the smem ring depth of the persistent kernels (0 = deepest)
 int g_gemm_bn = 0;           // aprb_set_option("gemm_bn"): force the persistent kernel's tile width (0 = by wave count)
