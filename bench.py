@@ -395,8 +395,8 @@ def run_ours(args):
     if args.upsamples == "nearest":
         pipes_full = [KFEPipeline(enc, cfg, limits, build_upsamples=True, stream=streams[k], clouds_per_segment=2 if P > 1 else 0)
                       for k in range(S)]
-        n_full = max(3, args.steps // 3)
-        ms_f, _, _, _ = timed(lambda i: fan_out(lambda k, j: pipes_full[k].forward(*pairs_dev[j % len(pairs_dev)]), i), n_full, 3)
+        n_full = max(4, args.steps // 2)
+        ms_f, _, _, _ = timed(lambda i: fan_out(lambda k, j: pipes_full[k].forward(*pairs_dev[j % len(pairs_dev)]), i), n_full, 4)
         tf_ = torch.tensor([ms_f], dtype=torch.float64, device=dev)
         if world > 1:
             import torch.distributed as dist
