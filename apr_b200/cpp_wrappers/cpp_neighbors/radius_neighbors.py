@@ -61,4 +61,4 @@ def batch_query(queries, supports, q_batches, s_batches, *, radius=0.1, max_neig
         idx = _ops.radius_neighbors(dq, ds, dql, dsl, r, max_count)
         width = max_count
     w = min(max_count, width)
-    return np.ascontiguousarray(idx[:, :w].cpu().numpy())
+    return _ops.to_host_numpy(idx[:, :w])

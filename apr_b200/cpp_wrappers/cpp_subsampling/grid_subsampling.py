@@ -53,7 +53,7 @@ def _run(points, batches, features, classes, sampleDl, method, max_p):
     res = _ops.grid_subsample(dp, db, float(np.float32(sampleDl)), int(max_p), features=df, classes=dc)
     if res[0].shape[0] < 1:
         raise RuntimeError("Error")
-    return tuple(t.cpu().numpy() for t in res)                           # classes come back [M, ldim]: wrapper.cpp:282-284
+    return tuple(_ops.to_host_numpy(t) for t in res)                     # classes come back [M, ldim]: wrapper.cpp:282-284
 
 
 def subsample_batch(points, batches, *, features=None, classes=None, sampleDl=0.1, method="barycenters", max_p=0,

@@ -60,6 +60,17 @@ def _pyramid_schedule(config):
         layer_blocks = []
 
 
+def _long(t):
+    """`.long()` of dataloader.py:164-166, written straight into page-locked memory when a CUDA context exists: the int64 index
+    matrices are 40 MB per KITTI pair and the caller ships them to the device next (trainer.py:299-305) — pageable, that copy
+    ran at ~6 GB/s (tools/dropin_profile.py)."""
+    if t.dtype == torch.int64 or t.numel() == 0 or not torch.cuda.is_available():
+        return t.long()
+    out = torch.empty(t.shape, dtype=torch.int64, pin_memory=True)
+    out.copy_(t)
+    return out
+
+
 def collate_fn_descriptor(list_data, config, neighborhood_limits):
     """dataloader.py:72-198. list_data = [(src_pcd, tgt_pcd, src_feats, tgt_feats, rot, trans, matching_inds,
     src_pcd_raw, tgt_pcd_raw, src_nghb, tgt_nghb, sample)] with exactly one pair."""
@@ -93,9 +104,9 @@ def collate_fn_descriptor(list_data, config, neighborhood_limits):
             pool_b = torch.zeros((0,), dtype=torch.int64)
             up_i = torch.zeros((0, 1), dtype=torch.int64)
         input_points += [batched_points.float()]
-        input_neighbors += [conv_i.long()]
-        input_pools += [pool_i.long()]
-        input_upsamples += [up_i.long()]
+        input_neighbors += [_long(conv_i)]
+        input_pools += [_long(pool_i)]
+        input_upsamples += [_long(up_i)]
         input_batches_len += [batched_lengths]
         batched_points, batched_lengths = pool_p, pool_b
         r_normal *= 2

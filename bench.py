@@ -477,7 +477,8 @@ def run_ours(args):
             gpu["features"] = batch["features"].to(dev)
             with torch.no_grad():
                 return enc(gpu).cpu()
-        one(0)
+        for i in range(2 * len(np_pairs)):                  # warm-up over every distinct pair: workspaces and the page-locked
+            one(i)                                           # staging blocks of torch's caching host allocator (size classes)
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         for i in range(n_steps):
@@ -485,7 +486,7 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         return 2.0 * n_steps / (time.perf_counter() - t0), int(y.shape[0])
 
-    dropin_value, _ = dropin_leg(3) if rank == 0 else (None, 0)
+    dropin_value, _ = dropin_leg(6) if rank == 0 else (None, 0)
 
     # ---- from RAW scans: pinned host [n, 4] float32 xyzr rows (datasets/kitti.py:191-194) -> H2D ->
     # first-level voxelisation at 0.3 m with open3d's voxel_down_sample semantics (kitti.py:588-589) -> the path -> D2H (fp32)
@@ -710,7 +711,7 @@ def run_ours(args):
                                     "aprb_voxel_downsample_raw at first_subsampling_dl (open3d 0.10 voxel_down_sample semantics: "
                                     "double arithmetic, origin = min - voxel/2; parity unpinned, open3d absent) -> pyramid + encoder "
                                     "-> D2H of the fp32 output; one stream sync per call, S streams free-running"},
-            "dropin_e2e": ({"value": dropin_value, "unit": UNIT, "sample": "3 steps x 1 pair on rank 0",
+            "dropin_e2e": ({"value": dropin_value, "unit": UNIT, "sample": "6 steps x 1 pair on rank 0, after a warm-up over every distinct pair",
                             "how": "strict drop-in, one pair per step like the reference: numpy in / numpy out through "
                                    "apr_b200.dataloader.collate_fn_descriptor (13 cpp_wrappers-compatible calls, each with its own "
                                    "H2D + D2H, int64 indices), H2D of the collated batch, the module-path encoder "
